@@ -1,0 +1,177 @@
+/*
+ * include/mgrl.h — C ABI of the B200-native batched MiniGrid simulator + PPO rollout kernels.
+ *
+ * The reference (Idokorro/MiniGrid-RL) is pure Python and has no FFI: the seam this library
+ * sits behind is the SB3 VecEnv protocol that /root/reference/src/ppo.py:118-126 constructs
+ * (make_vec_env -> VecTransposeImage -> VecFrameStack(4,'first')) and ppo.py:159 / :210 /
+ * :242 drive (reset / step).  Each entry point below names the reference interface it
+ * replaces.  INTEGRATION.md shows the ctypes binding and the VecEnv class that a
+ * maintainer of the reference would drop into ppo.py.
+ *
+ * Conventions
+ *  - every function returns 0 (MGRL_OK) or a negative mgrl_status; mgrl_last_error() holds
+ *    the message of the last failure on the calling thread.  No exception crosses the ABI.
+ *  - "_dev" pointers are device pointers owned by the caller (e.g. torch.Tensor.data_ptr());
+ *    "_host" pointers are host memory (pinned memory from mgrl_host_alloc is fastest).
+ *  - calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default
+ *    stream) unless documented otherwise.  A handle is bound to one device and is not
+ *    thread-safe; distinct handles are independent (one per GPU / rank).
+ *  - there is NO CPU implementation behind this ABI: without a CUDA device mgrl_create fails.
+ *
+ * State layout (140 bytes per environment, also the unit of get/set_state):
+ *   grid[121]  one "kind" byte per cell, grid[y*size+x]
+ *       0 empty (1,0,0)  1 wall (2,5,0)  2 goal (8,1,0)  3 lava (9,0,0)
+ *       8+c key  16+c ball  24+8*s+c door (s: 0 open 1 closed 2 locked)
+ *       64+8*m+c box (m: 0 empty, 1..6 holds a key of colour m-1)
+ *       colours c: red 0 green 1 blue 2 purple 3 yellow 4 grey 5
+ *   agent_x, agent_y, agent_dir, carrying(kind, 0 = nothing), step_count,
+ *   target_x, target_y (0xFF = none), target_action (0 = none), mission_id,
+ *   mission_done, latch_step, episode(u32), reset_draws(u16), error(u8), pad(u8)
+ * Mission ids: group*24 + type*6 + colour, type: key 0 ball 1 box 2 door 3;
+ *   group 0 "go to", 1 "toggle", 2 "pick up"; 72 "go to goal"; 73 "drop".
+ */
+#ifndef MGRL_H
+#define MGRL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGRL_ABI_VERSION 1
+#define MGRL_STATE_BYTES 140
+#define MGRL_OBS_BYTES 147       /* 7*7*3 */
+#define MGRL_N_MISSIONS 74
+#define MGRL_MISSION_TOKENS 32   /* environment.py:82 msn_len */
+#define MGRL_FRAMES 4            /* ppo.yaml:5 n_frames_stack */
+
+typedef enum {
+    MGRL_OK = 0,
+    MGRL_ERR_INVALID = -1,   /* bad argument / unsupported configuration */
+    MGRL_ERR_CUDA = -2,      /* CUDA runtime error (message in mgrl_last_error) */
+    MGRL_ERR_NO_DEVICE = -3, /* no CUDA device: this library has no CPU path */
+    MGRL_ERR_ENV = -4        /* an environment flagged an error (invalid action, rejection cap) */
+} mgrl_status;
+
+typedef enum { MGRL_OBS_HWC = 0, MGRL_OBS_CHW = 1 } mgrl_obs_layout;
+/* cfg.env.problem, custom_env.py:134-152 ('full' and 'mov' are not supported) */
+typedef enum { MGRL_MULTI = 0, MGRL_GTO = 1, MGRL_GTG = 2, MGRL_OPN = 3, MGRL_PKP = 4, MGRL_DRP = 5 } mgrl_problem;
+
+/* mirrors cfg.env of hydra_configs/single.yaml:20-28 (+ batch placement) */
+typedef struct {
+    int32_t size;              /* env.size, 5..11 */
+    int32_t num_objects;       /* env.num_objects */
+    int32_t problem;           /* mgrl_problem */
+    int32_t mission;           /* env.mission: 0 go-to, 1 toggle, 2 pick-up, 5 go-to-goal, -1 = null (mixed) */
+    int32_t all_doors_open;    /* env.all_doors_open */
+    int32_t see_through_walls; /* env.see_through_walls */
+    int32_t max_steps;         /* size*size (custom_env.py:114); 0 = derive */
+    int32_t num_obstacles;     /* floor((size-2)^2 * percent_obstacles) if env.obstacles else 0 */
+    int32_t num_envs;          /* environments held by this handle (the local shard) */
+    int32_t obs_layout;        /* mgrl_obs_layout of every image this handle writes */
+    uint64_t env_id_base;      /* global id of local env 0 (rank * num_envs): RNG key, so results
+                                  do not depend on how envs are sharded across GPUs */
+} mgrl_config;
+
+typedef struct mgrl_env mgrl_env;
+
+int mgrl_abi_version(void);
+const char *mgrl_last_error(void);
+
+/* replaces make_vec_env(make_env, n_envs, ...) (ppo.py:118-122): allocates the device state */
+int mgrl_create(const mgrl_config *cfg, int device, mgrl_env **out);
+int mgrl_destroy(mgrl_env *env);
+
+/* pinned host memory for the *_host entry points */
+int mgrl_host_alloc(void **ptr, size_t bytes);
+int mgrl_host_free(void *ptr);
+
+/* ---- device-resident fast path ------------------------------------------------------ */
+
+/* replaces VecEnv.seed(seed) + VecEnv.reset() (ppo.py:134,210): fresh environments
+ * (latch cleared, episode 0) from RNG keys (seed, env_id_base+i); writes the first
+ * observation.  image_dev [N,147] in obs_layout, dir_dev [N], mission_dev [N] (mission id). */
+int mgrl_reset(mgrl_env *env, uint64_t seed, uint8_t *image_dev, uint8_t *dir_dev,
+               uint8_t *mission_dev, void *stream);
+
+/* replaces VecEnv.step(actions) for the un-stacked observation (SubprocVecEnv/DummyVecEnv
+ * step_wait over Monitor(Discrete2BoxWrapper(TokenizeVocabWrapper(PlaygroundEnv)))):
+ * PlaygroundEnv.step (custom_env.py:269-330) + auto-reset on done.
+ *   actions_dev [N] u8 in 0..6;  image_dev [N,147];  dir_dev [N];  mission_dev [N];
+ *   reward_dev [N] f32;  term_dev / trunc_dev [N] u8 (done = term|trunc,
+ *   info['TimeLimit.truncated'] = trunc & !term);
+ *   ep_len_dev [N] u8 or NULL: Monitor's episode length on done steps, else 0
+ *     (Monitor's episode return equals the reward of the done step: all others are 0);
+ *   term_image_dev [N,147] / term_dir_dev [N] or NULL: image and direction of
+ *     info['terminal_observation'], written only for environments that finished on this
+ *     step (its mission is the previous step's mission). */
+int mgrl_step(mgrl_env *env, const uint8_t *actions_dev, uint8_t *image_dev, uint8_t *dir_dev,
+              uint8_t *mission_dev, float *reward_dev, uint8_t *term_dev, uint8_t *trunc_dev,
+              uint8_t *ep_len_dev, uint8_t *term_image_dev, uint8_t *term_dir_dev, void *stream);
+
+/* T consecutive steps in ONE launch with the state tile kept in shared memory between
+ * steps (action-trace replay; BASELINE.json config 4 and the kernel benchmark).
+ * actions_dev [T,N]; outputs are [T,N,...] with the same meaning as mgrl_step; any output
+ * except reward/term/trunc may be NULL. */
+int mgrl_step_many(mgrl_env *env, int T, const uint8_t *actions_dev, uint8_t *image_dev,
+                   uint8_t *dir_dev, uint8_t *mission_dev, float *reward_dev, uint8_t *term_dev,
+                   uint8_t *trunc_dev, uint8_t *ep_len_dev, void *stream);
+
+/* canonical state dump / restore, bytes must equal num_envs*MGRL_STATE_BYTES.
+ * set_state also (re)sets the seed used by later auto-resets. */
+int mgrl_get_state(mgrl_env *env, void *dst_dev, size_t bytes, void *stream);
+int mgrl_set_state(mgrl_env *env, const void *src_dev, size_t bytes, uint64_t seed, void *stream);
+/* same, host buffers; synchronous */
+int mgrl_get_state_host(mgrl_env *env, void *dst_host, size_t bytes, void *stream);
+int mgrl_set_state_host(mgrl_env *env, const void *src_host, size_t bytes, uint64_t seed, void *stream);
+/* raw device pointer to the [N,140] state array (zero-copy inspection) */
+int mgrl_state_ptr(mgrl_env *env, void **state_dev);
+
+/* current observation of every environment without stepping (gen_obs) */
+int mgrl_observe(mgrl_env *env, uint8_t *image_dev, uint8_t *dir_dev, uint8_t *mission_dev, void *stream);
+/* replaces minigrid FullyObsWrapper (experts_test.py:29): image [N,size,size,3], agent = (10,0,dir) */
+int mgrl_full_obs(mgrl_env *env, uint8_t *image_dev, void *stream);
+/* max over environments of the per-env error byte (synchronises the stream) */
+int mgrl_error_flags(mgrl_env *env, int *flags_out, void *stream);
+
+/* replaces VecFrameStack(4,'first').step_wait on all three keys (ppo.py:126):
+ * shift by one frame, zero the history of finished envs, append the newest frame.
+ *   stack_image_dev [N,4,147] (== (N,12,7,7) for CHW frames), stack_dir_dev [N,16] one-hot
+ *   (Discrete2BoxWrapper, environment.py:144-149), stack_mission_dev [N,128] int64 tokens
+ *   (TokenizeVocabWrapper, environment.py:91-112) from token_table_dev [74,32] int64.
+ *   done_dev NULL = reset (clear all history). */
+int mgrl_stack_push(int num_envs, const uint8_t *image_dev, const uint8_t *dir_dev,
+                    const uint8_t *mission_dev, const uint8_t *done_dev, const int64_t *token_table_dev,
+                    uint8_t *stack_image_dev, uint8_t *stack_dir_dev, int64_t *stack_mission_dev,
+                    void *stream);
+
+/* replaces SB3 RolloutBuffer.compute_returns_and_advantage (float32, same operation order):
+ * rewards/values/advantages/returns [T,N] f32, episode_starts [T,N] u8, last_values [N],
+ * last_dones [N] u8. */
+int mgrl_gae(const float *rewards_dev, const float *values_dev, const uint8_t *episode_starts_dev,
+             const float *last_values_dev, const uint8_t *last_dones_dev, double gamma,
+             double gae_lambda, int T, int N, float *advantages_dev, float *returns_dev, void *stream);
+
+/* ---- host-buffer drop-in path (what B200VecEnv.reset/step with numpy arrays calls) --- */
+
+/* VecEnv.reset(): stacked observation dict into host buffers; synchronous.
+ *   image_host [N,4,147] u8, direction_host [N,16] u8, mission_host [N,128] i64 */
+int mgrl_vec_reset_host(mgrl_env *env, uint64_t seed, uint8_t *image_host, uint8_t *direction_host,
+                        int64_t *mission_host, void *stream);
+/* VecEnv.step(actions): actions_host [N] u8 -> stacked obs, rewards [N] f32, term/trunc [N],
+ * ep_len [N], term_image_host [N,147] + term_dir_host [N] (last frame of the terminal
+ * observation, rows of finished envs only; both may be NULL).  Copies H2D/D2H inside;
+ * synchronous. */
+int mgrl_vec_step_host(mgrl_env *env, const uint8_t *actions_host, uint8_t *image_host,
+                       uint8_t *direction_host, int64_t *mission_host, float *reward_host,
+                       uint8_t *term_host, uint8_t *trunc_host, uint8_t *ep_len_host,
+                       uint8_t *term_image_host, uint8_t *term_dir_host, void *stream);
+/* mission-id -> token table used by the host path and by mgrl_stack_push callers: [74,32] i64 */
+int mgrl_set_token_table(mgrl_env *env, const int64_t *table_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGRL_H */

@@ -1,0 +1,50 @@
+"""Mission strings and their token encoding.
+
+Mission text is produced at /root/reference/src/custom_env.py:185,197,208,213,259 and
+tokenised by TokenizeVocabWrapper (environment.py:69-112): vocabulary
+[' ', '\\n', '-', ':', ',', '.', 'a'..'z'] -> indices 0..31, zero padded to 32 tokens.
+The simulator stores a one-byte mission id; this module is the id <-> text <-> tokens map.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+COLOURS = ["red", "green", "blue", "purple", "yellow", "grey"]      # upstream COLOR_TO_IDX order
+TYPES = ["key", "ball", "box", "door"]
+COMMANDS = ["go to", "toggle", "pick up"]                            # msn_commands[0..2], custom_env.py:87-94
+N_MISSIONS = 74
+MISSION_GOAL, MISSION_DROP = 72, 73
+MSN_LEN = 32
+VOCAB = [" ", "\n", "-", ":", ",", "."] + [chr(c) for c in range(ord("a"), ord("z") + 1)]
+
+
+def mission_string(mid: int) -> str:
+    if mid == MISSION_GOAL:
+        return "go to goal"
+    if mid == MISSION_DROP:
+        return "drop"
+    if not 0 <= mid < 72:
+        raise ValueError(f"bad mission id {mid}")
+    group, rem = divmod(mid, 24)
+    typ, colour = divmod(rem, 6)
+    return f"{COMMANDS[group]} {COLOURS[colour]} {TYPES[typ]}"
+
+
+MISSIONS = [mission_string(i) for i in range(N_MISSIONS)]
+_IDS = {s: i for i, s in enumerate(MISSIONS)}
+
+
+def mission_id(text: str) -> int:
+    return _IDS[text]
+
+
+def tokenize(text: str) -> np.ndarray:
+    out = np.zeros(MSN_LEN, np.int64)
+    for i, ch in enumerate(text.lower()):
+        out[i] = VOCAB.index(ch)
+    return out
+
+
+def token_table() -> np.ndarray:
+    """[74, 32] int64: row = mission id."""
+    return np.stack([tokenize(s) for s in MISSIONS])

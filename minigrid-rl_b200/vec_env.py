@@ -1,0 +1,412 @@
+"""Vector-environment front-ends over the C-ABI CUDA library.
+
+`B200VecEnv` duck-types the Stable-Baselines3 `VecEnv` that the reference builds at
+/root/reference/src/ppo.py:118-126 (make_vec_env(make_env) -> VecTransposeImage ->
+VecFrameStack(4, channels_order='first')) and drives at ppo.py:159,210,242: numpy in, numpy
+out, same observation dict (`image` (N,12,7,7) u8, `direction` (N,16) u8, `mission` (N,128)
+i64), float32 rewards, bool dones and SB3-style infos (`terminal_observation`,
+`TimeLimit.truncated`, `episode`).  It needs neither SB3 nor gymnasium nor torch.
+
+`DeviceEnv` is the device-resident fast path used by the rollout engine and the benchmark:
+torch CUDA tensors in and out, nothing crosses PCIe.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+
+import numpy as np
+
+from . import _native as nat
+from .config import EnvConfig, PROBLEMS
+from .missions import MISSIONS, token_table
+
+OBS_BYTES = 147
+STATE_BYTES = 140
+FRAMES = 4
+
+# numpy view of the 140-byte state record (include/mgrl.h)
+STATE_DTYPE = np.dtype([
+    ("grid", np.uint8, (121,)),
+    ("agent_x", np.uint8), ("agent_y", np.uint8), ("agent_dir", np.uint8),
+    ("carrying", np.uint8), ("step_count", np.uint8),
+    ("target_x", np.uint8), ("target_y", np.uint8), ("target_action", np.uint8),
+    ("mission_id", np.uint8), ("mission_done", np.uint8), ("latch_step", np.uint8),
+    ("episode", np.uint32), ("reset_draws", np.uint16), ("error", np.uint8), ("pad", np.uint8),
+])
+
+
+def _native_config(cfg: EnvConfig, num_envs: int, env_id_base: int, chw: bool) -> nat.Config:
+    cfg.validate()
+    return nat.Config(cfg.size, cfg.num_objects, PROBLEMS[cfg.problem],
+                      -1 if cfg.mission is None else int(cfg.mission), int(cfg.all_doors_open),
+                      int(cfg.see_through_walls), cfg.max_steps, cfg.num_obstacles, int(num_envs),
+                      1 if chw else 0, int(env_id_base))
+
+
+class _Handle:
+    """Owns one mgrl_env."""
+
+    def __init__(self, cfg: EnvConfig, num_envs: int, device: int, env_id_base: int, chw: bool):
+        self.lib = nat.lib()
+        self.ncfg = _native_config(cfg, num_envs, env_id_base, chw)
+        self.ptr = C.c_void_p()
+        nat.check(self.lib.mgrl_create(C.byref(self.ncfg), int(device), C.byref(self.ptr)), "mgrl_create")
+
+    def close(self):
+        if self.ptr:
+            self.lib.mgrl_destroy(self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ----------------------------------------------------------------------------- spaces (duck types)
+class Box:
+    def __init__(self, low, high, shape, dtype):
+        self.low, self.high, self.shape, self.dtype = low, high, tuple(shape), np.dtype(dtype)
+
+    def __repr__(self):
+        return f"Box({self.low}, {self.high}, {self.shape}, {self.dtype})"
+
+
+class Discrete:
+    def __init__(self, n):
+        self.n, self.shape, self.dtype = int(n), (), np.dtype(np.int64)
+
+    def sample(self):
+        return int(np.random.randint(self.n))
+
+    def __repr__(self):
+        return f"Discrete({self.n})"
+
+
+class DictSpace:
+    def __init__(self, spaces):
+        self.spaces = dict(sorted(spaces.items()))   # gymnasium sorts plain-dict keys
+
+    def __getitem__(self, k):
+        return self.spaces[k]
+
+    def keys(self):
+        return self.spaces.keys()
+
+    def items(self):
+        return self.spaces.items()
+
+    def __repr__(self):
+        return f"Dict({self.spaces})"
+
+
+class _Pinned:
+    """numpy array over pinned host memory from mgrl_host_alloc."""
+
+    def __init__(self, lib, shape, dtype):
+        self.lib = lib
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        self.ptr = C.c_void_p()
+        nat.check(lib.mgrl_host_alloc(C.byref(self.ptr), nbytes), "mgrl_host_alloc")
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(self.ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self.array[...] = 0
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.lib.mgrl_host_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+
+_EMPTY_INFO: dict = {}
+
+
+class B200VecEnv:
+    """Drop-in for the reference's stacked SB3 VecEnv (host numpy surface)."""
+
+    metadata = {"render_modes": []}
+
+    def __init__(self, cfg: EnvConfig | None = None, num_envs: int = 16, seed: int | None = None,
+                 device: int = 0, env_id_base: int = 0, n_frames_stack: int = 4):
+        if n_frames_stack != FRAMES:
+            raise ValueError("only n_frames_stack == 4 is built (hydra_configs/algorithm/ppo.yaml:5)")
+        self.cfg = cfg or EnvConfig()
+        self.num_envs = int(num_envs)
+        self._seed = 0 if seed is None else int(seed)
+        self._h = _Handle(self.cfg, self.num_envs, device, env_id_base, chw=True)
+        lib = self._h.lib
+        self._table = np.ascontiguousarray(token_table())
+        nat.check(lib.mgrl_set_token_table(self._h.ptr, self._table.ctypes.data_as(C.c_void_p)), "set_token_table")
+        n = self.num_envs
+        self.observation_space = DictSpace({
+            "direction": Box(0, 1, (4 * FRAMES,), np.uint8),
+            "image": Box(0, 255, (3 * FRAMES, 7, 7), np.uint8),
+            "mission": Box(0, 32, (32 * FRAMES,), np.int64),
+        })
+        self.action_space = Discrete(7)
+        # the stacked observation is double-buffered in pinned memory: the arrays returned
+        # by step t stay valid until step t+2, and step t+1 reads the history frames of
+        # info['terminal_observation'] from them without copying
+        self._obs_bufs = [{
+            "image": _Pinned(lib, (n, 3 * FRAMES, 7, 7), np.uint8),
+            "direction": _Pinned(lib, (n, 4 * FRAMES), np.uint8),
+            "mission": _Pinned(lib, (n, 32 * FRAMES), np.int64),
+        } for _ in range(2)]
+        self._cur = 0
+        self._p = {
+            "actions": _Pinned(lib, (n,), np.uint8),
+            "reward": _Pinned(lib, (n,), np.float32),
+            "term": _Pinned(lib, (n,), np.uint8),
+            "trunc": _Pinned(lib, (n,), np.uint8),
+            "ep_len": _Pinned(lib, (n,), np.uint8),
+            "term_image": _Pinned(lib, (n, 3, 7, 7), np.uint8),
+            "term_dir": _Pinned(lib, (n,), np.uint8),
+        }
+        self._actions = None
+        self._t0 = time.time()
+        self.reset_infos = [dict() for _ in range(n)]
+        self.render_mode = None
+
+    # ------------------------------------------------------------------ VecEnv protocol
+    def seed(self, seed=None):
+        if seed is not None:
+            self._seed = int(seed)
+        return [self._seed + i for i in range(self.num_envs)]
+
+    def _obs(self):
+        b = self._obs_bufs[self._cur]
+        return {"direction": b["direction"].array, "image": b["image"].array, "mission": b["mission"].array}
+
+    def reset(self):
+        b = self._obs_bufs[self._cur]
+        nat.check(self._h.lib.mgrl_vec_reset_host(
+            self._h.ptr, self._seed, b["image"].ptr, b["direction"].ptr, b["mission"].ptr, None), "vec_reset")
+        return self._obs()
+
+    def step_async(self, actions):
+        a = np.asarray(actions)
+        if a.shape != (self.num_envs,):
+            raise ValueError(f"actions must have shape ({self.num_envs},), got {a.shape}")
+        if a.size and (a.min() < 0 or a.max() > 6):
+            raise ValueError(f"Unknown action: {int(a.max() if a.max() > 6 else a.min())}")  # upstream step raises
+        self._p["actions"].array[:] = a
+        self._actions = a
+
+    def step_wait(self):
+        p = self._p
+        prev = self._obs()           # terminal_observation needs the three frames before the terminal one
+        self._cur ^= 1
+        b = self._obs_bufs[self._cur]
+        nat.check(self._h.lib.mgrl_vec_step_host(
+            self._h.ptr, p["actions"].ptr, b["image"].ptr, b["direction"].ptr, b["mission"].ptr,
+            p["reward"].ptr, p["term"].ptr, p["trunc"].ptr, p["ep_len"].ptr, p["term_image"].ptr,
+            p["term_dir"].ptr, None), "vec_step")
+        term, trunc = p["term"].array, p["trunc"].array
+        dones = (term | trunc).astype(bool)
+        infos = [_EMPTY_INFO] * self.num_envs
+        now = time.time()
+        for i in np.flatnonzero(dones):
+            tdir = np.zeros(4, np.uint8)
+            tdir[p["term_dir"].array[i]] = 1
+            infos[i] = {
+                "terminal_observation": {
+                    "direction": np.concatenate([prev["direction"][i, 4:], tdir]),
+                    "image": np.concatenate([prev["image"][i, 3:], p["term_image"].array[i]], axis=0),
+                    "mission": np.concatenate([prev["mission"][i, 32:], prev["mission"][i, 96:]]),
+                },
+                "TimeLimit.truncated": bool(trunc[i] and not term[i]),
+                "episode": {"r": float(p["reward"].array[i]), "l": int(p["ep_len"].array[i]),
+                            "t": round(now - self._t0, 6)},
+            }
+        return self._obs(), p["reward"].array, dones, infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def close(self):
+        for v in self._p.values():
+            v.free()
+        for b in self._obs_bufs:
+            for v in b.values():
+                v.free()
+        self._h.close()
+
+    def render(self, mode=None):
+        raise NotImplementedError("rendering is outside the hot path")
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        return [False] * self.num_envs
+
+    def get_attr(self, name, indices=None):
+        idx = range(self.num_envs) if indices is None else np.atleast_1d(indices)
+        if name == "mission":
+            st = self.get_state()
+            return [MISSIONS[int(st["mission_id"][i])] for i in idx]
+        if name in ("agent_pos", "agent_dir", "step_count", "mission_done"):
+            st = self.get_state()
+            if name == "agent_pos":
+                return [(int(st["agent_x"][i]), int(st["agent_y"][i])) for i in idx]
+            return [int(st[name][i]) for i in idx]
+        if name == "render_mode":
+            return [None for _ in idx]
+        raise AttributeError(name)
+
+    def set_attr(self, name, value, indices=None):
+        raise AttributeError(f"attribute {name} cannot be set on device-resident environments")
+
+    def env_method(self, name, *a, indices=None, **k):
+        raise AttributeError(f"env_method({name}) is not available on device-resident environments")
+
+    # ------------------------------------------------------------------ extras
+    def get_state(self) -> np.ndarray:
+        """Canonical [N] structured state dump (copied to the host)."""
+        out = np.zeros(self.num_envs, STATE_DTYPE)
+        nat.check(self._h.lib.mgrl_get_state_host(self._h.ptr, out.ctypes.data_as(C.c_void_p), out.nbytes, None),
+                  "get_state_host")
+        return out
+
+    def set_state(self, state: np.ndarray, seed: int | None = None) -> None:
+        """Restore a canonical state dump (the frame-stack history is left as is)."""
+        st = np.ascontiguousarray(state)
+        assert st.nbytes == self.num_envs * STATE_BYTES
+        if seed is not None:
+            self._seed = int(seed)
+        nat.check(self._h.lib.mgrl_set_state_host(self._h.ptr, st.ctypes.data_as(C.c_void_p), st.nbytes,
+                                                  self._seed, None), "set_state_host")
+
+    def mission_strings(self):
+        return self.get_attr("mission")
+
+
+# ================================================================================= device path
+class DeviceEnv:
+    """Device-resident environments: torch CUDA tensors in/out, no host copies.
+
+    Observations are un-stacked frames ([N,147] u8 in CHW or HWC order); the frame stack of
+    the policy input is gathered on the fly by the rollout engine."""
+
+    def __init__(self, cfg: EnvConfig | None = None, num_envs: int = 65536, seed: int = 0,
+                 device: int | None = None, env_id_base: int = 0, chw: bool = True):
+        import torch
+        if not torch.cuda.is_available():
+            raise nat.NativeError("DeviceEnv needs a CUDA device (no CPU fallback)")
+        self.torch = torch
+        self.cfg = cfg or EnvConfig()
+        self.num_envs = int(num_envs)
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self.seed = int(seed)
+        self._h = _Handle(self.cfg, self.num_envs, self.device_index, env_id_base, chw)
+        n = self.num_envs
+        u8 = dict(dtype=torch.uint8, device=self.device)
+        self.image = torch.zeros((n, OBS_BYTES), **u8)
+        self.dir = torch.zeros(n, **u8)
+        self.mission = torch.zeros(n, **u8)
+        self.reward = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.term = torch.zeros(n, **u8)
+        self.trunc = torch.zeros(n, **u8)
+        self.ep_len = torch.zeros(n, **u8)
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _ptr(t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    def reset(self, seed: int | None = None):
+        if seed is not None:
+            self.seed = int(seed)
+        nat.check(self._h.lib.mgrl_reset(self._h.ptr, self.seed, self._ptr(self.image), self._ptr(self.dir),
+                                         self._ptr(self.mission), self._stream()), "mgrl_reset")
+        return self.image, self.dir, self.mission
+
+    def step(self, actions, image=None, dir=None, mission=None, reward=None, term=None, trunc=None,
+             ep_len=None, term_image=None, term_dir=None):
+        """One vector step.  Output tensors default to this object's buffers."""
+        image = self.image if image is None else image
+        dir = self.dir if dir is None else dir
+        mission = self.mission if mission is None else mission
+        reward = self.reward if reward is None else reward
+        term = self.term if term is None else term
+        trunc = self.trunc if trunc is None else trunc
+        ep_len = self.ep_len if ep_len is None else ep_len
+        assert actions.dtype == self.torch.uint8 and actions.is_cuda and actions.numel() == self.num_envs
+        nat.check(self._h.lib.mgrl_step(
+            self._h.ptr, self._ptr(actions), self._ptr(image), self._ptr(dir), self._ptr(mission),
+            self._ptr(reward), self._ptr(term), self._ptr(trunc), self._ptr(ep_len), self._ptr(term_image),
+            self._ptr(term_dir), self._stream()), "mgrl_step")
+        return image, reward, term, trunc
+
+    def step_many(self, actions, image=None, dir=None, mission=None, reward=None, term=None, trunc=None,
+                  ep_len=None):
+        """T steps in one launch; actions [T,N] u8; outputs [T,N,...] (image/dir/mission/ep_len optional)."""
+        T = int(actions.shape[0])
+        assert actions.dtype == self.torch.uint8 and actions.is_cuda and actions.shape[1] == self.num_envs
+        assert actions.is_contiguous()
+        nat.check(self._h.lib.mgrl_step_many(
+            self._h.ptr, T, self._ptr(actions), self._ptr(image), self._ptr(dir), self._ptr(mission),
+            self._ptr(reward), self._ptr(term), self._ptr(trunc), self._ptr(ep_len), self._stream()),
+            "mgrl_step_many")
+
+    def observe(self):
+        nat.check(self._h.lib.mgrl_observe(self._h.ptr, self._ptr(self.image), self._ptr(self.dir),
+                                           self._ptr(self.mission), self._stream()), "mgrl_observe")
+        return self.image, self.dir, self.mission
+
+    def full_obs(self):
+        S = self.cfg.size
+        out = self.torch.zeros((self.num_envs, S, S, 3), dtype=self.torch.uint8, device=self.device)
+        nat.check(self._h.lib.mgrl_full_obs(self._h.ptr, self._ptr(out), self._stream()), "mgrl_full_obs")
+        return out
+
+    def get_state(self):
+        out = self.torch.empty((self.num_envs, STATE_BYTES), dtype=self.torch.uint8, device=self.device)
+        nat.check(self._h.lib.mgrl_get_state(self._h.ptr, self._ptr(out), out.numel(), self._stream()), "get_state")
+        return out
+
+    def set_state(self, state, seed: int | None = None):
+        if seed is not None:
+            self.seed = int(seed)
+        assert state.is_cuda and state.dtype == self.torch.uint8 and state.numel() == self.num_envs * STATE_BYTES
+        state = state.contiguous()
+        nat.check(self._h.lib.mgrl_set_state(self._h.ptr, self._ptr(state), state.numel(), self.seed,
+                                             self._stream()), "set_state")
+
+    def get_state_numpy(self) -> np.ndarray:
+        return self.get_state().cpu().numpy().view(STATE_DTYPE).reshape(-1)
+
+    def set_state_numpy(self, state: np.ndarray, seed: int | None = None):
+        t = self.torch.from_numpy(np.ascontiguousarray(state).view(np.uint8).reshape(-1, STATE_BYTES).copy())
+        self.set_state(t.to(self.device), seed)
+
+    def error_flags(self) -> int:
+        flags = C.c_int(0)
+        nat.check(self._h.lib.mgrl_error_flags(self._h.ptr, C.byref(flags), self._stream()), "error_flags")
+        return flags.value
+
+    def close(self):
+        self._h.close()
+
+
+def gae(rewards, values, episode_starts, last_values, last_dones, gamma: float, gae_lambda: float,
+        advantages=None, returns=None):
+    """SB3 RolloutBuffer.compute_returns_and_advantage on device tensors ([T,N] f32 / u8)."""
+    import torch
+    T, N = rewards.shape
+    for t in (rewards, values, episode_starts, last_values, last_dones):
+        assert t.is_cuda and t.is_contiguous()
+    assert rewards.dtype == torch.float32 and values.dtype == torch.float32
+    assert episode_starts.dtype == torch.uint8 and last_dones.dtype == torch.uint8
+    advantages = torch.empty_like(rewards) if advantages is None else advantages
+    returns = torch.empty_like(rewards) if returns is None else returns
+    s = C.c_void_p(torch.cuda.current_stream(rewards.device).cuda_stream)
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    nat.check(nat.lib().mgrl_gae(p(rewards), p(values), p(episode_starts), p(last_values), p(last_dones),
+                                 float(gamma), float(gae_lambda), T, N, p(advantages), p(returns), s), "mgrl_gae")
+    return advantages, returns

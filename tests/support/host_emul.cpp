@@ -1,0 +1,49 @@
+// tests/support/host_emul.cpp — TEST INFRASTRUCTURE.
+// Compiles the product's per-environment device functions (minigrid-rl_b200/csrc/mgrl_core.cuh)
+// for the HOST so that the kernel logic can be compared with the CPU oracle in the CPU-only
+// test tier (-m "not gpu").  Never linked into the product; the product has no CPU path.
+#include <cstddef>
+#include "mgrl_core.cuh"
+
+using namespace mgrl;
+
+extern "C" {
+
+void emul_generate(const EnvCfg* cfg, uint64_t seed, uint64_t env_id, EnvState* s) { generate(*s, *cfg, seed, env_id); }
+
+void emul_step(const EnvCfg* cfg, const float* lut, EnvState* s, int action, float* reward, uint8_t* term,
+               uint8_t* trunc, uint8_t* carry_obs) {
+    StepOut o = env_step(*s, action, cfg->size, cfg->max_steps, lut);
+    *reward = o.reward; *term = o.terminated; *trunc = o.truncated; *carry_obs = o.carry_obs;
+}
+
+void emul_obs(const EnvCfg* cfg, const EnvState* s, int carrying, int layout, uint8_t* out) {
+    if (layout == OBS_HWC) encode_view<OBS_HWC>(*s, carrying, cfg->size, cfg->see_through_walls != 0, out);
+    else encode_view<OBS_CHW>(*s, carrying, cfg->size, cfg->see_through_walls != 0, out);
+}
+
+void emul_full_obs(const EnvCfg* cfg, const EnvState* s, uint8_t* out) { encode_full(*s, cfg->size, out); }
+
+uint32_t emul_kind_encode(int k) { return kind_encode(k); }
+
+// DummyVecEnv-style vector step, same contract as the CUDA step kernel
+void emul_vec_step(const EnvCfg* cfg, uint64_t seed, uint64_t base, int n, const float* lut, EnvState* st,
+                   const uint8_t* act, uint8_t* obs, uint8_t* dir, uint8_t* mis, float* rew, uint8_t* term,
+                   uint8_t* trunc, uint8_t* ep_len, uint8_t* term_obs) {
+    for (int i = 0; i < n; ++i) {
+        EnvState& s = st[i];
+        StepOut o = env_step(s, act[i], cfg->size, cfg->max_steps, lut);
+        rew[i] = o.reward; term[i] = o.terminated; trunc[i] = o.truncated;
+        const bool done = o.terminated | o.truncated;
+        ep_len[i] = done ? s.step_count : 0;
+        int carry = o.carry_obs;
+        if (done) {
+            encode_view<OBS_HWC>(s, carry, cfg->size, cfg->see_through_walls != 0, term_obs + (size_t)i * kObsBytes);
+            generate(s, *cfg, seed, base + (uint64_t)i);
+            carry = 0;
+        }
+        encode_view<OBS_HWC>(s, carry, cfg->size, cfg->see_through_walls != 0, obs + (size_t)i * kObsBytes);
+        dir[i] = s.agent_dir; mis[i] = s.mission_id;
+    }
+}
+}

@@ -1,0 +1,300 @@
+"""GPU tier: the CUDA simulator (through the C ABI) against the CPU oracle, bit-exact.
+
+Covers reset/layout generation, single steps, the multi-step kernel, auto-reset, terminal
+observations, the golden traces recorded from the reference, BASELINE.json's full sizes
+(65 536 envs x 128 steps for GTO / PKP / TGL / ALL) and shard invariance."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import minigrid_rl_b200 as mg  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+TRACES = sorted(glob.glob(os.path.join(GOLDEN, "trace_*.npz")))
+
+CONFIGS = {
+    "gtg": dict(problem="multi", mission=5),
+    "gto": dict(problem="multi", mission=0),
+    "pkp": dict(problem="multi", mission=2),
+    "tgl": dict(problem="multi", mission=1),
+    "all": dict(problem="multi", mission=None),
+    "all_vis": dict(problem="multi", mission=None, see_through_walls=False),
+    "all_open_n6": dict(problem="multi", mission=None, all_doors_open=True, num_objects=6),
+    "all_s9": dict(problem="multi", mission=None, size=9),
+    "lava": dict(problem="multi", mission=None, obstacles=True),
+    "single_gtg_obst": dict(problem="gtg", mission=None, num_objects=6, obstacles=True, see_through_walls=False),
+    "single_opn": dict(problem="opn", mission=None),
+    "single_drp": dict(problem="drp", mission=None),
+}
+
+
+def biased_actions(rs, n):
+    a = rs.randint(0, 7, size=n).astype(np.uint8)
+    long_lived = (np.arange(n) % 3) != 0
+    redo = long_lived & (a == 6) & (rs.rand(n) < 0.97)
+    a[redo] = rs.choice([2, 2, 2, 0, 1, 3, 5, 5, 4], size=int(redo.sum())).astype(np.uint8)
+    return a
+
+
+def assert_state_equal(dev_env, oracle_env, ctx):
+    got = dev_env.get_state_numpy()
+    for name in orc.STATE_DTYPE.names:
+        if not np.array_equal(got[name], oracle_env.states[name]):
+            bad = np.argwhere(got[name] != oracle_env.states[name])[0]
+            raise AssertionError(f"{ctx}: state.{name} differs first at {bad}")
+
+
+def hwc(image, n):
+    return image.cpu().numpy().reshape(n, 7, 7, 3)
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_reset_and_steps_match_oracle(name):
+    kw = CONFIGS[name]
+    n, T = 1000, 150      # 1000 = 7 full tiles + a ragged one
+    env = mg.DeviceEnv(mg.EnvConfig(**kw), num_envs=n, seed=77, env_id_base=5000, chw=False)
+    o = orc.OracleVecEnv(orc.make_config(**kw), n, seed=77, env_id_base=5000, nthreads=8)
+    img, d, m = env.reset()
+    o.reset()
+    assert_state_equal(env, o, f"{name} reset")
+    assert np.array_equal(hwc(img, n), o.obs)
+    assert np.array_equal(d.cpu().numpy(), o.dir) and np.array_equal(m.cpu().numpy(), o.mission)
+    rs = np.random.RandomState(9)
+    term_img = torch.zeros((n, 147), dtype=torch.uint8, device="cuda")
+    term_dir = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    dones = 0
+    for t in range(T):
+        a = biased_actions(rs, n)
+        env.step(torch.from_numpy(a).cuda(), term_image=term_img, term_dir=term_dir)
+        pre_dir = o.states["agent_dir"].copy()
+        o.step(a)
+        ctx = f"{name} t={t}"
+        assert np.array_equal(hwc(env.image, n), o.obs), ctx
+        assert np.array_equal(env.reward.cpu().numpy().view(np.uint32), o.reward.view(np.uint32)), ctx
+        assert np.array_equal(env.term.cpu().numpy(), o.term), ctx
+        assert np.array_equal(env.trunc.cpu().numpy(), o.trunc), ctx
+        assert np.array_equal(env.ep_len.cpu().numpy(), o.ep_len), ctx
+        assert np.array_equal(env.dir.cpu().numpy(), o.dir), ctx
+        assert np.array_equal(env.mission.cpu().numpy(), o.mission), ctx
+        done = (o.term | o.trunc).astype(bool)
+        assert np.array_equal(hwc(term_img, n)[done], o.term_obs[done]), ctx
+        dones += int(done.sum())
+        if t % 10 == 0 or t == T - 1:
+            assert_state_equal(env, o, ctx)
+        del pre_dir
+    assert dones > n
+    assert env.error_flags() == 0
+    env.close()
+
+
+def test_terminal_direction_output():
+    kw = dict(problem="multi", mission=None)
+    n = 512
+    env = mg.DeviceEnv(mg.EnvConfig(**kw), num_envs=n, seed=5, chw=True)
+    o = orc.OracleVecEnv(orc.make_config(**kw), n, seed=5)
+    env.reset(); o.reset()
+    rs = np.random.RandomState(1)
+    term_dir = torch.full((n,), 255, dtype=torch.uint8, device="cuda")
+    lut = orc.reward_lut(121)
+    for t in range(20):
+        a = rs.randint(0, 7, size=n).astype(np.uint8)
+        # oracle terminal direction: step a copy of each env without auto-reset
+        want = np.full(n, 255, np.uint8)
+        for i in range(n):
+            s = o.states[i:i + 1].copy()
+            _, te, tr, _ = orc.step_one(o.cfg, lut, s, int(a[i]))
+            if te or tr:
+                want[i] = s["agent_dir"][0]
+        term_dir.fill_(255)
+        env.step(torch.from_numpy(a).cuda(), term_dir=term_dir)
+        o.step(a)
+        assert np.array_equal(term_dir.cpu().numpy(), want), t
+    env.close()
+
+
+def test_chw_layout_is_transposed_hwc():
+    kw = dict(problem="multi", mission=None)
+    n = 300
+    a_env = mg.DeviceEnv(mg.EnvConfig(**kw), num_envs=n, seed=3, chw=False)
+    b_env = mg.DeviceEnv(mg.EnvConfig(**kw), num_envs=n, seed=3, chw=True)
+    ia, _, _ = a_env.reset()
+    ib, _, _ = b_env.reset()
+    rs = np.random.RandomState(0)
+    for t in range(30):
+        a = torch.from_numpy(biased_actions(rs, n)).cuda()
+        a_env.step(a); b_env.step(a)
+        x = a_env.image.cpu().numpy().reshape(n, 7, 7, 3).transpose(0, 3, 1, 2)
+        y = b_env.image.cpu().numpy().reshape(n, 3, 7, 7)
+        assert np.array_equal(x, y)
+    a_env.close(); b_env.close()
+
+
+@pytest.mark.parametrize("path", TRACES, ids=[os.path.basename(p)[6:-4] for p in TRACES])
+def test_golden_reference_traces_on_gpu(path):
+    """Traces recorded from the unmodified reference PlaygroundEnv, replayed on the GPU."""
+    z = np.load(path)
+    kw = json.loads(bytes(z["cfg_json"]).decode())
+    E, T = z["init_state"].shape[0], z["actions"].shape[0]
+    env = mg.DeviceEnv(mg.EnvConfig(**kw), num_envs=E, seed=int(z["seed"]), chw=False)
+    img, d, m = env.reset()
+    got = env.get_state_numpy()
+    for name in orc.STATE_DTYPE.names:
+        assert np.array_equal(got[name], z["init_state"][name]), name
+    assert np.array_equal(hwc(img, E), z["init_obs"])
+    term_img = torch.zeros((E, 147), dtype=torch.uint8, device="cuda")
+    for t in range(T):
+        env.step(torch.from_numpy(z["actions"][t]).cuda(), term_image=term_img)
+        assert np.array_equal(hwc(env.image, E), z["obs"][t]), t
+        assert np.array_equal(env.reward.cpu().numpy().view(np.uint32), z["reward"][t].view(np.uint32)), t
+        assert np.array_equal(env.term.cpu().numpy(), z["term"][t]), t
+        assert np.array_equal(env.trunc.cpu().numpy(), z["trunc"][t]), t
+        assert np.array_equal(env.dir.cpu().numpy(), z["dir"][t]), t
+        done = (z["term"][t] | z["trunc"][t]).astype(bool)
+        assert np.array_equal(hwc(term_img, E)[done], z["term_obs"][t][done]), t
+        got = env.get_state_numpy()
+        for name in orc.STATE_DTYPE.names:
+            assert np.array_equal(got[name], z["state"][t][name]), (t, name)
+    # mission tokens: host table indexed by the device mission id == reference tokens
+    assert np.array_equal(mg.token_table()[env.mission.cpu().numpy()].astype(np.int8), z["tokens"][T - 1])
+    env.close()
+
+
+@pytest.mark.parametrize("task,mission", [("GTO", 0), ("PKP", 2), ("TGL", 1), ("ALL", None)])
+def test_full_size_rollout_matches_oracle(task, mission):
+    """BASELINE.json configs 2-5 at per-GPU size: 65 536 envs x 128 steps, every output."""
+    n, T = 65536, 128
+    kw = dict(problem="multi", mission=mission)
+    env = mg.DeviceEnv(mg.EnvConfig(**kw), num_envs=n, seed=42, chw=True)
+    o = orc.OracleVecEnv(orc.make_config(**kw), n, seed=42, nthreads=16)
+    env.reset(); o.reset()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    actions = torch.randint(0, 7, (T, n), dtype=torch.uint8, device="cuda", generator=g)
+    # half of the population avoids `done` so that long episodes, doors and truncation occur
+    keep = (torch.arange(n, device="cuda") % 2 == 0)
+    alt = torch.randint(0, 6, (T, n), dtype=torch.uint8, device="cuda", generator=g)
+    actions = torch.where((actions == 6) & keep, alt, actions).contiguous()
+    image = torch.empty((T, n, 147), dtype=torch.uint8, device="cuda")
+    dirs = torch.empty((T, n), dtype=torch.uint8, device="cuda")
+    mis = torch.empty((T, n), dtype=torch.uint8, device="cuda")
+    rew = torch.empty((T, n), dtype=torch.float32, device="cuda")
+    term = torch.empty((T, n), dtype=torch.uint8, device="cuda")
+    trunc = torch.empty((T, n), dtype=torch.uint8, device="cuda")
+    eplen = torch.empty((T, n), dtype=torch.uint8, device="cuda")
+    env.step_many(actions, image, dirs, mis, rew, term, trunc, eplen)
+    torch.cuda.synchronize()
+    a_np = actions.cpu().numpy()
+    n_trunc = n_success = 0
+    for t in range(T):
+        o.step(a_np[t], want_term_obs=False)
+        want_chw = o.obs.transpose(0, 3, 1, 2).reshape(n, 147)
+        assert np.array_equal(image[t].cpu().numpy(), want_chw), (task, t)
+        assert np.array_equal(rew[t].cpu().numpy().view(np.uint32), o.reward.view(np.uint32)), (task, t)
+        assert np.array_equal(term[t].cpu().numpy(), o.term), (task, t)
+        assert np.array_equal(trunc[t].cpu().numpy(), o.trunc), (task, t)
+        assert np.array_equal(eplen[t].cpu().numpy(), o.ep_len), (task, t)
+        assert np.array_equal(dirs[t].cpu().numpy(), o.dir), (task, t)
+        assert np.array_equal(mis[t].cpu().numpy(), o.mission), (task, t)
+        n_trunc += int(o.trunc.sum()); n_success += int((o.reward > 0).sum())
+    assert_state_equal(env, o, f"{task} final")
+    assert n_trunc > 0 and n_success > 0
+    assert env.error_flags() == 0
+    env.close()
+
+
+def test_step_many_equals_repeated_step():
+    kw = dict(problem="multi", mission=None, see_through_walls=False)
+    n, T = 3000, 40
+    a_env = mg.DeviceEnv(mg.EnvConfig(**kw), num_envs=n, seed=8, chw=True)
+    b_env = mg.DeviceEnv(mg.EnvConfig(**kw), num_envs=n, seed=8, chw=True)
+    a_env.reset(); b_env.reset()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    actions = torch.randint(0, 7, (T, n), dtype=torch.uint8, device="cuda", generator=g)
+    image = torch.empty((T, n, 147), dtype=torch.uint8, device="cuda")
+    rew = torch.empty((T, n), dtype=torch.float32, device="cuda")
+    term = torch.empty((T, n), dtype=torch.uint8, device="cuda")
+    trunc = torch.empty((T, n), dtype=torch.uint8, device="cuda")
+    a_env.step_many(actions, image, None, None, rew, term, trunc, None)
+    for t in range(T):
+        b_env.step(actions[t])
+        assert torch.equal(b_env.image, image[t]) and torch.equal(b_env.reward, rew[t])
+        assert torch.equal(b_env.term, term[t]) and torch.equal(b_env.trunc, trunc[t])
+    assert torch.equal(a_env.get_state(), b_env.get_state())
+    a_env.close(); b_env.close()
+
+
+def test_results_do_not_depend_on_sharding():
+    """One handle of 4096 envs == two handles of 2048 with env_id_base offsets (multi-GPU sharding)."""
+    kw = dict(problem="multi", mission=None)
+    n = 4096
+    whole = mg.DeviceEnv(mg.EnvConfig(**kw), num_envs=n, seed=99, env_id_base=0)
+    lo = mg.DeviceEnv(mg.EnvConfig(**kw), num_envs=n // 2, seed=99, env_id_base=0)
+    hi = mg.DeviceEnv(mg.EnvConfig(**kw), num_envs=n // 2, seed=99, env_id_base=n // 2)
+    whole.reset(); lo.reset(); hi.reset()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for t in range(60):
+        a = torch.randint(0, 7, (n,), dtype=torch.uint8, device="cuda", generator=g)
+        whole.step(a); lo.step(a[: n // 2].contiguous()); hi.step(a[n // 2:].contiguous())
+        assert torch.equal(whole.image, torch.cat([lo.image, hi.image]))
+        assert torch.equal(whole.reward, torch.cat([lo.reward, hi.reward]))
+    assert torch.equal(whole.get_state(), torch.cat([lo.get_state(), hi.get_state()]))
+    for e in (whole, lo, hi):
+        e.close()
+
+
+def test_set_state_round_trip_and_replay():
+    kw = dict(problem="multi", mission=1)
+    n = 777
+    o = orc.OracleVecEnv(orc.make_config(**kw), n, seed=12)
+    o.reset()
+    rs = np.random.RandomState(2)
+    for _ in range(25):
+        o.step(biased_actions(rs, n))
+    env = mg.DeviceEnv(mg.EnvConfig(**kw), num_envs=n, seed=0, chw=False)
+    env.set_state_numpy(o.states, seed=12)
+    img, d, m = env.observe()
+    assert np.array_equal(hwc(img, n), np.stack([orc.gen_obs(o.cfg, o.states[i:i + 1]) for i in range(n)]))
+    for _ in range(30):
+        a = biased_actions(rs, n)
+        env.step(torch.from_numpy(a).cuda()); o.step(a)
+        assert np.array_equal(hwc(env.image, n), o.obs)
+    assert_state_equal(env, o, "replay")
+    env.close()
+
+
+def test_full_obs_matches_oracle():
+    kw = dict(problem="gtg", mission=None, num_objects=6, obstacles=True)
+    n = 200
+    env = mg.DeviceEnv(mg.EnvConfig(**kw), num_envs=n, seed=1337)
+    o = orc.OracleVecEnv(orc.make_config(**kw), n, seed=1337)
+    env.reset(); o.reset()
+    assert np.array_equal(env.full_obs().cpu().numpy(), o.full_obs())
+    env.close()
+
+
+def test_gae_bit_exact_vs_oracle():
+    rs = np.random.RandomState(0)
+    for T, N in [(3, 1), (128, 4099), (1024, 16)]:
+        r = (rs.rand(T, N) < 0.05).astype(np.float32) * rs.rand(T, N).astype(np.float32)
+        v = rs.randn(T, N).astype(np.float32)
+        es = (rs.rand(T, N) < 0.1).astype(np.uint8)
+        lv = rs.randn(N).astype(np.float32)
+        ld = (rs.rand(N) < 0.1).astype(np.uint8)
+        gamma, lam = 0.8108071290665859, 0.9452281119742252      # algorithm/ppo.yaml:29,32
+        want_adv, want_ret = orc.gae(r, v, es, lv, ld, gamma, lam)
+        c = lambda x: torch.from_numpy(x).cuda()  # noqa: E731
+        adv, ret = mg.vec_env.gae(c(r), c(v), c(es), c(lv), c(ld), gamma, lam)
+        assert np.array_equal(adv.cpu().numpy().view(np.uint32), want_adv.view(np.uint32))
+        assert np.array_equal(ret.cpu().numpy().view(np.uint32), want_ret.view(np.uint32))
+    # SURVEY App. C-13 hand example
+    c = lambda x, dt: torch.tensor(x, dtype=dt, device="cuda")  # noqa: E731
+    adv, ret = mg.vec_env.gae(c([[0.], [0.], [1.]], torch.float32), c([[.5], [.5], [.5]], torch.float32),
+                              c([[1], [0], [0]], torch.uint8), c([.5], torch.float32), c([1], torch.uint8), 0.9, 0.8)
+    assert np.allclose(adv.cpu().numpy().ravel(), [0.1732, 0.31, 0.5], rtol=1e-6)
+    assert np.allclose(ret.cpu().numpy().ravel(), [0.6732, 0.81, 1.0], rtol=1e-6)

@@ -1,0 +1,87 @@
+"""GPU tier: the drop-in host surface (B200VecEnv: numpy in / numpy out, SB3 VecEnv protocol after
+VecTransposeImage + VecFrameStack(4,'first')) against the oracle env + numpy SB3-wrapper oracle."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import minigrid_rl_b200 as mg  # noqa: E402
+from oracle import oracle as orc, sb3_oracle  # noqa: E402
+
+
+def biased_actions(rs, n):
+    a = rs.randint(0, 7, size=n)
+    long_lived = (np.arange(n) % 3) != 0
+    redo = long_lived & (a == 6) & (rs.rand(n) < 0.97)
+    a[redo] = rs.choice([2, 2, 2, 0, 1, 3, 5, 5, 4], size=int(redo.sum()))
+    return a
+
+
+@pytest.mark.parametrize("kw", [dict(problem="multi", mission=5), dict(problem="multi", mission=None),
+                                dict(problem="multi", mission=1, see_through_walls=False)],
+                         ids=["gtg", "all", "tgl_vis"])
+def test_vec_env_matches_sb3_stack_semantics(kw):
+    n, T = 48, 400
+    env = mg.B200VecEnv(mg.EnvConfig(**kw), num_envs=n, seed=42)
+    assert env.observation_space["image"].shape == (12, 7, 7)
+    assert env.observation_space["direction"].shape == (16,)
+    assert env.observation_space["mission"].shape == (128,) and env.action_space.n == 7
+    assert list(env.observation_space.keys()) == ["direction", "image", "mission"]
+    o = orc.OracleVecEnv(orc.make_config(**kw), n, seed=42)
+    table = mg.token_table()
+    fs_img = sb3_oracle.FrameStack(n, (3, 7, 7), np.uint8)
+    fs_dir = sb3_oracle.FrameStack(n, (4,), np.uint8)
+    fs_mis = sb3_oracle.FrameStack(n, (32,), np.int64)
+
+    obs = env.reset()
+    o.reset()
+    assert np.array_equal(obs["image"], fs_img.reset(o.obs.transpose(0, 3, 1, 2)))
+    assert np.array_equal(obs["direction"], fs_dir.reset(sb3_oracle.one_hot_dir(o.dir)))
+    assert np.array_equal(obs["mission"], fs_mis.reset(table[o.mission]))
+    assert obs["mission"].dtype == np.int64 and obs["image"].dtype == np.uint8
+    rs = np.random.RandomState(0)
+    lut = orc.reward_lut(121)
+    n_done = n_trunc = 0
+    for t in range(T):
+        a = biased_actions(rs, n)
+        # terminal direction / mission from the oracle, before its auto-reset
+        pre_mission = o.mission.copy()
+        tdir = np.zeros(n, np.uint8)
+        for i in range(n):
+            s = o.states[i:i + 1].copy()
+            orc.step_one(o.cfg, lut, s, int(a[i]))
+            tdir[i] = s["agent_dir"][0]
+        obs, rew, dones, infos = env.step(a)
+        o.step(a.astype(np.uint8))
+        want_done = (o.term | o.trunc).astype(bool)
+        want_img, term_img = fs_img.update(o.obs.transpose(0, 3, 1, 2), want_done, o.term_obs.transpose(0, 3, 1, 2))
+        want_dir, term_dir = fs_dir.update(sb3_oracle.one_hot_dir(o.dir), want_done, sb3_oracle.one_hot_dir(tdir))
+        want_mis, term_mis = fs_mis.update(table[o.mission], want_done, table[pre_mission])
+        assert np.array_equal(obs["image"], want_img), t
+        assert np.array_equal(obs["direction"], want_dir), t
+        assert np.array_equal(obs["mission"], want_mis), t
+        assert rew.dtype == np.float32 and np.array_equal(rew.view(np.uint32), o.reward.view(np.uint32)), t
+        assert dones.dtype == bool and np.array_equal(dones, want_done), t
+        assert len(infos) == n
+        for i in range(n):
+            if want_done[i]:
+                info = infos[i]
+                assert np.array_equal(info["terminal_observation"]["image"], term_img[i]), (t, i)
+                assert np.array_equal(info["terminal_observation"]["direction"], term_dir[i]), (t, i)
+                assert np.array_equal(info["terminal_observation"]["mission"], term_mis[i]), (t, i)
+                assert info["TimeLimit.truncated"] == bool(o.trunc[i] and not o.term[i])
+                assert info["episode"]["l"] == int(o.ep_len[i])
+                assert np.float32(info["episode"]["r"]) == o.reward[i]
+                n_trunc += int(info["TimeLimit.truncated"])
+            else:
+                assert "terminal_observation" not in infos[i]
+        n_done += int(want_done.sum())
+    assert n_done > 50 and n_trunc > 0
+    st = env.get_state()
+    for name in orc.STATE_DTYPE.names:
+        assert np.array_equal(st[name], o.states[name]), name
+    assert env.get_attr("mission") == [mg.MISSIONS[i] for i in o.mission]
+    with pytest.raises(ValueError):
+        env.step(np.full(n, 7))
+    env.close()

@@ -1,0 +1,79 @@
+"""CPU tier: host-side logic and the C-ABI library surface (no compute without a GPU)."""
+import ctypes as C
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+
+import minigrid_rl_b200 as mg
+from minigrid_rl_b200 import _native as nat
+from oracle import sb3_oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "mgrl.h")).read()
+    declared = sorted(set(re.findall(r"\b(mgrl_[a-z_]+)\s*\(", hdr)))
+    assert len(declared) >= 20
+    handle = C.CDLL(mg.library_path())
+    for name in declared:
+        assert hasattr(handle, name), f"libmgrl.so does not export {name}"
+    assert sorted(nat.EXPORTS) == declared, "python binding table out of sync with include/mgrl.h"
+    assert mg.lib().mgrl_abi_version() == 1
+
+
+def test_create_fails_loudly_without_gpu_or_with_bad_config():
+    import torch
+    lib = mg.lib()
+    ptr = C.c_void_p()
+    bad = nat.Config(11, 4, 0, 3, 0, 1, 121, 0, 16, 1, 0)      # mission 3 ('drop' on multi) is invalid
+    rc = lib.mgrl_create(C.byref(bad), 0, C.byref(ptr))
+    assert rc < 0 and lib.mgrl_last_error()
+    if not torch.cuda.is_available():
+        ok = nat.Config(11, 4, 0, 5, 0, 1, 121, 0, 16, 1, 0)
+        assert lib.mgrl_create(C.byref(ok), 0, C.byref(ptr)) == -3   # MGRL_ERR_NO_DEVICE
+        with pytest.raises(mg.NativeError):
+            mg.B200VecEnv(num_envs=4)
+
+
+def test_mission_table_matches_reference_tokens():
+    # tokens recorded from the reference's TokenizeVocabWrapper (oracle/gen_golden.py)
+    table = mg.token_table()
+    seen = set()
+    for path in sorted(glob.glob(os.path.join(GOLDEN, "trace_*.npz"))):
+        z = np.load(path)
+        ids = z["state"]["mission_id"]
+        assert np.array_equal(table[ids].astype(np.int8), z["tokens"])
+        assert np.array_equal(table[z["init_state"]["mission_id"]].astype(np.int8), z["init_tokens"])
+        seen |= set(np.unique(ids).tolist())
+        for s in z["missions"]:
+            assert mg.mission_string(mg.mission_id(str(s))) == str(s)
+    assert len(seen) >= 56      # every mission the five tasks can produce shows up in the fixtures
+    # SURVEY App. C-12
+    assert mg.tokenize("go to goal")[:11].tolist() == [12, 20, 0, 25, 20, 0, 12, 20, 6, 17, 0]
+    assert np.array_equal(sb3_oracle.tokenize("pick up purple ball"), mg.tokenize("pick up purple ball"))
+
+
+def test_config_mirrors_reference_keys():
+    cfg = mg.EnvConfig.from_cfg(dict(problem="multi", mission=None, all_doors_open=False, size=11,
+                                     num_objects=4, see_through_walls=True, obstacles=True,
+                                     percent_obstacles=0.05))
+    assert cfg.max_steps == 121 and cfg.num_obstacles == 4
+    assert mg.EnvConfig.for_task("TGL").mission == 1 and mg.EnvConfig.for_task("ALL").mission is None
+    with pytest.raises(ValueError):
+        mg.EnvConfig(problem="full").validate()
+
+
+def test_frame_stack_oracle_known_answers():
+    # SURVEY App. C-14
+    fs = sb3_oracle.FrameStack(2, (1,), np.int64)
+    assert fs.reset(np.array([[1], [10]])).tolist() == [[0, 0, 0, 1], [0, 0, 0, 10]]
+    s, _ = fs.update(np.array([[2], [11]]), np.array([False, False]), None)
+    assert s.tolist() == [[0, 0, 1, 2], [0, 0, 10, 11]]
+    s, term = fs.update(np.array([[3], [50]]), np.array([False, True]), np.array([[0], [12]]))
+    assert s.tolist() == [[0, 1, 2, 3], [0, 0, 0, 50]]
+    assert term[1].tolist() == [0, 10, 11, 12]
