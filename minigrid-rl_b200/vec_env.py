@@ -228,6 +228,20 @@ class B200VecEnv:
         self.step_async(actions)
         return self.step_wait()
 
+    def step_arrays(self, actions):
+        """`step` without the per-env Python info dicts: returns (obs, rewards, term, trunc, ep_len,
+        term_image, term_dir) as pinned numpy arrays straight from mgrl_vec_step_host."""
+        p = self._p
+        p["actions"].array[:] = actions
+        self._cur ^= 1
+        b = self._obs_bufs[self._cur]
+        nat.check(self._h.lib.mgrl_vec_step_host(
+            self._h.ptr, p["actions"].ptr, b["image"].ptr, b["direction"].ptr, b["mission"].ptr,
+            p["reward"].ptr, p["term"].ptr, p["trunc"].ptr, p["ep_len"].ptr, p["term_image"].ptr,
+            p["term_dir"].ptr, None), "vec_step")
+        return (self._obs(), p["reward"].array, p["term"].array, p["trunc"].array, p["ep_len"].array,
+                p["term_image"].array, p["term_dir"].array)
+
     def close(self):
         for v in self._p.values():
             v.free()
