@@ -28,10 +28,10 @@ T_ROLLOUT = 128
 TASK = "GTO"
 SEED = 42
 # HBM-compulsory bytes per env-step of the step kernel when the 140-B state stays on chip
-# (L2 / shared memory): action 1 + image 147 + dir 1 + mission 1 + reward 4 + term 1 + trunc 1 + ep_len 1
-BYTES_PER_ENV_STEP = 157
+# (L2 / shared memory): action 1 + image record 148 + dir 1 + mission 1 + reward 4 + term 1 + trunc 1 + ep_len 1
+BYTES_PER_ENV_STEP = 158
 # with the state streamed from/to HBM as well (N*140 B larger than L2): + 2*140
-BYTES_PER_ENV_STEP_STREAMED = 157 + 280
+BYTES_PER_ENV_STEP_STREAMED = 158 + 280
 
 
 def load_peaks():
@@ -173,12 +173,12 @@ def main():
     n, T = args.envs, T_ROLLOUT
     W, K = max(args.warmup, 3), args.steps
     cfg = mg.EnvConfig.for_task(TASK)
-    env = mg.DeviceEnv(cfg, num_envs=n, seed=SEED, env_id_base=rank * n, chw=True)
+    env = mg.DeviceEnv(cfg, num_envs=n, seed=SEED, env_id_base=rank * n, layout="hwc148")
     env.reset()
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     actions = torch.randint(0, 7, (T, n), dtype=torch.uint8, device=dev, generator=g)
     u8 = dict(dtype=torch.uint8, device=dev)
-    image = torch.empty((T, n, 147), **u8)        # 1.2 GB rollout buffer (> L2)
+    image = torch.empty((T, n, 148), **u8)        # 1.2 GB rollout buffer (> L2), 148-B packed HWC records
     dirs = torch.empty((T, n), **u8); mis = torch.empty((T, n), **u8)
     rew = torch.empty((T, n), dtype=torch.float32, device=dev)
     term = torch.empty((T, n), **u8); trunc = torch.empty((T, n), **u8); eplen = torch.empty((T, n), **u8)
@@ -272,11 +272,11 @@ def main():
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"{TASK} multi-room 11x11 (BASELINE configs[1]), {n} envs/GPU, rollout {T} steps, "
                                    "uniform random u8 actions resident in HBM",
-                       "l2": "outputs stream into a 1.2 GB [T,N,147] rollout buffer (> 126 MB L2); the 9.2 MB state "
+                       "l2": "outputs stream into a 1.2 GB [T,N,148] rollout buffer (> 126 MB L2); the 9.2 MB state "
                              "array is L2-resident by design and is not counted in the algorithmic bytes",
                        "path": "mgrl_step x T (one launch per env step, as a policy-in-the-loop rollout issues it)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "env_kernel<CHW,see_through,STEP>", "peak_source": peak_src,
+                         "traffic": None, "kernel": "env_kernel<HWC148,see_through,STEP>", "peak_source": peak_src,
                          "bytes_per_env_step": BYTES_PER_ENV_STEP, "us_per_launch": us_per_launch},
             "step_many": {"value": many_value, "unit": "env-steps/s", "ms_per_step": ms_many / K,
                           "achieved_gbs": BYTES_PER_ENV_STEP * many_value / world / 1e9,

@@ -55,7 +55,10 @@ typedef enum {
     MGRL_ERR_ENV = -4        /* an environment flagged an error (invalid action, rejection cap) */
 } mgrl_status;
 
-typedef enum { MGRL_OBS_HWC = 0, MGRL_OBS_CHW = 1 } mgrl_obs_layout;
+/* image record layouts: HWC = image[vx][vy][c] (MiniGrid native), CHW = image[c][vx][vy] (after SB3
+ * VecTransposeImage), both 147 bytes per environment; HWC148 = HWC with one zero pad byte, i.e. a
+ * 148-byte record pitch, which lets the kernel emit aligned 32-bit stores (fastest). */
+typedef enum { MGRL_OBS_HWC = 0, MGRL_OBS_CHW = 1, MGRL_OBS_HWC148 = 2 } mgrl_obs_layout;
 /* cfg.env.problem, custom_env.py:134-152 ('full' and 'mov' are not supported) */
 typedef enum { MGRL_MULTI = 0, MGRL_GTO = 1, MGRL_GTG = 2, MGRL_OPN = 3, MGRL_PKP = 4, MGRL_DRP = 5 } mgrl_problem;
 
@@ -92,19 +95,20 @@ int mgrl_host_free(void *ptr);
 
 /* replaces VecEnv.seed(seed) + VecEnv.reset() (ppo.py:134,210): fresh environments
  * (latch cleared, episode 0) from RNG keys (seed, env_id_base+i); writes the first
- * observation.  image_dev [N,147] in obs_layout, dir_dev [N], mission_dev [N] (mission id). */
+ * observation.  image_dev [N,pitch] in obs_layout (pitch 147 or 148), dir_dev [N], mission_dev [N]
+ * (mission id). */
 int mgrl_reset(mgrl_env *env, uint64_t seed, uint8_t *image_dev, uint8_t *dir_dev,
                uint8_t *mission_dev, void *stream);
 
 /* replaces VecEnv.step(actions) for the un-stacked observation (SubprocVecEnv/DummyVecEnv
  * step_wait over Monitor(Discrete2BoxWrapper(TokenizeVocabWrapper(PlaygroundEnv)))):
  * PlaygroundEnv.step (custom_env.py:269-330) + auto-reset on done.
- *   actions_dev [N] u8 in 0..6;  image_dev [N,147];  dir_dev [N];  mission_dev [N];
+ *   actions_dev [N] u8 in 0..6;  image_dev [N,pitch];  dir_dev [N];  mission_dev [N];
  *   reward_dev [N] f32;  term_dev / trunc_dev [N] u8 (done = term|trunc,
  *   info['TimeLimit.truncated'] = trunc & !term);
  *   ep_len_dev [N] u8 or NULL: Monitor's episode length on done steps, else 0
  *     (Monitor's episode return equals the reward of the done step: all others are 0);
- *   term_image_dev [N,147] / term_dir_dev [N] or NULL: image and direction of
+ *   term_image_dev [N,pitch] / term_dir_dev [N] or NULL: image and direction of
  *     info['terminal_observation'], written only for environments that finished on this
  *     step (its mission is the previous step's mission). */
 int mgrl_step(mgrl_env *env, const uint8_t *actions_dev, uint8_t *image_dev, uint8_t *dir_dev,

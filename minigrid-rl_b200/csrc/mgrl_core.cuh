@@ -4,7 +4,7 @@
 // __host__ __device__ inline code over a state reference so that (a) the CUDA kernels in
 // mgrl_kernels.cu run it one-lane-per-environment on shared-memory-resident tiles and
 // (b) tests/ can compile the very same functions for the host and compare them with the
-// CPU oracle without a GPU (tests/host_emul.cpp; test infrastructure, not a fallback).
+// CPU oracle without a GPU (tests/support/host_emul.cpp; test infrastructure, not a fallback).
 //
 // Reference behaviour implemented (paths relative to /root/reference/src/):
 //   env_step      : [UPSTREAM] MiniGridEnv.step + PlaygroundEnv.step      custom_env.py:269-330
@@ -37,8 +37,8 @@ constexpr int A_LEFT = 0, A_RIGHT = 1, A_FORWARD = 2, A_PICKUP = 3, A_DROP = 4, 
 constexpr int P_MULTI = 0, P_GTO = 1, P_GTG = 2, P_OPN = 3, P_PKP = 4, P_DRP = 5;
 constexpr int MISSION_GOAL = 72, MISSION_DROP = 73;
 constexpr int ERR_BAD_ACTION = 1, ERR_TRIES = 2;
-constexpr int OBS_HWC = 0;  // image[vx][vy][c]  (MiniGrid native)
-constexpr int OBS_CHW = 1;  // image[c][vx][vy]  (after SB3 VecTransposeImage)
+constexpr int OBS_HWC = 0;  // image[vx][vy][c]  (MiniGrid native), 147-byte records
+constexpr int OBS_CHW = 1;  // image[c][vx][vy]  (after SB3 VecTransposeImage), 147-byte records
 
 struct EnvState {  // 140 bytes = 35 words (odd word stride: conflict-free lane-per-env smem access)
     uint8_t grid[kGridCells];
@@ -110,35 +110,49 @@ MGRL_HD uint32_t kind_encode(int k) {
 // ---------------------------------------------------------------------------------- RNG
 // Philox4x32-10, key = seed, counter = (block, episode, env_lo, env_hi).  Draw d of an
 // episode is word d&3 of block d>>2; below(n) = mulhi32(word, n).
+//
+// The generator consumes draws through a 4-word *window*: sync() makes blocks A = d>>2 and
+// B = A+1 current (one Philox site per generator iteration, so lanes of a warp that sit at
+// different draw counts still execute the rounds together), peek(i) returns word d+i for
+// i < 4, and the caller then advances ndraw by what it used.
 struct Rng {
     uint32_t k0, k1, e0, e1, episode;
     uint32_t ndraw;
-    uint32_t buf[4];
+    uint32_t blk;  // block id held in a[]; b[] holds blk+1
+    uint32_t a[4], b[4];
 
-    MGRL_HD void init(uint64_t seed, uint64_t env_id, uint32_t ep) {
-        k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
-        e0 = (uint32_t)env_id; e1 = (uint32_t)(env_id >> 32);
-        episode = ep; ndraw = 0;
-    }
-    MGRL_HD void refill() {
-        uint32_t c0 = ndraw >> 2, c1 = episode, c2 = e0, c3 = e1, a = k0, b = k1;
+    MGRL_HD static void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t ka, uint32_t kb,
+                               uint32_t* out) {
 #pragma unroll
         for (int r = 0; r < 10; ++r) {
             const uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
             const uint32_t h1 = mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
-            c0 = h1 ^ c1 ^ a; c1 = l1; c2 = h0 ^ c3 ^ b; c3 = l0;
-            a += 0x9E3779B9u; b += 0xBB67AE85u;
+            c0 = h1 ^ c1 ^ ka; c1 = l1; c2 = h0 ^ c3 ^ kb; c3 = l0;
+            ka += 0x9E3779B9u; kb += 0xBB67AE85u;
         }
-        buf[0] = c0; buf[1] = c1; buf[2] = c2; buf[3] = c3;
+        out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
     }
-    MGRL_HD uint32_t below(uint32_t n) {
-        const uint32_t w = ndraw & 3u;
-        if (w == 0) refill();
-        ++ndraw;
-        const uint32_t v = w == 0 ? buf[0] : w == 1 ? buf[1] : w == 2 ? buf[2] : buf[3];
-        return mulhi32(v, n);
+    MGRL_HD void init(uint64_t seed, uint64_t env_id, uint32_t ep) {
+        k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
+        e0 = (uint32_t)env_id; e1 = (uint32_t)(env_id >> 32);
+        episode = ep; ndraw = 0; blk = 0;
+        philox(0, episode, e0, e1, k0, k1, a);
+        philox(1, episode, e0, e1, k0, k1, b);
     }
-    MGRL_HD int randint(int a, int b) { return a + (int)below((uint32_t)(b - a + 1)); }  // inclusive
+    // re-establish a[] = block(ndraw>>2), b[] = the block after it
+    MGRL_HD void sync() {
+        if ((ndraw >> 2) != blk) {  // the window moved by exactly one block (<= 4 draws per iteration)
+            blk = ndraw >> 2;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = b[i];
+            philox(blk + 1, episode, e0, e1, k0, k1, b);
+        }
+    }
+    // word ndraw+i, i in 0..3
+    MGRL_HD uint32_t peek(int i) const {
+        const int w = (int)(ndraw & 3u) + i;  // 0..6
+        return w == 0 ? a[0] : w == 1 ? a[1] : w == 2 ? a[2] : w == 3 ? a[3] : w == 4 ? b[0] : w == 5 ? b[1] : b[2];
+    }
 };
 
 // --------------------------------------------------------------------------------- step
@@ -227,29 +241,81 @@ MGRL_HD StepOut env_step(EnvState& s, int action, int S, int max_steps, const fl
 // -------------------------------------------------------------------------- observation
 // View cell (vx,vy) shows world cell agent + (vx-3)*right + (6-vy)*dir.  The border of the
 // grid is always wall and out-of-grid cells render as wall, so coordinates are clamped
-// instead of bounds-checked.  `out` receives 147 bytes in LAYOUT order.
+// instead of bounds-checked.  The map is separable: the forward coordinate depends only on
+// vy and the sideways coordinate only on vx, so 7+7 clamped offsets replace 49x2 clamps:
+//     grid index of view cell (vx,vy) = ro[vx] + fo[vy].
+constexpr int kObsPitch148 = 148;  // word-aligned record: 49 x (type,colour,state) + 1 pad byte
+constexpr int OBS_HWC148 = 2;      // image[vx][vy][c], record pitch 148 B (fast path: packed word stores)
+
 template <int LAYOUT>
 MGRL_HD int obs_index(int vx, int vy, int c) {
-    return LAYOUT == OBS_HWC ? (vx * kView + vy) * 3 + c : c * (kView * kView) + vx * kView + vy;
+    return LAYOUT == OBS_CHW ? c * (kView * kView) + vx * kView + vy : (vx * kView + vy) * 3 + c;
 }
 
 MGRL_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-template <int LAYOUT>
-MGRL_HD void encode_view_see_through(const EnvState& s, int carrying, int S, uint8_t* out) {
+struct ViewMap {
+    int fo[kView], ro[kView];
+};
+
+MGRL_HD void view_map(const EnvState& s, int S, ViewMap& m) {
     const int dir = s.agent_dir;
-    const int dx = (dir == 0) - (dir == 2), dy = (dir == 1) - (dir == 3);
-    const int rx = -dy, ry = dx;
-    const int bx = s.agent_x - 3 * rx + 6 * dx, by = s.agent_y - 3 * ry + 6 * dy;  // world of view (0,0)
+    const bool even = (dir & 1) == 0;                 // forward axis is x for east/west
+    const int sf = dir < 2 ? 1 : -1;                  // forward step: +1 east/south, -1 west/north
+    const int sr = (dir == 0 || dir == 3) ? 1 : -1;   // sideways (view-x) step
+    const int af = even ? s.agent_x : s.agent_y, ar = even ? s.agent_y : s.agent_x;
+    const int mf = even ? 1 : S, mr = even ? S : 1;
+#pragma unroll
+    for (int i = 0; i < kView; ++i) {
+        m.fo[i] = clampi(af + (6 - i) * sf, 0, S - 1) * mf;
+        m.ro[i] = clampi(ar + (i - 3) * sr, 0, S - 1) * mr;
+    }
+}
+
+// lut[k] = kind_encode(k) for k < 128 (shared memory on the device)
+MGRL_HD void fill_kind_lut(uint32_t* lut, int tid, int nthreads) {
+    for (int k = tid; k < 128; k += nthreads) lut[k] = kind_encode(k);
+}
+
+MGRL_HD uint32_t pack3(uint32_t lo, uint32_t hi, int shift_bytes) {  // bytes of (hi:lo) >> 8*shift, hi's top byte is 0
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(lo, hi, shift_bytes == 0 ? 0x4210 : shift_bytes == 1 ? 0x5421 : 0x6542);
+#else
+    return shift_bytes == 0 ? (lo | (hi << 24)) : shift_bytes == 1 ? ((lo >> 8) | (hi << 16)) : ((lo >> 16) | (hi << 8));
+#endif
+}
+
+// fast path: see-through view, HWC, 37 aligned words (148 B) per environment
+MGRL_HD void encode_view_packed(const EnvState& s, int carrying, int S, const uint32_t* lut, uint32_t* out) {
+    ViewMap m;
+    view_map(s, S, m);
+    uint32_t e[4];
+#pragma unroll
+    for (int c = 0; c < kView * kView; ++c) {
+        const int vx = c / kView, vy = c % kView;
+        const int k = (c == 3 * kView + 6) ? carrying : (int)s.grid[m.ro[vx] + m.fo[vy]];
+        e[c & 3] = lut[k];
+        if ((c & 3) == 3) {
+            const int w = (c >> 2) * 3;
+            out[w] = pack3(e[0], e[1], 0);
+            out[w + 1] = pack3(e[1], e[2], 1);
+            out[w + 2] = pack3(e[2], e[3], 2);
+        }
+    }
+    out[36] = e[0];  // cell 48 + pad byte
+}
+
+// byte-granular path (any layout, 147-byte records; also used for terminal observations)
+template <int LAYOUT>
+MGRL_HD void encode_view_see_through(const EnvState& s, int carrying, int S, const uint32_t* lut, uint8_t* out) {
+    ViewMap m;
+    view_map(s, S, m);
 #pragma unroll
     for (int vx = 0; vx < kView; ++vx) {
 #pragma unroll
         for (int vy = 0; vy < kView; ++vy) {
-            const int wx = clampi(bx + vx * rx - vy * dx, 0, S - 1);
-            const int wy = clampi(by + vx * ry - vy * dy, 0, S - 1);
-            int k = s.grid[wy * S + wx];
-            if (vx == 3 && vy == 6) k = carrying;
-            const uint32_t e = kind_encode(k);
+            const int k = (vx == 3 && vy == 6) ? carrying : (int)s.grid[m.ro[vx] + m.fo[vy]];
+            const uint32_t e = lut[k];
             out[obs_index<LAYOUT>(vx, vy, 0)] = (uint8_t)e;
             out[obs_index<LAYOUT>(vx, vy, 1)] = (uint8_t)(e >> 8);
             out[obs_index<LAYOUT>(vx, vy, 2)] = (uint8_t)(e >> 16);
@@ -259,18 +325,13 @@ MGRL_HD void encode_view_see_through(const EnvState& s, int carrying, int S, uin
 
 // see_through_walls == false: [UPSTREAM] Grid.process_vis, mask kept as a 49-bit set
 template <int LAYOUT>
-MGRL_HD void encode_view_occluded(const EnvState& s, int carrying, int S, uint8_t* out) {
-    const int dir = s.agent_dir;
-    const int dx = (dir == 0) - (dir == 2), dy = (dir == 1) - (dir == 3);
-    const int rx = -dy, ry = dx;
-    const int bx = s.agent_x - 3 * rx + 6 * dx, by = s.agent_y - 3 * ry + 6 * dy;
+MGRL_HD void encode_view_occluded(const EnvState& s, int carrying, int S, const uint32_t* lut, uint8_t* out) {
+    ViewMap m;
+    view_map(s, S, m);
     uint64_t opaque = 0;  // bit vx*7+vy
     for (int vx = 0; vx < kView; ++vx)
-        for (int vy = 0; vy < kView; ++vy) {
-            const int wx = clampi(bx + vx * rx - vy * dx, 0, S - 1);
-            const int wy = clampi(by + vx * ry - vy * dy, 0, S - 1);
-            if (k_opaque(s.grid[wy * S + wx])) opaque |= 1ull << (vx * kView + vy);
-        }
+        for (int vy = 0; vy < kView; ++vy)
+            if (k_opaque(s.grid[m.ro[vx] + m.fo[vy]])) opaque |= 1ull << (vx * kView + vy);
     uint64_t mask = 1ull << (3 * kView + 6);
     for (int j = kView - 1; j >= 0; --j) {
         for (int i = 0; i < kView - 1; ++i) {
@@ -288,21 +349,25 @@ MGRL_HD void encode_view_occluded(const EnvState& s, int carrying, int S, uint8_
     }
     for (int vx = 0; vx < kView; ++vx)
         for (int vy = 0; vy < kView; ++vy) {
-            const int wx = clampi(bx + vx * rx - vy * dx, 0, S - 1);
-            const int wy = clampi(by + vx * ry - vy * dy, 0, S - 1);
-            int k = s.grid[wy * S + wx];
-            if (vx == 3 && vy == 6) k = carrying;
-            const uint32_t e = ((mask >> (vx * kView + vy)) & 1ull) ? kind_encode(k) : 0u;
-            out[obs_index<LAYOUT>(vx, vy, 0)] = (uint8_t)e;
-            out[obs_index<LAYOUT>(vx, vy, 1)] = (uint8_t)(e >> 8);
-            out[obs_index<LAYOUT>(vx, vy, 2)] = (uint8_t)(e >> 16);
+            const int k = (vx == 3 && vy == 6) ? carrying : (int)s.grid[m.ro[vx] + m.fo[vy]];
+            const uint32_t e = ((mask >> (vx * kView + vy)) & 1ull) ? lut[k] : 0u;
+            const int pitch_layout = LAYOUT == OBS_HWC148 ? OBS_HWC : LAYOUT;
+            out[obs_index<pitch_layout>(vx, vy, 0)] = (uint8_t)e;
+            out[obs_index<pitch_layout>(vx, vy, 1)] = (uint8_t)(e >> 8);
+            out[obs_index<pitch_layout>(vx, vy, 2)] = (uint8_t)(e >> 16);
         }
+    if (LAYOUT == OBS_HWC148) out[147] = 0;
 }
 
+// record pitch of a layout
+MGRL_HD constexpr int obs_pitch(int layout) { return layout == OBS_HWC148 ? kObsPitch148 : kObsBytes; }
+
+// out must be 4-byte aligned for OBS_HWC148
 template <int LAYOUT>
-MGRL_HD void encode_view(const EnvState& s, int carrying, int S, bool see_through, uint8_t* out) {
-    if (see_through) encode_view_see_through<LAYOUT>(s, carrying, S, out);
-    else encode_view_occluded<LAYOUT>(s, carrying, S, out);
+MGRL_HD void encode_view(const EnvState& s, int carrying, int S, bool see_through, const uint32_t* lut, uint8_t* out) {
+    if (!see_through) encode_view_occluded<LAYOUT>(s, carrying, S, lut, out);
+    else if (LAYOUT == OBS_HWC148) encode_view_packed(s, carrying, S, lut, reinterpret_cast<uint32_t*>(out));
+    else encode_view_see_through<LAYOUT>(s, carrying, S, lut, out);
 }
 
 // [UPSTREAM] FullyObsWrapper: image[x][y][c], agent cell (10, 0, dir)
@@ -317,96 +382,19 @@ MGRL_HD void encode_full(const EnvState& s, int S, uint8_t* out) {
 }
 
 // ----------------------------------------------------------------------------- generator
-// Object list entry: type(3) | colour(3) <<3 | x <<6 | y <<10
+// PlaygroundEnv._gen_grid (custom_env.py:122-267) with the map generators (:371-555 single
+// room, :595-2034 two/three/four rooms) as ONE flattened task machine.
+//
+// The reference is a long sequence of rejection loops ("draw a position, retry until it is
+// admissible") whose number and kind depend on earlier draws.  Run lane-per-environment that
+// diverges badly, so the generator is written as a single loop whose body performs exactly
+// one *try* of the lane's current task: every placement kind (goal, agent, key / key-in-box,
+// distractor, single-room object, obstacle) shares the same draw-test-commit code, driven by
+// per-lane flags.  Lanes that need more tries simply take more iterations while the others
+// move on to their next task, and the Philox rounds run at one site per iteration.
+// The draw order is the reference's; the CPU oracle consumes the same stream.
 constexpr int T_KEY = 0, T_BALL = 1, T_BOX = 2, T_DOOR = 3, T_GOAL = 4;
 constexpr int kMaxObjs = 40;
-
-struct Gen {
-    EnvState& s;
-    const EnvCfg& cfg;
-    Rng rng;
-    int S, mid;
-    int agent_x, agent_y, goal_x, goal_y;
-    int nobjs;
-    uint32_t pool;        // bit (slot*6 + sorted colour index): remaining (type, colour) pairs
-    uint32_t pool_types;  // 3 bits per slot: object type of that slot
-    uint16_t objs[kMaxObjs];
-
-    MGRL_HD Gen(EnvState& st, const EnvCfg& c) : s(st), cfg(c) {}
-
-    // COLOR_NAMES sorted alphabetically (blue green grey purple red yellow) -> COLOR_TO_IDX
-    MGRL_HD static int sorted_colour(int i) { return (int)((0x403512u >> (4 * i)) & 0xFu); }
-    MGRL_HD static int sorted_index(int colour) { return (int)((0x253014u >> (4 * colour)) & 0xFu); }
-
-    MGRL_HD uint8_t& cell(int x, int y) { return s.grid[y * S + x]; }
-    MGRL_HD void add_obj(int type, int colour, int x, int y) {
-        if (nobjs < kMaxObjs) objs[nobjs] = (uint16_t)(type | (colour << 3) | (x << 6) | (y << 10));
-        ++nobjs;
-    }
-    MGRL_HD bool on_obj(int x, int y) const {
-        const int key = (x << 6) | (y << 10);
-        for (int i = 0; i < nobjs && i < kMaxObjs; ++i)
-            if ((objs[i] & 0xFFC0) == key) return true;
-        return false;
-    }
-    MGRL_HD void pool_fill(int t0, int t1, int t2, int t3, int ntypes) {
-        pool_types = (uint32_t)(t0 | (t1 << 3) | (t2 << 6) | (t3 << 9));
-        pool = (1u << (6 * ntypes)) - 1u;
-    }
-    MGRL_HD void pool_remove(int type, int colour) {
-        for (int slot = 0; slot < 4; ++slot)
-            if ((int)((pool_types >> (3 * slot)) & 7u) == type) pool &= ~(1u << (slot * 6 + sorted_index(colour)));
-    }
-    MGRL_HD void pool_take(int& type, int& colour) {  // choice(pool) then remove
-        const int i = (int)rng.below((uint32_t)popc32(pool));
-        const int bit = nth_set_bit(pool, i);
-        pool &= ~(1u << bit);
-        type = (int)((pool_types >> (3 * (bit / 6))) & 7u);
-        colour = sorted_colour(bit % 6);
-    }
-    MGRL_HD static int obj_kind(int type, int colour) {
-        return type == T_KEY ? K_KEY + colour : type == T_BALL ? K_BALL + colour
-             : type == T_BOX ? K_BOX + colour : type == T_DOOR ? K_DOOR + 8 + colour : K_GOAL;
-    }
-    MGRL_HD bool next2door(int x, int y) {  // custom_env.py:2036-2046
-        return k_is_door(cell(x - 1, y)) || k_is_door(cell(x + 1, y)) || k_is_door(cell(x, y - 1)) ||
-               k_is_door(cell(x, y + 1));
-    }
-    // [UPSTREAM] place_obj over the whole grid
-    MGRL_HD void place_obj(int kind, int& px, int& py) {
-        int x = 0, y = 0, tries = 0;
-        for (;;) {
-            x = (int)rng.below((uint32_t)S);
-            y = (int)rng.below((uint32_t)S);
-            if (++tries >= kMaxTries) { s.error |= ERR_TRIES; break; }
-            if (cell(x, y) != K_EMPTY) continue;
-            if (x == agent_x && y == agent_y) continue;
-            break;
-        }
-        cell(x, y) = (uint8_t)kind;
-        px = x; py = y;
-    }
-    MGRL_HD void place_agent() {  // [UPSTREAM] place_agent
-        int x, y;
-        agent_x = agent_y = -1;
-        place_obj(K_EMPTY, x, y);
-        agent_x = x; agent_y = y;
-        s.agent_x = (uint8_t)x; s.agent_y = (uint8_t)y;
-        s.agent_dir = (uint8_t)rng.below(4);
-    }
-    MGRL_HD void place_goal_away_from_doors() {
-        int x, y, tries = 0;
-        for (;;) {
-            place_obj(K_GOAL, x, y);
-            if (next2door(x, y) && ++tries < kMaxTries) { cell(x, y) = K_EMPTY; continue; }
-            break;
-        }
-        goal_x = x; goal_y = y;
-        add_obj(T_GOAL, 0, x, y);
-    }
-};
-
-struct Room { int x0, x1, y0, y1; };
 
 // Keys placed in `room` when the agent starts in `agent_room`: up to
 // two door indices, 7 = none.  One byte per agent room: low nibble = first key, high = second.
@@ -438,213 +426,250 @@ MGRL_HD int room_of(int nrooms, int mid, int x, int y) {
     return left ? (upper ? 0 : 1) : (upper ? 2 : 3);
 }
 
-// 2 rooms: L R; 3 rooms: UL LL R; 4 rooms: UL LL UR LR (interior rectangles, inclusive)
-MGRL_HD Room room_rect(int nrooms, int r, int S, int m) {
-    Room R;
-    const bool left = nrooms == 2 ? r == 0 : r < 2;
-    const bool full_height = nrooms == 2 || (nrooms == 3 && r == 2);
-    const bool upper = (r & 1) == 0;
-    R.x0 = left ? 1 : m + 1; R.x1 = left ? m - 1 : S - 2;
-    R.y0 = (full_height || upper) ? 1 : m + 1;
-    R.y1 = (full_height || !upper) ? S - 2 : m - 1;
-    return R;
+// COLOR_NAMES sorted alphabetically (blue green grey purple red yellow) <-> COLOR_TO_IDX
+MGRL_HD int sorted_colour(int i) { return (int)((0x403512u >> (4 * i)) & 0xFu); }
+MGRL_HD int sorted_index(int colour) { return (int)((0x253014u >> (4 * colour)) & 0xFu); }
+MGRL_HD int obj_kind(int type, int colour) {
+    return type == T_KEY ? K_KEY + colour : type == T_BALL ? K_BALL + colour
+         : type == T_BOX ? K_BOX + colour : type == T_DOOR ? K_DOOR + 8 + colour : K_GOAL;
 }
 
-// _generate_{2,3,4}_rooms as one table-driven routine (custom_env.py:617-2034)
-MGRL_HD void generate_rooms(Gen& g, int nrooms) {
-    const int S = g.S, m = g.mid, n = g.cfg.num_objects;
-    g.pool_fill(T_KEY, T_BALL, T_BOX, 0, 3);
-    for (int i = 1; i < S - 1; ++i) g.cell(m, i) = K_WALL;
-    if (nrooms == 3) for (int i = 1; i < m; ++i) g.cell(i, m) = K_WALL;
-    if (nrooms == 4) for (int i = 1; i < S - 1; ++i) g.cell(i, m) = K_WALL;
+enum GenStage : int {
+    G_CMD = 0,   // multi: mission command (if cfg.mission is null) and room count
+    G_DOORPROP,  // door colour / locked / key_in_box
+    G_DOORCELL,  // door position (/ is_open)
+    G_OBJ,       // single-room object: pool draw + place_obj
+    G_GOAL,      // goal (multi: not next to a door)
+    G_AGENT,     // place_agent
+    G_KEY,       // key or box-with-key of a locked door
+    G_DIST,      // distractor object of a room
+    G_OBST,      // obstacle
+    G_TARGET,    // target selection
+    G_DONE
+};
 
-    int counts[4];
-    const int nl = n / 2, nr = n - nl;
-    if (nrooms == 2) { counts[0] = nl; counts[1] = nr; counts[2] = counts[3] = 0; }
-    else if (nrooms == 3) { counts[0] = nl / 2; counts[1] = nl - nl / 2; counts[2] = nr; counts[3] = 0; }
-    else { counts[0] = nl / 2; counts[1] = nl - nl / 2; counts[2] = nr / 2; counts[3] = nr - nr / 2; }
-
-    // door properties: colour (without replacement), locked, key_in_box  — packed 8 bits/door
-    uint32_t doors = 0;  // per door: colour(3) | locked<<3 | key_in_box<<4
-    uint32_t colours = 0x3Fu;
-    const int ndoors = nrooms == 2 ? 1 : nrooms;
-    for (int d = 0; d < ndoors; ++d) {
-        const int i = (int)g.rng.below((uint32_t)popc32(colours));
-        const int bit = nth_set_bit(colours, i);
-        colours &= ~(1u << bit);
-        const int colour = Gen::sorted_colour(bit);
-        const int locked = g.cfg.all_doors_open ? 0 : (g.rng.below(2) == 0);
-        const int kib = g.rng.below(2) == 0;
-        if (locked) { g.pool_remove(T_KEY, colour); if (kib) g.pool_remove(T_BOX, colour); }
-        doors |= (uint32_t)(colour | (locked << 3) | (kib << 4)) << (8 * d);
-    }
-    // door cells: (horizontal?, lo, hi) per door in the reference's order
-    for (int d = 0; d < ndoors; ++d) {
-        bool horizontal; int lo, hi;
-        if (nrooms == 2) { horizontal = false; lo = 1; hi = S - 2; }
-        else if (nrooms == 3) { horizontal = d == 0; lo = d == 2 ? m + 1 : 1; hi = d == 2 ? S - 2 : m - 1; }
-        else { horizontal = d < 2; lo = (d & 1) ? m + 1 : 1; hi = (d & 1) ? S - 2 : m - 1; }
-        const int p = g.rng.randint(lo, hi);
-        const int is_open = g.cfg.all_doors_open ? (g.rng.below(2) == 0) : 0;
-        const int props = (int)((doors >> (8 * d)) & 0xFFu);
-        const int colour = props & 7, locked = (props >> 3) & 1;
-        const int state = is_open ? 0 : (locked ? 2 : 1);
-        const int x = horizontal ? p : m, y = horizontal ? m : p;
-        g.cell(x, y) = (uint8_t)(K_DOOR + 8 * state + colour);
-        g.add_obj(T_DOOR, colour, x, y);
-    }
-    g.place_goal_away_from_doors();
-    g.place_agent();
-    const int agent_room = room_of(nrooms, m, g.agent_x, g.agent_y);
-    const int goal_room = room_of(nrooms, m, g.goal_x, g.goal_y);
-
-    for (int r = 0; r < nrooms; ++r) {
-        const Room R = room_rect(nrooms, r, S, m);
-        int kx = -1, ky = -1;
-        for (int j = 0; j < 2; ++j) {
-            const int d = key_door(nrooms, r, agent_room, j);
-            if (d == 7) continue;
-            const int props = (int)((doors >> (8 * d)) & 0xFFu);
-            const int colour = props & 7;
-            if (!((props >> 3) & 1)) continue;  // key only for a locked door
-            int x = 0, y = 0, tries = 0;
-            for (;;) {
-                x = g.rng.randint(R.x0, R.x1);
-                y = g.rng.randint(R.y0, R.y1);
-                if (++tries >= kMaxTries) { g.s.error |= ERR_TRIES; break; }
-                if (x == g.goal_x && y == g.goal_y) continue;
-                if (r == agent_room && x == g.agent_x && y == g.agent_y) continue;
-                if (x == kx && y == ky) continue;
-                if (g.next2door(x, y)) continue;
-                break;
-            }
-            if ((props >> 4) & 1) {  // Box(colour, Key(colour))
-                g.cell(x, y) = (uint8_t)(K_BOX + 8 * (colour + 1) + colour);
-                g.add_obj(T_BOX, colour, x, y);
-            } else {
-                g.cell(x, y) = (uint8_t)(K_KEY + colour);
-                g.add_obj(T_KEY, colour, x, y);
-            }
-            counts[r]--;
-            if (j == 0) { kx = x; ky = y; }
-        }
-        if (goal_room == r) counts[r]--;
-        // reference quirk (custom_env.py:1119, 1660): the lower-left loop uses the upper-left counter
-        const int loops = (nrooms >= 3 && r == 1) ? counts[0] : counts[r];
-        for (int q = 0; q < loops; ++q) {
-            int type, colour;
-            g.pool_take(type, colour);
-            int x = 0, y = 0, tries = 0;
-            for (;;) {
-                x = g.rng.randint(R.x0, R.x1);
-                y = g.rng.randint(R.y0, R.y1);
-                if (++tries >= kMaxTries) { g.s.error |= ERR_TRIES; break; }
-                if (g.on_obj(x, y)) continue;
-                if (x == g.agent_x && y == g.agent_y) continue;
-                if (g.next2door(x, y)) continue;
-                break;
-            }
-            g.cell(x, y) = (uint8_t)Gen::obj_kind(type, colour);
-            g.add_obj(type, colour, x, y);
-        }
-    }
-}
-
-// single-room generators (custom_env.py:371-555)
-MGRL_HD void generate_single(Gen& g, int problem) {
-    if (problem == P_GTG) g.pool_fill(T_BOX, T_DOOR, T_KEY, T_BALL, 4);
-    else if (problem == P_OPN) g.pool_fill(T_BOX, T_DOOR, 0, 0, 2);
-    else if (problem == P_PKP) g.pool_fill(T_KEY, T_BOX, T_BALL, 0, 3);
-    else g.pool_fill(T_KEY, T_BALL, T_BOX, T_DOOR, 4);
-    for (int i = 0; i < g.cfg.num_objects; ++i) {
-        int type, colour, x, y;
-        g.pool_take(type, colour);
-        g.place_obj(Gen::obj_kind(type, colour), x, y);
-        g.add_obj(type, colour, x, y);
-    }
-    if (problem == P_GTG || problem == P_DRP) {
-        int x, y;
-        g.place_obj(K_GOAL, x, y);
-        g.goal_x = x; g.goal_y = y;
-        g.add_obj(T_GOAL, 0, x, y);
-    }
-    g.place_agent();
-}
-
-// obstacles (custom_env.py:155-172)
-MGRL_HD void place_obstacles(Gen& g) {
-    const int S = g.S;
-    for (int i = 0; i < g.cfg.num_obstacles; ++i) {
-        if (g.cfg.problem == P_MULTI) {
-            int x = 0, y = 0, tries = 0;
-            for (;;) {
-                x = g.rng.randint(1, S - 2);
-                y = g.rng.randint(1, S - 2);
-                if (++tries >= kMaxTries) { g.s.error |= ERR_TRIES; break; }
-                if (x == g.mid || y == g.mid) continue;
-                if (g.on_obj(x, y)) continue;
-                if (x == g.agent_x && y == g.agent_y) continue;
-                if (g.next2door(x, y)) continue;
-                break;
-            }
-            g.cell(x, y) = K_LAVA;
-        } else {
-            int x, y;
-            const int kind = g.rng.below(2) == 0 ? K_LAVA : K_WALL;
-            g.place_obj(kind, x, y);
-        }
-    }
-}
-
-// PlaygroundEnv._gen_grid (custom_env.py:122-267) for episode s.episode of env `env_id`.
-// Leaves mission_done / latch_step untouched (they survive resets in the reference).
 MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t env_id) {
-    Gen g(s, cfg);
-    g.S = cfg.size; g.mid = cfg.size / 2;
-    g.agent_x = g.agent_y = g.goal_x = g.goal_y = -1;
-    g.nobjs = 0; g.pool = 0; g.pool_types = 0;
-    g.rng.init(seed, env_id, s.episode);
-    const int S = g.S;
+    const int S = cfg.size, m = S / 2;
+    const bool multi = cfg.problem == P_MULTI;
+    // ---- grid: empty interior, wall border (Grid.wall_rect, custom_env.py:132)
     for (int i = 0; i < kGridCells; ++i) s.grid[i] = K_EMPTY;
     for (int i = 0; i < S; ++i) {
-        g.cell(i, 0) = K_WALL; g.cell(i, S - 1) = K_WALL; g.cell(0, i) = K_WALL; g.cell(S - 1, i) = K_WALL;
+        s.grid[i] = K_WALL; s.grid[(S - 1) * S + i] = K_WALL; s.grid[i * S] = K_WALL; s.grid[i * S + S - 1] = K_WALL;
     }
-    s.carrying = 0; s.step_count = 0;
-    s.target_x = s.target_y = kNone; s.target_action = 0;
+    s.carrying = 0; s.step_count = 0;                                  // [UPSTREAM] MiniGridEnv.reset
+    s.target_x = s.target_y = kNone; s.target_action = 0;              // :125-127
 
-    int cmd;
-    if (cfg.problem == P_MULTI) {
-        cmd = cfg.mission >= 0 ? cfg.mission : (int)((0x5210u >> (4 * g.rng.below(4))) & 0xFu);  // choice([0,1,2,5])
-        generate_rooms(g, g.rng.randint(2, 4));
-    } else {
-        generate_single(g, cfg.problem);
-        cmd = cfg.problem == P_GTO ? 0 : cfg.problem == P_GTG ? 5 : cfg.problem == P_OPN ? 1
-            : cfg.problem == P_PKP ? 2 : 3;
-    }
-    if (cfg.num_obstacles > 0) place_obstacles(g);
+    Rng rng;
+    rng.init(seed, env_id, s.episode);
 
-    // target selection (custom_env.py:174-267)
-    if (cmd <= 2) {
-        const int n = g.nobjs < kMaxObjs ? g.nobjs : kMaxObjs;
-        int o = 0, tries = 0;
-        for (;;) {
-            o = g.objs[g.rng.below((uint32_t)n)];
+    // ---- per-lane task state
+    int stage = multi ? G_CMD : G_OBJ;
+    int cmd = multi ? cfg.mission
+                    : (cfg.problem == P_GTO ? 0 : cfg.problem == P_GTG ? 5 : cfg.problem == P_OPN ? 1
+                                                : cfg.problem == P_PKP ? 2 : 3);
+    int nrooms = 0, ndoors = 0, d = 0;          // door loop
+    uint32_t doors = 0;                          // per door: colour(3) | locked<<3 | key_in_box<<4
+    uint32_t colours = 0x3Fu;                    // remaining door colours (sorted-name order)
+    uint32_t pool = 0, pool_types = 0;           // remaining (type, colour) pairs; 3 bits of type per slot
+    int agent_x = -1, agent_y = -1, goal_x = -1, goal_y = -1, agent_room = 0, goal_room = 0;
+    int r = 0, ph = 0, q = 0, loops = 0, kx = -1, ky = -1;   // room walk
+    uint32_t counts = 0;                         // 4 signed bytes: distractor budget per room
+    int obj_i = 0, obst_i = 0, tries = 0;
+    int pend_type = 0, pend_colour = 0;          // object being placed
+    bool pre_done = false;                       // the task's pool / kind draw has happened
+    int nobjs = 0;
+    uint16_t objs[kMaxObjs];                     // type | colour<<3 | x<<6 | y<<10, insertion order
+
+    // pool of (type, colour) pairs in the reference's comprehension order
+    if (multi) { pool_types = T_KEY | (T_BALL << 3) | (T_BOX << 6); pool = (1u << 18) - 1u; }
+    else if (cfg.problem == P_GTG) { pool_types = T_BOX | (T_DOOR << 3) | (T_KEY << 6) | (T_BALL << 9); pool = (1u << 24) - 1u; }
+    else if (cfg.problem == P_OPN) { pool_types = T_BOX | (T_DOOR << 3); pool = (1u << 12) - 1u; }
+    else if (cfg.problem == P_PKP) { pool_types = T_KEY | (T_BOX << 3) | (T_BALL << 6); pool = (1u << 18) - 1u; }
+    else { pool_types = T_KEY | (T_BALL << 3) | (T_BOX << 6) | (T_DOOR << 9); pool = (1u << 24) - 1u; }
+    if (!multi && cfg.num_objects == 0) stage = (cfg.problem == P_GTG || cfg.problem == P_DRP) ? G_GOAL : G_AGENT;
+
+#define MGRL_CNT(rr) ((int)(int8_t)((counts >> (8 * (rr))) & 0xFFu))
+#define MGRL_CNT_DEC(rr) counts = (counts & ~(0xFFu << (8 * (rr)))) | ((uint32_t)((MGRL_CNT(rr) - 1) & 0xFF) << (8 * (rr)))
+
+    while (stage != G_DONE) {
+        rng.sync();
+        int used = 0;
+
+        if (stage == G_CMD) {  // _generate_multi_map :601-611
+            if (cmd < 0) cmd = (int)((0x5210u >> (4 * mulhi32(rng.peek(used++), 4))) & 0xFu);  // choice([0,1,2,5])
+            nrooms = 2 + (int)mulhi32(rng.peek(used++), 3);                                     // randint(2,4)
+            ndoors = nrooms == 2 ? 1 : nrooms;
+            for (int i = 1; i < S - 1; ++i) s.grid[i * S + m] = K_WALL;                         // wall x = mid
+            if (nrooms >= 3) {
+                const int hi = nrooms == 3 ? m : S - 1;
+                for (int i = 1; i < hi; ++i) s.grid[m * S + i] = K_WALL;                        // wall y = mid
+            }
+            const int n = cfg.num_objects, nl = n / 2, nr = n - nl;
+            int c0, c1, c2 = 0, c3 = 0;
+            if (nrooms == 2) { c0 = nl; c1 = nr; }
+            else if (nrooms == 3) { c0 = nl / 2; c1 = nl - nl / 2; c2 = nr; }
+            else { c0 = nl / 2; c1 = nl - nl / 2; c2 = nr / 2; c3 = nr - nr / 2; }
+            counts = (uint32_t)(c0 & 0xFF) | ((uint32_t)(c1 & 0xFF) << 8) | ((uint32_t)(c2 & 0xFF) << 16) |
+                     ((uint32_t)(c3 & 0xFF) << 24);
+            stage = G_DOORPROP; d = 0;
+        } else if (stage == G_DOORPROP) {  // :635-643, :880-908, :1324-1362
+            const int i = (int)mulhi32(rng.peek(used++), (uint32_t)popc32(colours));
+            const int bit = nth_set_bit(colours, i);
+            colours &= ~(1u << bit);
+            const int colour = sorted_colour(bit);
+            const int locked = cfg.all_doors_open ? 0 : (mulhi32(rng.peek(used++), 2) == 0);  // choice([True, False])
+            const int kib = mulhi32(rng.peek(used++), 2) == 0;
+            if (locked) {  // obj_choice.remove(('key', c)) [, ('box', c)]: pool slots are key, ball, box
+                pool &= ~(1u << (0 * 6 + sorted_index(colour)));
+                if (kib) pool &= ~(1u << (2 * 6 + sorted_index(colour)));
+            }
+            doors |= (uint32_t)(colour | (locked << 3) | (kib << 4)) << (8 * d);
+            if (++d == ndoors) { stage = G_DOORCELL; d = 0; }
+        } else if (stage == G_DOORCELL) {  // :646-650, :911-929, :1365-1390
+            bool horizontal; int lo, hi;
+            if (nrooms == 2) { horizontal = false; lo = 1; hi = S - 2; }
+            else if (nrooms == 3) { horizontal = d == 0; lo = d == 2 ? m + 1 : 1; hi = d == 2 ? S - 2 : m - 1; }
+            else { horizontal = d < 2; lo = (d & 1) ? m + 1 : 1; hi = (d & 1) ? S - 2 : m - 1; }
+            const int p = lo + (int)mulhi32(rng.peek(used++), (uint32_t)(hi - lo + 1));
+            const int is_open = cfg.all_doors_open ? (mulhi32(rng.peek(used++), 2) == 0) : 0;
+            const int props = (int)((doors >> (8 * d)) & 0xFFu);
+            const int colour = props & 7, state = is_open ? 0 : (((props >> 3) & 1) ? 2 : 1);
+            const int x = horizontal ? p : m, y = horizontal ? m : p;
+            s.grid[y * S + x] = (uint8_t)(K_DOOR + 8 * state + colour);
+            if (nobjs < kMaxObjs) objs[nobjs] = (uint16_t)(T_DOOR | (colour << 3) | (x << 6) | (y << 10));
+            ++nobjs;
+            if (++d == ndoors) stage = G_GOAL;
+        } else if (stage == G_TARGET) {  // :174-210
+            const int n = nobjs < kMaxObjs ? nobjs : kMaxObjs;
+            const int o = objs[mulhi32(rng.peek(used++), (uint32_t)n)];
             const int t = o & 7;
             const bool ok = cmd == 0 ? t != T_GOAL : cmd == 1 ? (t == T_BOX || t == T_DOOR)
                                                               : (t == T_BOX || t == T_KEY || t == T_BALL);
-            if (ok) break;
-            if (++tries >= kMaxTries) { s.error |= ERR_TRIES; break; }
+            if (!ok && ++tries >= kMaxTries) s.error |= ERR_TRIES;
+            if (ok || tries >= kMaxTries) {
+                s.mission_id = (uint8_t)(cmd * 24 + t * 6 + ((o >> 3) & 7));
+                s.target_x = (uint8_t)((o >> 6) & 15); s.target_y = (uint8_t)((o >> 10) & 15);
+                s.target_action = (uint8_t)(cmd == 0 ? A_DONE : cmd == 1 ? A_TOGGLE : A_PICKUP);
+                stage = G_DONE;
+            }
+        } else {
+            // ---- one placement try, shared by G_OBJ / G_GOAL / G_AGENT / G_KEY / G_DIST / G_OBST
+            const bool whole_grid = stage == G_OBJ || stage == G_GOAL || stage == G_AGENT || (stage == G_OBST && !multi);
+            // pre-draw once per task: pool entry (choice + remove) or obstacle kind
+            if (!pre_done && (stage == G_OBJ || stage == G_DIST)) {
+                const int i = (int)mulhi32(rng.peek(used++), (uint32_t)popc32(pool));
+                const int bit = nth_set_bit(pool, i);
+                pool &= ~(1u << bit);
+                pend_type = (int)((pool_types >> (3 * (bit / 6))) & 7u);
+                pend_colour = sorted_colour(bit % 6);
+                pre_done = true;
+            } else if (!pre_done && stage == G_OBST && !multi) {
+                pend_type = mulhi32(rng.peek(used++), 2) == 0 ? K_LAVA : K_WALL;  // choice([Lava(), Wall()])
+                pre_done = true;
+            }
+            // room rectangle (inclusive) or the whole grid (place_obj draws over [0,S))
+            int x0, x1, y0, y1;
+            if (whole_grid) { x0 = 0; x1 = S - 1; y0 = 0; y1 = S - 1; }
+            else if (stage == G_OBST) { x0 = 1; x1 = S - 2; y0 = 1; y1 = S - 2; }
+            else {
+                const bool left = nrooms == 2 ? r == 0 : r < 2;
+                const bool full_height = nrooms == 2 || (nrooms == 3 && r == 2);
+                const bool upper = (r & 1) == 0;
+                x0 = left ? 1 : m + 1; x1 = left ? m - 1 : S - 2;
+                y0 = (full_height || upper) ? 1 : m + 1;
+                y1 = (full_height || !upper) ? S - 2 : m - 1;
+            }
+            const int x = x0 + (int)mulhi32(rng.peek(used++), (uint32_t)(x1 - x0 + 1));
+            const int y = y0 + (int)mulhi32(rng.peek(used++), (uint32_t)(y1 - y0 + 1));
+            const int here = s.grid[y * S + x];
+            // admissibility
+            bool ok;
+            const bool at_agent = x == agent_x && y == agent_y;
+            bool n2d = false;
+            if (multi && stage != G_AGENT && x >= 1 && x <= S - 2 && y >= 1 && y <= S - 2)  // next2door :2036-2046
+                n2d = k_is_door(s.grid[y * S + x - 1]) || k_is_door(s.grid[y * S + x + 1]) ||
+                      k_is_door(s.grid[(y - 1) * S + x]) || k_is_door(s.grid[(y + 1) * S + x]);
+            if (whole_grid) ok = here == K_EMPTY && !at_agent && !(stage == G_GOAL && multi && n2d);  // place_obj
+            else if (stage == G_KEY)
+                ok = !(x == goal_x && y == goal_y) && !(r == agent_room && at_agent) && !(x == kx && y == ky) && !n2d;
+            else if (stage == G_DIST) ok = here == K_EMPTY && !at_agent && !n2d;   // objs occupy exactly the non-empty cells
+            else ok = x != m && y != m && (here == K_EMPTY || here == K_LAVA) && !at_agent && !n2d;  // lava, multi
+            if (!ok && ++tries >= kMaxTries) { s.error |= ERR_TRIES; ok = true; }
+            if (ok) {
+                tries = 0; pre_done = false;
+                if (stage == G_OBJ) {
+                    s.grid[y * S + x] = (uint8_t)obj_kind(pend_type, pend_colour);
+                    if (nobjs < kMaxObjs) objs[nobjs] = (uint16_t)(pend_type | (pend_colour << 3) | (x << 6) | (y << 10));
+                    ++nobjs;
+                    if (++obj_i == cfg.num_objects)
+                        stage = (cfg.problem == P_GTG || cfg.problem == P_DRP) ? G_GOAL : G_AGENT;
+                } else if (stage == G_GOAL) {
+                    s.grid[y * S + x] = K_GOAL;
+                    goal_x = x; goal_y = y;
+                    if (nobjs < kMaxObjs) objs[nobjs] = (uint16_t)(T_GOAL | (x << 6) | (y << 10));
+                    ++nobjs;
+                    stage = G_AGENT;
+                } else if (stage == G_AGENT) {
+                    agent_x = x; agent_y = y;
+                    s.agent_x = (uint8_t)x; s.agent_y = (uint8_t)y;
+                    s.agent_dir = (uint8_t)mulhi32(rng.peek(used++), 4);
+                    if (multi) {
+                        agent_room = room_of(nrooms, m, agent_x, agent_y);
+                        goal_room = room_of(nrooms, m, goal_x, goal_y);
+                        stage = G_KEY; r = 0; ph = 0; kx = ky = -1;   // resolved to a real task below
+                    } else {
+                        stage = G_OBST;
+                    }
+                } else if (stage == G_KEY) {
+                    const int props = (int)((doors >> (8 * d)) & 0xFFu);
+                    const int colour = props & 7;
+                    const bool kib = (props >> 4) & 1;
+                    s.grid[y * S + x] = (uint8_t)(kib ? K_BOX + 8 * (colour + 1) + colour : K_KEY + colour);
+                    if (nobjs < kMaxObjs) objs[nobjs] = (uint16_t)((kib ? T_BOX : T_KEY) | (colour << 3) | (x << 6) | (y << 10));
+                    ++nobjs;
+                    MGRL_CNT_DEC(r);
+                    if (ph == 0) { kx = x; ky = y; }
+                    ++ph;
+                } else if (stage == G_DIST) {
+                    s.grid[y * S + x] = (uint8_t)obj_kind(pend_type, pend_colour);
+                    if (nobjs < kMaxObjs) objs[nobjs] = (uint16_t)(pend_type | (pend_colour << 3) | (x << 6) | (y << 10));
+                    ++nobjs;
+                    ++q;
+                } else {  // G_OBST
+                    s.grid[y * S + x] = (uint8_t)(multi ? K_LAVA : pend_type);
+                    ++obst_i;
+                }
+                // ---- next task of the room walk (keys of the room, then its distractors)
+                if (stage == G_KEY || stage == G_DIST) {
+                    stage = G_OBST;
+                    while (r < nrooms) {
+                        if (ph < 2) {
+                            d = key_door(nrooms, r, agent_room, ph);
+                            if (d != 7 && ((doors >> (8 * d + 3)) & 1u)) { stage = G_KEY; break; }
+                            ++ph;
+                        } else if (ph == 2) {
+                            if (goal_room == r) MGRL_CNT_DEC(r);
+                            // reference quirk (custom_env.py:1119, 1660): the lower-left loop uses the upper-left counter
+                            loops = (nrooms >= 3 && r == 1) ? MGRL_CNT(0) : MGRL_CNT(r);
+                            q = 0; ph = 3;
+                        } else {
+                            if (q < loops) { stage = G_DIST; break; }
+                            ++r; ph = 0; kx = ky = -1;
+                        }
+                    }
+                }
+                if (stage == G_OBST && obst_i >= cfg.num_obstacles) stage = cmd <= 2 ? G_TARGET : G_DONE;
+            }
         }
-        s.mission_id = (uint8_t)(cmd * 24 + (o & 7) * 6 + ((o >> 3) & 7));
-        s.target_x = (uint8_t)((o >> 6) & 15); s.target_y = (uint8_t)((o >> 10) & 15);
-        s.target_action = (uint8_t)(cmd == 0 ? A_DONE : cmd == 1 ? A_TOGGLE : A_PICKUP);
-    } else if (cmd == 3) {
-        s.mission_id = MISSION_DROP; s.target_action = A_DROP;
-    } else {
-        s.mission_id = MISSION_GOAL;
-        s.target_x = (uint8_t)g.goal_x; s.target_y = (uint8_t)g.goal_y;
+        rng.ndraw += (uint32_t)used;
     }
-    s.reset_draws = (uint16_t)g.rng.ndraw;
+#undef MGRL_CNT
+#undef MGRL_CNT_DEC
+    if (cmd == 3) { s.mission_id = MISSION_DROP; s.target_action = A_DROP; }           // :212-214
+    else if (cmd == 5) {                                                                 // :258-267
+        s.mission_id = MISSION_GOAL; s.target_x = (uint8_t)goal_x; s.target_y = (uint8_t)goal_y;
+    }
+    s.reset_draws = (uint16_t)rng.ndraw;
     s.episode += 1;
 }
 

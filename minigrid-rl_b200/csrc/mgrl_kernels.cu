@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -26,19 +27,19 @@ using namespace mgrl;
 
 namespace {
 
-constexpr int TILE = 128;                 // environments per CTA
 constexpr int STATE_WORDS = 35;           // sizeof(EnvState) / 4
 constexpr int MODE_STEP = 0, MODE_RESET = 1, MODE_OBSERVE = 2;
 
 static_assert(sizeof(EnvState) == MGRL_STATE_BYTES, "ABI state size");
-static_assert((TILE * sizeof(EnvState)) % 16 == 0 && (TILE * kObsBytes) % 16 == 0, "tile alignment");
 
 struct EnvParams {
     EnvCfg cfg;
     uint64_t seed;
     uint64_t env_id_base;
     int n;
-    int T;  // env_many_kernel only
+    int T;       // env_many_kernel only
+    int spread;  // 1: deal finished environments round-robin over the CTA's warps (shortest critical
+                 //    path, for small batches); 0: pack them into the first warps (fewest issue slots)
     EnvState* states;
     const float* reward_lut;  // [max_steps+1] device
     const uint8_t* actions;
@@ -53,44 +54,31 @@ struct EnvParams {
     uint8_t* term_dir;
 };
 
-// ---- cooperative tile copies (coalesced; 16-byte vectors when the tile is full) -------------
-__device__ __forceinline__ void tile_load(void* smem, const void* gmem, int bytes, int tid) {
-    if ((bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(gmem) & 15) == 0) {
-        const uint4* g = reinterpret_cast<const uint4*>(gmem);
-        uint4* s = reinterpret_cast<uint4*>(smem);
-        for (int i = tid; i < (bytes >> 4); i += TILE) s[i] = g[i];
+// ---- cooperative tile copies (coalesced; 16-byte vectors when size and address allow) -------
+template <int TILE>
+__device__ __forceinline__ void tile_copy(void* dst, const void* src, int bytes, int tid) {
+    if ((bytes & 15) == 0 && ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0) {
+        const uint4* g = reinterpret_cast<const uint4*>(src);
+        uint4* d = reinterpret_cast<uint4*>(dst);
+        for (int i = tid; i < (bytes >> 4); i += TILE) d[i] = g[i];
+    } else if ((bytes & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 3) == 0) {
+        const uint32_t* g = reinterpret_cast<const uint32_t*>(src);
+        uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+        for (int i = tid; i < (bytes >> 2); i += TILE) d[i] = g[i];
     } else {
-        const uint32_t* g = reinterpret_cast<const uint32_t*>(gmem);
-        uint32_t* s = reinterpret_cast<uint32_t*>(smem);
-        for (int i = tid; i < (bytes >> 2); i += TILE) s[i] = g[i];
-    }
-}
-__device__ __forceinline__ void tile_store_words(void* gmem, const void* smem, int bytes, int tid) {
-    if ((bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(gmem) & 15) == 0) {
-        uint4* g = reinterpret_cast<uint4*>(gmem);
-        const uint4* s = reinterpret_cast<const uint4*>(smem);
-        for (int i = tid; i < (bytes >> 4); i += TILE) g[i] = s[i];
-    } else {
-        uint32_t* g = reinterpret_cast<uint32_t*>(gmem);
-        const uint32_t* s = reinterpret_cast<const uint32_t*>(smem);
-        for (int i = tid; i < (bytes >> 2); i += TILE) g[i] = s[i];
-    }
-}
-__device__ __forceinline__ void tile_store_bytes(uint8_t* gmem, const uint8_t* smem, int bytes, int tid) {
-    if ((reinterpret_cast<uintptr_t>(gmem) & 15) == 0) {
-        const int n16 = bytes >> 4;
-        uint4* g = reinterpret_cast<uint4*>(gmem);
-        const uint4* s = reinterpret_cast<const uint4*>(smem);
-        for (int i = tid; i < n16; i += TILE) g[i] = s[i];
-        for (int i = (n16 << 4) + tid; i < bytes; i += TILE) gmem[i] = smem[i];
-    } else {
-        for (int i = tid; i < bytes; i += TILE) gmem[i] = smem[i];
+        const uint8_t* g = reinterpret_cast<const uint8_t*>(src);
+        uint8_t* d = reinterpret_cast<uint8_t*>(dst);
+        const int n16 = (reinterpret_cast<uintptr_t>(dst) & 15) == 0 ? (bytes >> 4) : 0;  // smem src is 16-B aligned
+        for (int i = tid; i < n16; i += TILE) reinterpret_cast<uint4*>(d)[i] = reinterpret_cast<const uint4*>(g)[i];
+        for (int i = (n16 << 4) + tid; i < bytes; i += TILE) d[i] = g[i];
     }
 }
 
+template <int TILE>
 struct TileSmem {
     alignas(16) uint32_t state[TILE * STATE_WORDS];
-    alignas(16) uint8_t obs[TILE * kObsBytes];
+    alignas(16) uint8_t obs[TILE * kObsPitch148];
+    uint32_t kind_lut[128];
     float lut[kGridCells + 1];
     uint16_t done_list[TILE];
     uint8_t carry[TILE];
@@ -98,10 +86,11 @@ struct TileSmem {
 };
 
 // one simulator step of the tile held in `sm` (state already resident); writes the per-step
-// outputs of global env index base+tid; leaves the new observation bytes in sm.obs
-template <int LAYOUT, bool SEE, int MODE>
-__device__ __forceinline__ void tile_step(TileSmem& sm, const EnvParams& p, int tile0, int nv, int tid,
+// outputs of global env index tile0+tid; leaves the new observation records in sm.obs
+template <int LAYOUT, bool SEE, int MODE, int TILE>
+__device__ __forceinline__ void tile_step(TileSmem<TILE>& sm, const EnvParams& p, int tile0, int nv, int tid,
                                           size_t out_off /* element offset of this step's [N] outputs */) {
+    constexpr int PITCH = obs_pitch(LAYOUT);
     EnvState* st = reinterpret_cast<EnvState*>(sm.state);
     const bool active = tid < nv;
     const int S = p.cfg.size;
@@ -121,13 +110,16 @@ __device__ __forceinline__ void tile_step(TileSmem& sm, const EnvParams& p, int 
             if (done) sm.done_list[atomicAdd(&sm.n_done, 1)] = (uint16_t)tid;
         }
         __syncthreads();
-        // dense pass over the finished environments: terminal observation, then a new layout
+        // pass over the finished environments only: terminal observation, then a new layout
         const int nd = sm.n_done;
-        for (int i = tid; i < nd; i += TILE) {
-            const int e = sm.done_list[i];
+        constexpr int NW = TILE / 32;
+        const int slot = p.spread ? (tid & 31) * NW + (tid >> 5) : tid;  // which finished env this lane takes
+        if (slot < nd) {
+            const int e = sm.done_list[slot];
             EnvState& s = st[e];
             if (p.term_image)
-                encode_view<LAYOUT>(s, sm.carry[e], S, SEE, p.term_image + (out_off + tile0 + e) * kObsBytes);
+                encode_view<LAYOUT>(s, sm.carry[e], S, SEE, sm.kind_lut,
+                                    p.term_image + (out_off + tile0 + e) * PITCH);
             if (p.term_dir) p.term_dir[out_off + tile0 + e] = s.agent_dir;
             generate(s, p.cfg, p.seed, p.env_id_base + (uint64_t)(tile0 + e));
             sm.carry[e] = 0;
@@ -149,44 +141,51 @@ __device__ __forceinline__ void tile_step(TileSmem& sm, const EnvParams& p, int 
     if (active) {
         const EnvState& s = st[tid];
         const size_t gi = out_off + tile0 + tid;
-        if (p.image) encode_view<LAYOUT>(s, sm.carry[tid], S, SEE, sm.obs + tid * kObsBytes);
+        if (p.image) encode_view<LAYOUT>(s, sm.carry[tid], S, SEE, sm.kind_lut, sm.obs + tid * PITCH);
         if (p.dir) p.dir[gi] = s.agent_dir;
         if (p.mission) p.mission[gi] = s.mission_id;
     }
     __syncthreads();
-    if (p.image) tile_store_bytes(p.image + (out_off + tile0) * kObsBytes, sm.obs, nv * kObsBytes, tid);
+    if (p.image) tile_copy<TILE>(p.image + (out_off + tile0) * PITCH, sm.obs, nv * PITCH, tid);
 }
 
-template <int LAYOUT, bool SEE, int MODE>
+template <int TILE>
+__device__ __forceinline__ void tile_prologue(TileSmem<TILE>& sm, const EnvParams& p, int tid) {
+    fill_kind_lut(sm.kind_lut, tid, TILE);
+    for (int i = tid; i <= p.cfg.max_steps; i += TILE) sm.lut[i] = p.reward_lut[i];
+    if (tid == 0) sm.n_done = 0;
+}
+
+template <int LAYOUT, bool SEE, int MODE, int TILE>
 __global__ void __launch_bounds__(TILE) env_kernel(const EnvParams p) {
-    __shared__ TileSmem sm;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileSmem<TILE>& sm = *reinterpret_cast<TileSmem<TILE>*>(smem_raw);
     const int tid = threadIdx.x;
     const int tile0 = blockIdx.x * TILE;
     const int nv = min(TILE, p.n - tile0);
-    if (MODE != MODE_RESET) tile_load(sm.state, p.states + tile0, nv * (int)sizeof(EnvState), tid);
-    for (int i = tid; i <= p.cfg.max_steps; i += TILE) sm.lut[i] = p.reward_lut[i];
-    if (tid == 0) sm.n_done = 0;
+    if (MODE != MODE_RESET) tile_copy<TILE>(sm.state, p.states + tile0, nv * (int)sizeof(EnvState), tid);
+    tile_prologue<TILE>(sm, p, tid);
     __syncthreads();
-    tile_step<LAYOUT, SEE, MODE>(sm, p, tile0, nv, tid, 0);
-    if (MODE != MODE_OBSERVE) tile_store_words(p.states + tile0, sm.state, nv * (int)sizeof(EnvState), tid);
+    tile_step<LAYOUT, SEE, MODE, TILE>(sm, p, tile0, nv, tid, 0);
+    if (MODE != MODE_OBSERVE) tile_copy<TILE>(p.states + tile0, sm.state, nv * (int)sizeof(EnvState), tid);
 }
 
 // T steps per launch; the state tile never leaves shared memory between steps
-template <int LAYOUT, bool SEE>
+template <int LAYOUT, bool SEE, int TILE>
 __global__ void __launch_bounds__(TILE) env_many_kernel(const EnvParams p) {
-    __shared__ TileSmem sm;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileSmem<TILE>& sm = *reinterpret_cast<TileSmem<TILE>*>(smem_raw);
     const int tid = threadIdx.x;
     const int tile0 = blockIdx.x * TILE;
     const int nv = min(TILE, p.n - tile0);
-    tile_load(sm.state, p.states + tile0, nv * (int)sizeof(EnvState), tid);
-    for (int i = tid; i <= p.cfg.max_steps; i += TILE) sm.lut[i] = p.reward_lut[i];
-    if (tid == 0) sm.n_done = 0;
+    tile_copy<TILE>(sm.state, p.states + tile0, nv * (int)sizeof(EnvState), tid);
+    tile_prologue<TILE>(sm, p, tid);
     __syncthreads();
     for (int t = 0; t < p.T; ++t) {
-        tile_step<LAYOUT, SEE, MODE_STEP>(sm, p, tile0, nv, tid, (size_t)t * (size_t)p.n);
+        tile_step<LAYOUT, SEE, MODE_STEP, TILE>(sm, p, tile0, nv, tid, (size_t)t * (size_t)p.n);
         __syncthreads();  // sm.obs is rewritten by the next step
     }
-    tile_store_words(p.states + tile0, sm.state, nv * (int)sizeof(EnvState), tid);
+    tile_copy<TILE>(p.states + tile0, sm.state, nv * (int)sizeof(EnvState), tid);
 }
 
 __global__ void full_obs_kernel(const EnvState* __restrict__ states, int n, int S, uint8_t* __restrict__ out) {
@@ -296,6 +295,8 @@ struct mgrl_env {
     mgrl_config cfg;
     EnvCfg ecfg;
     int device;
+    int tile;    // environments per CTA (64 / 128 / 256)
+    int spread;  // reset scheduling, see EnvParams
     uint64_t seed;
     EnvState* states;
     float* lut;
@@ -318,40 +319,49 @@ EnvParams make_params(const mgrl_env* e) {
     p.env_id_base = e->cfg.env_id_base;
     p.n = e->cfg.num_envs;
     p.T = 1;
+    p.spread = e->spread;
     p.states = e->states;
     p.reward_lut = e->lut;
     return p;
 }
 
-template <int MODE>
-int launch_env(const mgrl_env* e, const EnvParams& p, cudaStream_t s) {
-    const int grid = (p.n + TILE - 1) / TILE;
-    const bool chw = e->cfg.obs_layout == MGRL_OBS_CHW;
-    const bool see = e->ecfg.see_through_walls != 0;
-    if (chw) {
-        if (see) env_kernel<OBS_CHW, true, MODE><<<grid, TILE, 0, s>>>(p);
-        else env_kernel<OBS_CHW, false, MODE><<<grid, TILE, 0, s>>>(p);
-    } else {
-        if (see) env_kernel<OBS_HWC, true, MODE><<<grid, TILE, 0, s>>>(p);
-        else env_kernel<OBS_HWC, false, MODE><<<grid, TILE, 0, s>>>(p);
-    }
+template <typename K>
+int launch_kernel(K kernel, size_t smem, int grid, int block, cudaStream_t s, const EnvParams& p) {
+    // > 48 KB of dynamic shared memory needs the opt-in attribute (idempotent, cheap)
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<grid, block, smem, s>>>(p);
     CUDA_TRY(cudaGetLastError());
     return MGRL_OK;
 }
 
-int launch_many(const mgrl_env* e, const EnvParams& p, cudaStream_t s) {
+template <int LAYOUT, bool SEE, int TILE>
+int launch_tile(int mode, bool many, const EnvParams& p, cudaStream_t s) {
     const int grid = (p.n + TILE - 1) / TILE;
-    const bool chw = e->cfg.obs_layout == MGRL_OBS_CHW;
+    const size_t smem = sizeof(TileSmem<TILE>);
+    if (many) return launch_kernel(env_many_kernel<LAYOUT, SEE, TILE>, smem, grid, TILE, s, p);
+    if (mode == MODE_STEP) return launch_kernel(env_kernel<LAYOUT, SEE, MODE_STEP, TILE>, smem, grid, TILE, s, p);
+    if (mode == MODE_RESET) return launch_kernel(env_kernel<LAYOUT, SEE, MODE_RESET, TILE>, smem, grid, TILE, s, p);
+    return launch_kernel(env_kernel<LAYOUT, SEE, MODE_OBSERVE, TILE>, smem, grid, TILE, s, p);
+}
+
+template <int LAYOUT, bool SEE>
+int launch_layout(const mgrl_env* e, int mode, bool many, const EnvParams& p, cudaStream_t s) {
+    if (e->tile == 256) return launch_tile<LAYOUT, SEE, 256>(mode, many, p, s);
+    if (e->tile == 64) return launch_tile<LAYOUT, SEE, 64>(mode, many, p, s);
+    return launch_tile<LAYOUT, SEE, 128>(mode, many, p, s);
+}
+
+int launch_env(const mgrl_env* e, int mode, bool many, const EnvParams& p, cudaStream_t s) {
     const bool see = e->ecfg.see_through_walls != 0;
-    if (chw) {
-        if (see) env_many_kernel<OBS_CHW, true><<<grid, TILE, 0, s>>>(p);
-        else env_many_kernel<OBS_CHW, false><<<grid, TILE, 0, s>>>(p);
-    } else {
-        if (see) env_many_kernel<OBS_HWC, true><<<grid, TILE, 0, s>>>(p);
-        else env_many_kernel<OBS_HWC, false><<<grid, TILE, 0, s>>>(p);
+    switch (e->cfg.obs_layout) {
+    case MGRL_OBS_CHW:
+        return see ? launch_layout<OBS_CHW, true>(e, mode, many, p, s) : launch_layout<OBS_CHW, false>(e, mode, many, p, s);
+    case MGRL_OBS_HWC148:
+        return see ? launch_layout<OBS_HWC148, true>(e, mode, many, p, s)
+                   : launch_layout<OBS_HWC148, false>(e, mode, many, p, s);
+    default:
+        return see ? launch_layout<OBS_HWC, true>(e, mode, many, p, s) : launch_layout<OBS_HWC, false>(e, mode, many, p, s);
     }
-    CUDA_TRY(cudaGetLastError());
-    return MGRL_OK;
 }
 
 int ensure_host_buffers(mgrl_env* e) {
@@ -410,7 +420,7 @@ int mgrl_create(const mgrl_config* cfg, int device, mgrl_env** out) {
     if (cfg->num_envs <= 0) return fail(MGRL_ERR_INVALID, "mgrl_create: num_envs must be positive%s");
     if (cfg->num_objects < 0 || cfg->num_objects > 18)
         return fail(MGRL_ERR_INVALID, "mgrl_create: num_objects must be in 0..18%s");
-    if (cfg->obs_layout != MGRL_OBS_HWC && cfg->obs_layout != MGRL_OBS_CHW)
+    if (cfg->obs_layout != MGRL_OBS_HWC && cfg->obs_layout != MGRL_OBS_CHW && cfg->obs_layout != MGRL_OBS_HWC148)
         return fail(MGRL_ERR_INVALID, "mgrl_create: bad obs_layout%s");
     DeviceGuard guard(device);
     mgrl_env* e = new (std::nothrow) mgrl_env();
@@ -418,6 +428,11 @@ int mgrl_create(const mgrl_config* cfg, int device, mgrl_env** out) {
     memset(e, 0, sizeof *e);
     e->cfg = *cfg;
     e->device = device;
+    // launch shape: small batches are latency-bound (deal resets over all warps), large ones issue-bound
+    e->tile = 128;
+    e->spread = cfg->num_envs <= 262144 ? 1 : 0;
+    if (const char* t = getenv("MGRL_TILE")) e->tile = atoi(t) == 256 ? 256 : atoi(t) == 64 ? 64 : 128;
+    if (const char* t = getenv("MGRL_SPREAD")) e->spread = atoi(t) != 0;
     e->ecfg.size = cfg->size;
     e->ecfg.num_objects = cfg->num_objects;
     e->ecfg.problem = cfg->problem;
@@ -480,7 +495,7 @@ int mgrl_reset(mgrl_env* e, uint64_t seed, uint8_t* image, uint8_t* dir, uint8_t
     e->seed = seed;
     EnvParams p = make_params(e);
     p.image = image; p.dir = dir; p.mission = mission;
-    return launch_env<MODE_RESET>(e, p, (cudaStream_t)stream);
+    return launch_env(e, MODE_RESET, false, p, (cudaStream_t)stream);
 }
 
 int mgrl_step(mgrl_env* e, const uint8_t* actions, uint8_t* image, uint8_t* dir, uint8_t* mission, float* reward,
@@ -492,7 +507,7 @@ int mgrl_step(mgrl_env* e, const uint8_t* actions, uint8_t* image, uint8_t* dir,
     EnvParams p = make_params(e);
     p.actions = actions; p.image = image; p.dir = dir; p.mission = mission; p.reward = reward;
     p.term = term; p.trunc = trunc; p.ep_len = ep_len; p.term_image = term_image; p.term_dir = term_dir;
-    return launch_env<MODE_STEP>(e, p, (cudaStream_t)stream);
+    return launch_env(e, MODE_STEP, false, p, (cudaStream_t)stream);
 }
 
 int mgrl_step_many(mgrl_env* e, int T, const uint8_t* actions, uint8_t* image, uint8_t* dir, uint8_t* mission,
@@ -505,7 +520,7 @@ int mgrl_step_many(mgrl_env* e, int T, const uint8_t* actions, uint8_t* image, u
     p.T = T;
     p.actions = actions; p.image = image; p.dir = dir; p.mission = mission; p.reward = reward;
     p.term = term; p.trunc = trunc; p.ep_len = ep_len;
-    return launch_many(e, p, (cudaStream_t)stream);
+    return launch_env(e, MODE_STEP, true, p, (cudaStream_t)stream);
 }
 
 int mgrl_observe(mgrl_env* e, uint8_t* image, uint8_t* dir, uint8_t* mission, void* stream) {
@@ -513,7 +528,7 @@ int mgrl_observe(mgrl_env* e, uint8_t* image, uint8_t* dir, uint8_t* mission, vo
     DeviceGuard guard(e->device);
     EnvParams p = make_params(e);
     p.image = image; p.dir = dir; p.mission = mission;
-    return launch_env<MODE_OBSERVE>(e, p, (cudaStream_t)stream);
+    return launch_env(e, MODE_OBSERVE, false, p, (cudaStream_t)stream);
 }
 
 int mgrl_get_state(mgrl_env* e, void* dst, size_t bytes, void* stream) {
@@ -631,6 +646,8 @@ int mgrl_vec_reset_host(mgrl_env* e, uint64_t seed, uint8_t* image_host, uint8_t
                         int64_t* mission_host, void* stream) {
     if (!e) return fail(MGRL_ERR_INVALID, "mgrl_vec_reset_host: null handle%s");
     if (!e->table_set) return fail(MGRL_ERR_INVALID, "mgrl_vec_reset_host: call mgrl_set_token_table first%s");
+    if (e->cfg.obs_layout == MGRL_OBS_HWC148)
+        return fail(MGRL_ERR_INVALID, "mgrl_vec_reset_host: the host path needs a 147-byte layout (CHW or HWC)%s");
     DeviceGuard guard(e->device);
     cudaStream_t s = (cudaStream_t)stream;
     int rc = ensure_host_buffers(e);

@@ -36,12 +36,17 @@ STATE_DTYPE = np.dtype([
 ])
 
 
-def _native_config(cfg: EnvConfig, num_envs: int, env_id_base: int, chw: bool) -> nat.Config:
+LAYOUTS = {"hwc": (0, 147), "chw": (1, 147), "hwc148": (2, 148)}
+
+
+def _native_config(cfg: EnvConfig, num_envs: int, env_id_base: int, layout) -> nat.Config:
     cfg.validate()
+    if isinstance(layout, bool):
+        layout = "chw" if layout else "hwc"
     return nat.Config(cfg.size, cfg.num_objects, PROBLEMS[cfg.problem],
                       -1 if cfg.mission is None else int(cfg.mission), int(cfg.all_doors_open),
                       int(cfg.see_through_walls), cfg.max_steps, cfg.num_obstacles, int(num_envs),
-                      1 if chw else 0, int(env_id_base))
+                      LAYOUTS[layout][0], int(env_id_base))
 
 
 class _Handle:
@@ -305,7 +310,7 @@ class DeviceEnv:
     the policy input is gathered on the fly by the rollout engine."""
 
     def __init__(self, cfg: EnvConfig | None = None, num_envs: int = 65536, seed: int = 0,
-                 device: int | None = None, env_id_base: int = 0, chw: bool = True):
+                 device: int | None = None, env_id_base: int = 0, chw: bool = True, layout: str | None = None):
         import torch
         if not torch.cuda.is_available():
             raise nat.NativeError("DeviceEnv needs a CUDA device (no CPU fallback)")
@@ -315,10 +320,12 @@ class DeviceEnv:
         self.device_index = torch.cuda.current_device() if device is None else int(device)
         self.device = torch.device("cuda", self.device_index)
         self.seed = int(seed)
-        self._h = _Handle(self.cfg, self.num_envs, self.device_index, env_id_base, chw)
+        self.layout = layout or ("chw" if chw else "hwc")
+        self.pitch = LAYOUTS[self.layout][1]
+        self._h = _Handle(self.cfg, self.num_envs, self.device_index, env_id_base, self.layout)
         n = self.num_envs
         u8 = dict(dtype=torch.uint8, device=self.device)
-        self.image = torch.zeros((n, OBS_BYTES), **u8)
+        self.image = torch.zeros((n, self.pitch), **u8)
         self.dir = torch.zeros(n, **u8)
         self.mission = torch.zeros(n, **u8)
         self.reward = torch.zeros(n, dtype=torch.float32, device=self.device)

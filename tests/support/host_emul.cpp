@@ -7,6 +7,13 @@
 
 using namespace mgrl;
 
+static const uint32_t* host_lut() {
+    static uint32_t lut[128];
+    static bool init = false;
+    if (!init) { fill_kind_lut(lut, 0, 1); init = true; }
+    return lut;
+}
+
 extern "C" {
 
 void emul_generate(const EnvCfg* cfg, uint64_t seed, uint64_t env_id, EnvState* s) { generate(*s, *cfg, seed, env_id); }
@@ -18,8 +25,10 @@ void emul_step(const EnvCfg* cfg, const float* lut, EnvState* s, int action, flo
 }
 
 void emul_obs(const EnvCfg* cfg, const EnvState* s, int carrying, int layout, uint8_t* out) {
-    if (layout == OBS_HWC) encode_view<OBS_HWC>(*s, carrying, cfg->size, cfg->see_through_walls != 0, out);
-    else encode_view<OBS_CHW>(*s, carrying, cfg->size, cfg->see_through_walls != 0, out);
+    const bool see = cfg->see_through_walls != 0;
+    if (layout == OBS_HWC) encode_view<OBS_HWC>(*s, carrying, cfg->size, see, host_lut(), out);
+    else if (layout == OBS_CHW) encode_view<OBS_CHW>(*s, carrying, cfg->size, see, host_lut(), out);
+    else encode_view<OBS_HWC148>(*s, carrying, cfg->size, see, host_lut(), out);
 }
 
 void emul_full_obs(const EnvCfg* cfg, const EnvState* s, uint8_t* out) { encode_full(*s, cfg->size, out); }
@@ -38,11 +47,11 @@ void emul_vec_step(const EnvCfg* cfg, uint64_t seed, uint64_t base, int n, const
         ep_len[i] = done ? s.step_count : 0;
         int carry = o.carry_obs;
         if (done) {
-            encode_view<OBS_HWC>(s, carry, cfg->size, cfg->see_through_walls != 0, term_obs + (size_t)i * kObsBytes);
+            encode_view<OBS_HWC>(s, carry, cfg->size, cfg->see_through_walls != 0, host_lut(), term_obs + (size_t)i * kObsBytes);
             generate(s, *cfg, seed, base + (uint64_t)i);
             carry = 0;
         }
-        encode_view<OBS_HWC>(s, carry, cfg->size, cfg->see_through_walls != 0, obs + (size_t)i * kObsBytes);
+        encode_view<OBS_HWC>(s, carry, cfg->size, cfg->see_through_walls != 0, host_lut(), obs + (size_t)i * kObsBytes);
         dir[i] = s.agent_dir; mis[i] = s.mission_id;
     }
 }

@@ -97,16 +97,22 @@ def test_golden_traces_through_product_core(path):
 
 def test_chw_layout_is_transpose_of_hwc():
     import ctypes as C
-    cfg = orc.make_config(problem="multi", mission=None, see_through_walls=False)
-    o = orc.OracleVecEnv(cfg, 64, seed=3)
-    o.reset()
-    for i in range(64):
+    o = None
+    for see in (False, True):
+      cfg = orc.make_config(problem="multi", mission=None, see_through_walls=see)
+      o = orc.OracleVecEnv(cfg, 64, seed=3)
+      o.reset()
+      for i in range(64):
         hwc = np.zeros((7, 7, 3), np.uint8)
         chw = np.zeros((3, 7, 7), np.uint8)
         emul.lib().emul_obs(C.byref(cfg), emul.p(o.states[i:i + 1]), 9, 0, emul.p(hwc))
         emul.lib().emul_obs(C.byref(cfg), emul.p(o.states[i:i + 1]), 9, 1, emul.p(chw))
         assert np.array_equal(chw, hwc.transpose(2, 0, 1))
+        packed = np.full(148, 255, np.uint8)      # 148-byte-pitch packed record == HWC + one zero pad byte
+        emul.lib().emul_obs(C.byref(cfg), emul.p(o.states[i:i + 1]), 9, 2, emul.p(packed))
+        assert np.array_equal(packed[:147].reshape(7, 7, 3), hwc) and packed[147] == 0
         assert tuple(hwc[3, 6]) == (5, 1, 0)  # carried green key shown on the agent's cell
+        assert np.array_equal(hwc, orc.gen_obs(cfg, o.states[i:i + 1], carrying=9))
 
 
 def test_kind_encode_table():

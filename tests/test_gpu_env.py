@@ -119,21 +119,28 @@ def test_terminal_direction_output():
     env.close()
 
 
-def test_chw_layout_is_transposed_hwc():
-    kw = dict(problem="multi", mission=None)
+@pytest.mark.parametrize("see", [True, False], ids=["see_through", "occluded"])
+def test_layouts_agree(see):
+    """CHW == transposed HWC; HWC148 == HWC records with one zero pad byte (incl. terminal observations)."""
+    kw = dict(problem="multi", mission=None, see_through_walls=see)
     n = 300
-    a_env = mg.DeviceEnv(mg.EnvConfig(**kw), num_envs=n, seed=3, chw=False)
-    b_env = mg.DeviceEnv(mg.EnvConfig(**kw), num_envs=n, seed=3, chw=True)
-    ia, _, _ = a_env.reset()
-    ib, _, _ = b_env.reset()
+    envs = {k: mg.DeviceEnv(mg.EnvConfig(**kw), num_envs=n, seed=3, layout=k) for k in ("hwc", "chw", "hwc148")}
+    for e in envs.values():
+        e.reset()
+    tims = {k: torch.zeros((n, e.pitch), dtype=torch.uint8, device="cuda") for k, e in envs.items()}
     rs = np.random.RandomState(0)
-    for t in range(30):
+    for t in range(40):
         a = torch.from_numpy(biased_actions(rs, n)).cuda()
-        a_env.step(a); b_env.step(a)
-        x = a_env.image.cpu().numpy().reshape(n, 7, 7, 3).transpose(0, 3, 1, 2)
-        y = b_env.image.cpu().numpy().reshape(n, 3, 7, 7)
-        assert np.array_equal(x, y)
-    a_env.close(); b_env.close()
+        for k, e in envs.items():
+            e.step(a, term_image=tims[k])
+        done = (envs["hwc"].term | envs["hwc"].trunc).bool().cpu().numpy()
+        for img in (lambda k: envs[k].image, lambda k: tims[k][torch.from_numpy(done).cuda()]):
+            x = img("hwc").cpu().numpy().reshape(-1, 7, 7, 3)
+            assert np.array_equal(x.transpose(0, 3, 1, 2), img("chw").cpu().numpy().reshape(-1, 3, 7, 7))
+            p = img("hwc148").cpu().numpy()
+            assert np.array_equal(p[:, :147].reshape(-1, 7, 7, 3), x) and not p[:, 147].any()
+    for e in envs.values():
+        e.close()
 
 
 @pytest.mark.parametrize("path", TRACES, ids=[os.path.basename(p)[6:-4] for p in TRACES])
@@ -171,7 +178,8 @@ def test_full_size_rollout_matches_oracle(task, mission):
     """BASELINE.json configs 2-5 at per-GPU size: 65 536 envs x 128 steps, every output."""
     n, T = 65536, 128
     kw = dict(problem="multi", mission=mission)
-    env = mg.DeviceEnv(mg.EnvConfig(**kw), num_envs=n, seed=42, chw=True)
+    layout = "hwc148" if task in ("GTO", "ALL") else "chw"
+    env = mg.DeviceEnv(mg.EnvConfig(**kw), num_envs=n, seed=42, layout=layout)
     o = orc.OracleVecEnv(orc.make_config(**kw), n, seed=42, nthreads=16)
     env.reset(); o.reset()
     g = torch.Generator(device="cuda").manual_seed(1)
@@ -180,7 +188,7 @@ def test_full_size_rollout_matches_oracle(task, mission):
     keep = (torch.arange(n, device="cuda") % 2 == 0)
     alt = torch.randint(0, 6, (T, n), dtype=torch.uint8, device="cuda", generator=g)
     actions = torch.where((actions == 6) & keep, alt, actions).contiguous()
-    image = torch.empty((T, n, 147), dtype=torch.uint8, device="cuda")
+    image = torch.empty((T, n, env.pitch), dtype=torch.uint8, device="cuda")
     dirs = torch.empty((T, n), dtype=torch.uint8, device="cuda")
     mis = torch.empty((T, n), dtype=torch.uint8, device="cuda")
     rew = torch.empty((T, n), dtype=torch.float32, device="cuda")
@@ -193,8 +201,11 @@ def test_full_size_rollout_matches_oracle(task, mission):
     n_trunc = n_success = 0
     for t in range(T):
         o.step(a_np[t], want_term_obs=False)
-        want_chw = o.obs.transpose(0, 3, 1, 2).reshape(n, 147)
-        assert np.array_equal(image[t].cpu().numpy(), want_chw), (task, t)
+        if layout == "chw":
+            want = o.obs.transpose(0, 3, 1, 2).reshape(n, 147)
+        else:
+            want = np.concatenate([o.obs.reshape(n, 147), np.zeros((n, 1), np.uint8)], axis=1)
+        assert np.array_equal(image[t].cpu().numpy(), want), (task, t)
         assert np.array_equal(rew[t].cpu().numpy().view(np.uint32), o.reward.view(np.uint32)), (task, t)
         assert np.array_equal(term[t].cpu().numpy(), o.term), (task, t)
         assert np.array_equal(trunc[t].cpu().numpy(), o.trunc), (task, t)
