@@ -65,7 +65,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def count_since(self, t0):
+        return sum(1 for t, _ in self.rows if t >= t0)
 
     def __exit__(self, *a):
         if self.proc:
@@ -75,10 +78,13 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
 
-    def summary(self):
+    def summary(self, t0=0.0, t1=float("inf")):
+        """median SM clock / reasons over the samples taken in [t0, t1] (while the workload ran)"""
         sm, smax, reasons = [], 0.0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for t, r in self.rows:
+            if not (t0 <= t <= t1):
+                continue
             try:
                 sm.append(float(r[0])); smax = max(smax, float(r[1]))
                 for name, v in zip(names, r[3:7]):
@@ -193,17 +199,25 @@ def main():
         torch.cuda.synchronize()
 
     # de-synchronise episode phases (warm up >= 121 steps), then W warm-up bench steps
-    for _ in range(W):
-        rollout()
-    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
+        for _ in range(W):
+            rollout()
         barrier()
+        t_load0 = time.perf_counter()
         e0.record()
         for _ in range(K):
             rollout()
         e1.record()
         barrier()
+        # the timed region is tens of milliseconds; keep the identical load running (untimed) until
+        # nvidia-smi (100 ms period) has sampled it a few times, so the clock record is meaningful
+        while rank == 0 and clocks.proc and clocks.count_since(t_load0) < 8 and time.perf_counter() - t_load0 < 4.0:
+            rollout()
+            torch.cuda.synchronize()
+        t_load1 = time.perf_counter()
+        barrier()
+    clock_summary = clocks.summary(t_load0, t_load1)
     ms = e0.elapsed_time(e1)
     if dist is not None:
         tmax = torch.tensor([ms], device=dev)
@@ -282,7 +296,7 @@ def main():
                           "achieved_gbs": BYTES_PER_ENV_STEP * many_value / world / 1e9,
                           "frac": BYTES_PER_ENV_STEP * many_value / world / 1e9 / peak,
                           "note": "mgrl_step_many: T steps per launch, state tile resident in shared memory"},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clock_summary,
             "env_error_flags": err,
         }
         print(json.dumps(line))

@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (read here, no GPU): key raw metrics, instruction share per kernel phase
+(between barriers) and the hottest source lines.  usage: python profiles/ncu_summary.py gpurun_out/prof_rNN.ncu-rep"""
+import collections
+import csv
+import subprocess
+import sys
+
+rep = sys.argv[1]
+top_n = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+
+
+def ncu(*args):
+    return subprocess.run(["ncu", "-i", rep, *args], capture_output=True, text=True).stdout
+
+
+rows = list(csv.reader(ncu("--page", "raw", "--csv").splitlines()))
+hdr, units = rows[0], rows[1]
+KEYS = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "launch__waves_per_multiprocessor", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__cycles_active.avg",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed_op_local_ld.sum",
+        "smsp__inst_executed_op_local_st.sum", "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum"]
+r = rows[2]
+print("== raw metrics (first captured launch) ==")
+for k in KEYS:
+    if k in hdr:
+        i = hdr.index(k)
+        print(f"{k} = {r[i]} {units[i]}")
+for i, h in enumerate(hdr):
+    if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("_per_issue_active.ratio"):
+        try:
+            if float(r[i]) > 0.3:
+                print(f"{h} = {r[i]}")
+        except ValueError:
+            pass
+
+rows = list(csv.reader(ncu("--page", "source", "--csv", "--print-source", "cuda,sass").splitlines()))
+agg = collections.OrderedDict()
+cur_file = kernel = first = None
+col = {}
+for r in rows:
+    if not r:
+        continue
+    if r[0] == "File Path":
+        cur_file = r[1].split("/")[-1]; continue
+    if r[0] == "Function Name":
+        kernel = r[1]; first = first or kernel; continue
+    if r[0] == "Line No":
+        col = {n: i for i, n in enumerate(r)}; continue
+    if kernel != first or r[0] == "":
+        continue
+    try:
+        line = int(r[0])
+    except ValueError:
+        continue
+    if line == 0:
+        continue
+    a = agg.setdefault((cur_file, line), [r[1], 0.0, 0.0, 0.0])
+    a[1] += float(r[col["Instructions Executed"]] or 0)
+    a[2] += float(r[col["Thread Instructions Executed"]] or 0)
+    a[3] += float(r[col["# Samples"]] or 0)
+tot = sum(a[1] for a in agg.values()) or 1
+tots = sum(a[3] for a in agg.values()) or 1
+print(f"\n== hottest source lines of {first} (total warp-instructions {tot:.0f}, samples {tots:.0f}) ==")
+for (f, l), (src, inst, tin, smp) in sorted(agg.items(), key=lambda kv: -kv[1][3])[:top_n]:
+    print(f"{f}:{l:4d} samples={100*smp/tots:4.1f}% inst={100*inst/tot:4.1f}% lanes={tin/max(inst,1):5.1f} | {src.strip()[:80]}")
