@@ -36,7 +36,7 @@ constexpr int K_EMPTY = 0, K_WALL = 1, K_GOAL = 2, K_LAVA = 3, K_KEY = 8, K_BALL
 constexpr int A_LEFT = 0, A_RIGHT = 1, A_FORWARD = 2, A_PICKUP = 3, A_DROP = 4, A_TOGGLE = 5, A_DONE = 6;
 constexpr int P_MULTI = 0, P_GTO = 1, P_GTG = 2, P_OPN = 3, P_PKP = 4, P_DRP = 5;
 constexpr int MISSION_GOAL = 72, MISSION_DROP = 73;
-constexpr int ERR_BAD_ACTION = 1, ERR_TRIES = 2;
+constexpr int ERR_BAD_ACTION = 1, ERR_TRIES = 2, ERR_SYNC = 4;  // ERR_SYNC: a prepared layout never arrived (kernel bug guard)
 constexpr int OBS_HWC = 0;  // image[vx][vy][c]  (MiniGrid native), 147-byte records
 constexpr int OBS_CHW = 1;  // image[c][vx][vy]  (after SB3 VecTransposeImage), 147-byte records
 
@@ -109,51 +109,19 @@ MGRL_HD uint32_t kind_encode(int k) {
 
 // ---------------------------------------------------------------------------------- RNG
 // Philox4x32-10, key = seed, counter = (block, episode, env_lo, env_hi).  Draw d of an
-// episode is word d&3 of block d>>2; below(n) = mulhi32(word, n).
-//
-// The generator consumes draws through a 4-word *window*: sync() makes blocks A = d>>2 and
-// B = A+1 current (one Philox site per generator iteration, so lanes of a warp that sit at
-// different draw counts still execute the rounds together), peek(i) returns word d+i for
-// i < 4, and the caller then advances ndraw by what it used.
-struct Rng {
-    uint32_t k0, k1, e0, e1, episode;
-    uint32_t ndraw;
-    uint32_t blk;  // block id held in a[]; b[] holds blk+1
-    uint32_t a[4], b[4];
-
-    MGRL_HD static void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t ka, uint32_t kb,
-                               uint32_t* out) {
+// episode is word d&3 of block d>>2; below(n) = mulhi32(word, n).  The generator computes the
+// first kDrawBuf draws of an episode up front (16 blocks, straight-line, all lanes converged)
+// into a lane-interleaved buffer and indexes it; draws beyond that (p < 0.5 %) are recomputed.
+MGRL_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t ka, uint32_t kb, uint32_t* out) {
 #pragma unroll
-        for (int r = 0; r < 10; ++r) {
-            const uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
-            const uint32_t h1 = mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
-            c0 = h1 ^ c1 ^ ka; c1 = l1; c2 = h0 ^ c3 ^ kb; c3 = l0;
-            ka += 0x9E3779B9u; kb += 0xBB67AE85u;
-        }
-        out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ ka; c1 = l1; c2 = h0 ^ c3 ^ kb; c3 = l0;
+        ka += 0x9E3779B9u; kb += 0xBB67AE85u;
     }
-    MGRL_HD void init(uint64_t seed, uint64_t env_id, uint32_t ep) {
-        k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
-        e0 = (uint32_t)env_id; e1 = (uint32_t)(env_id >> 32);
-        episode = ep; ndraw = 0; blk = 0;
-        philox(0, episode, e0, e1, k0, k1, a);
-        philox(1, episode, e0, e1, k0, k1, b);
-    }
-    // re-establish a[] = block(ndraw>>2), b[] = the block after it
-    MGRL_HD void sync() {
-        if ((ndraw >> 2) != blk) {  // the window moved by exactly one block (<= 4 draws per iteration)
-            blk = ndraw >> 2;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = b[i];
-            philox(blk + 1, episode, e0, e1, k0, k1, b);
-        }
-    }
-    // word ndraw+i, i in 0..3
-    MGRL_HD uint32_t peek(int i) const {
-        const int w = (int)(ndraw & 3u) + i;  // 0..6
-        return w == 0 ? a[0] : w == 1 ? a[1] : w == 2 ? a[2] : w == 3 ? a[3] : w == 4 ? b[0] : w == 5 ? b[1] : b[2];
-    }
-};
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
 
 // --------------------------------------------------------------------------------- step
 struct StepOut {
@@ -381,20 +349,31 @@ MGRL_HD void encode_full(const EnvState& s, int S, uint8_t* out) {
         }
 }
 
+
 // ----------------------------------------------------------------------------- generator
 // PlaygroundEnv._gen_grid (custom_env.py:122-267) with the map generators (:371-555 single
-// room, :595-2034 two/three/four rooms) as ONE flattened task machine.
+// room, :595-2034 two/three/four rooms).
 //
-// The reference is a long sequence of rejection loops ("draw a position, retry until it is
-// admissible") whose number and kind depend on earlier draws.  Run lane-per-environment that
-// diverges badly, so the generator is written as a single loop whose body performs exactly
-// one *try* of the lane's current task: every placement kind (goal, agent, key / key-in-box,
-// distractor, single-room object, obstacle) shares the same draw-test-commit code, driven by
-// per-lane flags.  Lanes that need more tries simply take more iterations while the others
-// move on to their next task, and the Philox rounds run at one site per iteration.
+// The reference is a long chain of rejection loops ("draw a position, retry until it is
+// admissible") whose number and kind depend on earlier draws.  It is run here one lane per
+// environment on DENSE warps (every lane starts a layout at the same time), shaped so the lanes
+// stay converged for as long as the data allows:
+//   1. all Philox blocks of the episode are computed up front (no per-draw RNG branch);
+//   2. the multi-room prologue (mission, room count, door colours/locks, door cells) is
+//      straight-line code over the maximum of four doors, predicated per lane;
+//   3. every placement kind (goal, agent, key / key-in-box, distractor, single-room object,
+//      obstacle) is one shared draw-test-commit body; a lane's sequence of key/distractor tasks
+//      is a byte string looked up in a table indexed by (rooms, agent room, goal room, locked
+//      doors), so advancing to the next task is a byte fetch instead of a nested room walk;
+//   4. cells next to a door carry a flag bit while the layout is built, so "empty and not
+//      next to a door" (next2door, :2036-2046) is one compare of the byte already loaded.
 // The draw order is the reference's; the CPU oracle consumes the same stream.
 constexpr int T_KEY = 0, T_BALL = 1, T_BOX = 2, T_DOOR = 3, T_GOAL = 4;
-constexpr int kMaxObjs = 40;
+constexpr int kDrawBuf = 64;            // draws precomputed per generation = 16 Philox blocks
+constexpr int kGridWords = 31;          // words 0..30 of EnvState cover grid[121] + agent x/y/dir
+constexpr int kTaskBytes = 32;          // task string: [0] = n, [1..n] = tasks
+constexpr int kTaskEntries = 3 * 4 * 4 * 16;
+constexpr uint32_t kDoorFlag = 0x80u;   // "next to a door" mark on a grid byte (kinds are < 128)
 
 // Keys placed in `room` when the agent starts in `agent_room`: up to
 // two door indices, 7 = none.  One byte per agent room: low nibble = first key, high = second.
@@ -434,114 +413,284 @@ MGRL_HD int obj_kind(int type, int colour) {
          : type == T_BOX ? K_BOX + colour : type == T_DOOR ? K_DOOR + 8 + colour : K_GOAL;
 }
 
-enum GenStage : int {
-    G_CMD = 0,   // multi: mission command (if cfg.mission is null) and room count
-    G_DOORPROP,  // door colour / locked / key_in_box
-    G_DOORCELL,  // door position (/ is_open)
-    G_OBJ,       // single-room object: pool draw + place_obj
-    G_GOAL,      // goal (multi: not next to a door)
-    G_AGENT,     // place_agent
-    G_KEY,       // key or box-with-key of a locked door
-    G_DIST,      // distractor object of a room
-    G_OBST,      // obstacle
-    G_TARGET,    // target selection
-    G_DONE
+// task byte: kind (bits 0-1: 1 = key of a locked door, 2 = distractor) | room << 2 | door << 4 | second << 6
+constexpr int TASK_KEY = 1, TASK_DIST = 2;
+MGRL_HD int task_index(int nrooms, int agent_room, int goal_room, uint32_t locked) {
+    return (((nrooms - 2) * 4 + agent_room) * 4 + goal_room) * 16 + (int)locked;
+}
+
+// The per-room walk of _generate_{2,3,4}_rooms (:652-855, :931-1297, :1392-2034) for one
+// (rooms, agent room, goal room, locked doors) combination: keys of the room's locked doors first
+// (each uses up one of the room's distractor slots), one slot less in the goal's room, then the
+// room's distractors.  Reference quirk (:1119, :1660): the lower-left loop reads the upper-left counter.
+inline void build_task_string(int nrooms, int agent_room, int goal_room, uint32_t locked, int num_objects, uint8_t* out) {
+    const int nl = num_objects / 2, nr = num_objects - nl;
+    int cnt[4] = {0, 0, 0, 0};
+    if (nrooms == 2) { cnt[0] = nl; cnt[1] = nr; }
+    else if (nrooms == 3) { cnt[0] = nl / 2; cnt[1] = nl - nl / 2; cnt[2] = nr; }
+    else { cnt[0] = nl / 2; cnt[1] = nl - nl / 2; cnt[2] = nr / 2; cnt[3] = nr - nr / 2; }
+    int n = 0;
+    for (int i = 0; i < kTaskBytes; ++i) out[i] = 0;
+    if (agent_room >= nrooms || goal_room >= nrooms) return;
+    for (int r = 0; r < nrooms; ++r) {
+        for (int j = 0; j < 2; ++j) {
+            const int d = key_door(nrooms, r, agent_room, j);
+            if (d != 7 && ((locked >> d) & 1u)) {
+                if (n < kTaskBytes - 1) out[1 + n++] = (uint8_t)(TASK_KEY | (r << 2) | (d << 4) | (j << 6));
+                --cnt[r];
+            }
+        }
+        if (goal_room == r) --cnt[r];
+        const int loops = (nrooms >= 3 && r == 1) ? cnt[0] : cnt[r];
+        for (int q = 0; q < loops; ++q)
+            if (n < kTaskBytes - 1) out[1 + n++] = (uint8_t)(TASK_DIST | (r << 2));
+    }
+    out[0] = (uint8_t)n;
+}
+inline void build_task_table(int num_objects, uint8_t* table /* [kTaskEntries * kTaskBytes] */) {
+    for (int nrooms = 2; nrooms <= 4; ++nrooms)
+        for (int a = 0; a < 4; ++a)
+            for (int g = 0; g < 4; ++g)
+                for (uint32_t l = 0; l < 16; ++l)
+                    build_task_string(nrooms, a, g, l, num_objects, table + (size_t)task_index(nrooms, a, g, l) * kTaskBytes);
+}
+// words 0..30 of a fresh S x S grid: empty interior, wall border (Grid.wall_rect, custom_env.py:132)
+inline void build_empty_grid(int S, uint32_t* words /* [kGridWords] */) {
+    uint8_t g[kGridWords * 4];
+    for (int i = 0; i < kGridWords * 4; ++i) g[i] = K_EMPTY;
+    for (int i = 0; i < S; ++i) { g[i] = K_WALL; g[(S - 1) * S + i] = K_WALL; g[i * S] = K_WALL; g[i * S + S - 1] = K_WALL; }
+    for (int i = 0; i < kGridWords; ++i)
+        words[i] = (uint32_t)g[4 * i] | ((uint32_t)g[4 * i + 1] << 8) | ((uint32_t)g[4 * i + 2] << 16) | ((uint32_t)g[4 * i + 3] << 24);
+}
+
+// what a generation reads besides the configuration
+struct GenIO {
+    uint32_t* draws;           // this lane's draw buffer: word i at draws[i * stride]
+    int stride;                // 32 on the device (lane-interleaved shared memory), 1 on the host
+    const uint8_t* tasks;      // [kTaskEntries][kTaskBytes] task strings of cfg.num_objects
+    const uint32_t* empty;     // [kGridWords] fresh grid
 };
 
-MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t env_id) {
+enum GenStage : int { G_OBJ = 0, G_GOAL, G_AGENT, G_KEY, G_DIST, G_OBST, G_PLACED };
+
+// Builds the layout of `episode` into s: grid, agent, target, mission, carrying = 0, step_count = 0,
+// episode = episode + 1, reset_draws; ORs ERR_TRIES into s.error.  mission_done / latch_step are
+// not touched (they survive a reset in the reference).
+MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t env_id, uint32_t episode, const GenIO& io) {
     const int S = cfg.size, m = S / 2;
     const bool multi = cfg.problem == P_MULTI;
-    // ---- grid: empty interior, wall border (Grid.wall_rect, custom_env.py:132)
-    for (int i = 0; i < kGridCells; ++i) s.grid[i] = K_EMPTY;
-    for (int i = 0; i < S; ++i) {
-        s.grid[i] = K_WALL; s.grid[(S - 1) * S + i] = K_WALL; s.grid[i * S] = K_WALL; s.grid[i * S + S - 1] = K_WALL;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const uint32_t e0 = (uint32_t)env_id, e1 = (uint32_t)(env_id >> 32);
+    const int ds = io.stride;
+
+    // ---- 1. all draws of the episode
+    for (int b = 0; b < kDrawBuf / 4; ++b) {
+        uint32_t w[4];
+        philox4x32_10((uint32_t)b, episode, e0, e1, k0, k1, w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) io.draws[(4 * b + j) * ds] = w[j];
     }
-    s.carrying = 0; s.step_count = 0;                                  // [UPSTREAM] MiniGridEnv.reset
-    s.target_x = s.target_y = kNone; s.target_action = 0;              // :125-127
+    int nd = 0;  // draws consumed
+    auto draw = [&](int i) -> uint32_t {  // word nd + i
+        const int idx = nd + i;
+        if (idx < kDrawBuf) return io.draws[idx * ds];
+        uint32_t w[4];
+        philox4x32_10((uint32_t)(idx >> 2), episode, e0, e1, k0, k1, w);
+        const int j = idx & 3;
+        return j == 0 ? w[0] : j == 1 ? w[1] : j == 2 ? w[2] : w[3];
+    };
+    // placed objects, insertion order: type | colour<<3 | x<<6 | y<<10.  Entry i lives in draw slot i,
+    // which is dead by then (every object consumes at least one draw before it is recorded).
+    int nobjs = 0;
+    auto push_obj = [&](int type, int colour, int x, int y) {
+        io.draws[nobjs * ds] = (uint32_t)(type | (colour << 3) | (x << 6) | (y << 10));
+        ++nobjs;
+    };
 
-    Rng rng;
-    rng.init(seed, env_id, s.episode);
+    // ---- fresh grid (Grid.wall_rect) and per-episode fields ([UPSTREAM] MiniGridEnv.reset, :125-127)
+    uint32_t* gw = reinterpret_cast<uint32_t*>(&s);
+#pragma unroll
+    for (int i = 0; i < kGridWords; ++i) gw[i] = io.empty[i];
+    s.carrying = 0; s.step_count = 0;
+    s.target_x = s.target_y = kNone; s.target_action = 0;
 
-    // ---- per-lane task state
-    int stage = multi ? G_CMD : G_OBJ;
     int cmd = multi ? cfg.mission
                     : (cfg.problem == P_GTO ? 0 : cfg.problem == P_GTG ? 5 : cfg.problem == P_OPN ? 1
                                                 : cfg.problem == P_PKP ? 2 : 3);
-    int nrooms = 0, ndoors = 0, d = 0;          // door loop
-    uint32_t doors = 0;                          // per door: colour(3) | locked<<3 | key_in_box<<4
-    uint32_t colours = 0x3Fu;                    // remaining door colours (sorted-name order)
-    uint32_t pool = 0, pool_types = 0;           // remaining (type, colour) pairs; 3 bits of type per slot
-    int agent_x = -1, agent_y = -1, goal_x = -1, goal_y = -1, agent_room = 0, goal_room = 0;
-    int r = 0, ph = 0, q = 0, loops = 0, kx = -1, ky = -1;   // room walk
-    uint32_t counts = 0;                         // 4 signed bytes: distractor budget per room
-    int obj_i = 0, obst_i = 0, tries = 0;
-    int pend_type = 0, pend_colour = 0;          // object being placed
-    bool pre_done = false;                       // the task's pool / kind draw has happened
-    int nobjs = 0;
-    uint16_t objs[kMaxObjs];                     // type | colour<<3 | x<<6 | y<<10, insertion order
-
-    // pool of (type, colour) pairs in the reference's comprehension order
+    int nrooms = 0, ndoors = 0;
+    uint32_t doors = 0;          // per door: colour(3) | locked<<3 | key_in_box<<4
+    uint32_t locked_mask = 0;
+    uint32_t colours = 0x3Fu;    // remaining door colours (sorted-name order)
+    uint32_t pool, pool_types;   // remaining (type, colour) pairs; 3 bits of type per 6-colour slot
     if (multi) { pool_types = T_KEY | (T_BALL << 3) | (T_BOX << 6); pool = (1u << 18) - 1u; }
     else if (cfg.problem == P_GTG) { pool_types = T_BOX | (T_DOOR << 3) | (T_KEY << 6) | (T_BALL << 9); pool = (1u << 24) - 1u; }
     else if (cfg.problem == P_OPN) { pool_types = T_BOX | (T_DOOR << 3); pool = (1u << 12) - 1u; }
     else if (cfg.problem == P_PKP) { pool_types = T_KEY | (T_BOX << 3) | (T_BALL << 6); pool = (1u << 18) - 1u; }
     else { pool_types = T_KEY | (T_BALL << 3) | (T_BOX << 6) | (T_DOOR << 9); pool = (1u << 24) - 1u; }
-    if (!multi && cfg.num_objects == 0) stage = (cfg.problem == P_GTG || cfg.problem == P_DRP) ? G_GOAL : G_AGENT;
 
-#define MGRL_CNT(rr) ((int)(int8_t)((counts >> (8 * (rr))) & 0xFFu))
-#define MGRL_CNT_DEC(rr) counts = (counts & ~(0xFFu << (8 * (rr)))) | ((uint32_t)((MGRL_CNT(rr) - 1) & 0xFF) << (8 * (rr)))
-
-    while (stage != G_DONE) {
-        rng.sync();
-        int used = 0;
-
-        if (stage == G_CMD) {  // _generate_multi_map :601-611
-            if (cmd < 0) cmd = (int)((0x5210u >> (4 * mulhi32(rng.peek(used++), 4))) & 0xFu);  // choice([0,1,2,5])
-            nrooms = 2 + (int)mulhi32(rng.peek(used++), 3);                                     // randint(2,4)
-            ndoors = nrooms == 2 ? 1 : nrooms;
-            for (int i = 1; i < S - 1; ++i) s.grid[i * S + m] = K_WALL;                         // wall x = mid
-            if (nrooms >= 3) {
-                const int hi = nrooms == 3 ? m : S - 1;
-                for (int i = 1; i < hi; ++i) s.grid[m * S + i] = K_WALL;                        // wall y = mid
+    // ---- 2. multi-room prologue (_generate_multi_map :601-611, doors :635-650, :880-929, :1324-1390)
+    if (multi) {
+        if (cmd < 0) { cmd = (int)((0x5210u >> (4 * mulhi32(draw(0), 4))) & 0xFu); ++nd; }  // choice([0,1,2,5])
+        nrooms = 2 + (int)mulhi32(draw(0), 3); ++nd;                                         // randint(2,4)
+        ndoors = nrooms == 2 ? 1 : nrooms;
+        const int hi = nrooms == 3 ? m : S - 1;
+        for (int i = 1; i < S - 1; ++i) {
+            s.grid[i * S + m] = K_WALL;                                  // wall x = mid
+            if (nrooms >= 3 && i < hi) s.grid[m * S + i] = K_WALL;      // wall y = mid
+        }
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            if (d < ndoors) {
+                const int i = (int)mulhi32(draw(0), (uint32_t)popc32(colours));
+                const int bit = nth_set_bit(colours, i);
+                colours &= ~(1u << bit);
+                const int colour = sorted_colour(bit);
+                int used = 1;
+                const int locked = cfg.all_doors_open ? 0 : (mulhi32(draw(used++), 2) == 0);  // choice([True, False])
+                const int kib = mulhi32(draw(used++), 2) == 0;
+                nd += used;
+                if (locked) {  // obj_choice.remove(('key', c)) [, ('box', c)]: pool slots are key, ball, box
+                    pool &= ~(1u << (0 * 6 + sorted_index(colour)));
+                    if (kib) pool &= ~(1u << (2 * 6 + sorted_index(colour)));
+                }
+                doors |= (uint32_t)(colour | (locked << 3) | (kib << 4)) << (8 * d);
+                locked_mask |= (uint32_t)locked << d;
             }
-            const int n = cfg.num_objects, nl = n / 2, nr = n - nl;
-            int c0, c1, c2 = 0, c3 = 0;
-            if (nrooms == 2) { c0 = nl; c1 = nr; }
-            else if (nrooms == 3) { c0 = nl / 2; c1 = nl - nl / 2; c2 = nr; }
-            else { c0 = nl / 2; c1 = nl - nl / 2; c2 = nr / 2; c3 = nr - nr / 2; }
-            counts = (uint32_t)(c0 & 0xFF) | ((uint32_t)(c1 & 0xFF) << 8) | ((uint32_t)(c2 & 0xFF) << 16) |
-                     ((uint32_t)(c3 & 0xFF) << 24);
-            stage = G_DOORPROP; d = 0;
-        } else if (stage == G_DOORPROP) {  // :635-643, :880-908, :1324-1362
-            const int i = (int)mulhi32(rng.peek(used++), (uint32_t)popc32(colours));
-            const int bit = nth_set_bit(colours, i);
-            colours &= ~(1u << bit);
-            const int colour = sorted_colour(bit);
-            const int locked = cfg.all_doors_open ? 0 : (mulhi32(rng.peek(used++), 2) == 0);  // choice([True, False])
-            const int kib = mulhi32(rng.peek(used++), 2) == 0;
-            if (locked) {  // obj_choice.remove(('key', c)) [, ('box', c)]: pool slots are key, ball, box
-                pool &= ~(1u << (0 * 6 + sorted_index(colour)));
-                if (kib) pool &= ~(1u << (2 * 6 + sorted_index(colour)));
+        }
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            if (d < ndoors) {
+                bool horizontal; int lo, hi2;
+                if (nrooms == 2) { horizontal = false; lo = 1; hi2 = S - 2; }
+                else if (nrooms == 3) { horizontal = d == 0; lo = d == 2 ? m + 1 : 1; hi2 = d == 2 ? S - 2 : m - 1; }
+                else { horizontal = d < 2; lo = (d & 1) ? m + 1 : 1; hi2 = (d & 1) ? S - 2 : m - 1; }
+                const int p = lo + (int)mulhi32(draw(0), (uint32_t)(hi2 - lo + 1)); ++nd;
+                int is_open = 0;
+                if (cfg.all_doors_open) { is_open = mulhi32(draw(0), 2) == 0; ++nd; }
+                const int props = (int)((doors >> (8 * d)) & 0xFFu);
+                const int colour = props & 7, state = is_open ? 0 : (((props >> 3) & 1) ? 2 : 1);
+                const int x = horizontal ? p : m, y = horizontal ? m : p;
+                const int c = y * S + x;
+                s.grid[c] = (uint8_t)(K_DOOR + 8 * state + colour);
+                s.grid[c - 1] |= kDoorFlag; s.grid[c + 1] |= kDoorFlag;
+                s.grid[c - S] |= kDoorFlag; s.grid[c + S] |= kDoorFlag;
+                push_obj(T_DOOR, colour, x, y);
             }
-            doors |= (uint32_t)(colour | (locked << 3) | (kib << 4)) << (8 * d);
-            if (++d == ndoors) { stage = G_DOORCELL; d = 0; }
-        } else if (stage == G_DOORCELL) {  // :646-650, :911-929, :1365-1390
-            bool horizontal; int lo, hi;
-            if (nrooms == 2) { horizontal = false; lo = 1; hi = S - 2; }
-            else if (nrooms == 3) { horizontal = d == 0; lo = d == 2 ? m + 1 : 1; hi = d == 2 ? S - 2 : m - 1; }
-            else { horizontal = d < 2; lo = (d & 1) ? m + 1 : 1; hi = (d & 1) ? S - 2 : m - 1; }
-            const int p = lo + (int)mulhi32(rng.peek(used++), (uint32_t)(hi - lo + 1));
-            const int is_open = cfg.all_doors_open ? (mulhi32(rng.peek(used++), 2) == 0) : 0;
-            const int props = (int)((doors >> (8 * d)) & 0xFFu);
-            const int colour = props & 7, state = is_open ? 0 : (((props >> 3) & 1) ? 2 : 1);
-            const int x = horizontal ? p : m, y = horizontal ? m : p;
-            s.grid[y * S + x] = (uint8_t)(K_DOOR + 8 * state + colour);
-            if (nobjs < kMaxObjs) objs[nobjs] = (uint16_t)(T_DOOR | (colour << 3) | (x << 6) | (y << 10));
-            ++nobjs;
-            if (++d == ndoors) stage = G_GOAL;
-        } else if (stage == G_TARGET) {  // :174-210
-            const int n = nobjs < kMaxObjs ? nobjs : kMaxObjs;
-            const int o = objs[mulhi32(rng.peek(used++), (uint32_t)n)];
+        }
+    }
+
+    // ---- 3. placements: one try of the lane's current task per iteration
+    const bool has_goal = multi || cfg.problem == P_GTG || cfg.problem == P_DRP;
+    int stage = multi ? G_GOAL : (cfg.num_objects > 0 ? G_OBJ : (has_goal ? G_GOAL : G_AGENT));
+    int agent_x = -1, agent_y = -1, goal_x = -1, goal_y = -1, agent_room = 0;
+    int r = 0, d = 0, second = 0, kx = -1, ky = -1;
+    int obj_i = 0, obst_i = 0, tries = 0, ti = 0, nt = 0;
+    int pend_type = 0, pend_colour = 0;
+    bool pre_done = false;        // the task's pool / kind draw has happened
+    const uint8_t* tasks = io.tasks;
+
+    while (stage != G_PLACED) {
+        const bool whole_grid = stage == G_OBJ || stage == G_GOAL || stage == G_AGENT || (stage == G_OBST && !multi);
+        // pre-draw once per task: pool entry (choice + remove) or obstacle kind
+        if (!pre_done && (stage == G_OBJ || stage == G_DIST)) {
+            const int i = (int)mulhi32(draw(0), (uint32_t)popc32(pool)); ++nd;
+            const int bit = nth_set_bit(pool, i);
+            pool &= ~(1u << bit);
+            pend_type = (int)((pool_types >> (3 * (bit / 6))) & 7u);
+            pend_colour = sorted_colour(bit % 6);
+            pre_done = true;
+        } else if (!pre_done && stage == G_OBST && !multi) {
+            pend_type = mulhi32(draw(0), 2) == 0 ? K_LAVA : K_WALL; ++nd;  // choice([Lava(), Wall()])
+            pre_done = true;
+        }
+        // room rectangle (inclusive) or the whole grid (place_obj draws over [0,S))
+        int x0, x1, y0, y1;
+        if (whole_grid) { x0 = 0; x1 = S - 1; y0 = 0; y1 = S - 1; }
+        else if (stage == G_OBST) { x0 = 1; x1 = S - 2; y0 = 1; y1 = S - 2; }
+        else {
+            const bool left = nrooms == 2 ? r == 0 : r < 2;
+            const bool full_height = nrooms == 2 || (nrooms == 3 && r == 2);
+            const bool upper = (r & 1) == 0;
+            x0 = left ? 1 : m + 1; x1 = left ? m - 1 : S - 2;
+            y0 = (full_height || upper) ? 1 : m + 1;
+            y1 = (full_height || !upper) ? S - 2 : m - 1;
+        }
+        const int x = x0 + (int)mulhi32(draw(0), (uint32_t)(x1 - x0 + 1));
+        const int y = y0 + (int)mulhi32(draw(1), (uint32_t)(y1 - y0 + 1));
+        nd += 2;
+        const int cell = y * S + x;
+        const int here = s.grid[cell];           // kind | kDoorFlag (flag only ever set on a multi map)
+        const bool at_agent = x == agent_x && y == agent_y;
+        bool ok;
+        if (stage == G_AGENT) ok = (here & 0x7F) == K_EMPTY;                        // place_agent: no next2door test
+        else if (whole_grid || stage == G_DIST) ok = here == K_EMPTY && !at_agent;  // place_obj (+ not next2door)
+        else if (stage == G_KEY)
+            ok = !(x == goal_x && y == goal_y) && !(r == agent_room && at_agent) && !(x == kx && y == ky) && !(here & kDoorFlag);
+        else ok = x != m && y != m && (here == K_EMPTY || here == K_LAVA) && !at_agent;  // lava on a multi map
+        if (!ok && ++tries >= kMaxTries) { s.error |= ERR_TRIES; ok = true; }
+        if (ok) {
+            tries = 0; pre_done = false;
+            bool next_task = false;
+            if (stage == G_OBJ) {
+                s.grid[cell] = (uint8_t)obj_kind(pend_type, pend_colour);
+                push_obj(pend_type, pend_colour, x, y);
+                if (++obj_i == cfg.num_objects) stage = has_goal ? G_GOAL : G_AGENT;
+            } else if (stage == G_GOAL) {
+                s.grid[cell] = (uint8_t)(K_GOAL | (here & kDoorFlag));
+                goal_x = x; goal_y = y;
+                push_obj(T_GOAL, 0, x, y);
+                stage = G_AGENT;
+            } else if (stage == G_AGENT) {
+                agent_x = x; agent_y = y;
+                s.agent_x = (uint8_t)x; s.agent_y = (uint8_t)y;
+                s.agent_dir = (uint8_t)mulhi32(draw(0), 4); ++nd;
+                if (multi) {
+                    agent_room = room_of(nrooms, m, agent_x, agent_y);
+                    const int goal_room = room_of(nrooms, m, goal_x, goal_y);
+                    tasks = io.tasks + (size_t)task_index(nrooms, agent_room, goal_room, locked_mask) * kTaskBytes;
+                    nt = tasks[0]; ti = 0;
+                    next_task = true;
+                } else {
+                    stage = G_OBST;
+                }
+            } else if (stage == G_KEY) {
+                const int props = (int)((doors >> (8 * d)) & 0xFFu);
+                const int colour = props & 7;
+                const bool kib = (props >> 4) & 1;
+                s.grid[cell] = (uint8_t)(kib ? K_BOX + 8 * (colour + 1) + colour : K_KEY + colour);
+                push_obj(kib ? T_BOX : T_KEY, colour, x, y);
+                if (!second) { kx = x; ky = y; }
+                next_task = true;
+            } else if (stage == G_DIST) {
+                s.grid[cell] = (uint8_t)obj_kind(pend_type, pend_colour);
+                push_obj(pend_type, pend_colour, x, y);
+                next_task = true;
+            } else {  // G_OBST
+                s.grid[cell] = (uint8_t)(multi ? K_LAVA : pend_type);
+                ++obst_i;
+            }
+            if (next_task) {  // next key / distractor of the room walk, then the obstacles
+                if (ti < nt) {
+                    const int t = tasks[1 + ti++];
+                    stage = (t & 3) == TASK_KEY ? G_KEY : G_DIST;
+                    r = (t >> 2) & 3; d = (t >> 4) & 3; second = (t >> 6) & 1;
+                } else {
+                    stage = G_OBST;
+                }
+            }
+            if (stage == G_OBST && obst_i >= cfg.num_obstacles) stage = G_PLACED;
+        }
+    }
+    if (multi) {  // drop the next-to-a-door marks
+#pragma unroll
+        for (int i = 0; i < kGridWords; ++i) gw[i] &= 0x7F7F7F7Fu;
+    }
+
+    // ---- 4. target selection (:174-267)
+    if (cmd <= 2) {
+        const int n = nobjs;
+        for (;;) {
+            const int o = (int)io.draws[(int)mulhi32(draw(0), (uint32_t)n) * ds]; ++nd;
             const int t = o & 7;
             const bool ok = cmd == 0 ? t != T_GOAL : cmd == 1 ? (t == T_BOX || t == T_DOOR)
                                                               : (t == T_BOX || t == T_KEY || t == T_BALL);
@@ -550,127 +699,28 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
                 s.mission_id = (uint8_t)(cmd * 24 + t * 6 + ((o >> 3) & 7));
                 s.target_x = (uint8_t)((o >> 6) & 15); s.target_y = (uint8_t)((o >> 10) & 15);
                 s.target_action = (uint8_t)(cmd == 0 ? A_DONE : cmd == 1 ? A_TOGGLE : A_PICKUP);
-                stage = G_DONE;
-            }
-        } else {
-            // ---- one placement try, shared by G_OBJ / G_GOAL / G_AGENT / G_KEY / G_DIST / G_OBST
-            const bool whole_grid = stage == G_OBJ || stage == G_GOAL || stage == G_AGENT || (stage == G_OBST && !multi);
-            // pre-draw once per task: pool entry (choice + remove) or obstacle kind
-            if (!pre_done && (stage == G_OBJ || stage == G_DIST)) {
-                const int i = (int)mulhi32(rng.peek(used++), (uint32_t)popc32(pool));
-                const int bit = nth_set_bit(pool, i);
-                pool &= ~(1u << bit);
-                pend_type = (int)((pool_types >> (3 * (bit / 6))) & 7u);
-                pend_colour = sorted_colour(bit % 6);
-                pre_done = true;
-            } else if (!pre_done && stage == G_OBST && !multi) {
-                pend_type = mulhi32(rng.peek(used++), 2) == 0 ? K_LAVA : K_WALL;  // choice([Lava(), Wall()])
-                pre_done = true;
-            }
-            // room rectangle (inclusive) or the whole grid (place_obj draws over [0,S))
-            int x0, x1, y0, y1;
-            if (whole_grid) { x0 = 0; x1 = S - 1; y0 = 0; y1 = S - 1; }
-            else if (stage == G_OBST) { x0 = 1; x1 = S - 2; y0 = 1; y1 = S - 2; }
-            else {
-                const bool left = nrooms == 2 ? r == 0 : r < 2;
-                const bool full_height = nrooms == 2 || (nrooms == 3 && r == 2);
-                const bool upper = (r & 1) == 0;
-                x0 = left ? 1 : m + 1; x1 = left ? m - 1 : S - 2;
-                y0 = (full_height || upper) ? 1 : m + 1;
-                y1 = (full_height || !upper) ? S - 2 : m - 1;
-            }
-            const int x = x0 + (int)mulhi32(rng.peek(used++), (uint32_t)(x1 - x0 + 1));
-            const int y = y0 + (int)mulhi32(rng.peek(used++), (uint32_t)(y1 - y0 + 1));
-            const int here = s.grid[y * S + x];
-            // admissibility
-            bool ok;
-            const bool at_agent = x == agent_x && y == agent_y;
-            bool n2d = false;
-            if (multi && stage != G_AGENT && x >= 1 && x <= S - 2 && y >= 1 && y <= S - 2)  // next2door :2036-2046
-                n2d = k_is_door(s.grid[y * S + x - 1]) || k_is_door(s.grid[y * S + x + 1]) ||
-                      k_is_door(s.grid[(y - 1) * S + x]) || k_is_door(s.grid[(y + 1) * S + x]);
-            if (whole_grid) ok = here == K_EMPTY && !at_agent && !(stage == G_GOAL && multi && n2d);  // place_obj
-            else if (stage == G_KEY)
-                ok = !(x == goal_x && y == goal_y) && !(r == agent_room && at_agent) && !(x == kx && y == ky) && !n2d;
-            else if (stage == G_DIST) ok = here == K_EMPTY && !at_agent && !n2d;   // objs occupy exactly the non-empty cells
-            else ok = x != m && y != m && (here == K_EMPTY || here == K_LAVA) && !at_agent && !n2d;  // lava, multi
-            if (!ok && ++tries >= kMaxTries) { s.error |= ERR_TRIES; ok = true; }
-            if (ok) {
-                tries = 0; pre_done = false;
-                if (stage == G_OBJ) {
-                    s.grid[y * S + x] = (uint8_t)obj_kind(pend_type, pend_colour);
-                    if (nobjs < kMaxObjs) objs[nobjs] = (uint16_t)(pend_type | (pend_colour << 3) | (x << 6) | (y << 10));
-                    ++nobjs;
-                    if (++obj_i == cfg.num_objects)
-                        stage = (cfg.problem == P_GTG || cfg.problem == P_DRP) ? G_GOAL : G_AGENT;
-                } else if (stage == G_GOAL) {
-                    s.grid[y * S + x] = K_GOAL;
-                    goal_x = x; goal_y = y;
-                    if (nobjs < kMaxObjs) objs[nobjs] = (uint16_t)(T_GOAL | (x << 6) | (y << 10));
-                    ++nobjs;
-                    stage = G_AGENT;
-                } else if (stage == G_AGENT) {
-                    agent_x = x; agent_y = y;
-                    s.agent_x = (uint8_t)x; s.agent_y = (uint8_t)y;
-                    s.agent_dir = (uint8_t)mulhi32(rng.peek(used++), 4);
-                    if (multi) {
-                        agent_room = room_of(nrooms, m, agent_x, agent_y);
-                        goal_room = room_of(nrooms, m, goal_x, goal_y);
-                        stage = G_KEY; r = 0; ph = 0; kx = ky = -1;   // resolved to a real task below
-                    } else {
-                        stage = G_OBST;
-                    }
-                } else if (stage == G_KEY) {
-                    const int props = (int)((doors >> (8 * d)) & 0xFFu);
-                    const int colour = props & 7;
-                    const bool kib = (props >> 4) & 1;
-                    s.grid[y * S + x] = (uint8_t)(kib ? K_BOX + 8 * (colour + 1) + colour : K_KEY + colour);
-                    if (nobjs < kMaxObjs) objs[nobjs] = (uint16_t)((kib ? T_BOX : T_KEY) | (colour << 3) | (x << 6) | (y << 10));
-                    ++nobjs;
-                    MGRL_CNT_DEC(r);
-                    if (ph == 0) { kx = x; ky = y; }
-                    ++ph;
-                } else if (stage == G_DIST) {
-                    s.grid[y * S + x] = (uint8_t)obj_kind(pend_type, pend_colour);
-                    if (nobjs < kMaxObjs) objs[nobjs] = (uint16_t)(pend_type | (pend_colour << 3) | (x << 6) | (y << 10));
-                    ++nobjs;
-                    ++q;
-                } else {  // G_OBST
-                    s.grid[y * S + x] = (uint8_t)(multi ? K_LAVA : pend_type);
-                    ++obst_i;
-                }
-                // ---- next task of the room walk (keys of the room, then its distractors)
-                if (stage == G_KEY || stage == G_DIST) {
-                    stage = G_OBST;
-                    while (r < nrooms) {
-                        if (ph < 2) {
-                            d = key_door(nrooms, r, agent_room, ph);
-                            if (d != 7 && ((doors >> (8 * d + 3)) & 1u)) { stage = G_KEY; break; }
-                            ++ph;
-                        } else if (ph == 2) {
-                            if (goal_room == r) MGRL_CNT_DEC(r);
-                            // reference quirk (custom_env.py:1119, 1660): the lower-left loop uses the upper-left counter
-                            loops = (nrooms >= 3 && r == 1) ? MGRL_CNT(0) : MGRL_CNT(r);
-                            q = 0; ph = 3;
-                        } else {
-                            if (q < loops) { stage = G_DIST; break; }
-                            ++r; ph = 0; kx = ky = -1;
-                        }
-                    }
-                }
-                if (stage == G_OBST && obst_i >= cfg.num_obstacles) stage = cmd <= 2 ? G_TARGET : G_DONE;
+                break;
             }
         }
-        rng.ndraw += (uint32_t)used;
-    }
-#undef MGRL_CNT
-#undef MGRL_CNT_DEC
-    if (cmd == 3) { s.mission_id = MISSION_DROP; s.target_action = A_DROP; }           // :212-214
-    else if (cmd == 5) {                                                                 // :258-267
+    } else if (cmd == 3) {                                                                // :212-214
+        s.mission_id = MISSION_DROP; s.target_action = A_DROP;
+    } else {                                                                              // :258-267
         s.mission_id = MISSION_GOAL; s.target_x = (uint8_t)goal_x; s.target_y = (uint8_t)goal_y;
     }
-    s.reset_draws = (uint16_t)rng.ndraw;
-    s.episode += 1;
+    s.reset_draws = (uint16_t)nd;
+    s.episode = episode + 1u;
+}
+
+// A finished environment takes over a prepared layout: everything generate() wrote, while the
+// mission latch survives the reset (Q1) and the error byte is sticky.
+MGRL_HD void adopt_layout(uint32_t* cur, const uint32_t* lay) {
+    // words 0..30 grid + agent x/y/dir; 31 = carrying, step_count, target_x, target_y;
+    // 32 = target_action, mission_id, mission_done, latch_step; 33 = episode; 34 = reset_draws, error, pad
+#pragma unroll
+    for (int i = 0; i < 32; ++i) cur[i] = lay[i];
+    cur[32] = (lay[32] & 0x0000FFFFu) | (cur[32] & 0xFFFF0000u);
+    cur[33] = lay[33];
+    cur[34] = (lay[34] & 0x0000FFFFu) | ((cur[34] | lay[34]) & 0x00FF0000u);
 }
 
 }  // namespace mgrl

@@ -2,17 +2,24 @@
 // simulator.  See DESIGN.md for the data layout and the roofline of each kernel.
 //
 // Kernel map (SURVEY.md §2.1 ids):
-//   env_kernel<LAYOUT,SEE,MODE>  K1+K2  step -> mission bookkeeping -> reward/done -> compacted
-//                                       auto-reset (layout generation) -> 7x7x3 encode
-//   env_many_kernel              K1+K2  T steps per launch, state tile resident in shared memory
+//   step_kernel<LAYOUT,SEE>      K1+K2  T >= 1 steps per launch: step -> mission bookkeeping -> reward/done ->
+//                                       auto-reset by adopting a prepared layout -> 7x7x3 encode; the same
+//                                       warps build new layouts in dense batches of 32 between steps
+//   reset_kernel                 K2     fresh environments + kDepth prepared layouts each (also after set_state)
 //   gae_kernel                   K4     SB3 GAE reverse scan
 //   stack_push_kernel                   VecFrameStack + Discrete2Box + TokenizeVocab gathers
 //
-// Thread mapping: one CTA = one tile of TILE consecutive environments, one lane per
-// environment for the dynamics; the tile's packed state (TILE x 140 B) and its observation
-// bytes (TILE x 147 B) are staged in shared memory so that every global access is a
-// coalesced 16-byte vector transfer.  Finished environments are compacted per CTA so the
-// (divergent, RNG-heavy) layout generator runs on dense lanes.
+// Thread mapping: one CTA = one tile of TILE consecutive environments, one lane per environment for
+// the dynamics; the tile's packed state (TILE x 140 B) lives in shared memory for the whole launch and
+// each warp stages its 32 observation records there so that every global access is a coalesced
+// 16-byte vector transfer.
+//
+// Auto-reset without divergence: the layout of (env, episode) depends only on the RNG key, never on
+// the actions, so it is built AHEAD of time.  Every environment owns kDepth layout slots in global
+// memory (L2-resident).  A finished environment copies the slot of its next episode and queues a
+// request to refill it; whenever 32 requests are waiting, the warp that is furthest ahead takes them
+// and runs the generator with all 32 lanes busy.  Warps never meet at a block barrier inside the step
+// loop, and the queue survives across launches, so one-step launches batch the same way.
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -28,7 +35,11 @@ using namespace mgrl;
 namespace {
 
 constexpr int STATE_WORDS = 35;           // sizeof(EnvState) / 4
-constexpr int MODE_STEP = 0, MODE_RESET = 1, MODE_OBSERVE = 2;
+constexpr int kDepth = 3;                 // layouts prepared ahead of time per environment
+constexpr int kQueueCap = 512;            // >= TILE * kDepth requests can be outstanding per tile
+constexpr uint32_t kNoEntry = 0xFFFFu;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int kSpinLimit = 1 << 20;
 
 static_assert(sizeof(EnvState) == MGRL_STATE_BYTES, "ABI state size");
 
@@ -37,10 +48,14 @@ struct EnvParams {
     uint64_t seed;
     uint64_t env_id_base;
     int n;
-    int T;       // env_many_kernel only
-    int spread;  // 1: deal finished environments round-robin over the CTA's warps (shortest critical
-                 //    path, for small batches); 0: pack them into the first warps (fewest issue slots)
-    EnvState* states;
+    int T;                    // steps per launch
+    EnvState* states;         // [n] current state of every environment
+    EnvState* slots;          // [kDepth][n] prepared layouts: slot (E % kDepth) holds episode E once its
+                              //   episode word (the tag, written last) reads E + 1
+    uint16_t* qsave;          // [tiles][kQueueCap] generation requests left over by the previous launch
+    uint32_t* qcount;         // [tiles]
+    const uint8_t* tasks;     // [kTaskEntries][kTaskBytes] (build_task_table)
+    const uint32_t* empty;    // [kGridWords] (build_empty_grid)
     const float* reward_lut;  // [max_steps+1] device
     const uint8_t* actions;
     uint8_t* image;
@@ -54,138 +69,306 @@ struct EnvParams {
     uint8_t* term_dir;
 };
 
-// ---- cooperative tile copies (coalesced; 16-byte vectors when size and address allow) -------
-template <int TILE>
-__device__ __forceinline__ void tile_copy(void* dst, const void* src, int bytes, int tid) {
+// ---- cooperative copies (coalesced; 16-byte vectors when size and address allow) ------------
+template <int NTHREADS>
+__device__ __forceinline__ void coop_copy(void* dst, const void* src, int bytes, int tid) {
     if ((bytes & 15) == 0 && ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0) {
         const uint4* g = reinterpret_cast<const uint4*>(src);
         uint4* d = reinterpret_cast<uint4*>(dst);
-        for (int i = tid; i < (bytes >> 4); i += TILE) d[i] = g[i];
+        for (int i = tid; i < (bytes >> 4); i += NTHREADS) d[i] = g[i];
     } else if ((bytes & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 3) == 0) {
         const uint32_t* g = reinterpret_cast<const uint32_t*>(src);
         uint32_t* d = reinterpret_cast<uint32_t*>(dst);
-        for (int i = tid; i < (bytes >> 2); i += TILE) d[i] = g[i];
+        for (int i = tid; i < (bytes >> 2); i += NTHREADS) d[i] = g[i];
     } else {
         const uint8_t* g = reinterpret_cast<const uint8_t*>(src);
         uint8_t* d = reinterpret_cast<uint8_t*>(dst);
         const int n16 = (reinterpret_cast<uintptr_t>(dst) & 15) == 0 ? (bytes >> 4) : 0;  // smem src is 16-B aligned
-        for (int i = tid; i < n16; i += TILE) reinterpret_cast<uint4*>(d)[i] = reinterpret_cast<const uint4*>(g)[i];
-        for (int i = (n16 << 4) + tid; i < bytes; i += TILE) d[i] = g[i];
+        for (int i = tid; i < n16; i += NTHREADS) reinterpret_cast<uint4*>(d)[i] = reinterpret_cast<const uint4*>(g)[i];
+        for (int i = (n16 << 4) + tid; i < bytes; i += NTHREADS) d[i] = g[i];
     }
 }
 
-template <int TILE>
+__device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+
+// Shared memory of one tile.  Warps are independent between the prologue and the epilogue: each
+// owns 32 environments (state + a staging area for their observation records) and the tile shares
+// a queue of layout requests and NB draw buffers for the warps that serve it.
+template <int TILE, int NB>
 struct TileSmem {
     alignas(16) uint32_t state[TILE * STATE_WORDS];
-    alignas(16) uint8_t obs[TILE * kObsPitch148];
+    alignas(16) uint8_t obs[TILE / 32][32 * kObsPitch148];   // per warp: observation staging / layout scratch
+    alignas(16) uint32_t draws[NB][kDrawBuf * 32];            // lane-interleaved Philox draws of a serving warp
     uint32_t kind_lut[128];
     float lut[kGridCells + 1];
-    uint16_t done_list[TILE];
-    uint8_t carry[TILE];
-    int n_done;
+    uint32_t empty[kGridWords];
+    uint16_t queue[kQueueCap];   // ring of requests: local env | slot << 8; kNoEntry = not written yet
+    uint32_t q_head, q_tail;
+    int lock[NB];
+    int warp_t[TILE / 32];       // steps finished by each warp
 };
+static_assert(32 * kObsPitch148 >= 32 * STATE_WORDS * 4, "layout scratch must fit the staging area");
 
-// one simulator step of the tile held in `sm` (state already resident); writes the per-step
-// outputs of global env index tile0+tid; leaves the new observation records in sm.obs
-template <int LAYOUT, bool SEE, int MODE, int TILE>
-__device__ __forceinline__ void tile_step(TileSmem<TILE>& sm, const EnvParams& p, int tile0, int nv, int tid,
-                                          size_t out_off /* element offset of this step's [N] outputs */) {
+template <int TILE, int NB>
+__device__ __forceinline__ void tile_prologue(TileSmem<TILE, NB>& sm, const EnvParams& p, int tid) {
+    fill_kind_lut(sm.kind_lut, tid, TILE);
+    for (int i = tid; i <= p.cfg.max_steps; i += TILE) sm.lut[i] = p.reward_lut[i];
+    for (int i = tid; i < kGridWords; i += TILE) sm.empty[i] = p.empty[i];
+}
+
+// queue a layout request for every lane of `mask` (warp-aggregated; call converged)
+template <int TILE, int NB>
+__device__ __forceinline__ void push_requests(TileSmem<TILE, NB>& sm, unsigned mask, uint32_t entry, int lane) {
+    if (mask == 0u) return;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&sm.q_tail, (uint32_t)__popc(mask));
+    base = __shfl_sync(FULL, base, leader);
+    if ((mask >> lane) & 1u) {
+        const uint32_t pos = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+        *reinterpret_cast<volatile uint16_t*>(&sm.queue[pos & (kQueueCap - 1)]) = (uint16_t)entry;
+    }
+}
+
+// Take up to 32 requests off the tile's queue and build their layouts, one lane each (dense
+// generation).  A full batch is required unless `partial` (the caller is waiting for a layout).
+// Returns false when there was nothing to take or no draw buffer was free.  Call converged.
+template <int TILE, int NB>
+__device__ __noinline__ bool serve_queue(TileSmem<TILE, NB>& sm, const EnvParams& p, int tile0, int warp, int lane,
+                                         bool partial) {
+    int b = -1, h = 0, n = 0;
+    if (lane == 0) {
+        const uint32_t head = *reinterpret_cast<volatile uint32_t*>(&sm.q_head);
+        const uint32_t avail = *reinterpret_cast<volatile uint32_t*>(&sm.q_tail) - head;
+        n = avail >= 32u ? 32 : (partial ? (int)avail : 0);
+        if (n > 0) {
+            for (int i = 0; i < NB && b < 0; ++i)
+                if (atomicCAS(&sm.lock[i], 0, 1) == 0) b = i;
+            if (b >= 0) {
+                if (atomicCAS(&sm.q_head, head, head + (uint32_t)n) != head) { atomicExch(&sm.lock[b], 0); b = -1; }
+                else h = (int)head;
+            }
+        }
+    }
+    b = __shfl_sync(FULL, b, 0);
+    if (b < 0) return false;
+    h = __shfl_sync(FULL, h, 0);
+    n = __shfl_sync(FULL, n, 0);
+    if (lane < n) {
+        volatile uint16_t* q = reinterpret_cast<volatile uint16_t*>(&sm.queue[(h + lane) & (kQueueCap - 1)]);
+        uint32_t ent;
+        while ((ent = *q) == kNoEntry) {}
+        *q = (uint16_t)kNoEntry;
+        const int e = (int)(ent & 0xFFu), j = (int)(ent >> 8);
+        uint32_t* slot = reinterpret_cast<uint32_t*>(p.slots + (size_t)j * p.n + tile0 + e);
+        const uint32_t episode = __ldcg(slot + 33) - 1u + kDepth;   // the slot's old layout was adopted
+        uint32_t* sc = reinterpret_cast<uint32_t*>(sm.obs[warp]) + lane * STATE_WORDS;
+        sc[32] = 0u; sc[34] = 0u;
+        GenIO io;
+        io.draws = sm.draws[b] + lane; io.stride = 32; io.tasks = p.tasks; io.empty = sm.empty;
+        generate(*reinterpret_cast<EnvState*>(sc), p.cfg, p.seed, p.env_id_base + (uint64_t)(tile0 + e), episode, io);
+#pragma unroll
+        for (int i = 0; i < STATE_WORDS; ++i)
+            if (i != 33) __stcg(slot + i, sc[i]);
+        __threadfence();
+        __stcg(slot + 33, sc[33]);   // the tag: readers that see episode + 1 also see the layout
+    }
+    __syncwarp();
+    if (lane == 0) { __threadfence_block(); atomicExch(&sm.lock[b], 0); }
+    return true;
+}
+
+// T simulator steps of one tile.  No block-wide barrier inside the loop.
+template <int LAYOUT, bool SEE, int TILE, int NB>
+__global__ void __launch_bounds__(TILE, TILE == 128 ? 4 : 7) step_kernel(const EnvParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileSmem<TILE, NB>& sm = *reinterpret_cast<TileSmem<TILE, NB>*>(smem_raw);
     constexpr int PITCH = obs_pitch(LAYOUT);
-    EnvState* st = reinterpret_cast<EnvState*>(sm.state);
-    const bool active = tid < nv;
+    constexpr int NW = TILE / 32;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile0 = blockIdx.x * TILE;
+    const int nv = min(TILE, p.n - tile0);
     const int S = p.cfg.size;
 
-    if (MODE == MODE_STEP) {
+    coop_copy<TILE>(sm.state, p.states + tile0, nv * (int)sizeof(EnvState), tid);
+    tile_prologue<TILE, NB>(sm, p, tid);
+    {   // requests the previous launch left behind
+        const uint32_t nq = p.qcount[blockIdx.x];
+        const uint16_t* qs = p.qsave + (size_t)blockIdx.x * kQueueCap;
+        for (int i = tid; i < kQueueCap; i += TILE) sm.queue[i] = (uint32_t)i < nq ? qs[i] : (uint16_t)kNoEntry;
+        if (tid == 0) { sm.q_head = 0u; sm.q_tail = nq; }
+        if (tid < NB) sm.lock[tid] = 0;
+        if (tid < NW) sm.warp_t[tid] = 0;
+    }
+    __syncthreads();
+
+    const bool active = tid < nv;
+    uint32_t* cur = sm.state + tid * STATE_WORDS;
+    EnvState& s = *reinterpret_cast<EnvState*>(cur);
+    uint8_t* stage = sm.obs[warp];
+    const int nvw = max(0, min(32, nv - warp * 32));
+    volatile int* warp_t = sm.warp_t;
+
+    for (int t = 0; t < p.T; ++t) {
+        const size_t gi = (size_t)t * (size_t)p.n + (size_t)(tile0 + tid);
+        bool done = false;
+        int carry = 0;
         if (active) {
-            EnvState& s = st[tid];
-            const int a = p.actions[out_off + tile0 + tid];
-            const StepOut o = env_step(s, a, S, p.cfg.max_steps, sm.lut);
-            const size_t gi = out_off + tile0 + tid;
+            const StepOut o = env_step(s, p.actions[gi], S, p.cfg.max_steps, sm.lut);
             p.reward[gi] = o.reward;
             p.term[gi] = o.terminated;
             p.trunc[gi] = o.truncated;
-            const bool done = o.terminated | o.truncated;
+            done = o.terminated | o.truncated;
             if (p.ep_len) p.ep_len[gi] = done ? s.step_count : (uint8_t)0;
-            sm.carry[tid] = o.carry_obs;
-            if (done) sm.done_list[atomicAdd(&sm.n_done, 1)] = (uint16_t)tid;
+            carry = o.carry_obs;
+            if (done) {   // info['terminal_observation']
+                if (p.term_image) encode_view<LAYOUT>(s, carry, S, SEE, sm.kind_lut, p.term_image + gi * PITCH);
+                if (p.term_dir) p.term_dir[gi] = s.agent_dir;
+            }
         }
-        __syncthreads();
-        // pass over the finished environments only: terminal observation, then a new layout
-        const int nd = sm.n_done;
-        constexpr int NW = TILE / 32;
-        const int slot = p.spread ? (tid & 31) * NW + (tid >> 5) : tid;  // which finished env this lane takes
-        if (slot < nd) {
-            const int e = sm.done_list[slot];
-            EnvState& s = st[e];
-            if (p.term_image)
-                encode_view<LAYOUT>(s, sm.carry[e], S, SEE, sm.kind_lut,
-                                    p.term_image + (out_off + tile0 + e) * PITCH);
-            if (p.term_dir) p.term_dir[out_off + tile0 + e] = s.agent_dir;
-            generate(s, p.cfg, p.seed, p.env_id_base + (uint64_t)(tile0 + e));
-            sm.carry[e] = 0;
-        }
-        __syncthreads();
-        if (tid == 0) sm.n_done = 0;
-    } else if (MODE == MODE_RESET) {
-        if (active) {
-            uint32_t* w = sm.state + tid * STATE_WORDS;
+        if (__any_sync(FULL, done)) {
+            // finished environments adopt the layout prepared for their next episode and ask for another
+            bool pending = done;
+            const uint32_t E = s.episode;
+            const int j = (int)(E % kDepth);
+            const uint32_t* slot = reinterpret_cast<const uint32_t*>(p.slots + (size_t)j * p.n + tile0 + tid);
+            const uint32_t entry = (uint32_t)tid | ((uint32_t)j << 8);
+            int spins = 0;
+            for (;;) {
+                bool ready = false;
+                if (pending && ld_volatile(slot + 33) == E + 1u) {
+                    __threadfence();
+                    uint32_t w[STATE_WORDS];
 #pragma unroll
-            for (int i = 0; i < STATE_WORDS; ++i) w[i] = 0u;
-            generate(st[tid], p.cfg, p.seed, p.env_id_base + (uint64_t)(tile0 + tid));
-            sm.carry[tid] = 0;
+                    for (int i = 0; i < STATE_WORDS; ++i) w[i] = __ldcg(slot + i);
+                    adopt_layout(cur, w);
+                    ready = true; pending = false; carry = 0;
+                }
+                push_requests<TILE, NB>(sm, __ballot_sync(FULL, ready), entry, lane);
+                if (!__any_sync(FULL, pending)) break;
+                // a layout is not there yet: serve the queue ourselves (any batch size), else back off
+                if (!serve_queue<TILE, NB>(sm, p, tile0, warp, lane, true)) __nanosleep(200);
+                if (++spins > kSpinLimit) {
+                    if (pending) s.error |= ERR_SYNC;
+                    break;
+                }
+            }
         }
-    } else {
-        if (active) sm.carry[tid] = st[tid].carrying;
+        if (active) {
+            if (p.image) encode_view<LAYOUT>(s, carry, S, SEE, sm.kind_lut, stage + lane * PITCH);
+            if (p.dir) p.dir[gi] = s.agent_dir;
+            if (p.mission) p.mission[gi] = s.mission_id;
+        }
+        __syncwarp();
+        if (p.image && nvw > 0)
+            coop_copy<32>(p.image + ((size_t)t * (size_t)p.n + (size_t)(tile0 + warp * 32)) * PITCH, stage, nvw * PITCH, lane);
+        __syncwarp();
+        // the warp that is furthest ahead builds the next batch of layouts
+        if (lane == 0) warp_t[warp] = t + 1;
+        bool lead = true;
+#pragma unroll
+        for (int w2 = 0; w2 < NW; ++w2) lead = lead && warp_t[w2] <= t + 1;
+        if (lead) serve_queue<TILE, NB>(sm, p, tile0, warp, lane, false);
     }
-
-    if (active) {
-        const EnvState& s = st[tid];
-        const size_t gi = out_off + tile0 + tid;
-        if (p.image) encode_view<LAYOUT>(s, sm.carry[tid], S, SEE, sm.kind_lut, sm.obs + tid * PITCH);
-        if (p.dir) p.dir[gi] = s.agent_dir;
-        if (p.mission) p.mission[gi] = s.mission_id;
+    // keep serving full batches until every warp of the tile has finished its steps
+    for (int spins = 0; spins < kSpinLimit; ++spins) {
+        bool all = true;
+#pragma unroll
+        for (int w2 = 0; w2 < NW; ++w2) all = all && warp_t[w2] >= p.T;
+        if (all) break;
+        if (!serve_queue<TILE, NB>(sm, p, tile0, warp, lane, false)) __nanosleep(100);
     }
     __syncthreads();
-    if (p.image) tile_copy<TILE>(p.image + (out_off + tile0) * PITCH, sm.obs, nv * PITCH, tid);
+    coop_copy<TILE>(p.states + tile0, sm.state, nv * (int)sizeof(EnvState), tid);
+    {   // requests still queued travel to the next launch
+        const uint32_t head = sm.q_head, nq = sm.q_tail - head;
+        uint16_t* qs = p.qsave + (size_t)blockIdx.x * kQueueCap;
+        for (uint32_t i = tid; i < nq; i += TILE) qs[i] = sm.queue[(head + i) & (kQueueCap - 1)];
+        if (tid == 0) p.qcount[blockIdx.x] = nq;
+    }
 }
 
-template <int TILE>
-__device__ __forceinline__ void tile_prologue(TileSmem<TILE>& sm, const EnvParams& p, int tid) {
+// reset (PRIME = false): fresh environments, episode 0 built in place, episodes 1..kDepth into the slots,
+// first observation.  PRIME = true (after mgrl_set_state): only the slots, for episodes E..E+kDepth-1.
+template <int LAYOUT, bool SEE, bool PRIME, int TILE>
+struct ResetSmem {
+    alignas(16) uint32_t state[TILE * STATE_WORDS];
+    alignas(16) uint8_t obs[TILE / 32][32 * kObsPitch148];
+    alignas(16) uint32_t draws[TILE / 32][kDrawBuf * 32];
+    uint32_t kind_lut[128];
+    uint32_t empty[kGridWords];
+};
+
+template <int LAYOUT, bool SEE, bool PRIME, int TILE>
+__global__ void __launch_bounds__(TILE) reset_kernel(const EnvParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using Smem = ResetSmem<LAYOUT, SEE, PRIME, TILE>;
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    constexpr int PITCH = obs_pitch(LAYOUT);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile0 = blockIdx.x * TILE;
+    const int nv = min(TILE, p.n - tile0);
+    if (PRIME) coop_copy<TILE>(sm.state, p.states + tile0, nv * (int)sizeof(EnvState), tid);
     fill_kind_lut(sm.kind_lut, tid, TILE);
-    for (int i = tid; i <= p.cfg.max_steps; i += TILE) sm.lut[i] = p.reward_lut[i];
-    if (tid == 0) sm.n_done = 0;
-}
-
-template <int LAYOUT, bool SEE, int MODE, int TILE>
-__global__ void __launch_bounds__(TILE) env_kernel(const EnvParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileSmem<TILE>& sm = *reinterpret_cast<TileSmem<TILE>*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int tile0 = blockIdx.x * TILE;
-    const int nv = min(TILE, p.n - tile0);
-    if (MODE != MODE_RESET) tile_copy<TILE>(sm.state, p.states + tile0, nv * (int)sizeof(EnvState), tid);
-    tile_prologue<TILE>(sm, p, tid);
+    for (int i = tid; i < kGridWords; i += TILE) sm.empty[i] = p.empty[i];
+    if (tid == 0) p.qcount[blockIdx.x] = 0u;
     __syncthreads();
-    tile_step<LAYOUT, SEE, MODE, TILE>(sm, p, tile0, nv, tid, 0);
-    if (MODE != MODE_OBSERVE) tile_copy<TILE>(p.states + tile0, sm.state, nv * (int)sizeof(EnvState), tid);
-}
-
-// T steps per launch; the state tile never leaves shared memory between steps
-template <int LAYOUT, bool SEE, int TILE>
-__global__ void __launch_bounds__(TILE) env_many_kernel(const EnvParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileSmem<TILE>& sm = *reinterpret_cast<TileSmem<TILE>*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int tile0 = blockIdx.x * TILE;
-    const int nv = min(TILE, p.n - tile0);
-    tile_copy<TILE>(sm.state, p.states + tile0, nv * (int)sizeof(EnvState), tid);
-    tile_prologue<TILE>(sm, p, tid);
-    __syncthreads();
-    for (int t = 0; t < p.T; ++t) {
-        tile_step<LAYOUT, SEE, MODE_STEP, TILE>(sm, p, tile0, nv, tid, (size_t)t * (size_t)p.n);
-        __syncthreads();  // sm.obs is rewritten by the next step
+    const bool active = tid < nv;
+    uint32_t* cur = sm.state + tid * STATE_WORDS;
+    EnvState& s = *reinterpret_cast<EnvState*>(cur);
+    GenIO io;
+    io.draws = sm.draws[warp] + lane; io.stride = 32; io.tasks = p.tasks; io.empty = sm.empty;
+    const uint64_t env_id = p.env_id_base + (uint64_t)(tile0 + tid);
+    if (active) {
+        if (!PRIME) {
+#pragma unroll
+            for (int i = 0; i < STATE_WORDS; ++i) cur[i] = 0u;
+            generate(s, p.cfg, p.seed, env_id, 0u, io);
+        }
+        uint32_t* sc = reinterpret_cast<uint32_t*>(sm.obs[warp]) + lane * STATE_WORDS;
+        for (int k = 0; k < kDepth; ++k) {
+            const uint32_t episode = s.episode + (uint32_t)k;
+            sc[32] = 0u; sc[34] = 0u;
+            generate(*reinterpret_cast<EnvState*>(sc), p.cfg, p.seed, env_id, episode, io);
+            uint32_t* slot = reinterpret_cast<uint32_t*>(p.slots + (size_t)(episode % kDepth) * p.n + tile0 + tid);
+#pragma unroll
+            for (int i = 0; i < STATE_WORDS; ++i) slot[i] = sc[i];
+        }
     }
-    tile_copy<TILE>(p.states + tile0, sm.state, nv * (int)sizeof(EnvState), tid);
+    if (PRIME) return;
+    __syncwarp();
+    uint8_t* stage = sm.obs[warp];
+    if (active) {
+        if (p.image) encode_view<LAYOUT>(s, 0, p.cfg.size, SEE, sm.kind_lut, stage + lane * PITCH);
+        if (p.dir) p.dir[tile0 + tid] = s.agent_dir;
+        if (p.mission) p.mission[tile0 + tid] = s.mission_id;
+    }
+    __syncthreads();
+    const int nvw = max(0, min(32, nv - warp * 32));
+    if (p.image && nvw > 0) coop_copy<32>(p.image + (size_t)(tile0 + warp * 32) * PITCH, stage, nvw * PITCH, lane);
+    coop_copy<TILE>(p.states + tile0, sm.state, nv * (int)sizeof(EnvState), tid);
+}
+
+// gen_obs of the current states without stepping
+template <int LAYOUT, bool SEE, int TILE>
+__global__ void __launch_bounds__(TILE) observe_kernel(const EnvParams p) {
+    __shared__ uint32_t kind_lut[128];
+    const int tid = threadIdx.x;
+    const int i = blockIdx.x * TILE + tid;
+    constexpr int PITCH = obs_pitch(LAYOUT);
+    fill_kind_lut(kind_lut, tid, TILE);
+    __syncthreads();
+    if (i >= p.n) return;
+    EnvState s = p.states[i];
+    uint32_t rec[kObsPitch148 / 4];
+    uint8_t* out = reinterpret_cast<uint8_t*>(rec);
+    if (p.image) {
+        encode_view<LAYOUT>(s, s.carrying, p.cfg.size, SEE, kind_lut, out);
+        uint8_t* dst = p.image + (size_t)i * PITCH;
+        for (int b = 0; b < PITCH; ++b) dst[b] = out[b];
+    }
+    if (p.dir) p.dir[i] = s.agent_dir;
+    if (p.mission) p.mission[i] = s.mission_id;
 }
 
 __global__ void full_obs_kernel(const EnvState* __restrict__ states, int n, int S, uint8_t* __restrict__ out) {
@@ -295,10 +478,14 @@ struct mgrl_env {
     mgrl_config cfg;
     EnvCfg ecfg;
     int device;
-    int tile;    // environments per CTA (64 / 128 / 256)
-    int spread;  // reset scheduling, see EnvParams
+    int tile;    // environments per CTA (64 / 128)
     uint64_t seed;
     EnvState* states;
+    EnvState* slots;     // [kDepth][N]
+    uint16_t* qsave;     // [tiles(64)][kQueueCap]
+    uint32_t* qcount;    // [tiles(64)]
+    uint8_t* tasks;
+    uint32_t* empty;
     float* lut;
     int* err_flags;
     // host-path (VecEnv drop-in) buffers, allocated on first use
@@ -319,48 +506,55 @@ EnvParams make_params(const mgrl_env* e) {
     p.env_id_base = e->cfg.env_id_base;
     p.n = e->cfg.num_envs;
     p.T = 1;
-    p.spread = e->spread;
     p.states = e->states;
+    p.slots = e->slots;
+    p.qsave = e->qsave;
+    p.qcount = e->qcount;
+    p.tasks = e->tasks;
+    p.empty = e->empty;
     p.reward_lut = e->lut;
     return p;
 }
 
+constexpr int MODE_STEP = 0, MODE_RESET = 1, MODE_PRIME = 2, MODE_OBSERVE = 3;
+
 template <typename K>
 int launch_kernel(K kernel, size_t smem, int grid, int block, cudaStream_t s, const EnvParams& p) {
     // > 48 KB of dynamic shared memory needs the opt-in attribute (idempotent, cheap)
-    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kernel<<<grid, block, smem, s>>>(p);
     CUDA_TRY(cudaGetLastError());
     return MGRL_OK;
 }
 
-template <int LAYOUT, bool SEE, int TILE>
-int launch_tile(int mode, bool many, const EnvParams& p, cudaStream_t s) {
+template <int LAYOUT, bool SEE, int TILE, int NB>
+int launch_tile(int mode, const EnvParams& p, cudaStream_t s) {
     const int grid = (p.n + TILE - 1) / TILE;
-    const size_t smem = sizeof(TileSmem<TILE>);
-    if (many) return launch_kernel(env_many_kernel<LAYOUT, SEE, TILE>, smem, grid, TILE, s, p);
-    if (mode == MODE_STEP) return launch_kernel(env_kernel<LAYOUT, SEE, MODE_STEP, TILE>, smem, grid, TILE, s, p);
-    if (mode == MODE_RESET) return launch_kernel(env_kernel<LAYOUT, SEE, MODE_RESET, TILE>, smem, grid, TILE, s, p);
-    return launch_kernel(env_kernel<LAYOUT, SEE, MODE_OBSERVE, TILE>, smem, grid, TILE, s, p);
+    if (mode == MODE_STEP)
+        return launch_kernel(step_kernel<LAYOUT, SEE, TILE, NB>, sizeof(TileSmem<TILE, NB>), grid, TILE, s, p);
+    if (mode == MODE_RESET)
+        return launch_kernel(reset_kernel<LAYOUT, SEE, false, TILE>, sizeof(ResetSmem<LAYOUT, SEE, false, TILE>), grid, TILE, s, p);
+    if (mode == MODE_PRIME)
+        return launch_kernel(reset_kernel<LAYOUT, SEE, true, TILE>, sizeof(ResetSmem<LAYOUT, SEE, true, TILE>), grid, TILE, s, p);
+    return launch_kernel(observe_kernel<LAYOUT, SEE, TILE>, 0, grid, TILE, s, p);
 }
 
 template <int LAYOUT, bool SEE>
-int launch_layout(const mgrl_env* e, int mode, bool many, const EnvParams& p, cudaStream_t s) {
-    if (e->tile == 256) return launch_tile<LAYOUT, SEE, 256>(mode, many, p, s);
-    if (e->tile == 64) return launch_tile<LAYOUT, SEE, 64>(mode, many, p, s);
-    return launch_tile<LAYOUT, SEE, 128>(mode, many, p, s);
+int launch_layout(const mgrl_env* e, int mode, const EnvParams& p, cudaStream_t s) {
+    if (e->tile == 64) return launch_tile<LAYOUT, SEE, 64, 1>(mode, p, s);
+    return launch_tile<LAYOUT, SEE, 128, 2>(mode, p, s);
 }
 
-int launch_env(const mgrl_env* e, int mode, bool many, const EnvParams& p, cudaStream_t s) {
+int launch_env(const mgrl_env* e, int mode, const EnvParams& p, cudaStream_t s) {
     const bool see = e->ecfg.see_through_walls != 0;
     switch (e->cfg.obs_layout) {
     case MGRL_OBS_CHW:
-        return see ? launch_layout<OBS_CHW, true>(e, mode, many, p, s) : launch_layout<OBS_CHW, false>(e, mode, many, p, s);
+        return see ? launch_layout<OBS_CHW, true>(e, mode, p, s) : launch_layout<OBS_CHW, false>(e, mode, p, s);
     case MGRL_OBS_HWC148:
-        return see ? launch_layout<OBS_HWC148, true>(e, mode, many, p, s)
-                   : launch_layout<OBS_HWC148, false>(e, mode, many, p, s);
+        return see ? launch_layout<OBS_HWC148, true>(e, mode, p, s) : launch_layout<OBS_HWC148, false>(e, mode, p, s);
     default:
-        return see ? launch_layout<OBS_HWC, true>(e, mode, many, p, s) : launch_layout<OBS_HWC, false>(e, mode, many, p, s);
+        return see ? launch_layout<OBS_HWC, true>(e, mode, p, s) : launch_layout<OBS_HWC, false>(e, mode, p, s);
     }
 }
 
@@ -428,11 +622,8 @@ int mgrl_create(const mgrl_config* cfg, int device, mgrl_env** out) {
     memset(e, 0, sizeof *e);
     e->cfg = *cfg;
     e->device = device;
-    // launch shape: small batches are latency-bound (deal resets over all warps), large ones issue-bound
     e->tile = 128;
-    e->spread = cfg->num_envs <= 262144 ? 1 : 0;
-    if (const char* t = getenv("MGRL_TILE")) e->tile = atoi(t) == 256 ? 256 : atoi(t) == 64 ? 64 : 128;
-    if (const char* t = getenv("MGRL_SPREAD")) e->spread = atoi(t) != 0;
+    if (const char* t = getenv("MGRL_TILE")) e->tile = atoi(t) == 64 ? 64 : 128;
     e->ecfg.size = cfg->size;
     e->ecfg.num_objects = cfg->num_objects;
     e->ecfg.problem = cfg->problem;
@@ -453,8 +644,23 @@ int mgrl_create(const mgrl_config* cfg, int device, mgrl_env** out) {
         volatile double r = 1.0 - m;
         lut[k] = (float)r;
     }
+    // generator inputs: task strings of this num_objects and the fresh grid of this size
+    static thread_local uint8_t tasks[kTaskEntries * kTaskBytes];
+    uint32_t empty[kGridWords];
+    build_task_table(cfg->num_objects, tasks);
+    build_empty_grid(cfg->size, empty);
+    const size_t n_tiles = ((size_t)cfg->num_envs + 63) / 64;
     cudaError_t err = cudaMalloc(&e->states, (size_t)cfg->num_envs * sizeof(EnvState));
     if (err == cudaSuccess) err = cudaMemset(e->states, 0, (size_t)cfg->num_envs * sizeof(EnvState));
+    if (err == cudaSuccess) err = cudaMalloc(&e->slots, (size_t)kDepth * cfg->num_envs * sizeof(EnvState));
+    if (err == cudaSuccess) err = cudaMemset(e->slots, 0, (size_t)kDepth * cfg->num_envs * sizeof(EnvState));
+    if (err == cudaSuccess) err = cudaMalloc(&e->qsave, n_tiles * kQueueCap * sizeof(uint16_t));
+    if (err == cudaSuccess) err = cudaMalloc(&e->qcount, n_tiles * sizeof(uint32_t));
+    if (err == cudaSuccess) err = cudaMemset(e->qcount, 0, n_tiles * sizeof(uint32_t));
+    if (err == cudaSuccess) err = cudaMalloc(&e->tasks, sizeof tasks);
+    if (err == cudaSuccess) err = cudaMemcpy(e->tasks, tasks, sizeof tasks, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMalloc(&e->empty, sizeof empty);
+    if (err == cudaSuccess) err = cudaMemcpy(e->empty, empty, sizeof empty, cudaMemcpyHostToDevice);
     if (err == cudaSuccess) err = cudaMalloc(&e->lut, sizeof lut);
     if (err == cudaSuccess) err = cudaMemcpy(e->lut, lut, sizeof lut, cudaMemcpyHostToDevice);
     if (err == cudaSuccess) err = cudaMalloc(&e->err_flags, sizeof(int));
@@ -470,7 +676,7 @@ int mgrl_create(const mgrl_config* cfg, int device, mgrl_env** out) {
 int mgrl_destroy(mgrl_env* e) {
     if (!e) return MGRL_OK;
     DeviceGuard guard(e->device);
-    void* bufs[] = {e->states, e->lut, e->err_flags, e->h_actions, e->h_image, e->h_dir, e->h_mission, e->h_term,
+    void* bufs[] = {e->states, e->slots, e->qsave, e->qcount, e->tasks, e->empty, e->lut, e->err_flags, e->h_actions, e->h_image, e->h_dir, e->h_mission, e->h_term,
                     e->h_trunc, e->h_eplen, e->h_termimg, e->h_termdir, e->h_reward, e->h_stack_img, e->h_stack_dir,
                     e->h_stack_mis, e->h_table};
     for (void* b : bufs)
@@ -495,7 +701,7 @@ int mgrl_reset(mgrl_env* e, uint64_t seed, uint8_t* image, uint8_t* dir, uint8_t
     e->seed = seed;
     EnvParams p = make_params(e);
     p.image = image; p.dir = dir; p.mission = mission;
-    return launch_env(e, MODE_RESET, false, p, (cudaStream_t)stream);
+    return launch_env(e, MODE_RESET, p, (cudaStream_t)stream);
 }
 
 int mgrl_step(mgrl_env* e, const uint8_t* actions, uint8_t* image, uint8_t* dir, uint8_t* mission, float* reward,
@@ -507,7 +713,7 @@ int mgrl_step(mgrl_env* e, const uint8_t* actions, uint8_t* image, uint8_t* dir,
     EnvParams p = make_params(e);
     p.actions = actions; p.image = image; p.dir = dir; p.mission = mission; p.reward = reward;
     p.term = term; p.trunc = trunc; p.ep_len = ep_len; p.term_image = term_image; p.term_dir = term_dir;
-    return launch_env(e, MODE_STEP, false, p, (cudaStream_t)stream);
+    return launch_env(e, MODE_STEP, p, (cudaStream_t)stream);
 }
 
 int mgrl_step_many(mgrl_env* e, int T, const uint8_t* actions, uint8_t* image, uint8_t* dir, uint8_t* mission,
@@ -520,7 +726,7 @@ int mgrl_step_many(mgrl_env* e, int T, const uint8_t* actions, uint8_t* image, u
     p.T = T;
     p.actions = actions; p.image = image; p.dir = dir; p.mission = mission; p.reward = reward;
     p.term = term; p.trunc = trunc; p.ep_len = ep_len;
-    return launch_env(e, MODE_STEP, true, p, (cudaStream_t)stream);
+    return launch_env(e, MODE_STEP, p, (cudaStream_t)stream);
 }
 
 int mgrl_observe(mgrl_env* e, uint8_t* image, uint8_t* dir, uint8_t* mission, void* stream) {
@@ -528,7 +734,7 @@ int mgrl_observe(mgrl_env* e, uint8_t* image, uint8_t* dir, uint8_t* mission, vo
     DeviceGuard guard(e->device);
     EnvParams p = make_params(e);
     p.image = image; p.dir = dir; p.mission = mission;
-    return launch_env(e, MODE_OBSERVE, false, p, (cudaStream_t)stream);
+    return launch_env(e, MODE_OBSERVE, p, (cudaStream_t)stream);
 }
 
 int mgrl_get_state(mgrl_env* e, void* dst, size_t bytes, void* stream) {
@@ -545,7 +751,7 @@ int mgrl_set_state(mgrl_env* e, const void* src, size_t bytes, uint64_t seed, vo
     DeviceGuard guard(e->device);
     e->seed = seed;
     CUDA_TRY(cudaMemcpyAsync(e->states, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-    return MGRL_OK;
+    return launch_env(e, MODE_PRIME, make_params(e), (cudaStream_t)stream);   // layouts of the next episodes
 }
 
 int mgrl_get_state_host(mgrl_env* e, void* dst, size_t bytes, void* stream) {
@@ -565,6 +771,8 @@ int mgrl_set_state_host(mgrl_env* e, const void* src, size_t bytes, uint64_t see
     DeviceGuard guard(e->device);
     e->seed = seed;
     CUDA_TRY(cudaMemcpyAsync(e->states, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    const int rc = launch_env(e, MODE_PRIME, make_params(e), (cudaStream_t)stream);
+    if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     return MGRL_OK;
 }

@@ -3,6 +3,7 @@
 // for the HOST so that the kernel logic can be compared with the CPU oracle in the CPU-only
 // test tier (-m "not gpu").  Never linked into the product; the product has no CPU path.
 #include <cstddef>
+#include <cstring>
 #include "mgrl_core.cuh"
 
 using namespace mgrl;
@@ -14,9 +15,26 @@ static const uint32_t* host_lut() {
     return lut;
 }
 
+// generation inputs the kernels keep in device memory: task strings and the fresh grid of the configuration
+struct HostGen {
+    uint8_t tasks[kTaskEntries * kTaskBytes];
+    uint32_t empty[kGridWords];
+    uint32_t draws[kDrawBuf];
+    GenIO io;
+    explicit HostGen(const EnvCfg& cfg) {
+        build_task_table(cfg.num_objects, tasks);
+        build_empty_grid(cfg.size, empty);
+        io.draws = draws; io.stride = 1; io.tasks = tasks; io.empty = empty;
+    }
+};
+
 extern "C" {
 
-void emul_generate(const EnvCfg* cfg, uint64_t seed, uint64_t env_id, EnvState* s) { generate(*s, *cfg, seed, env_id); }
+// in-place generation of episode s->episode (what the reset kernel does)
+void emul_generate(const EnvCfg* cfg, uint64_t seed, uint64_t env_id, EnvState* s) {
+    HostGen g(*cfg);
+    generate(*s, *cfg, seed, env_id, s->episode, g.io);
+}
 
 void emul_step(const EnvCfg* cfg, const float* lut, EnvState* s, int action, float* reward, uint8_t* term,
                uint8_t* trunc, uint8_t* carry_obs) {
@@ -39,6 +57,7 @@ uint32_t emul_kind_encode(int k) { return kind_encode(k); }
 void emul_vec_step(const EnvCfg* cfg, uint64_t seed, uint64_t base, int n, const float* lut, EnvState* st,
                    const uint8_t* act, uint8_t* obs, uint8_t* dir, uint8_t* mis, float* rew, uint8_t* term,
                    uint8_t* trunc, uint8_t* ep_len, uint8_t* term_obs) {
+    HostGen g(*cfg);
     for (int i = 0; i < n; ++i) {
         EnvState& s = st[i];
         StepOut o = env_step(s, act[i], cfg->size, cfg->max_steps, lut);
@@ -48,7 +67,11 @@ void emul_vec_step(const EnvCfg* cfg, uint64_t seed, uint64_t base, int n, const
         int carry = o.carry_obs;
         if (done) {
             encode_view<OBS_HWC>(s, carry, cfg->size, cfg->see_through_walls != 0, host_lut(), term_obs + (size_t)i * kObsBytes);
-            generate(s, *cfg, seed, base + (uint64_t)i);
+            // the step kernel's path: a layout prepared ahead of time is adopted by the finished env
+            EnvState lay;
+            memset(&lay, 0, sizeof lay);
+            generate(lay, *cfg, seed, base + (uint64_t)i, s.episode, g.io);
+            adopt_layout(reinterpret_cast<uint32_t*>(&s), reinterpret_cast<const uint32_t*>(&lay));
             carry = 0;
         }
         encode_view<OBS_HWC>(s, carry, cfg->size, cfg->see_through_walls != 0, host_lut(), obs + (size_t)i * kObsBytes);
