@@ -78,12 +78,13 @@ MGRL_HD int popc32(uint32_t v) {
 }
 // position of the n-th (0-based) set bit of m
 MGRL_HD int nth_set_bit(uint32_t m, int n) {
-#if defined(__CUDA_ARCH__)
-    return (int)__fns(m, 0, n + 1);
-#else
-    for (int i = 0; i < n; ++i) m &= m - 1;
-    return __builtin_ctz(m);
-#endif
+    int pos = 0, t;
+    t = popc32(m & 0xFFFFu); if (n >= t) { n -= t; pos = 16; m >>= 16; }
+    t = popc32(m & 0xFFu);   if (n >= t) { n -= t; pos += 8; m >>= 8; }
+    t = popc32(m & 0xFu);    if (n >= t) { n -= t; pos += 4; m >>= 4; }
+    t = popc32(m & 0x3u);    if (n >= t) { n -= t; pos += 2; m >>= 2; }
+    t = (int)(m & 1u);       if (n >= t) { pos += 1; }
+    return pos;
 }
 
 MGRL_HD bool k_is_key(int k) { return (k >> 3) == 1; }
@@ -121,6 +122,18 @@ MGRL_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, u
         ka += 0x9E3779B9u; kb += 0xBB67AE85u;
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// one word of the stream, recomputed (draws beyond the precomputed buffer)
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+uint32_t philox_word(uint32_t idx, uint32_t episode, uint32_t e0, uint32_t e1, uint32_t k0, uint32_t k1) {
+    uint32_t w[4];
+    philox4x32_10(idx >> 2, episode, e0, e1, k0, k1, w);
+    const uint32_t j = idx & 3u;
+    return j == 0 ? w[0] : j == 1 ? w[1] : j == 2 ? w[2] : w[3];
 }
 
 // --------------------------------------------------------------------------------- step
@@ -253,21 +266,33 @@ MGRL_HD uint32_t pack3(uint32_t lo, uint32_t hi, int shift_bytes) {  // bytes of
 #endif
 }
 
-// fast path: see-through view, HWC, 37 aligned words (148 B) per environment
+// fast path: see-through view, HWC, 37 aligned words (148 B) per environment.  Row by row: the
+// sideways offset of a view row is computed once, the seven forward offsets stay in registers.
 MGRL_HD void encode_view_packed(const EnvState& s, int carrying, int S, const uint32_t* lut, uint32_t* out) {
-    ViewMap m;
-    view_map(s, S, m);
+    const int dir = s.agent_dir;
+    const bool even = (dir & 1) == 0;                 // forward axis is x for east/west
+    const int sf = dir < 2 ? 1 : -1;                  // forward step: +1 east/south, -1 west/north
+    const int sr = (dir == 0 || dir == 3) ? 1 : -1;   // sideways (view-x) step
+    const int af = even ? s.agent_x : s.agent_y, ar = even ? s.agent_y : s.agent_x;
+    const int mf = even ? 1 : S, mr = even ? S : 1;
+    int fo[kView];
+#pragma unroll
+    for (int i = 0; i < kView; ++i) fo[i] = clampi(af + (6 - i) * sf, 0, S - 1) * mf;
     uint32_t e[4];
 #pragma unroll
-    for (int c = 0; c < kView * kView; ++c) {
-        const int vx = c / kView, vy = c % kView;
-        const int k = (c == 3 * kView + 6) ? carrying : (int)s.grid[m.ro[vx] + m.fo[vy]];
-        e[c & 3] = lut[k];
-        if ((c & 3) == 3) {
-            const int w = (c >> 2) * 3;
-            out[w] = pack3(e[0], e[1], 0);
-            out[w + 1] = pack3(e[1], e[2], 1);
-            out[w + 2] = pack3(e[2], e[3], 2);
+    for (int vx = 0; vx < kView; ++vx) {
+        const uint8_t* row = s.grid + clampi(ar + (vx - 3) * sr, 0, S - 1) * mr;
+#pragma unroll
+        for (int vy = 0; vy < kView; ++vy) {
+            const int c = vx * kView + vy;
+            const int k = (c == 3 * kView + 6) ? carrying : (int)row[fo[vy]];
+            e[c & 3] = lut[k];
+            if ((c & 3) == 3) {
+                const int w = (c >> 2) * 3;
+                out[w] = pack3(e[0], e[1], 0);
+                out[w + 1] = pack3(e[1], e[2], 1);
+                out[w + 2] = pack3(e[2], e[3], 2);
+            }
         }
     }
     out[36] = e[0];  // cell 48 + pad byte
@@ -362,17 +387,16 @@ MGRL_HD void encode_full(const EnvState& s, int S, uint8_t* out) {
 //   2. the multi-room prologue (mission, room count, door colours/locks, door cells) is
 //      straight-line code over the maximum of four doors, predicated per lane;
 //   3. every placement kind (goal, agent, key / key-in-box, distractor, single-room object,
-//      obstacle) is one shared draw-test-commit body; a lane's sequence of key/distractor tasks
-//      is a byte string looked up in a table indexed by (rooms, agent room, goal room, locked
-//      doors), so advancing to the next task is a byte fetch instead of a nested room walk;
+//      obstacle) is one shared draw-test-commit body driven by a 32-bit task word (rectangle to
+//      draw from + admissibility flags); a lane's sequence of tasks is a row of a table indexed by
+//      (rooms, agent room, goal room, locked doors), so advancing to the next task is a word
+//      fetch instead of a nested room walk;
 //   4. cells next to a door carry a flag bit while the layout is built, so "empty and not
 //      next to a door" (next2door, :2036-2046) is one compare of the byte already loaded.
 // The draw order is the reference's; the CPU oracle consumes the same stream.
 constexpr int T_KEY = 0, T_BALL = 1, T_BOX = 2, T_DOOR = 3, T_GOAL = 4;
 constexpr int kDrawBuf = 64;            // draws precomputed per generation = 16 Philox blocks
 constexpr int kGridWords = 31;          // words 0..30 of EnvState cover grid[121] + agent x/y/dir
-constexpr int kTaskBytes = 32;          // task string: [0] = n, [1..n] = tasks
-constexpr int kTaskEntries = 3 * 4 * 4 * 16;
 constexpr uint32_t kDoorFlag = 0x80u;   // "next to a door" mark on a grid byte (kinds are < 128)
 
 // Keys placed in `room` when the agent starts in `agent_room`: up to
@@ -413,46 +437,98 @@ MGRL_HD int obj_kind(int type, int colour) {
          : type == T_BOX ? K_BOX + colour : type == T_DOOR ? K_DOOR + 8 + colour : K_GOAL;
 }
 
-// task byte: kind (bits 0-1: 1 = key of a locked door, 2 = distractor) | room << 2 | door << 4 | second << 6
-constexpr int TASK_KEY = 1, TASK_DIST = 2;
+// A placement task is one 32-bit word; a lane walks a zero-terminated list of them:
+//   bits 0-3 x0, 4-7 width, 8-11 y0, 12-15 height of the rectangle the position is drawn from
+//   bits 16-18 stage, 19-20 door (key tasks), 21 second key of the room, 22-23 room,
+//   bit 24 reject x == mid / y == mid (lava on a multi map), 25 lava may be overwritten,
+//   bit 26 only "not next to a door" is asked of the cell (key tasks), 27 agent (next2door ignored),
+//   bit 28 the agent's own cell is rejected
+// The list before the agent exists is configuration-constant (GenIO.prefix: objects, goal, agent); what
+// follows (keys of locked doors, distractors per room, obstacles) is a row of a table indexed by
+// (rooms, agent room, goal room, locked doors) built once per configuration on the host.
+enum GenStage : int { G_OBJ = 1, G_GOAL, G_AGENT, G_KEY, G_DIST, G_OBST };
+constexpr uint32_t TF_MID = 1u << 24, TF_LAVA = 1u << 25, TF_KEYMODE = 1u << 26, TF_AGENTMODE = 1u << 27, TF_AGENT_CELL = 1u << 28;
+constexpr int kTaskWords = 32;            // words per table row / prefix list, zero terminated
+constexpr int kTaskEntries = 3 * 4 * 4 * 16;
+
 MGRL_HD int task_index(int nrooms, int agent_room, int goal_room, uint32_t locked) {
     return (((nrooms - 2) * 4 + agent_room) * 4 + goal_room) * 16 + (int)locked;
+}
+inline uint32_t task_word(int stage, int x0, int x1, int y0, int y1, uint32_t flags, int room = 0, int door = 0, int second = 0) {
+    return (uint32_t)x0 | ((uint32_t)(x1 - x0 + 1) << 4) | ((uint32_t)y0 << 8) | ((uint32_t)(y1 - y0 + 1) << 12) |
+           ((uint32_t)stage << 16) | ((uint32_t)door << 19) | ((uint32_t)second << 21) | ((uint32_t)room << 22) | flags;
+}
+inline uint32_t room_task(int stage, int S, int nrooms, int r, uint32_t flags, int door, int second) {
+    const int m = S / 2;
+    const bool left = nrooms == 2 ? r == 0 : r < 2;
+    const bool full_height = nrooms == 2 || (nrooms == 3 && r == 2);
+    const bool upper = (r & 1) == 0;
+    const int x0 = left ? 1 : m + 1, x1 = left ? m - 1 : S - 2;
+    const int y0 = (full_height || upper) ? 1 : m + 1, y1 = (full_height || !upper) ? S - 2 : m - 1;
+    return task_word(stage, x0, x1, y0, y1, flags, r, door, second);
+}
+inline void append_obstacles(const EnvCfg& cfg, uint32_t* out, int& n) {
+    const int S = cfg.size;
+    const bool multi = cfg.problem == P_MULTI;
+    for (int i = 0; i < cfg.num_obstacles && n < kTaskWords - 1; ++i)
+        out[n++] = multi ? task_word(G_OBST, 1, S - 2, 1, S - 2, TF_MID | TF_LAVA | TF_AGENT_CELL)     // :155-172
+                         : task_word(G_OBST, 0, S - 1, 0, S - 1, TF_AGENT_CELL);                         // place_obj
 }
 
 // The per-room walk of _generate_{2,3,4}_rooms (:652-855, :931-1297, :1392-2034) for one
 // (rooms, agent room, goal room, locked doors) combination: keys of the room's locked doors first
 // (each uses up one of the room's distractor slots), one slot less in the goal's room, then the
 // room's distractors.  Reference quirk (:1119, :1660): the lower-left loop reads the upper-left counter.
-inline void build_task_string(int nrooms, int agent_room, int goal_room, uint32_t locked, int num_objects, uint8_t* out) {
-    const int nl = num_objects / 2, nr = num_objects - nl;
+inline void build_task_row(const EnvCfg& cfg, int nrooms, int agent_room, int goal_room, uint32_t locked, uint32_t* out) {
+    const int S = cfg.size, nl = cfg.num_objects / 2, nr = cfg.num_objects - nl;
     int cnt[4] = {0, 0, 0, 0};
     if (nrooms == 2) { cnt[0] = nl; cnt[1] = nr; }
     else if (nrooms == 3) { cnt[0] = nl / 2; cnt[1] = nl - nl / 2; cnt[2] = nr; }
     else { cnt[0] = nl / 2; cnt[1] = nl - nl / 2; cnt[2] = nr / 2; cnt[3] = nr - nr / 2; }
     int n = 0;
-    for (int i = 0; i < kTaskBytes; ++i) out[i] = 0;
+    for (int i = 0; i < kTaskWords; ++i) out[i] = 0u;
     if (agent_room >= nrooms || goal_room >= nrooms) return;
     for (int r = 0; r < nrooms; ++r) {
         for (int j = 0; j < 2; ++j) {
             const int d = key_door(nrooms, r, agent_room, j);
             if (d != 7 && ((locked >> d) & 1u)) {
-                if (n < kTaskBytes - 1) out[1 + n++] = (uint8_t)(TASK_KEY | (r << 2) | (d << 4) | (j << 6));
+                if (n < kTaskWords - 1)
+                    out[n++] = room_task(G_KEY, S, nrooms, r, TF_KEYMODE | (r == agent_room ? TF_AGENT_CELL : 0u), d, j);
                 --cnt[r];
             }
         }
         if (goal_room == r) --cnt[r];
         const int loops = (nrooms >= 3 && r == 1) ? cnt[0] : cnt[r];
         for (int q = 0; q < loops; ++q)
-            if (n < kTaskBytes - 1) out[1 + n++] = (uint8_t)(TASK_DIST | (r << 2));
+            if (n < kTaskWords - 1) out[n++] = room_task(G_DIST, S, nrooms, r, TF_AGENT_CELL, 0, 0);
     }
-    out[0] = (uint8_t)n;
+    append_obstacles(cfg, out, n);
 }
-inline void build_task_table(int num_objects, uint8_t* table /* [kTaskEntries * kTaskBytes] */) {
+// table[kTaskEntries][kTaskWords]; a single-room problem uses row 0 (its obstacles)
+inline void build_task_table(const EnvCfg& cfg, uint32_t* table) {
+    for (int i = 0; i < kTaskEntries * kTaskWords; ++i) table[i] = 0u;
+    if (cfg.problem != P_MULTI) {
+        int n = 0;
+        append_obstacles(cfg, table, n);
+        return;
+    }
     for (int nrooms = 2; nrooms <= 4; ++nrooms)
         for (int a = 0; a < 4; ++a)
             for (int g = 0; g < 4; ++g)
                 for (uint32_t l = 0; l < 16; ++l)
-                    build_task_string(nrooms, a, g, l, num_objects, table + (size_t)task_index(nrooms, a, g, l) * kTaskBytes);
+                    build_task_row(cfg, nrooms, a, g, l, table + (size_t)task_index(nrooms, a, g, l) * kTaskWords);
+}
+// tasks up to and including the agent: single-room objects (:371-555), goal, agent
+inline void build_task_prefix(const EnvCfg& cfg, uint32_t* out /* [kTaskWords] */) {
+    const int S = cfg.size;
+    const bool multi = cfg.problem == P_MULTI;
+    const bool has_goal = multi || cfg.problem == P_GTG || cfg.problem == P_DRP;
+    int n = 0;
+    for (int i = 0; i < kTaskWords; ++i) out[i] = 0u;
+    if (!multi)
+        for (int i = 0; i < cfg.num_objects && n < kTaskWords - 3; ++i) out[n++] = task_word(G_OBJ, 0, S - 1, 0, S - 1, TF_AGENT_CELL);
+    if (has_goal) out[n++] = task_word(G_GOAL, 0, S - 1, 0, S - 1, TF_AGENT_CELL);
+    out[n++] = task_word(G_AGENT, 0, S - 1, 0, S - 1, TF_AGENTMODE);
 }
 // words 0..30 of a fresh S x S grid: empty interior, wall border (Grid.wall_rect, custom_env.py:132)
 inline void build_empty_grid(int S, uint32_t* words /* [kGridWords] */) {
@@ -467,11 +543,10 @@ inline void build_empty_grid(int S, uint32_t* words /* [kGridWords] */) {
 struct GenIO {
     uint32_t* draws;           // this lane's draw buffer: word i at draws[i * stride]
     int stride;                // 32 on the device (lane-interleaved shared memory), 1 on the host
-    const uint8_t* tasks;      // [kTaskEntries][kTaskBytes] task strings of cfg.num_objects
+    const uint32_t* tasks;     // [kTaskEntries][kTaskWords] (build_task_table)
+    const uint32_t* prefix;    // [kTaskWords] (build_task_prefix)
     const uint32_t* empty;     // [kGridWords] fresh grid
 };
-
-enum GenStage : int { G_OBJ = 0, G_GOAL, G_AGENT, G_KEY, G_DIST, G_OBST, G_PLACED };
 
 // Builds the layout of `episode` into s: grid, agent, target, mission, carrying = 0, step_count = 0,
 // episode = episode + 1, reset_draws; ORs ERR_TRIES into s.error.  mission_done / latch_step are
@@ -484,6 +559,7 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
     const int ds = io.stride;
 
     // ---- 1. all draws of the episode
+#pragma unroll 1
     for (int b = 0; b < kDrawBuf / 4; ++b) {
         uint32_t w[4];
         philox4x32_10((uint32_t)b, episode, e0, e1, k0, k1, w);
@@ -494,22 +570,15 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
     auto draw = [&](int i) -> uint32_t {  // word nd + i
         const int idx = nd + i;
         if (idx < kDrawBuf) return io.draws[idx * ds];
-        uint32_t w[4];
-        philox4x32_10((uint32_t)(idx >> 2), episode, e0, e1, k0, k1, w);
-        const int j = idx & 3;
-        return j == 0 ? w[0] : j == 1 ? w[1] : j == 2 ? w[2] : w[3];
+        return philox_word((uint32_t)idx, episode, e0, e1, k0, k1);
     };
     // placed objects, insertion order: type | colour<<3 | x<<6 | y<<10.  Entry i lives in draw slot i,
     // which is dead by then (every object consumes at least one draw before it is recorded).
     int nobjs = 0;
-    auto push_obj = [&](int type, int colour, int x, int y) {
-        io.draws[nobjs * ds] = (uint32_t)(type | (colour << 3) | (x << 6) | (y << 10));
-        ++nobjs;
-    };
 
     // ---- fresh grid (Grid.wall_rect) and per-episode fields ([UPSTREAM] MiniGridEnv.reset, :125-127)
     uint32_t* gw = reinterpret_cast<uint32_t*>(&s);
-#pragma unroll
+#pragma unroll 4
     for (int i = 0; i < kGridWords; ++i) gw[i] = io.empty[i];
     s.carrying = 0; s.step_count = 0;
     s.target_x = s.target_y = kNone; s.target_action = 0;
@@ -517,10 +586,9 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
     int cmd = multi ? cfg.mission
                     : (cfg.problem == P_GTO ? 0 : cfg.problem == P_GTG ? 5 : cfg.problem == P_OPN ? 1
                                                 : cfg.problem == P_PKP ? 2 : 3);
-    int nrooms = 0, ndoors = 0;
+    int nrooms = 2;
     uint32_t doors = 0;          // per door: colour(3) | locked<<3 | key_in_box<<4
     uint32_t locked_mask = 0;
-    uint32_t colours = 0x3Fu;    // remaining door colours (sorted-name order)
     uint32_t pool, pool_types;   // remaining (type, colour) pairs; 3 bits of type per 6-colour slot
     if (multi) { pool_types = T_KEY | (T_BALL << 3) | (T_BOX << 6); pool = (1u << 18) - 1u; }
     else if (cfg.problem == P_GTG) { pool_types = T_BOX | (T_DOOR << 3) | (T_KEY << 6) | (T_BALL << 9); pool = (1u << 24) - 1u; }
@@ -532,13 +600,14 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
     if (multi) {
         if (cmd < 0) { cmd = (int)((0x5210u >> (4 * mulhi32(draw(0), 4))) & 0xFu); ++nd; }  // choice([0,1,2,5])
         nrooms = 2 + (int)mulhi32(draw(0), 3); ++nd;                                         // randint(2,4)
-        ndoors = nrooms == 2 ? 1 : nrooms;
+        const int ndoors = nrooms == 2 ? 1 : nrooms;
         const int hi = nrooms == 3 ? m : S - 1;
         for (int i = 1; i < S - 1; ++i) {
             s.grid[i * S + m] = K_WALL;                                  // wall x = mid
             if (nrooms >= 3 && i < hi) s.grid[m * S + i] = K_WALL;      // wall y = mid
         }
-#pragma unroll
+        uint32_t colours = 0x3Fu;    // remaining door colours (sorted-name order)
+#pragma unroll 1
         for (int d = 0; d < 4; ++d) {
             if (d < ndoors) {
                 const int i = (int)mulhi32(draw(0), (uint32_t)popc32(colours));
@@ -557,7 +626,7 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
                 locked_mask |= (uint32_t)locked << d;
             }
         }
-#pragma unroll
+#pragma unroll 1
         for (int d = 0; d < 4; ++d) {
             if (d < ndoors) {
                 bool horizontal; int lo, hi2;
@@ -574,115 +643,87 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
                 s.grid[c] = (uint8_t)(K_DOOR + 8 * state + colour);
                 s.grid[c - 1] |= kDoorFlag; s.grid[c + 1] |= kDoorFlag;
                 s.grid[c - S] |= kDoorFlag; s.grid[c + S] |= kDoorFlag;
-                push_obj(T_DOOR, colour, x, y);
+                io.draws[nobjs * ds] = (uint32_t)(T_DOOR | (colour << 3) | (x << 6) | (y << 10));
+                ++nobjs;
             }
         }
     }
 
     // ---- 3. placements: one try of the lane's current task per iteration
-    const bool has_goal = multi || cfg.problem == P_GTG || cfg.problem == P_DRP;
-    int stage = multi ? G_GOAL : (cfg.num_objects > 0 ? G_OBJ : (has_goal ? G_GOAL : G_AGENT));
-    int agent_x = -1, agent_y = -1, goal_x = -1, goal_y = -1, agent_room = 0;
-    int r = 0, d = 0, second = 0, kx = -1, ky = -1;
-    int obj_i = 0, obst_i = 0, tries = 0, ti = 0, nt = 0;
-    int pend_type = 0, pend_colour = 0;
-    bool pre_done = false;        // the task's pool / kind draw has happened
-    const uint8_t* tasks = io.tasks;
-
-    while (stage != G_PLACED) {
-        const bool whole_grid = stage == G_OBJ || stage == G_GOAL || stage == G_AGENT || (stage == G_OBST && !multi);
-        // pre-draw once per task: pool entry (choice + remove) or obstacle kind
-        if (!pre_done && (stage == G_OBJ || stage == G_DIST)) {
-            const int i = (int)mulhi32(draw(0), (uint32_t)popc32(pool)); ++nd;
+    // A task starts by fixing what it places: a pool entry (choice + remove: one draw), a door's key
+    // or key-in-box, the goal, lava or a drawn obstacle kind.
+    int kind = 0;           // kind byte the task writes
+    uint32_t objw = 0;      // type | colour << 3 of the object record
+    auto start_task = [&](uint32_t task, uint32_t word) {
+        const int stage = (int)((task >> 16) & 7u);
+        if (stage == G_OBJ || stage == G_DIST) {
+            const int i = (int)mulhi32(word, (uint32_t)popc32(pool)); ++nd;
             const int bit = nth_set_bit(pool, i);
             pool &= ~(1u << bit);
-            pend_type = (int)((pool_types >> (3 * (bit / 6))) & 7u);
-            pend_colour = sorted_colour(bit % 6);
-            pre_done = true;
-        } else if (!pre_done && stage == G_OBST && !multi) {
-            pend_type = mulhi32(draw(0), 2) == 0 ? K_LAVA : K_WALL; ++nd;  // choice([Lava(), Wall()])
-            pre_done = true;
+            const int type = (int)((pool_types >> (3 * (bit / 6))) & 7u), colour = sorted_colour(bit % 6);
+            kind = obj_kind(type, colour);
+            objw = (uint32_t)(type | (colour << 3));
+        } else if (stage == G_KEY) {
+            const int props = (int)((doors >> (8 * ((task >> 19) & 3u))) & 0xFFu);
+            const int colour = props & 7;
+            const bool kib = (props >> 4) & 1;
+            kind = kib ? K_BOX + 8 * (colour + 1) + colour : K_KEY + colour;
+            objw = (uint32_t)((kib ? T_BOX : T_KEY) | (colour << 3));
+        } else if (stage == G_OBST) {
+            kind = K_LAVA;
+            if (!multi) { kind = mulhi32(word, 2) == 0 ? K_LAVA : K_WALL; ++nd; }   // choice([Lava(), Wall()])
+        } else {
+            kind = K_GOAL; objw = T_GOAL;
         }
-        // room rectangle (inclusive) or the whole grid (place_obj draws over [0,S))
-        int x0, x1, y0, y1;
-        if (whole_grid) { x0 = 0; x1 = S - 1; y0 = 0; y1 = S - 1; }
-        else if (stage == G_OBST) { x0 = 1; x1 = S - 2; y0 = 1; y1 = S - 2; }
-        else {
-            const bool left = nrooms == 2 ? r == 0 : r < 2;
-            const bool full_height = nrooms == 2 || (nrooms == 3 && r == 2);
-            const bool upper = (r & 1) == 0;
-            x0 = left ? 1 : m + 1; x1 = left ? m - 1 : S - 2;
-            y0 = (full_height || upper) ? 1 : m + 1;
-            y1 = (full_height || !upper) ? S - 2 : m - 1;
-        }
-        const int x = x0 + (int)mulhi32(draw(0), (uint32_t)(x1 - x0 + 1));
-        const int y = y0 + (int)mulhi32(draw(1), (uint32_t)(y1 - y0 + 1));
+    };
+    const uint32_t* list = io.prefix;
+    int li = 0, tries = 0;
+    uint32_t task = list[0];
+    uint32_t agent_xy = 0xFFFFu, goal_xy = 0xFFFFu, key_xy = 0xFFFFu;   // x | y << 8
+    if (!multi) start_task(task, draw(0));
+    else { kind = K_GOAL; objw = T_GOAL; }
+
+    while (task != 0u) {
+        const uint32_t d0 = draw(0), d1 = draw(1), d2 = draw(2), d3 = draw(3);
+        const int x = (int)(task & 15u) + (int)mulhi32(d0, (task >> 4) & 15u);
+        const int y = (int)((task >> 8) & 15u) + (int)mulhi32(d1, (task >> 12) & 15u);
         nd += 2;
+        const uint32_t xy = (uint32_t)x | ((uint32_t)y << 8);
         const int cell = y * S + x;
-        const int here = s.grid[cell];           // kind | kDoorFlag (flag only ever set on a multi map)
-        const bool at_agent = x == agent_x && y == agent_y;
-        bool ok;
-        if (stage == G_AGENT) ok = (here & 0x7F) == K_EMPTY;                        // place_agent: no next2door test
-        else if (whole_grid || stage == G_DIST) ok = here == K_EMPTY && !at_agent;  // place_obj (+ not next2door)
-        else if (stage == G_KEY)
-            ok = !(x == goal_x && y == goal_y) && !(r == agent_room && at_agent) && !(x == kx && y == ky) && !(here & kDoorFlag);
-        else ok = x != m && y != m && (here == K_EMPTY || here == K_LAVA) && !at_agent;  // lava on a multi map
-        if (!ok && ++tries >= kMaxTries) { s.error |= ERR_TRIES; ok = true; }
-        if (ok) {
-            tries = 0; pre_done = false;
-            bool next_task = false;
-            if (stage == G_OBJ) {
-                s.grid[cell] = (uint8_t)obj_kind(pend_type, pend_colour);
-                push_obj(pend_type, pend_colour, x, y);
-                if (++obj_i == cfg.num_objects) stage = has_goal ? G_GOAL : G_AGENT;
-            } else if (stage == G_GOAL) {
-                s.grid[cell] = (uint8_t)(K_GOAL | (here & kDoorFlag));
-                goal_x = x; goal_y = y;
-                push_obj(T_GOAL, 0, x, y);
-                stage = G_AGENT;
-            } else if (stage == G_AGENT) {
-                agent_x = x; agent_y = y;
-                s.agent_x = (uint8_t)x; s.agent_y = (uint8_t)y;
-                s.agent_dir = (uint8_t)mulhi32(draw(0), 4); ++nd;
+        const uint32_t here = s.grid[cell];           // kind | kDoorFlag (flag only ever set on a multi map)
+        const uint32_t mask = (task & TF_KEYMODE) ? kDoorFlag : (task & TF_AGENTMODE) ? 0x7Fu : 0xFFu;
+        bool bad = (here & mask) != 0u && !((task & TF_LAVA) && here == (uint32_t)K_LAVA);
+        bad = bad || ((task & TF_AGENT_CELL) && xy == agent_xy) || xy == goal_xy || xy == key_xy;
+        bad = bad || ((task & TF_MID) && (x == m || y == m));
+        if (bad && ++tries >= kMaxTries) { s.error |= ERR_TRIES; bad = false; }
+        if (!bad) {
+            tries = 0;
+            const int stage = (int)((task >> 16) & 7u);
+            uint32_t next_word = d2;
+            if (stage == G_AGENT) {
+                agent_xy = xy;
+                s.agent_dir = (uint8_t)mulhi32(d2, 4); ++nd;
+                next_word = d3;
+                int row = 0;
                 if (multi) {
-                    agent_room = room_of(nrooms, m, agent_x, agent_y);
-                    const int goal_room = room_of(nrooms, m, goal_x, goal_y);
-                    tasks = io.tasks + (size_t)task_index(nrooms, agent_room, goal_room, locked_mask) * kTaskBytes;
-                    nt = tasks[0]; ti = 0;
-                    next_task = true;
-                } else {
-                    stage = G_OBST;
+                    const int gx = (int)(goal_xy & 0xFFu), gy = (int)(goal_xy >> 8);
+                    row = task_index(nrooms, room_of(nrooms, m, x, y), room_of(nrooms, m, gx, gy), locked_mask);
                 }
-            } else if (stage == G_KEY) {
-                const int props = (int)((doors >> (8 * d)) & 0xFFu);
-                const int colour = props & 7;
-                const bool kib = (props >> 4) & 1;
-                s.grid[cell] = (uint8_t)(kib ? K_BOX + 8 * (colour + 1) + colour : K_KEY + colour);
-                push_obj(kib ? T_BOX : T_KEY, colour, x, y);
-                if (!second) { kx = x; ky = y; }
-                next_task = true;
-            } else if (stage == G_DIST) {
-                s.grid[cell] = (uint8_t)obj_kind(pend_type, pend_colour);
-                push_obj(pend_type, pend_colour, x, y);
-                next_task = true;
-            } else {  // G_OBST
-                s.grid[cell] = (uint8_t)(multi ? K_LAVA : pend_type);
-                ++obst_i;
+                list = io.tasks + (size_t)row * kTaskWords;
+                li = -1;
+            } else {
+                s.grid[cell] = (uint8_t)((uint32_t)kind | (here & kDoorFlag));
+                if (stage != G_OBST) { io.draws[nobjs * ds] = objw | ((uint32_t)x << 6) | ((uint32_t)y << 10); ++nobjs; }
+                if (stage == G_GOAL) goal_xy = xy;
+                if (stage == G_KEY && !(task & (1u << 21))) key_xy = xy;
             }
-            if (next_task) {  // next key / distractor of the room walk, then the obstacles
-                if (ti < nt) {
-                    const int t = tasks[1 + ti++];
-                    stage = (t & 3) == TASK_KEY ? G_KEY : G_DIST;
-                    r = (t >> 2) & 3; d = (t >> 4) & 3; second = (t >> 6) & 1;
-                } else {
-                    stage = G_OBST;
-                }
-            }
-            if (stage == G_OBST && obst_i >= cfg.num_obstacles) stage = G_PLACED;
+            task = list[++li];
+            start_task(task, next_word);
         }
     }
+    s.agent_x = (uint8_t)(agent_xy & 0xFFu); s.agent_y = (uint8_t)(agent_xy >> 8);
     if (multi) {  // drop the next-to-a-door marks
-#pragma unroll
+#pragma unroll 4
         for (int i = 0; i < kGridWords; ++i) gw[i] &= 0x7F7F7F7Fu;
     }
 
@@ -705,7 +746,7 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
     } else if (cmd == 3) {                                                                // :212-214
         s.mission_id = MISSION_DROP; s.target_action = A_DROP;
     } else {                                                                              // :258-267
-        s.mission_id = MISSION_GOAL; s.target_x = (uint8_t)goal_x; s.target_y = (uint8_t)goal_y;
+        s.mission_id = MISSION_GOAL; s.target_x = (uint8_t)(goal_xy & 0xFFu); s.target_y = (uint8_t)(goal_xy >> 8);
     }
     s.reset_draws = (uint16_t)nd;
     s.episode = episode + 1u;

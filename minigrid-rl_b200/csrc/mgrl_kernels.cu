@@ -54,7 +54,8 @@ struct EnvParams {
                               //   episode word (the tag, written last) reads E + 1
     uint16_t* qsave;          // [tiles][kQueueCap] generation requests left over by the previous launch
     uint32_t* qcount;         // [tiles]
-    const uint8_t* tasks;     // [kTaskEntries][kTaskBytes] (build_task_table)
+    const uint32_t* tasks;    // [kTaskEntries][kTaskWords] (build_task_table)
+    const uint32_t* prefix;   // [kTaskWords] (build_task_prefix)
     const uint32_t* empty;    // [kGridWords] (build_empty_grid)
     const float* reward_lut;  // [max_steps+1] device
     const uint8_t* actions;
@@ -71,25 +72,105 @@ struct EnvParams {
 
 // ---- cooperative copies (coalesced; 16-byte vectors when size and address allow) ------------
 template <int NTHREADS>
-__device__ __forceinline__ void coop_copy(void* dst, const void* src, int bytes, int tid) {
+__device__ __noinline__ void coop_copy(void* dst, const void* src, int bytes, int tid) {
     if ((bytes & 15) == 0 && ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0) {
         const uint4* g = reinterpret_cast<const uint4*>(src);
         uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll 1
         for (int i = tid; i < (bytes >> 4); i += NTHREADS) d[i] = g[i];
     } else if ((bytes & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 3) == 0) {
         const uint32_t* g = reinterpret_cast<const uint32_t*>(src);
         uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+#pragma unroll 1
         for (int i = tid; i < (bytes >> 2); i += NTHREADS) d[i] = g[i];
     } else {
         const uint8_t* g = reinterpret_cast<const uint8_t*>(src);
         uint8_t* d = reinterpret_cast<uint8_t*>(dst);
         const int n16 = (reinterpret_cast<uintptr_t>(dst) & 15) == 0 ? (bytes >> 4) : 0;  // smem src is 16-B aligned
+#pragma unroll 1
         for (int i = tid; i < n16; i += NTHREADS) reinterpret_cast<uint4*>(d)[i] = reinterpret_cast<const uint4*>(g)[i];
+#pragma unroll 1
         for (int i = (n16 << 4) + tid; i < bytes; i += NTHREADS) d[i] = g[i];
     }
 }
 
-__device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+// one warp's 32 staged observation records -> global (the common case: full warp, 148-byte records)
+template <int PITCH>
+__device__ __forceinline__ void warp_copy_out(uint8_t* dst, const uint8_t* src, int nvw, int lane) {
+    if (PITCH == kObsPitch148 && nvw == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        const uint4* g = reinterpret_cast<const uint4*>(src);
+        uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+        for (int i = 0; i < (32 * kObsPitch148 / 16 + 31) / 32; ++i) {
+            const int j = i * 32 + lane;
+            if (j < 32 * kObsPitch148 / 16) __stcs(d + j, g[j]);   // streaming: the record is not read again here
+        }
+    } else {
+        coop_copy<32>(dst, src, nvw * PITCH, lane);
+    }
+}
+
+// ---- shared-memory-only observation encoder (the step kernel's fast path) --------------------
+// Same result as encode_view_packed (mgrl_core.cuh), written against 32-bit shared addresses so that
+// every access is an LDS/STS with one address instruction: per view row the 7 kind bytes are
+// gathered first, then their 7 LUT words, then packed into aligned words of the staged record.
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+
+__device__ __forceinline__ void encode_packed_smem(uint32_t state_sa, int agent_x, int agent_y, int dir, uint32_t carrying,
+                                                   int S, uint32_t lut_sa, uint32_t out_sa) {
+    const bool even = (dir & 1) == 0;
+    const int sf = dir < 2 ? 1 : -1;
+    const int sr = (dir == 0 || dir == 3) ? 1 : -1;
+    const int af = even ? agent_x : agent_y, ar = even ? agent_y : agent_x;
+    const int mf = even ? 1 : S, mr = even ? S : 1;
+    int cf[kView];
+#pragma unroll
+    for (int i = 0; i < kView; ++i) cf[i] = clampi(af + (6 - i) * sf, 0, S - 1);
+    uint32_t e[4];
+#pragma unroll
+    for (int vx = 0; vx < kView; ++vx) {
+        const uint32_t row = state_sa + (uint32_t)(clampi(ar + (vx - 3) * sr, 0, S - 1) * mr);
+        uint32_t k[kView], w[kView];
+#pragma unroll
+        for (int vy = 0; vy < kView; ++vy)
+            k[vy] = (vx == 3 && vy == 6) ? carrying : lds_u8(row + (uint32_t)(cf[vy] * mf));
+#pragma unroll
+        for (int vy = 0; vy < kView; ++vy) w[vy] = lds_u32(lut_sa + k[vy] * 4u);
+#pragma unroll
+        for (int vy = 0; vy < kView; ++vy) {
+            const int c = vx * kView + vy;
+            e[c & 3] = w[vy];
+            if ((c & 3) == 3) {
+                const uint32_t o = out_sa + (uint32_t)((c >> 2) * 12);
+                sts_u32(o, pack3(e[0], e[1], 0));
+                sts_u32(o + 4, pack3(e[1], e[2], 1));
+                sts_u32(o + 8, pack3(e[2], e[3], 2));
+            }
+        }
+    }
+    sts_u32(out_sa + 144, e[0]);  // cell 48 + pad byte
+}
+
+// layout slots are handed from the warp that built them to the lane that adopts them, both in the
+// same CTA (across launches the kernel boundary orders them): CTA-scope release / acquire on the tag
+__device__ __forceinline__ uint32_t ld_acquire_cta(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_cta(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.cta.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // Shared memory of one tile.  Warps are independent between the prologue and the epilogue: each
 // owns 32 environments (state + a staging area for their observation records) and the tile shares
@@ -102,6 +183,7 @@ struct TileSmem {
     uint32_t kind_lut[128];
     float lut[kGridCells + 1];
     uint32_t empty[kGridWords];
+    uint32_t prefix[kTaskWords];
     uint16_t queue[kQueueCap];   // ring of requests: local env | slot << 8; kNoEntry = not written yet
     uint32_t q_head, q_tail;
     int lock[NB];
@@ -114,6 +196,7 @@ __device__ __forceinline__ void tile_prologue(TileSmem<TILE, NB>& sm, const EnvP
     fill_kind_lut(sm.kind_lut, tid, TILE);
     for (int i = tid; i <= p.cfg.max_steps; i += TILE) sm.lut[i] = p.reward_lut[i];
     for (int i = tid; i < kGridWords; i += TILE) sm.empty[i] = p.empty[i];
+    for (int i = tid; i < kTaskWords; i += TILE) sm.prefix[i] = p.prefix[i];
 }
 
 // queue a layout request for every lane of `mask` (warp-aggregated; call converged)
@@ -165,13 +248,12 @@ __device__ __noinline__ bool serve_queue(TileSmem<TILE, NB>& sm, const EnvParams
         uint32_t* sc = reinterpret_cast<uint32_t*>(sm.obs[warp]) + lane * STATE_WORDS;
         sc[32] = 0u; sc[34] = 0u;
         GenIO io;
-        io.draws = sm.draws[b] + lane; io.stride = 32; io.tasks = p.tasks; io.empty = sm.empty;
+        io.draws = sm.draws[b] + lane; io.stride = 32; io.tasks = p.tasks; io.prefix = sm.prefix; io.empty = sm.empty;
         generate(*reinterpret_cast<EnvState*>(sc), p.cfg, p.seed, p.env_id_base + (uint64_t)(tile0 + e), episode, io);
 #pragma unroll
         for (int i = 0; i < STATE_WORDS; ++i)
             if (i != 33) __stcg(slot + i, sc[i]);
-        __threadfence();
-        __stcg(slot + 33, sc[33]);   // the tag: readers that see episode + 1 also see the layout
+        st_release_cta(slot + 33, sc[33]);   // the tag: readers that see episode + 1 also see the layout
     }
     __syncwarp();
     if (lane == 0) { __threadfence_block(); atomicExch(&sm.lock[b], 0); }
@@ -209,12 +291,17 @@ __global__ void __launch_bounds__(TILE, TILE == 128 ? 4 : 7) step_kernel(const E
     const int nvw = max(0, min(32, nv - warp * 32));
     volatile int* warp_t = sm.warp_t;
 
+    __builtin_assume(__isShared(stage));
+    __builtin_assume(__isShared(cur));
+    int action = active ? p.actions[tile0 + tid] : 0;
     for (int t = 0; t < p.T; ++t) {
         const size_t gi = (size_t)t * (size_t)p.n + (size_t)(tile0 + tid);
         bool done = false;
         int carry = 0;
+        const int a = action;
+        if (active && t + 1 < p.T) action = p.actions[gi + (size_t)p.n];   // next step's action, in flight during this one
         if (active) {
-            const StepOut o = env_step(s, p.actions[gi], S, p.cfg.max_steps, sm.lut);
+            const StepOut o = env_step(s, a, S, p.cfg.max_steps, sm.lut);
             p.reward[gi] = o.reward;
             p.term[gi] = o.terminated;
             p.trunc[gi] = o.truncated;
@@ -236,8 +323,7 @@ __global__ void __launch_bounds__(TILE, TILE == 128 ? 4 : 7) step_kernel(const E
             int spins = 0;
             for (;;) {
                 bool ready = false;
-                if (pending && ld_volatile(slot + 33) == E + 1u) {
-                    __threadfence();
+                if (pending && ld_acquire_cta(slot + 33) == E + 1u) {
                     uint32_t w[STATE_WORDS];
 #pragma unroll
                     for (int i = 0; i < STATE_WORDS; ++i) w[i] = __ldcg(slot + i);
@@ -255,13 +341,23 @@ __global__ void __launch_bounds__(TILE, TILE == 128 ? 4 : 7) step_kernel(const E
             }
         }
         if (active) {
-            if (p.image) encode_view<LAYOUT>(s, carry, S, SEE, sm.kind_lut, stage + lane * PITCH);
+            if (p.image) {
+                if (LAYOUT == OBS_HWC148 && SEE) {
+                    asm volatile("" ::: "memory");   // the state bytes written above are read through asm loads
+                    encode_packed_smem((uint32_t)__cvta_generic_to_shared(cur), s.agent_x, s.agent_y, s.agent_dir,
+                                       (uint32_t)carry, S, (uint32_t)__cvta_generic_to_shared(sm.kind_lut),
+                                       (uint32_t)__cvta_generic_to_shared(stage + lane * PITCH));
+                    asm volatile("" ::: "memory");
+                } else {
+                    encode_view<LAYOUT>(s, carry, S, SEE, sm.kind_lut, stage + lane * PITCH);
+                }
+            }
             if (p.dir) p.dir[gi] = s.agent_dir;
             if (p.mission) p.mission[gi] = s.mission_id;
         }
         __syncwarp();
         if (p.image && nvw > 0)
-            coop_copy<32>(p.image + ((size_t)t * (size_t)p.n + (size_t)(tile0 + warp * 32)) * PITCH, stage, nvw * PITCH, lane);
+            warp_copy_out<PITCH>(p.image + ((size_t)t * (size_t)p.n + (size_t)(tile0 + warp * 32)) * PITCH, stage, nvw, lane);
         __syncwarp();
         // the warp that is furthest ahead builds the next batch of layouts
         if (lane == 0) warp_t[warp] = t + 1;
@@ -297,6 +393,7 @@ struct ResetSmem {
     alignas(16) uint32_t draws[TILE / 32][kDrawBuf * 32];
     uint32_t kind_lut[128];
     uint32_t empty[kGridWords];
+    uint32_t prefix[kTaskWords];
 };
 
 template <int LAYOUT, bool SEE, bool PRIME, int TILE>
@@ -311,13 +408,14 @@ __global__ void __launch_bounds__(TILE) reset_kernel(const EnvParams p) {
     if (PRIME) coop_copy<TILE>(sm.state, p.states + tile0, nv * (int)sizeof(EnvState), tid);
     fill_kind_lut(sm.kind_lut, tid, TILE);
     for (int i = tid; i < kGridWords; i += TILE) sm.empty[i] = p.empty[i];
+    for (int i = tid; i < kTaskWords; i += TILE) sm.prefix[i] = p.prefix[i];
     if (tid == 0) p.qcount[blockIdx.x] = 0u;
     __syncthreads();
     const bool active = tid < nv;
     uint32_t* cur = sm.state + tid * STATE_WORDS;
     EnvState& s = *reinterpret_cast<EnvState*>(cur);
     GenIO io;
-    io.draws = sm.draws[warp] + lane; io.stride = 32; io.tasks = p.tasks; io.empty = sm.empty;
+    io.draws = sm.draws[warp] + lane; io.stride = 32; io.tasks = p.tasks; io.prefix = sm.prefix; io.empty = sm.empty;
     const uint64_t env_id = p.env_id_base + (uint64_t)(tile0 + tid);
     if (active) {
         if (!PRIME) {
@@ -484,7 +582,8 @@ struct mgrl_env {
     EnvState* slots;     // [kDepth][N]
     uint16_t* qsave;     // [tiles(64)][kQueueCap]
     uint32_t* qcount;    // [tiles(64)]
-    uint8_t* tasks;
+    uint32_t* tasks;
+    uint32_t* prefix;
     uint32_t* empty;
     float* lut;
     int* err_flags;
@@ -511,6 +610,7 @@ EnvParams make_params(const mgrl_env* e) {
     p.qsave = e->qsave;
     p.qcount = e->qcount;
     p.tasks = e->tasks;
+    p.prefix = e->prefix;
     p.empty = e->empty;
     p.reward_lut = e->lut;
     return p;
@@ -614,6 +714,8 @@ int mgrl_create(const mgrl_config* cfg, int device, mgrl_env** out) {
     if (cfg->num_envs <= 0) return fail(MGRL_ERR_INVALID, "mgrl_create: num_envs must be positive%s");
     if (cfg->num_objects < 0 || cfg->num_objects > 18)
         return fail(MGRL_ERR_INVALID, "mgrl_create: num_objects must be in 0..18%s");
+    if (cfg->num_obstacles < 0 || cfg->num_obstacles > 8)
+        return fail(MGRL_ERR_INVALID, "mgrl_create: num_obstacles must be in 0..8 (task rows hold 31 placements)%s");
     if (cfg->obs_layout != MGRL_OBS_HWC && cfg->obs_layout != MGRL_OBS_CHW && cfg->obs_layout != MGRL_OBS_HWC148)
         return fail(MGRL_ERR_INVALID, "mgrl_create: bad obs_layout%s");
     DeviceGuard guard(device);
@@ -645,9 +747,10 @@ int mgrl_create(const mgrl_config* cfg, int device, mgrl_env** out) {
         lut[k] = (float)r;
     }
     // generator inputs: task strings of this num_objects and the fresh grid of this size
-    static thread_local uint8_t tasks[kTaskEntries * kTaskBytes];
-    uint32_t empty[kGridWords];
-    build_task_table(cfg->num_objects, tasks);
+    static thread_local uint32_t tasks[kTaskEntries * kTaskWords];
+    uint32_t empty[kGridWords], prefix[kTaskWords];
+    build_task_table(e->ecfg, tasks);
+    build_task_prefix(e->ecfg, prefix);
     build_empty_grid(cfg->size, empty);
     const size_t n_tiles = ((size_t)cfg->num_envs + 63) / 64;
     cudaError_t err = cudaMalloc(&e->states, (size_t)cfg->num_envs * sizeof(EnvState));
@@ -659,6 +762,8 @@ int mgrl_create(const mgrl_config* cfg, int device, mgrl_env** out) {
     if (err == cudaSuccess) err = cudaMemset(e->qcount, 0, n_tiles * sizeof(uint32_t));
     if (err == cudaSuccess) err = cudaMalloc(&e->tasks, sizeof tasks);
     if (err == cudaSuccess) err = cudaMemcpy(e->tasks, tasks, sizeof tasks, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMalloc(&e->prefix, sizeof prefix);
+    if (err == cudaSuccess) err = cudaMemcpy(e->prefix, prefix, sizeof prefix, cudaMemcpyHostToDevice);
     if (err == cudaSuccess) err = cudaMalloc(&e->empty, sizeof empty);
     if (err == cudaSuccess) err = cudaMemcpy(e->empty, empty, sizeof empty, cudaMemcpyHostToDevice);
     if (err == cudaSuccess) err = cudaMalloc(&e->lut, sizeof lut);
@@ -676,7 +781,7 @@ int mgrl_create(const mgrl_config* cfg, int device, mgrl_env** out) {
 int mgrl_destroy(mgrl_env* e) {
     if (!e) return MGRL_OK;
     DeviceGuard guard(e->device);
-    void* bufs[] = {e->states, e->slots, e->qsave, e->qcount, e->tasks, e->empty, e->lut, e->err_flags, e->h_actions, e->h_image, e->h_dir, e->h_mission, e->h_term,
+    void* bufs[] = {e->states, e->slots, e->qsave, e->qcount, e->tasks, e->prefix, e->empty, e->lut, e->err_flags, e->h_actions, e->h_image, e->h_dir, e->h_mission, e->h_term,
                     e->h_trunc, e->h_eplen, e->h_termimg, e->h_termdir, e->h_reward, e->h_stack_img, e->h_stack_dir,
                     e->h_stack_mis, e->h_table};
     for (void* b : bufs)

@@ -59,9 +59,11 @@ for r in rows:
     if line == 0:
         continue
     a = agg.setdefault((cur_file, line), [r[1], 0.0, 0.0, 0.0])
-    a[1] += float(r[col["Instructions Executed"]] or 0)
-    a[2] += float(r[col["Thread Instructions Executed"]] or 0)
-    a[3] += float(r[col["# Samples"]] or 0)
+    try:
+        vals = [float(r[col[k]] or 0) for k in ("Instructions Executed", "Thread Instructions Executed", "# Samples")]
+    except (ValueError, IndexError):
+        continue   # a source line whose text broke the CSV quoting
+    a[1] += vals[0]; a[2] += vals[1]; a[3] += vals[2]
 tot = sum(a[1] for a in agg.values()) or 1
 tots = sum(a[3] for a in agg.values()) or 1
 print(f"\n== hottest source lines of {first} (total warp-instructions {tot:.0f}, samples {tots:.0f}) ==")
