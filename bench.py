@@ -5,7 +5,8 @@
 
 One bench "step" = one rollout pass over one batch: T=128 simulator steps of 65 536 GTO
 environments per GPU (BASELINE.json configs[1]), actions = synthetic uniform u8 resident in HBM,
-observations written to a [T,N,147] device rollout buffer (1.2 GB, larger than L2).
+observations written to a [T,N,148] device rollout buffer (1.2 GB, larger than L2).  The headline
+issues the rollout as one launch (mgrl_step_many); `per_step_launch` re-times it as T one-step launches.
 Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for how each field is defined.
 """
 from __future__ import annotations
@@ -189,7 +190,10 @@ def main():
     rew = torch.empty((T, n), dtype=torch.float32, device=dev)
     term = torch.empty((T, n), **u8); trunc = torch.empty((T, n), **u8); eplen = torch.empty((T, n), **u8)
 
-    def rollout():       # the per-step path a policy-in-the-loop rollout uses: one launch per env step
+    def rollout_many():  # the rollout as ONE launch: T steps per launch, state tile resident in shared memory
+        env.step_many(actions, image, dirs, mis, rew, term, trunc, eplen)
+
+    def rollout_steps():  # one launch per env step, the way a policy-in-the-loop rollout has to issue it
         for t in range(T):
             env.step(actions[t], image[t], dirs[t], mis[t], rew[t], term[t], trunc[t], eplen[t])
 
@@ -198,49 +202,47 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # de-synchronise episode phases (warm up >= 121 steps), then W warm-up bench steps
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        for _ in range(W):
-            rollout()
+    def timed(fn, k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
-        t_load0 = time.perf_counter()
         e0.record()
-        for _ in range(K):
-            rollout()
+        for _ in range(k):
+            fn()
         e1.record()
         barrier()
-        # the timed region is tens of milliseconds; keep the identical load running (untimed) until
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            tmax = torch.tensor([ms], device=dev)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            ms = float(tmax.item())
+        return ms
+
+    # W warm-up bench steps also de-synchronise the episode phases (>= 121 env steps)
+    with ClockSampler(local_rank) as clocks:
+        for _ in range(W):
+            rollout_many()
+        t_load0 = time.perf_counter()
+        ms = timed(rollout_many, K)
+        # the timed region is a few milliseconds; keep the identical load running (untimed) until
         # nvidia-smi (100 ms period) has sampled it a few times, so the clock record is meaningful
         while rank == 0 and clocks.proc and clocks.count_since(t_load0) < 8 and time.perf_counter() - t_load0 < 4.0:
-            rollout()
+            rollout_many()
             torch.cuda.synchronize()
         t_load1 = time.perf_counter()
         barrier()
     clock_summary = clocks.summary(t_load0, t_load1)
-    ms = e0.elapsed_time(e1)
-    if dist is not None:
-        tmax = torch.tensor([ms], device=dev)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms = float(tmax.item())
     total_env_steps = world * n * T * K
     value = total_env_steps / (ms / 1000.0)
-    launches = K * T
+    launches = K
     us_per_launch = 1000.0 * ms / launches
     peak, peak_src = load_peaks()
-    achieved = BYTES_PER_ENV_STEP * n / (us_per_launch * 1e-6) / 1e9
+    achieved = BYTES_PER_ENV_STEP * n * T / (us_per_launch * 1e-6) / 1e9
 
-    # multi-step kernel (state tile resident in shared memory for the whole rollout)
+    # the same rollout issued as T one-step launches (what a policy in the loop needs)
     for _ in range(2):
-        env.step_many(actions, image, dirs, mis, rew, term, trunc, eplen)
-    barrier()
-    e0.record()
-    for _ in range(K):
-        env.step_many(actions, image, dirs, mis, rew, term, trunc, eplen)
-    e1.record()
-    barrier()
-    ms_many = e0.elapsed_time(e1)
-    many_value = world * n * T * K / (ms_many / 1000.0)
+        rollout_steps()
+    ms_steps = timed(rollout_steps, K)
+    steps_value = world * n * T * K / (ms_steps / 1000.0)
     err = env.error_flags()
 
     # end to end: the host-buffer C-ABI call that B200VecEnv.step makes (pinned numpy in/out,
@@ -287,15 +289,19 @@ def main():
             "config": {"workload": f"{TASK} multi-room 11x11 (BASELINE configs[1]), {n} envs/GPU, rollout {T} steps, "
                                    "uniform random u8 actions resident in HBM",
                        "l2": "outputs stream into a 1.2 GB [T,N,148] rollout buffer (> 126 MB L2); the 9.2 MB state "
-                             "array is L2-resident by design and is not counted in the algorithmic bytes",
-                       "path": "mgrl_step x T (one launch per env step, as a policy-in-the-loop rollout issues it)"},
+                             "array and the 27.5 MB of prepared layouts are L2-resident by design and are not counted "
+                             "in the algorithmic bytes",
+                       "path": "mgrl_step_many: one launch = one rollout of T steps (actions known up front)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "env_kernel<HWC148,see_through,STEP>", "peak_source": peak_src,
-                         "bytes_per_env_step": BYTES_PER_ENV_STEP, "us_per_launch": us_per_launch},
-            "step_many": {"value": many_value, "unit": "env-steps/s", "ms_per_step": ms_many / K,
-                          "achieved_gbs": BYTES_PER_ENV_STEP * many_value / world / 1e9,
-                          "frac": BYTES_PER_ENV_STEP * many_value / world / 1e9 / peak,
-                          "note": "mgrl_step_many: T steps per launch, state tile resident in shared memory"},
+                         "traffic": None, "kernel": "step_kernel<HWC148,see_through,128,2>", "peak_source": peak_src,
+                         "bytes_per_env_step": BYTES_PER_ENV_STEP, "us_per_launch": us_per_launch,
+                         "env_steps_per_launch": n * T},
+            "per_step_launch": {"value": steps_value, "unit": "env-steps/s", "ms_per_step": ms_steps / K,
+                                "us_per_launch": 1000.0 * ms_steps / (K * T),
+                                "achieved_gbs": BYTES_PER_ENV_STEP * steps_value / world / 1e9,
+                                "frac": BYTES_PER_ENV_STEP * steps_value / world / 1e9 / peak,
+                                "note": "mgrl_step x T: the same kernel with one step per launch, as a rollout with a "
+                                        "policy in the loop issues it (latency-bound at this batch size)"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clock_summary,
             "env_error_flags": err,
         }

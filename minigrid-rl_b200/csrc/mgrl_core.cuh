@@ -145,18 +145,24 @@ struct StepOut {
 // [UPSTREAM] MiniGridEnv.step, then PlaygroundEnv.step's mission bookkeeping.
 // reward_lut[k] = float32(1 - 0.9*k/max_steps) computed in float64 on the host.
 MGRL_HD StepOut env_step(EnvState& s, int action, int S, int max_steps, const float* reward_lut) {
-    StepOut o;
-    float r = 0.0f;
-    bool term = false;
-    const int dir = s.agent_dir;
+    // the scalar fields travel as three words: 30 = grid[120], agent x, y, dir; 31 = carrying, step_count,
+    // target x, y; 32 = target_action, mission_id, mission_done, latch_step
+    uint32_t* w = reinterpret_cast<uint32_t*>(&s);
+    const uint32_t w30 = w[30], w31 = w[31], w32 = w[32];
+    const int dir = (int)(w30 >> 24);
+    int ax = (int)((w30 >> 8) & 0xFFu), ay = (int)((w30 >> 16) & 0xFFu);
+    int carrying = (int)(w31 & 0xFFu);
+    const int step = (int)((w31 >> 8) & 0xFFu) + 1;
+    const int tx = (int)((w31 >> 16) & 0xFFu), ty = (int)(w31 >> 24);
+    const int ta = (int)(w32 & 0xFFu), mission_id = (int)((w32 >> 8) & 0xFFu);
+    int mdone = (int)((w32 >> 16) & 0xFFu), latch = (int)(w32 >> 24);
     const int dx = (dir == 0) - (dir == 2), dy = (dir == 1) - (dir == 3);
-    int ax = s.agent_x, ay = s.agent_y;
-    const int step = s.step_count + 1;
-    s.step_count = (uint8_t)step;
     const int fidx = (ay + dy) * S + ax + dx;
     const int k = s.grid[fidx];
-    int carrying = s.carrying;
+    int nk = k;                // front cell after the action
     int ndir = dir;
+    bool term = false;
+    float r = 0.0f;
 
     if (action == A_LEFT) ndir = (dir + 3) & 3;
     else if (action == A_RIGHT) ndir = (dir + 1) & 3;
@@ -165,55 +171,47 @@ MGRL_HD StepOut env_step(EnvState& s, int action, int S, int max_steps, const fl
         if (k == K_GOAL) { term = true; r = reward_lut[step]; }
         if (k == K_LAVA) term = true;
     } else if (action == A_PICKUP) {
-        if (k_pickable(k) && carrying == 0) { carrying = k; s.grid[fidx] = K_EMPTY; }
+        if (k_pickable(k) && carrying == 0) { carrying = k; nk = K_EMPTY; }
     } else if (action == A_DROP) {
-        if (k == K_EMPTY && carrying != 0) { s.grid[fidx] = (uint8_t)carrying; carrying = 0; }
+        if (k == K_EMPTY && carrying != 0) { nk = carrying; carrying = 0; }
     } else if (action == A_TOGGLE) {
+        const int st = (k - K_DOOR) >> 3, c = k & 7;
         if (k_is_door(k)) {
-            const int st = (k - K_DOOR) >> 3, c = k & 7;
-            if (st == 2) {  // locked: opens only for a Key of its colour
-                if (k_is_key(carrying) && (carrying & 7) == c) s.grid[fidx] = (uint8_t)(K_DOOR + c);
-            } else {
-                s.grid[fidx] = (uint8_t)(K_DOOR + 8 * (st ^ 1) + c);
-            }
+            if (st != 2) nk = K_DOOR + 8 * (st ^ 1) + c;
+            else if (k_is_key(carrying) && (carrying & 7) == c) nk = K_DOOR + c;   // locked: needs a Key of its colour
         } else if (k_is_box(k)) {  // the box is replaced by its contents
             const int m = (k - K_BOX) >> 3;
-            s.grid[fidx] = (uint8_t)(m ? K_KEY + m - 1 : K_EMPTY);
+            nk = m ? K_KEY + m - 1 : K_EMPTY;
         }
     } else if (action != A_DONE) {
         s.error |= ERR_BAD_ACTION;  // upstream raises ValueError
     }
-    s.agent_x = (uint8_t)ax; s.agent_y = (uint8_t)ay; s.agent_dir = (uint8_t)ndir;
+    if (nk != k) s.grid[fidx] = (uint8_t)nk;
+    StepOut o;
     o.truncated = step >= max_steps;
     o.carry_obs = (uint8_t)carrying;  // the observation is rendered here (custom_env.py:270)
 
     if (term) {  // custom_env.py:272-277
-        if (s.mission_id != MISSION_GOAL) { s.mission_done = 0; s.latch_step = 0; r = 0.0f; }
+        if (mission_id != MISSION_GOAL) { mdone = 0; latch = 0; r = 0.0f; }
     } else {
-        const int ndx = (ndir == 0) - (ndir == 2), ndy = (ndir == 1) - (ndir == 3);
-        const int fx = ax + ndx, fy = ay + ndy;
-        if (action == A_TOGGLE) {  // :279-283 colour match only
-            const int f = s.grid[fy * S + fx];
-            if (k_is_door(f) && carrying != 0 && (f & 7) == (carrying & 7)) carrying = 0;
-        }
-        if (!s.mission_done) {  // :288-317
-            const int ta = s.target_action;
-            bool latch = false;
-            if (s.target_x != kNone) {
-                if (ta) latch = (fx == s.target_x && fy == s.target_y && action == ta);
-                else latch = (ax == s.target_x && ay == s.target_y);
-            } else {
-                latch = (ta != 0 && action == ta);
-            }
-            if (latch) { s.mission_done = 1; s.latch_step = (uint8_t)step; }
+        const int fx = ax + (ndir == 0) - (ndir == 2), fy = ay + (ndir == 1) - (ndir == 3);
+        // :279-283 colour match only; a toggle neither turns nor moves, so the front cell is the one just rewritten
+        if (action == A_TOGGLE && k_is_door(nk) && carrying != 0 && (nk & 7) == (carrying & 7)) carrying = 0;
+        if (!mdone) {  // :288-317
+            bool hit;
+            if (tx != kNone) hit = ta ? (fx == tx && fy == ty && action == ta) : (ax == tx && ay == ty);
+            else hit = ta != 0 && action == ta;
+            if (hit) { mdone = 1; latch = step; }
         }
         if (action == A_DONE) {  // :319-328
-            r = s.mission_done ? reward_lut[s.latch_step] : 0.0f;
-            s.mission_done = 0; s.latch_step = 0;
+            r = mdone ? reward_lut[latch] : 0.0f;
+            mdone = 0; latch = 0;
             term = true;
         }
     }
-    s.carrying = (uint8_t)carrying;
+    w[30] = (w30 & 0xFFu) | ((uint32_t)ax << 8) | ((uint32_t)ay << 16) | ((uint32_t)ndir << 24);
+    w[31] = (uint32_t)carrying | ((uint32_t)step << 8) | (w31 & 0xFFFF0000u);
+    w[32] = (w32 & 0xFFFFu) | ((uint32_t)mdone << 16) | ((uint32_t)latch << 24);
     o.reward = r;
     o.terminated = term;
     return o;

@@ -161,17 +161,6 @@ __device__ __forceinline__ void encode_packed_smem(uint32_t state_sa, int agent_
     sts_u32(out_sa + 144, e[0]);  // cell 48 + pad byte
 }
 
-// layout slots are handed from the warp that built them to the lane that adopts them, both in the
-// same CTA (across launches the kernel boundary orders them): CTA-scope release / acquire on the tag
-__device__ __forceinline__ uint32_t ld_acquire_cta(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.cta.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_cta(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.cta.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 // Shared memory of one tile.  Warps are independent between the prologue and the epilogue: each
 // owns 32 environments (state + a staging area for their observation records) and the tile shares
 // a queue of layout requests and NB draw buffers for the warps that serve it.
@@ -188,6 +177,7 @@ struct TileSmem {
     uint32_t q_head, q_tail;
     int lock[NB];
     int warp_t[TILE / 32];       // steps finished by each warp
+    uint8_t ready[kDepth][TILE]; // low byte of each slot's tag (episode + 1 of the layout it holds)
 };
 static_assert(32 * kObsPitch148 >= 32 * STATE_WORDS * 4, "layout scratch must fit the staging area");
 
@@ -251,9 +241,11 @@ __device__ __noinline__ bool serve_queue(TileSmem<TILE, NB>& sm, const EnvParams
         io.draws = sm.draws[b] + lane; io.stride = 32; io.tasks = p.tasks; io.prefix = sm.prefix; io.empty = sm.empty;
         generate(*reinterpret_cast<EnvState*>(sc), p.cfg, p.seed, p.env_id_base + (uint64_t)(tile0 + e), episode, io);
 #pragma unroll
-        for (int i = 0; i < STATE_WORDS; ++i)
-            if (i != 33) __stcg(slot + i, sc[i]);
-        st_release_cta(slot + 33, sc[33]);   // the tag: readers that see episode + 1 also see the layout
+        for (int i = 0; i < STATE_WORDS; ++i) __stcg(slot + i, sc[i]);
+        // hand-off inside the CTA: layout (global) -> fence -> tag byte (shared); the adopting lane
+        // reads the tag byte, fences, then reads the layout
+        __threadfence_block();
+        *reinterpret_cast<volatile uint8_t*>(&sm.ready[j][e]) = (uint8_t)sc[33];
     }
     __syncwarp();
     if (lane == 0) { __threadfence_block(); atomicExch(&sm.lock[b], 0); }
@@ -281,6 +273,9 @@ __global__ void __launch_bounds__(TILE, TILE == 128 ? 4 : 7) step_kernel(const E
         if (tid == 0) { sm.q_head = 0u; sm.q_tail = nq; }
         if (tid < NB) sm.lock[tid] = 0;
         if (tid < NW) sm.warp_t[tid] = 0;
+#pragma unroll
+        for (int j = 0; j < kDepth; ++j)
+            sm.ready[j][tid] = tid < nv ? (uint8_t)reinterpret_cast<const uint32_t*>(p.slots + (size_t)j * p.n + tile0 + tid)[33] : (uint8_t)0;
     }
     __syncthreads();
 
@@ -320,10 +315,12 @@ __global__ void __launch_bounds__(TILE, TILE == 128 ? 4 : 7) step_kernel(const E
             const int j = (int)(E % kDepth);
             const uint32_t* slot = reinterpret_cast<const uint32_t*>(p.slots + (size_t)j * p.n + tile0 + tid);
             const uint32_t entry = (uint32_t)tid | ((uint32_t)j << 8);
+            const volatile uint8_t* tag = &sm.ready[j][tid];
             int spins = 0;
             for (;;) {
                 bool ready = false;
-                if (pending && ld_acquire_cta(slot + 33) == E + 1u) {
+                if (pending && *tag == (uint8_t)(E + 1u)) {
+                    __threadfence_block();
                     uint32_t w[STATE_WORDS];
 #pragma unroll
                     for (int i = 0; i < STATE_WORDS; ++i) w[i] = __ldcg(slot + i);
