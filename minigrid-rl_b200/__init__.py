@@ -14,3 +14,7 @@ __all__ = [
     "EnvConfig", "MISSIONS", "mission_id", "mission_string", "token_table", "tokenize",
     "NativeError", "lib", "build_library", "library_path", "B200VecEnv", "DeviceEnv",
 ]
+from .policy import Policy  # noqa: E402
+from .ppo import PPOConfig, RolloutEngine, Updater  # noqa: E402
+
+__all__ += ["Policy", "PPOConfig", "RolloutEngine", "Updater"]

@@ -1,0 +1,229 @@
+"""Policy of the reference (CustomPPOPolicy over CustomExtractor) held as plain torch tensors.
+
+Mirrors /root/reference/src/policies.py:21-120 (extractor built from hydra_configs/single.yaml:38-57 with
+n_frames_stack = 4), policies.py:227-257 (CustomPPOPolicy, init_weights) and the parts of SB3's
+ActorCriticPolicy it inherits (MlpExtractor pi/vf 208->64->64 Tanh, action_net, value_net, Categorical).
+Parameter names are SB3's state_dict names so checkpoints can travel both ways.
+
+Two consumers share the same parameter tensors:
+  * the rollout: `pack()` lays the weights out for the hand-written CUDA forward kernel
+    (csrc/mgrl_policy.cu, `mgrl_policy_forward`), including the mission look-up table;
+  * the PPO update: `evaluate()` is the differentiable torch expression of the same network (autograd).
+The GRU over the stacked mission tokens is evaluated on the 74 x 4 distinct (mission, frames-in-stack)
+sequences only (the mission is constant within an episode), never per observation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _native as nat
+from .missions import N_MISSIONS, token_table
+
+N_ACTIONS = 7
+N_WEIGHTS = 84940
+# float offsets of the packed buffer, identical to csrc/mgrl_policy.cu
+_L = {}
+_off = 0
+for _name, _size in [("W1", 48 * 16), ("B1", 16), ("W2", 64 * 32), ("B2", 32), ("W3", 128 * 64), ("B3", 64),
+                     ("WD", 16 * 16), ("BD", 16), ("PI1", 208 * 64), ("PI1B", 64), ("PI2", 64 * 64), ("PI2B", 64),
+                     ("VF1", 208 * 64), ("VF1B", 64), ("VF2", 64 * 64), ("VF2B", 64), ("WA", 64 * 8), ("BA", 8),
+                     ("WV", 64), ("BV", 4), ("LUT", N_MISSIONS * 4 * 128)]:
+    _L[_name] = (_off, _size)
+    _off += _size
+assert _off == N_WEIGHTS
+WEIGHT_LAYOUT = dict(_L)
+
+_PREFIX = "features_extractor.extractors."
+SHAPES = {
+    _PREFIX + "direction.direction_Linear_0.weight": (16, 16),
+    _PREFIX + "direction.direction_Linear_0.bias": (16,),
+    _PREFIX + "image.image_Conv2d_0.weight": (16, 12, 2, 2),
+    _PREFIX + "image.image_Conv2d_0.bias": (16,),
+    _PREFIX + "image.image_Conv2d_3.weight": (32, 16, 2, 2),
+    _PREFIX + "image.image_Conv2d_3.bias": (32,),
+    _PREFIX + "image.image_Conv2d_5.weight": (64, 32, 2, 2),
+    _PREFIX + "image.image_Conv2d_5.bias": (64,),
+    _PREFIX + "mission.mission_Embedding_0.weight": (32, 32),
+    _PREFIX + "mission.mission_GRU_1.weight_ih_l0": (384, 32),
+    _PREFIX + "mission.mission_GRU_1.weight_hh_l0": (384, 128),
+    _PREFIX + "mission.mission_GRU_1.bias_ih_l0": (384,),
+    _PREFIX + "mission.mission_GRU_1.bias_hh_l0": (384,),
+    "mlp_extractor.policy_net.0.weight": (64, 208), "mlp_extractor.policy_net.0.bias": (64,),
+    "mlp_extractor.policy_net.2.weight": (64, 64), "mlp_extractor.policy_net.2.bias": (64,),
+    "mlp_extractor.value_net.0.weight": (64, 208), "mlp_extractor.value_net.0.bias": (64,),
+    "mlp_extractor.value_net.2.weight": (64, 64), "mlp_extractor.value_net.2.bias": (64,),
+    "action_net.weight": (7, 64), "action_net.bias": (7,),
+    "value_net.weight": (1, 64), "value_net.bias": (1,),
+}
+N_PARAMS = sum(int(np.prod(s)) for s in SHAPES.values())      # 110 216
+
+
+class Policy:
+    """Parameters + the two evaluation paths.  Works on any torch device for `evaluate` (the update's autograd
+    path and the CPU tests of the data-parallel logic); `pack` / `forward_rollout` need CUDA."""
+
+    def __init__(self, device="cuda", seed: int = 0, fp32_strict: bool = True):
+        import torch
+        self.torch = torch
+        self.fp32_strict = fp32_strict      # False = allow TF32 in the library kernels of the update, like ppo.py:29-32
+        self.device = torch.device(device)
+        g = torch.Generator().manual_seed(seed)
+        self.params = {}
+        for name, shape in SHAPES.items():
+            self.params[name] = self._init(name, shape, g).to(self.device).requires_grad_(True)
+        # the GRU runs through torch.nn.GRU (cuDNN on the device) on the 296 distinct sequences; the module's
+        # parameters ARE the canonical tensors
+        self._gru = torch.nn.GRU(32, 128, 1, True, True).to(self.device)
+        for n in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"):
+            key = _PREFIX + "mission.mission_GRU_1." + n
+            with torch.no_grad():
+                getattr(self._gru, n).copy_(self.params[key])
+            self.params[key] = getattr(self._gru, n)
+        # stacked mission token sequences: row m*4 + age = [zeros * (3-age) frames | tokens(m) * (age+1) frames]
+        tt = torch.from_numpy(token_table())
+        seq = torch.zeros((N_MISSIONS * 4, 128), dtype=torch.int64)
+        for age in range(4):
+            for f in range(3 - age, 4):
+                seq[age::4, f * 32:(f + 1) * 32] = tt
+        self.sequences = seq.to(self.device)
+        self._packed = None
+
+    # ---------------------------------------------------------------- init (policies.py:246-257 + torch defaults)
+    def _init(self, name, shape, g):
+        torch = self.torch
+        if name.endswith("bias") and "GRU" not in name:
+            return torch.zeros(shape)
+        if "Conv2d" in name:
+            w = torch.empty(shape)
+            torch.nn.init.orthogonal_(w, gain=math.sqrt(2), generator=g)
+            return w
+        if "Embedding" in name:
+            return torch.randn(shape, generator=g)
+        if "GRU" in name:
+            k = 1.0 / math.sqrt(128)
+            return (torch.rand(shape, generator=g) * 2 - 1) * k
+        w = torch.randn(shape, generator=g)                       # every Linear: unit-norm rows, gain ignored
+        return w / torch.sqrt(w.pow(2).sum(1, keepdim=True))
+
+    def parameters(self):
+        return list(self.params.values())
+
+    def state_dict(self):
+        return {k: v.detach().clone() for k, v in self.params.items()}
+
+    def load_state_dict(self, sd):
+        torch = self.torch
+        with torch.no_grad():
+            for k, v in self.params.items():
+                v.copy_(torch.as_tensor(sd[k]).to(v.device, v.dtype).reshape(v.shape))
+        self._packed = None
+
+    def load_oracle(self, oracle_policy):
+        """copy the weights of an oracle.policy_oracle.OraclePolicy (tests)"""
+        o = oracle_policy
+        m = {
+            _PREFIX + "direction.direction_Linear_0": o.direction[0], _PREFIX + "image.image_Conv2d_0": o.image[0],
+            _PREFIX + "image.image_Conv2d_3": o.image[3], _PREFIX + "image.image_Conv2d_5": o.image[5],
+            "mlp_extractor.policy_net.0": o.pi[0], "mlp_extractor.policy_net.2": o.pi[2],
+            "mlp_extractor.value_net.0": o.vf[0], "mlp_extractor.value_net.2": o.vf[2],
+            "action_net": o.action_net, "value_net": o.value_net,
+        }
+        sd = {}
+        for k, mod in m.items():
+            sd[k + ".weight"], sd[k + ".bias"] = mod.weight.detach(), mod.bias.detach()
+        sd[_PREFIX + "mission.mission_Embedding_0.weight"] = o.embedding.weight.detach()
+        for n in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"):
+            sd[_PREFIX + "mission.mission_GRU_1." + n] = getattr(o.gru, n).detach()
+        self.load_state_dict(sd)
+
+    # ---------------------------------------------------------------- mission look-up table
+    def mission_lut(self):
+        """[74*4, 128]: GRU(Embedding(tokens)) final hidden state of every distinct stacked mission (differentiable)."""
+        torch = self.torch
+        P = self.params
+        x = torch.nn.functional.embedding(self.sequences, P[_PREFIX + "mission.mission_Embedding_0.weight"])
+        if x.is_cuda:
+            self._gru.flatten_parameters()
+        # cuDNN would run the GRU in TF32 by default; the table feeds the fp32 rollout kernel (parity bar 1e-5)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=not self.fp32_strict):
+            _, h = self._gru(x)
+        return h[-1]
+
+    # ---------------------------------------------------------------- differentiable evaluation (PPO update)
+    def evaluate(self, image_u8, dir_onehot, mission_row, lut=None):
+        """image_u8 [B,12,7,7] (channels = frame*3 + c, H = view x, W = view y), dir_onehot [B,16], mission_row [B]
+        (= mission*4 + age) -> logits [B,7], values [B]."""
+        F = self.torch.nn.functional
+        P = self.params
+        lut = self.mission_lut() if lut is None else lut
+        with self.torch.backends.cudnn.flags(enabled=True, allow_tf32=not self.fp32_strict):
+            return self._evaluate(image_u8, dir_onehot, mission_row, lut, F, P)
+
+    def _evaluate(self, image_u8, dir_onehot, mission_row, lut, F, P):
+        x = image_u8.float() / 255.0
+        x = F.max_pool2d(F.relu(F.conv2d(x, P[_PREFIX + "image.image_Conv2d_0.weight"], P[_PREFIX + "image.image_Conv2d_0.bias"])), 2)
+        x = F.relu(F.conv2d(x, P[_PREFIX + "image.image_Conv2d_3.weight"], P[_PREFIX + "image.image_Conv2d_3.bias"]))
+        x = F.relu(F.conv2d(x, P[_PREFIX + "image.image_Conv2d_5.weight"], P[_PREFIX + "image.image_Conv2d_5.bias"])).flatten(1)
+        d = F.linear(dir_onehot.float(), P[_PREFIX + "direction.direction_Linear_0.weight"],
+                     P[_PREFIX + "direction.direction_Linear_0.bias"])
+        f = self.torch.cat([d, x, lut[mission_row.long()]], dim=1)
+        t = self.torch.tanh
+        hp = t(F.linear(t(F.linear(f, P["mlp_extractor.policy_net.0.weight"], P["mlp_extractor.policy_net.0.bias"])),
+                        P["mlp_extractor.policy_net.2.weight"], P["mlp_extractor.policy_net.2.bias"]))
+        hv = t(F.linear(t(F.linear(f, P["mlp_extractor.value_net.0.weight"], P["mlp_extractor.value_net.0.bias"])),
+                        P["mlp_extractor.value_net.2.weight"], P["mlp_extractor.value_net.2.bias"]))
+        return (F.linear(hp, P["action_net.weight"], P["action_net.bias"]),
+                F.linear(hv, P["value_net.weight"], P["value_net.bias"]).squeeze(-1))
+
+    # ---------------------------------------------------------------- packed weights for the CUDA forward kernel
+    def pack(self):
+        torch = self.torch
+        P = {k: v.detach() for k, v in self.params.items()}
+        out = torch.zeros(N_WEIGHTS, dtype=torch.float32, device=self.device)
+
+        def put(name, t):
+            o, n = WEIGHT_LAYOUT[name]
+            t = t.reshape(-1)
+            out[o:o + t.numel()] = t
+
+        # conv weights [co][ci][ky][kx] -> [(ci, ky, kx)][co] ; conv2/3 inputs are ordered (ky, kx, ci)
+        put("W1", P[_PREFIX + "image.image_Conv2d_0.weight"].permute(1, 2, 3, 0))
+        put("B1", P[_PREFIX + "image.image_Conv2d_0.bias"])
+        put("W2", P[_PREFIX + "image.image_Conv2d_3.weight"].permute(2, 3, 1, 0))
+        put("B2", P[_PREFIX + "image.image_Conv2d_3.bias"])
+        put("W3", P[_PREFIX + "image.image_Conv2d_5.weight"].permute(2, 3, 1, 0))
+        put("B3", P[_PREFIX + "image.image_Conv2d_5.bias"])
+        put("WD", P[_PREFIX + "direction.direction_Linear_0.weight"].t())
+        put("BD", P[_PREFIX + "direction.direction_Linear_0.bias"])
+        for tag, net in (("PI", "policy_net"), ("VF", "value_net")):
+            put(tag + "1", P[f"mlp_extractor.{net}.0.weight"].t()); put(tag + "1B", P[f"mlp_extractor.{net}.0.bias"])
+            put(tag + "2", P[f"mlp_extractor.{net}.2.weight"].t()); put(tag + "2B", P[f"mlp_extractor.{net}.2.bias"])
+        wa = torch.zeros((64, 8), device=self.device); wa[:, :7] = P["action_net.weight"].t()
+        ba = torch.zeros(8, device=self.device); ba[:7] = P["action_net.bias"]
+        put("WA", wa); put("BA", ba)
+        put("WV", P["value_net.weight"]); put("BV", P["value_net.bias"])
+        with torch.no_grad():
+            put("LUT", self.mission_lut())
+        self._packed = out.contiguous()
+        return self._packed
+
+    def packed(self):
+        return self._packed if self._packed is not None else self.pack()
+
+    def invalidate(self):
+        self._packed = None
+
+    def forward_rollout(self, frames, dirs, mission, time_index, prev_age, prev_done, age_out, value, action=None,
+                        logp=None, logits=None, start_out=None, seed=0, env_id_base=0, step=0):
+        """launch mgrl_policy_forward on the current stream (frames [B,N,148] u8, dirs [B,N] u8, mission [N] u8)"""
+        torch = self.torch
+        n = int(mission.shape[0])
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
+        s = C.c_void_p(torch.cuda.current_stream(frames.device).cuda_stream)
+        nat.check(nat.lib().mgrl_policy_forward(
+            p(self.packed()), p(frames), p(dirs), p(mission), p(prev_age), p(prev_done), p(age_out), p(start_out),
+            p(action), p(logp), p(value), p(logits), n, int(time_index), int(seed), int(env_id_base), int(step), s),
+            "mgrl_policy_forward")

