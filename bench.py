@@ -157,6 +157,8 @@ def main():
     ap.add_argument("--envs", type=int, default=N_ENVS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ppo", action="store_true")
+    ap.add_argument("--ppo-iters", type=int, default=2)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -245,34 +247,90 @@ def main():
     steps_value = world * n * T * K / (ms_steps / 1000.0)
     err = env.error_flags()
 
-    # end to end: the host-buffer C-ABI call that B200VecEnv.step makes (pinned numpy in/out,
-    # stacked SB3 observation dict), H2D + D2H inside the timed region
+    # end to end through the C ABI with HOST buffers, H2D + D2H inside the timed region.
+    #  e2e          mgrl_vec_step_frames_host: pinned actions in, un-stacked observation + reward + flags out -- the
+    #               output set of the CPU arm (mg_vec_step), so the two arms are like for like;
+    #  e2e.stacked  mgrl_vec_step_host: the full SB3 drop-in (frame stack x4, one-hot direction, int64 mission
+    #               tokens: 1761 B per env-step over PCIe)
     e2e = None
     if not args.no_e2e:
         import numpy as np
+        acts_h = np.random.RandomState(rank).randint(0, 7, size=(16, n)).astype(np.uint8)
+        e2e_steps = 64
+
+        def time_host(step_fn):
+            for i in range(4):
+                step_fn(acts_h[i % 16])
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(e2e_steps):
+                step_fn(acts_h[i % 16])
+            torch.cuda.synchronize()
+            el = time.perf_counter() - t0
+            if dist is not None:
+                tm = torch.tensor([el], device=dev)
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                el = float(tm.item())
+            return world * n * e2e_steps / el
+
+        venv = mg.B200VecEnv(cfg, num_envs=n, seed=SEED, device=local_rank, env_id_base=rank * n, layout="hwc148")
+        venv.reset_frames()
+        v_frames = time_host(venv.step_frames)
+        venv.close()
         venv = mg.B200VecEnv(cfg, num_envs=n, seed=SEED, device=local_rank, env_id_base=rank * n)
         venv.reset()
-        acts_h = np.random.RandomState(rank).randint(0, 7, size=(16, n)).astype(np.uint8)
-        e2e_steps = 32
-        for i in range(4):
-            venv.step_arrays(acts_h[i % 16])
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            venv.step_arrays(acts_h[i % 16])
-        torch.cuda.synchronize()
-        el = time.perf_counter() - t0
-        if dist is not None:
-            tm = torch.tensor([el], device=dev)
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            el = float(tm.item())
-        h2d = n * 1
-        d2h = n * (4 * 147 + 16 + 128 * 8 + 4 + 1 + 1 + 1 + 147 + 1)
-        e2e = {"value": world * n * e2e_steps / el, "unit": "env-steps/s",
-               "h2d_bytes_per_step": h2d * T, "d2h_bytes_per_step": d2h * T,
-               "api": "B200VecEnv.step_arrays -> mgrl_vec_step_host (pinned numpy in/out, stacked obs dict)",
-               "sample": f"{e2e_steps} vector steps of {n} envs per rank"}
+        v_stacked = time_host(venv.step_arrays)
         venv.close()
+        e2e = {"value": v_frames, "unit": "env-steps/s",
+               "h2d_bytes_per_step": n * 1 * T, "d2h_bytes_per_step": n * (148 + 1 + 1 + 4 + 1 + 1 + 1) * T,
+               "api": "B200VecEnv.step_frames -> mgrl_vec_step_frames_host (pinned numpy in/out, un-stacked observation: "
+                      "the outputs of the CPU arm's vector step)",
+               "sample": f"{e2e_steps} vector steps of {n} envs per rank",
+               "stacked": {"value": v_stacked, "unit": "env-steps/s",
+                           "d2h_bytes_per_step": n * (4 * 147 + 16 + 128 * 8 + 4 + 1 + 1 + 1 + 147 + 1) * T,
+                           "api": "B200VecEnv.step_arrays -> mgrl_vec_step_host (SB3 observation dict: 4-frame stack, "
+                                  "one-hot direction, int64 mission tokens)"}}
+
+    # PPO frames/sec (SB3 `time/fps`: env frames per wall second over rollout + update), BASELINE.json's second figure:
+    # policy-in-the-loop rollout (2 launches per step) + GAE + n_epochs of minibatch updates, gradients all-reduced
+    ppo_line = None
+    if not args.no_ppo:
+        env.close()
+        del image, dirs, mis, rew, term, trunc, eplen, actions
+        torch.cuda.empty_cache()
+        penv = mg.DeviceEnv(cfg, num_envs=n, seed=SEED, env_id_base=rank * n, layout="hwc148")
+        pcfg = mg.PPOConfig(n_steps=T, batch_size=n * T // 32, n_epochs=4)
+        eng = mg.RolloutEngine(penv, mg.Policy(dev, seed=SEED), pcfg, dist=dist if world > 1 else None, seed=SEED)
+        eng.iteration(1.0)                                   # warm-up: cuDNN autotune, allocator, layouts in L2
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        t_roll = t_upd = 0.0
+        barrier()
+        for it in range(args.ppo_iters):
+            ev[0].record()
+            eng.collect(); eng.bootstrap_truncated(); eng.compute_advantages()
+            ev[1].record()
+            eng.updater.set_progress(1.0 - it / max(args.ppo_iters, 1))
+            n_mb = eng.update()
+            eng.shift()
+            ev[2].record()
+            torch.cuda.synchronize()
+            t_roll += ev[0].elapsed_time(ev[1]); t_upd += ev[1].elapsed_time(ev[2])
+        barrier()
+        tt = torch.tensor([t_roll, t_upd], device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_roll, t_upd = float(tt[0]), float(tt[1])
+        frames = world * n * T * args.ppo_iters
+        ppo_line = {"value": frames / ((t_roll + t_upd) / 1000.0), "unit": "frames/s",
+                    "rollout_env_steps_per_s": frames / (t_roll / 1000.0), "rollout_ms": t_roll / args.ppo_iters,
+                    "update_ms": t_upd / args.ppo_iters, "iterations": args.ppo_iters,
+                    "config": {"n_steps": T, "n_envs_per_gpu": n, "batch_size_per_gpu": pcfg.batch_size, "n_epochs": 4,
+                               "minibatches_per_iteration": n_mb, "policy": "CustomPPOPolicy 110216 params, fp32",
+                               "rollout": "mgrl_policy_forward + mgrl_step per step (hand-written kernels)",
+                               "update": "torch autograd on library kernels (cuDNN/cuBLAS, TF32 off)",
+                               "all_reduces_per_optimizer_step": 2 if world > 1 else 0},
+                    "env_error_flags": penv.error_flags()}
+        env = penv
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -302,6 +360,7 @@ def main():
                                 "frac": BYTES_PER_ENV_STEP * steps_value / world / 1e9 / peak,
                                 "note": "mgrl_step x T: the same kernel with one step per launch, as a rollout with a "
                                         "policy in the loop issues it (latency-bound at this batch size)"},
+            "ppo": ppo_line,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clock_summary,
             "env_error_flags": err,
         }

@@ -192,6 +192,16 @@ int mgrl_vec_step_host(mgrl_env *env, const uint8_t *actions_host, uint8_t *imag
                        uint8_t *direction_host, int64_t *mission_host, float *reward_host,
                        uint8_t *term_host, uint8_t *trunc_host, uint8_t *ep_len_host,
                        uint8_t *term_image_host, uint8_t *term_dir_host, void *stream);
+/* The same two calls without the SB3 wrapper stack: the un-stacked observation (what PlaygroundEnv.step +
+ * Discrete2BoxWrapper's input look like before VecTransposeImage / VecFrameStack / TokenizeVocabWrapper) goes to
+ * host buffers: image_host [N,pitch] in the handle's obs_layout, dir_host [N], mission_host [N] (mission ids),
+ * reward / term / trunc / ep_len [N], term_image_host [N,pitch] + term_dir_host [N] (rows of finished envs; may be
+ * NULL).  This is the output set of the CPU oracle's mg_vec_step, i.e. the like-for-like end-to-end path. */
+int mgrl_vec_reset_frames_host(mgrl_env *env, uint64_t seed, uint8_t *image_host, uint8_t *dir_host,
+                               uint8_t *mission_host, void *stream);
+int mgrl_vec_step_frames_host(mgrl_env *env, const uint8_t *actions_host, uint8_t *image_host, uint8_t *dir_host,
+                              uint8_t *mission_host, float *reward_host, uint8_t *term_host, uint8_t *trunc_host,
+                              uint8_t *ep_len_host, uint8_t *term_image_host, uint8_t *term_dir_host, void *stream);
 /* mission-id -> token table used by the host path and by mgrl_stack_push callers: [74,32] i64 */
 int mgrl_set_token_table(mgrl_env *env, const int64_t *table_host);
 

@@ -659,20 +659,20 @@ int ensure_host_buffers(mgrl_env* e) {
     if (e->host_ready) return MGRL_OK;
     const size_t n = (size_t)e->cfg.num_envs;
     CUDA_TRY(cudaMalloc(&e->h_actions, n));
-    CUDA_TRY(cudaMalloc(&e->h_image, n * kObsBytes));
+    CUDA_TRY(cudaMalloc(&e->h_image, n * kObsPitch148));
     CUDA_TRY(cudaMalloc(&e->h_dir, n));
     CUDA_TRY(cudaMalloc(&e->h_mission, n));
     CUDA_TRY(cudaMalloc(&e->h_term, n));
     CUDA_TRY(cudaMalloc(&e->h_trunc, n));
     CUDA_TRY(cudaMalloc(&e->h_eplen, n));
-    CUDA_TRY(cudaMalloc(&e->h_termimg, n * kObsBytes));
+    CUDA_TRY(cudaMalloc(&e->h_termimg, n * kObsPitch148));
     CUDA_TRY(cudaMalloc(&e->h_termdir, n));
     CUDA_TRY(cudaMemset(e->h_termdir, 0, n));
     CUDA_TRY(cudaMalloc(&e->h_reward, n * sizeof(float)));
     CUDA_TRY(cudaMalloc(&e->h_stack_img, n * MGRL_FRAMES * kObsBytes));
     CUDA_TRY(cudaMalloc(&e->h_stack_dir, n * 16));
     CUDA_TRY(cudaMalloc(&e->h_stack_mis, n * MGRL_FRAMES * MGRL_MISSION_TOKENS * sizeof(int64_t)));
-    CUDA_TRY(cudaMemset(e->h_termimg, 0, n * kObsBytes));
+    CUDA_TRY(cudaMemset(e->h_termimg, 0, n * kObsPitch148));
     e->host_ready = true;
     return MGRL_OK;
 }
@@ -969,6 +969,49 @@ int mgrl_vec_reset_host(mgrl_env* e, uint64_t seed, uint8_t* image_host, uint8_t
     if (rc) return rc;
     rc = copy_stacked_out(e, image_host, direction_host, mission_host, s);
     if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return MGRL_OK;
+}
+
+int mgrl_vec_reset_frames_host(mgrl_env* e, uint64_t seed, uint8_t* image_host, uint8_t* dir_host, uint8_t* mission_host,
+                               void* stream) {
+    if (!e || !image_host || !dir_host || !mission_host) return fail(MGRL_ERR_INVALID, "mgrl_vec_reset_frames_host: null argument%s");
+    DeviceGuard guard(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = ensure_host_buffers(e);
+    if (rc) return rc;
+    rc = mgrl_reset(e, seed, e->h_image, e->h_dir, e->h_mission, stream);
+    if (rc) return rc;
+    const size_t n = (size_t)e->cfg.num_envs, pitch = e->cfg.obs_layout == MGRL_OBS_HWC148 ? kObsPitch148 : kObsBytes;
+    CUDA_TRY(cudaMemcpyAsync(image_host, e->h_image, n * pitch, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(dir_host, e->h_dir, n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(mission_host, e->h_mission, n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return MGRL_OK;
+}
+
+int mgrl_vec_step_frames_host(mgrl_env* e, const uint8_t* actions_host, uint8_t* image_host, uint8_t* dir_host,
+                              uint8_t* mission_host, float* reward_host, uint8_t* term_host, uint8_t* trunc_host,
+                              uint8_t* ep_len_host, uint8_t* term_image_host, uint8_t* term_dir_host, void* stream) {
+    if (!e || !actions_host || !image_host || !dir_host || !mission_host || !reward_host || !term_host || !trunc_host)
+        return fail(MGRL_ERR_INVALID, "mgrl_vec_step_frames_host: null argument%s");
+    if (!e->host_ready) return fail(MGRL_ERR_INVALID, "mgrl_vec_step_frames_host: call mgrl_vec_reset_frames_host first%s");
+    DeviceGuard guard(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)e->cfg.num_envs, pitch = e->cfg.obs_layout == MGRL_OBS_HWC148 ? kObsPitch148 : kObsBytes;
+    CUDA_TRY(cudaMemcpyAsync(e->h_actions, actions_host, n, cudaMemcpyHostToDevice, s));
+    int rc = mgrl_step(e, e->h_actions, e->h_image, e->h_dir, e->h_mission, e->h_reward, e->h_term, e->h_trunc,
+                       e->h_eplen, term_image_host ? e->h_termimg : nullptr, term_dir_host ? e->h_termdir : nullptr, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(image_host, e->h_image, n * pitch, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(dir_host, e->h_dir, n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(mission_host, e->h_mission, n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(reward_host, e->h_reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(term_host, e->h_term, n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(trunc_host, e->h_trunc, n, cudaMemcpyDeviceToHost, s));
+    if (ep_len_host) CUDA_TRY(cudaMemcpyAsync(ep_len_host, e->h_eplen, n, cudaMemcpyDeviceToHost, s));
+    if (term_image_host) CUDA_TRY(cudaMemcpyAsync(term_image_host, e->h_termimg, n * pitch, cudaMemcpyDeviceToHost, s));
+    if (term_dir_host) CUDA_TRY(cudaMemcpyAsync(term_dir_host, e->h_termdir, n, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return MGRL_OK;
 }

@@ -163,14 +163,21 @@ class Policy:
             return self._evaluate(image_u8, dir_onehot, mission_row, lut, F, P)
 
     def _evaluate(self, image_u8, dir_onehot, mission_row, lut, F, P):
+        torch = self.torch
+        B = image_u8.shape[0]
+        c = _PREFIX + "image.image_Conv2d_"
+        # the three 2x2 convolutions as patch GEMMs (7x7 images: the library convolution's backward is ~8x slower here)
         x = image_u8.float() / 255.0
-        x = F.max_pool2d(F.relu(F.conv2d(x, P[_PREFIX + "image.image_Conv2d_0.weight"], P[_PREFIX + "image.image_Conv2d_0.bias"])), 2)
-        x = F.relu(F.conv2d(x, P[_PREFIX + "image.image_Conv2d_3.weight"], P[_PREFIX + "image.image_Conv2d_3.bias"]))
-        x = F.relu(F.conv2d(x, P[_PREFIX + "image.image_Conv2d_5.weight"], P[_PREFIX + "image.image_Conv2d_5.bias"])).flatten(1)
+        p = x.unfold(2, 2, 1).unfold(3, 2, 1).permute(0, 2, 3, 1, 4, 5).reshape(B * 36, 48)          # (ci, kh, kw)
+        h = torch.relu(F.linear(p, P[c + "0.weight"].reshape(16, 48), P[c + "0.bias"]))
+        h = h.view(B, 3, 2, 3, 2, 16).amax(dim=(2, 4))                                                # MaxPool2d(2): 6x6 -> 3x3
+        p = h.unfold(1, 2, 1).unfold(2, 2, 1).reshape(B * 4, 64)                                      # (ci, kh, kw)
+        h = torch.relu(F.linear(p, P[c + "3.weight"].reshape(32, 64), P[c + "3.bias"])).view(B, 128)  # (oh, ow, c2)
+        x = torch.relu(F.linear(h, P[c + "5.weight"].permute(0, 2, 3, 1).reshape(64, 128), P[c + "5.bias"]))
         d = F.linear(dir_onehot.float(), P[_PREFIX + "direction.direction_Linear_0.weight"],
                      P[_PREFIX + "direction.direction_Linear_0.bias"])
-        f = self.torch.cat([d, x, lut[mission_row.long()]], dim=1)
-        t = self.torch.tanh
+        f = torch.cat([d, x, F.embedding(mission_row.long(), lut)], dim=1)
+        t = torch.tanh
         hp = t(F.linear(t(F.linear(f, P["mlp_extractor.policy_net.0.weight"], P["mlp_extractor.policy_net.0.bias"])),
                         P["mlp_extractor.policy_net.2.weight"], P["mlp_extractor.policy_net.2.bias"]))
         hv = t(F.linear(t(F.linear(f, P["mlp_extractor.value_net.0.weight"], P["mlp_extractor.value_net.0.bias"])),

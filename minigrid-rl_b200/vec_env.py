@@ -136,13 +136,14 @@ class B200VecEnv:
     metadata = {"render_modes": []}
 
     def __init__(self, cfg: EnvConfig | None = None, num_envs: int = 16, seed: int | None = None,
-                 device: int = 0, env_id_base: int = 0, n_frames_stack: int = 4):
+                 device: int = 0, env_id_base: int = 0, n_frames_stack: int = 4, layout: str = "chw"):
         if n_frames_stack != FRAMES:
             raise ValueError("only n_frames_stack == 4 is built (hydra_configs/algorithm/ppo.yaml:5)")
         self.cfg = cfg or EnvConfig()
         self.num_envs = int(num_envs)
         self._seed = 0 if seed is None else int(seed)
-        self._h = _Handle(self.cfg, self.num_envs, device, env_id_base, chw=True)
+        self.layout, self.pitch = layout, LAYOUTS[layout][1]     # "hwc148" serves step_frames only (fast records)
+        self._h = _Handle(self.cfg, self.num_envs, device, env_id_base, layout)
         lib = self._h.lib
         self._table = np.ascontiguousarray(token_table())
         nat.check(lib.mgrl_set_token_table(self._h.ptr, self._table.ctypes.data_as(C.c_void_p)), "set_token_table")
@@ -171,6 +172,7 @@ class B200VecEnv:
             "term_image": _Pinned(lib, (n, 3, 7, 7), np.uint8),
             "term_dir": _Pinned(lib, (n,), np.uint8),
         }
+        self._frames = None
         self._actions = None
         self._t0 = time.time()
         self.reset_infos = [dict() for _ in range(n)]
@@ -247,7 +249,38 @@ class B200VecEnv:
         return (self._obs(), p["reward"].array, p["term"].array, p["trunc"].array, p["ep_len"].array,
                 p["term_image"].array, p["term_dir"].array)
 
+    # ------------------------------------------------------------------ un-stacked host path
+    def _frame_bufs(self):
+        if self._frames is None:
+            lib, n = self._h.lib, self.num_envs
+            self._frames = {"image": _Pinned(lib, (n, self.pitch), np.uint8), "dir": _Pinned(lib, (n,), np.uint8),
+                            "mission": _Pinned(lib, (n,), np.uint8), "term_image": _Pinned(lib, (n, self.pitch), np.uint8)}
+        return self._frames
+
+    def reset_frames(self):
+        """reset() without the SB3 wrapper stack: (image [N,pitch] u8 in this env's layout, dir [N], mission id [N])."""
+        f = self._frame_bufs()
+        nat.check(self._h.lib.mgrl_vec_reset_frames_host(self._h.ptr, self._seed, f["image"].ptr, f["dir"].ptr,
+                                                         f["mission"].ptr, None), "vec_reset_frames")
+        return f["image"].array, f["dir"].array, f["mission"].array
+
+    def step_frames(self, actions, want_terminal: bool = False):
+        """step() without the SB3 wrapper stack (same outputs as the CPU oracle's vector step): pinned numpy arrays
+        (image, dir, mission id, reward, term, trunc, ep_len[, term_image, term_dir]) via mgrl_vec_step_frames_host."""
+        p, f = self._p, self._frame_bufs()
+        p["actions"].array[:] = actions
+        nat.check(self._h.lib.mgrl_vec_step_frames_host(
+            self._h.ptr, p["actions"].ptr, f["image"].ptr, f["dir"].ptr, f["mission"].ptr, p["reward"].ptr, p["term"].ptr,
+            p["trunc"].ptr, p["ep_len"].ptr, f["term_image"].ptr if want_terminal else None,
+            p["term_dir"].ptr if want_terminal else None, None), "vec_step_frames")
+        out = (f["image"].array, f["dir"].array, f["mission"].array, p["reward"].array, p["term"].array, p["trunc"].array,
+               p["ep_len"].array)
+        return out + ((f["term_image"].array, p["term_dir"].array) if want_terminal else ())
+
     def close(self):
+        if self._frames is not None:
+            for v in self._frames.values():
+                v.free()
         for v in self._p.values():
             v.free()
         for b in self._obs_bufs:

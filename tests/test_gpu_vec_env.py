@@ -85,3 +85,27 @@ def test_vec_env_matches_sb3_stack_semantics(kw):
     with pytest.raises(ValueError):
         env.step(np.full(n, 7))
     env.close()
+
+
+def test_step_frames_host_path_matches_oracle():
+    """mgrl_vec_step_frames_host: the un-stacked host path (like for like with the CPU arm of bench.py)."""
+    kw = dict(problem="multi", mission=None)
+    n = 700
+    for layout in ("hwc148", "hwc"):
+        env = mg.B200VecEnv(mg.EnvConfig(**kw), num_envs=n, seed=9, env_id_base=64, layout=layout)
+        o = orc.OracleVecEnv(orc.make_config(**kw), n, seed=9, env_id_base=64)
+        img, d, m = env.reset_frames()
+        o.reset()
+        assert np.array_equal(img[:, :147].reshape(n, 7, 7, 3), o.obs) and np.array_equal(d, o.dir) and np.array_equal(m, o.mission)
+        rs = np.random.RandomState(3)
+        for t in range(60):
+            a = biased_actions(rs, n).astype(np.uint8)
+            img, d, m, rew, term, trunc, ep_len, timg, tdir = env.step_frames(a, want_terminal=True)
+            o.step(a)
+            assert np.array_equal(img[:, :147].reshape(n, 7, 7, 3), o.obs), t
+            assert np.array_equal(d, o.dir) and np.array_equal(m, o.mission), t
+            assert np.array_equal(rew.view(np.uint32), o.reward.view(np.uint32)), t
+            assert np.array_equal(term, o.term) and np.array_equal(trunc, o.trunc) and np.array_equal(ep_len, o.ep_len), t
+            done = (o.term | o.trunc).astype(bool)
+            assert np.array_equal(timg[done][:, :147].reshape(-1, 7, 7, 3), o.term_obs[done]), t
+        env.close()
