@@ -137,13 +137,23 @@ __device__ __forceinline__ void encode_packed_smem(uint32_t state_sa, int agent_
 #pragma unroll
     for (int i = 0; i < kView; ++i) cf[i] = clampi(af + (6 - i) * sf, 0, S - 1);
     uint32_t e[4];
+    // software pipeline over the view rows: the kind bytes of row vx+1 are in flight while row vx goes
+    // through the LUT and is packed, so each row exposes one shared-memory latency instead of two
+    uint32_t k[kView], kn[kView];
+    {
+        const uint32_t row = state_sa + (uint32_t)(clampi(ar - 3 * sr, 0, S - 1) * mr);
+#pragma unroll
+        for (int vy = 0; vy < kView; ++vy) k[vy] = lds_u8(row + (uint32_t)(cf[vy] * mf));
+    }
 #pragma unroll
     for (int vx = 0; vx < kView; ++vx) {
-        const uint32_t row = state_sa + (uint32_t)(clampi(ar + (vx - 3) * sr, 0, S - 1) * mr);
-        uint32_t k[kView], w[kView];
+        if (vx + 1 < kView) {
+            const uint32_t row = state_sa + (uint32_t)(clampi(ar + (vx + 1 - 3) * sr, 0, S - 1) * mr);
 #pragma unroll
-        for (int vy = 0; vy < kView; ++vy)
-            k[vy] = (vx == 3 && vy == 6) ? carrying : lds_u8(row + (uint32_t)(cf[vy] * mf));
+            for (int vy = 0; vy < kView; ++vy)
+                kn[vy] = (vx + 1 == 3 && vy == 6) ? carrying : lds_u8(row + (uint32_t)(cf[vy] * mf));
+        }
+        uint32_t w[kView];
 #pragma unroll
         for (int vy = 0; vy < kView; ++vy) w[vy] = lds_u32(lut_sa + k[vy] * 4u);
 #pragma unroll
@@ -157,6 +167,8 @@ __device__ __forceinline__ void encode_packed_smem(uint32_t state_sa, int agent_
                 sts_u32(o + 8, pack3(e[2], e[3], 2));
             }
         }
+#pragma unroll
+        for (int vy = 0; vy < kView; ++vy) k[vy] = kn[vy];
     }
     sts_u32(out_sa + 144, e[0]);  // cell 48 + pad byte
 }

@@ -9,9 +9,11 @@
 // 128-float feature depends only on (mission id, frames in the stack) -> table [74*4][128] recomputed by the
 // host whenever the weights change.
 //
-// Mapping: one thread = one observation, 64 observations per CTA.  All weight reads are warp-uniform 16-byte
-// read-only loads (one L1 transaction broadcast to the warp); each thread keeps up to 64 accumulators in
-// registers and its activations in a private 293-word shared-memory block (odd pitch: conflict free).
+// Mapping: 64 observations per CTA, 256 threads: a lane owns one observation (its activations live in a private
+// 293-word shared-memory block, odd pitch: conflict free) and FOUR warps share each group of 32 observations,
+// splitting every layer by output (pooled cells for conv1, output positions for conv2, 16 of the 64 channels for
+// conv3 and the hidden layers).  All weight reads are therefore warp-uniform 16-byte read-only loads (one
+// transaction broadcast to the warp); with 24 warps per SM their L2 latency is covered by the other warps.
 // fp32 FMA throughout (single-pass TF32 would miss the 1e-5 parity bar).
 #include <cuda_runtime.h>
 
@@ -82,83 +84,101 @@ __device__ __forceinline__ void fma_row(float* acc, float x, const float* __rest
     }
 }
 
-// 64-wide hidden layer: out = tanh(W^T in + b), `in` and `out` in this thread's shared block
+constexpr int PARTS = 4;           // warps sharing one group of 32 observations
+constexpr int NT = OB * PARTS;     // threads per CTA
+
+// 16 of the 64 outputs of two hidden layers at once (policy and value net read the same input):
+// acc_a += in_a[k] * wa[k][c0..c0+16), acc_b += in_b[k] * wb[k][c0..c0+16)
 template <int K>
-__device__ __forceinline__ void dense64_tanh(const float* __restrict__ wt, const float* __restrict__ bias, const float* in,
-                                             float* out) {
-    float acc[64];
+__device__ __forceinline__ void dense16x2(const float* __restrict__ wa, const float* __restrict__ ba, const float* in_a,
+                                          const float* __restrict__ wb, const float* __restrict__ bb, const float* in_b,
+                                          int c0, float* acc_a, float* acc_b) {
 #pragma unroll
-    for (int i = 0; i < 64; ++i) acc[i] = __ldg(bias + i);
-#pragma unroll 2
-    for (int k = 0; k < K; ++k) fma_row<64>(acc, in[k], wt + k * 64);
+    for (int i = 0; i < 16; ++i) { acc_a[i] = __ldg(ba + c0 + i); acc_b[i] = __ldg(bb + c0 + i); }
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+        fma_row<16>(acc_a, in_a[k], wa + k * 64 + c0);
+        fma_row<16>(acc_b, in_b[k], wb + k * 64 + c0);
+    }
 #pragma unroll
-    for (int i = 0; i < 64; ++i) out[i] = tanhf(acc[i]);
+    for (int i = 0; i < 16; ++i) { acc_a[i] = tanhf(acc_a[i]); acc_b[i] = tanhf(acc_b[i]); }
 }
 
-__global__ void __launch_bounds__(OB) policy_forward_kernel(const PolicyArgs p) {
+__global__ void __launch_bounds__(NT, 3) policy_forward_kernel(const PolicyArgs p) {
     extern __shared__ __align__(16) float smem[];
     __shared__ uint8_t s_age[OB];
     const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int part = warp >> 1;                 // 0..3: which slice of every layer this warp computes
+    const int ob = (warp & 1) * 32 + lane;      // observation of this lane within the CTA
     const int i0 = blockIdx.x * OB;
-    const int i = i0 + tid;
+    const int i = i0 + ob;
     const int nv = min(OB, p.n - i0);
+    const bool valid = ob < nv;
     const float* __restrict__ w = p.w;
 
     // ---- frames of history available (VecFrameStack zero-fills what precedes the episode)
-    int age = 0;
-    if (i < p.n) {
-        const bool start = p.prev_done == nullptr || p.prev_done[i] != 0;
-        age = start ? 0 : min((int)(p.prev_age ? p.prev_age[i] : 0) + 1, 3);
-        p.age_out[i] = (uint8_t)age;
-        if (p.start_out) p.start_out[i] = start;
+    if (tid < OB) {
+        int a = 0;
+        if (tid < nv) {
+            const int gi = i0 + tid;
+            const bool start = p.prev_done == nullptr || p.prev_done[gi] != 0;
+            a = start ? 0 : min((int)(p.prev_age ? p.prev_age[gi] : 0) + 1, 3);
+            p.age_out[gi] = (uint8_t)a;
+            if (p.start_out) p.start_out[gi] = start;
+        }
+        s_age[tid] = (uint8_t)a;
     }
-    s_age[tid] = (uint8_t)age;
     __syncthreads();
+    const int age = s_age[ob];
 
-    // ---- gather the 4-frame stack: coalesced reads of [nv x 148 B] per frame, scattered to per-thread blocks
+    // ---- gather the 4-frame stack: coalesced reads of [nv x 148 B] per frame, scattered to per-observation blocks
     uint32_t* blocks = reinterpret_cast<uint32_t*>(smem);
     for (int f = 0; f < 4; ++f) {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(p.frames + ((size_t)(p.b - 3 + f) * p.n + i0) * 148);
-        for (int e = tid; e < nv * FRAME_WORDS; e += OB) {
+        for (int e = tid; e < nv * FRAME_WORDS; e += NT) {
             const int o = e / FRAME_WORDS, j = e - o * FRAME_WORDS;
             blocks[o * PITCH + f * FRAME_WORDS + j] = (3 - f) <= (int)s_age[o] ? src[e] : 0u;
         }
     }
     __syncthreads();
-    if (i >= p.n) return;
 
-    float* blk = smem + tid * PITCH;
+    float* blk = smem + ob * PITCH;
     const uint8_t* px = reinterpret_cast<const uint8_t*>(blk);
 
-    // ---- image: Conv2d(12,16,2) + ReLU + MaxPool2d(2)  (7x7 -> 6x6 -> 3x3), input / 255
-    for (int q = 0; q < 9; ++q) {
-        const int qh = q / 3, qw = q - qh * 3;
-        float pooled[16];
+    // ---- image: Conv2d(12,16,2) + ReLU + MaxPool2d(2)  (7x7 -> 6x6 -> 3x3), input / 255; pooled cells q = part, part+4, 8
+    if (valid) {
+        for (int q = part; q < 9; q += PARTS) {
+            const int qh = q / 3, qw = q - qh * 3;
+            float pooled[16];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) pooled[c] = -3.0e38f;
-        for (int s = 0; s < 4; ++s) {
-            const int ph = 2 * qh + (s >> 1), pw = 2 * qw + (s & 1);
-            float acc[16];
+            for (int c = 0; c < 16; ++c) pooled[c] = -3.0e38f;
+            for (int s = 0; s < 4; ++s) {
+                const int ph = 2 * qh + (s >> 1), pw = 2 * qw + (s & 1);
+                float acc[16];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) acc[c] = 0.0f;
-            for (int f = 0; f < 4; ++f) {
+                for (int c = 0; c < 16; ++c) acc[c] = 0.0f;
+                for (int f = 0; f < 4; ++f) {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const int cell = (ph + (kk >> 1)) * 7 + pw + (kk & 1);
-                    const uint8_t* b = px + f * 148 + cell * 3;
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const int cell = (ph + (kk >> 1)) * 7 + pw + (kk & 1);
+                        const uint8_t* b = px + f * 148 + cell * 3;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c)
-                        fma_row<16>(acc, (float)b[c] * (1.0f / 255.0f), w + W1 + (((f * 3 + c) * 4 + kk) * 16));
+                        for (int c = 0; c < 3; ++c)
+                            fma_row<16>(acc, (float)b[c] * (1.0f / 255.0f), w + W1 + (((f * 3 + c) * 4 + kk) * 16));
+                    }
                 }
+#pragma unroll
+                for (int c = 0; c < 16; ++c) pooled[c] = fmaxf(pooled[c], acc[c]);
             }
 #pragma unroll
-            for (int c = 0; c < 16; ++c) pooled[c] = fmaxf(pooled[c], acc[c]);
+            for (int c = 0; c < 16; ++c) blk[POOL_OFF + q * 16 + c] = fmaxf(pooled[c] + __ldg(w + B1 + c), 0.0f);
         }
-#pragma unroll
-        for (int c = 0; c < 16; ++c) blk[POOL_OFF + q * 16 + c] = fmaxf(pooled[c] + __ldg(w + B1 + c), 0.0f);
     }
-    // ---- Conv2d(16,32,2) + ReLU  (3x3 -> 2x2); output (o, c2) at words [o*32 + c2] over the consumed frames
-    for (int o = 0; o < 4; ++o) {
+    __syncthreads();
+    // ---- Conv2d(16,32,2) + ReLU  (3x3 -> 2x2): output position o = part, at words [o*32 + c2] over the consumed frames
+    if (valid) {
+        const int o = part;
         float acc[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) acc[c] = __ldg(w + B2 + c);
@@ -170,64 +190,84 @@ __global__ void __launch_bounds__(OB) policy_forward_kernel(const PolicyArgs p) 
 #pragma unroll
         for (int c = 0; c < 32; ++c) blk[o * 32 + c] = fmaxf(acc[c], 0.0f);
     }
-    // ---- Conv2d(32,64,2) + ReLU + Flatten  (2x2 -> 1x1)
-    float feat_img[64];
-    {
+    __syncthreads();
+    // ---- Conv2d(32,64,2) + ReLU + Flatten  (2x2 -> 1x1): channels [16 part, 16 part + 16)
+    const int c0 = part * 16;
+    float fa[16], fb[16];
+    if (valid) {
 #pragma unroll
-        for (int c = 0; c < 64; ++c) feat_img[c] = __ldg(w + B3 + c);
-#pragma unroll 2
-        for (int j = 0; j < 128; ++j) fma_row<64>(feat_img, blk[j], w + W3 + j * 64);
+        for (int c = 0; c < 16; ++c) fa[c] = __ldg(w + B3 + c0 + c);
+#pragma unroll 4
+        for (int j = 0; j < 128; ++j) fma_row<16>(fa, blk[j], w + W3 + j * 64 + c0);
     }
-    // ---- direction: Linear(16,16) on the stacked one-hot (frames older than the episode are all-zero)
-    float feat_dir[16];
+    __syncthreads();          // conv2's output is consumed: the block becomes the 208 features
+    if (valid) {
+        // features = [direction 0:16 | image 16:80 | mission 80:208]  (policies.py:83-102)
 #pragma unroll
-    for (int c = 0; c < 16; ++c) feat_dir[c] = __ldg(w + BD + c);
-    for (int f = 0; f < 4; ++f) {
-        if ((3 - f) <= age) {
-            const int d = p.dirs[(size_t)(p.b - 3 + f) * p.n + i] & 3;
-            fma_row<16>(feat_dir, 1.0f, w + WD + (f * 4 + d) * 16);
+        for (int c = 0; c < 16; ++c) blk[16 + c0 + c] = fmaxf(fa[c], 0.0f);
+        if (part == 0) {      // direction: Linear(16,16) on the stacked one-hot (frames older than the episode are zero)
+            float fd[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) fd[c] = __ldg(w + BD + c);
+            for (int f = 0; f < 4; ++f) {
+                if ((3 - f) <= age) {
+                    const int d = p.dirs[(size_t)(p.b - 3 + f) * p.n + i] & 3;
+                    fma_row<16>(fd, 1.0f, w + WD + (f * 4 + d) * 16);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 16; ++c) blk[c] = fd[c];
         }
-    }
-    // features = [direction 0:16 | image 16:80 | mission 80:208]  (policies.py:83-102)
+        const float4* row = reinterpret_cast<const float4*>(w + LUT + ((int)p.mission[i] * 4 + age) * 128) + part * 8;
 #pragma unroll
-    for (int c = 0; c < 16; ++c) blk[c] = feat_dir[c];
-#pragma unroll
-    for (int c = 0; c < 64; ++c) blk[16 + c] = fmaxf(feat_img[c], 0.0f);
-    {
-        const float4* row = reinterpret_cast<const float4*>(w + LUT + ((int)p.mission[i] * 4 + age) * 128);
-#pragma unroll 8
-        for (int c = 0; c < 32; ++c) {
+        for (int c = 0; c < 8; ++c) {
             const float4 v = __ldg(row + c);
-            blk[80 + 4 * c] = v.x; blk[81 + 4 * c] = v.y; blk[82 + 4 * c] = v.z; blk[83 + 4 * c] = v.w;
+            float* d = blk + 80 + part * 32 + 4 * c;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
         }
     }
-    // ---- policy head
-    dense64_tanh<208>(w + PI1, w + PI1B, blk, blk + H_OFF);
-    dense64_tanh<64>(w + PI2, w + PI2B, blk + H_OFF, blk + H_OFF);
+    __syncthreads();
+    // ---- first hidden layer of the policy and the value net (208 -> 64 each, Tanh)
+    if (valid) dense16x2<208>(w + PI1, w + PI1B, blk, w + VF1, w + VF1B, blk, c0, fa, fb);
+    __syncthreads();          // every part has read the features
+    if (valid) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { blk[H_OFF + c0 + c] = fa[c]; blk[c0 + c] = fb[c]; }
+    }
+    __syncthreads();
+    // ---- second hidden layer (64 -> 64, Tanh): policy reads [208,272), value reads [0,64)
+    if (valid) dense16x2<64>(w + PI2, w + PI2B, blk + H_OFF, w + VF2, w + VF2B, blk, c0, fa, fb);
+    __syncthreads();
+    if (valid) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { blk[64 + c0 + c] = fa[c]; blk[128 + c0 + c] = fb[c]; }
+    }
+    __syncthreads();
+    if (!valid) return;
+    if (part == 1) {          // value_net
+        float v = __ldg(w + BV);
+#pragma unroll 8
+        for (int k = 0; k < 64; ++k) v = fmaf(blk[128 + k], __ldg(w + WV + k), v);
+        p.value[i] = v;
+    }
+    if (part != 0) return;
+    // ---- action_net + Categorical(logits): log-softmax, inverse-CDF sample on one Philox uniform per (env, step)
     float lg[8];
 #pragma unroll
     for (int a = 0; a < 8; ++a) lg[a] = __ldg(w + BA + a);
 #pragma unroll 4
-    for (int k = 0; k < 64; ++k) fma_row<8>(lg, blk[H_OFF + k], w + WA + k * 8);
-    // ---- value head
-    dense64_tanh<208>(w + VF1, w + VF1B, blk, blk + H_OFF);
-    dense64_tanh<64>(w + VF2, w + VF2B, blk + H_OFF, blk + H_OFF);
-    float v = __ldg(w + BV);
-#pragma unroll 8
-    for (int k = 0; k < 64; ++k) v = fmaf(blk[H_OFF + k], __ldg(w + WV + k), v);
-    p.value[i] = v;
+    for (int k = 0; k < 64; ++k) fma_row<8>(lg, blk[64 + k], w + WA + k * 8);
     if (p.logits) {
 #pragma unroll
         for (int a = 0; a < 7; ++a) p.logits[(size_t)i * 7 + a] = lg[a];
     }
-    // ---- Categorical(logits): log-softmax, inverse-CDF sample on one Philox uniform per (env, step)
     if (p.action) {
         float m = lg[0];
 #pragma unroll
         for (int a = 1; a < 7; ++a) m = fmaxf(m, lg[a]);
-        float e[7], sum = 0.0f;
+        float sum = 0.0f;
 #pragma unroll
-        for (int a = 0; a < 7; ++a) { e[a] = expf(lg[a] - m); sum += e[a]; }
+        for (int a = 0; a < 7; ++a) sum += expf(lg[a] - m);
         const float lse = m + logf(sum);
         float u;
         philox_u01(p.seed, p.env_id_base + (uint64_t)i, p.step, u);
@@ -270,7 +310,7 @@ int mgrl_policy_forward(const float* weights_dev, const uint8_t* frames_dev, con
     const size_t smem = (size_t)OB * PITCH * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
-        policy_forward_kernel<<<(num_envs + OB - 1) / OB, OB, smem, (cudaStream_t)stream>>>(a);
+        policy_forward_kernel<<<(num_envs + OB - 1) / OB, NT, smem, (cudaStream_t)stream>>>(a);
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) {

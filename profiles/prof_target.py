@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Fixed launch sequence for ncu (deterministic -s/-c): reset, WARM rollout launches, then the launches to capture.
    python profiles/prof_target.py many   -> step_kernel launches: 3 warm-up + 2 (T=128 steps per launch)
-   python profiles/prof_target.py step   -> step_kernel launches: 384 warm-up + 128 (one step per launch)"""
+   python profiles/prof_target.py step   -> step_kernel launches: 384 warm-up + 128 (one step per launch)
+   python profiles/prof_target.py ppo    -> 2 rollouts of 32 steps: policy_forward_kernel + step_kernel per step"""
 import os
 import sys
 
@@ -23,7 +24,13 @@ image = torch.empty((T, n, 148), **u8)
 dirs = torch.empty((T, n), **u8); mis = torch.empty((T, n), **u8)
 rew = torch.empty((T, n), dtype=torch.float32, device=dev)
 term = torch.empty((T, n), **u8); trunc = torch.empty((T, n), **u8); eplen = torch.empty((T, n), **u8)
-if mode == "many":
+if mode == "ppo":      # policy_forward_kernel + step_kernel, two launches per rollout step
+    del image
+    eng = mg.RolloutEngine(env, mg.Policy(dev, seed=1), mg.PPOConfig(n_steps=32, batch_size=n * 32 // 8), seed=1,
+                           keep_terminal_frames=False)
+    for _ in range(2):
+        eng.collect()
+elif mode == "many":
     for _ in range(5):
         env.step_many(actions, image, dirs, mis, rew, term, trunc, eplen)
 else:

@@ -1,19 +1,25 @@
 #!/bin/sh
-# Run under gpurun from the repo root:  gpurun --timeout 1500 -- 'sh profiles/run_profile.sh r03'
-# 1) plain bench (the number), 2) ncu launch list of the profiling target, 3) one full capture of the
-#    step kernel in each mode.  Outputs land in gpurun_out/ (copy summaries into profiles/).
+# Run under gpurun from the repo root:  gpurun --timeout 1500 -- 'sh profiles/run_profile.sh r08'
+# 1) plain bench (the number), 2) ncu launch list of the bench command's kernel path (prof_target.py issues the same
+#    launches deterministically), 3) one `--set full` capture per kernel.  Outputs land in gpurun_out/.
 TAG=${1:-r01}
 mkdir -p gpurun_out
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 echo "bench rc=$?"; cat gpurun_out/bench_$TAG.json
-for MODE in many step; do
+BENCH="python bench.py --steps 2 --warmup 3 --no-ppo --no-e2e --no-cpu-baseline"
+$BENCH > gpurun_out/plain_bench_$TAG.log 2>&1 &&
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+    --log-file gpurun_out/launches_bench_$TAG.csv $BENCH > gpurun_out/ncu_launches_bench_$TAG.log 2>&1
+echo "ncu launches bench rc=$?"
+for MODE in many step ppo; do
   python profiles/prof_target.py $MODE > gpurun_out/plain_${MODE}_$TAG.log 2>&1 || { echo "plain $MODE failed"; continue; }
-  if [ $MODE = many ]; then SKIP=3; CNT=2; LS=0; LC=8; else SKIP=400; CNT=2; LS=384; LC=128; fi
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:step_kernel -s $LS -c $LC --csv \
-      --log-file gpurun_out/launches_${MODE}_$TAG.csv python profiles/prof_target.py $MODE > gpurun_out/ncu_launches_${MODE}_$TAG.log 2>&1
-  echo "ncu launches $MODE rc=$?"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:step_kernel -s $SKIP -c $CNT \
+  case $MODE in
+    many) K=step_kernel; SKIP=3; CNT=1;;
+    step) K=step_kernel; SKIP=400; CNT=1;;
+    ppo)  K=policy_forward; SKIP=40; CNT=1;;
+  esac
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -s $SKIP -c $CNT \
       -o gpurun_out/prof_${MODE}_$TAG -f python profiles/prof_target.py $MODE > gpurun_out/ncu_full_${MODE}_$TAG.log 2>&1
   echo "ncu full $MODE rc=$?"
 done
-ls -la gpurun_out
+ls gpurun_out | grep $TAG
