@@ -351,7 +351,11 @@ def main():
                              "in the algorithmic bytes",
                        "path": "mgrl_step_many: one launch = one rollout of T steps (actions known up front)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "step_kernel<HWC148,see_through,128,2>", "peak_source": peak_src,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this
+                         # kernel at this shape (profiles/r1b_ncu_full_many.txt); algorithmic bytes = 158 * n * T
+                         "traffic": 1.3598e9 if (n, T) == (N_ENVS, T_ROLLOUT) else None, "traffic_unit": "bytes/launch",
+                         "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n * T,
+                         "kernel": "step_kernel<HWC148,see_through,128,2>", "peak_source": peak_src,
                          "bytes_per_env_step": BYTES_PER_ENV_STEP, "us_per_launch": us_per_launch,
                          "env_steps_per_launch": n * T},
             "per_step_launch": {"value": steps_value, "unit": "env-steps/s", "ms_per_step": ms_steps / K,
