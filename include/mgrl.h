@@ -160,12 +160,14 @@ int mgrl_gae(const float *rewards_dev, const float *values_dev, const uint8_t *e
 
 /* ---- policy forward for the rollout (K3) ---------------------------------------------- */
 #define MGRL_POLICY_WEIGHTS 84940 /* floats in the packed weight buffer, layout in csrc/mgrl_policy.cu */
+#define MGRL_POLICY_DETERMINISTIC 1 /* flags: action = argmax(logits) instead of a sample (evaluate_policy, ppo.py:161) */
 
 /* replaces CustomPPOPolicy.forward (policies.py:227-244, CustomExtractor policies.py:21-120) together with
  * the VecFrameStack(4,'first') / VecTransposeImage it reads through (ppo.py:124-126), for the rollout:
  * gathers the 4-frame stack of every environment from an un-stacked HWC148 frame buffer (records of time
  * index b-3..b; frames older than the episode are zero), runs extractor + MLPs + heads in fp32 and samples
- * the action by inverse CDF on one Philox uniform keyed by (seed, env_id_base + i, step).
+ * the action by inverse CDF on one Philox uniform keyed by (seed, env_id_base + i, step), or takes the argmax
+ * when flags has MGRL_POLICY_DETERMINISTIC.
  *   frames_dev [>= b+1, N, 148] u8, dirs_dev [>= b+1, N] u8, mission_dev [N] (time b);
  *   prev_age_dev / prev_done_dev [N] or NULL (NULL = first observation after a reset): age = frames of
  *   history available, 0..3, written to age_out_dev [N]; start_out_dev [N] or NULL = episode_start flag;
@@ -175,7 +177,7 @@ int mgrl_policy_forward(const float *weights_dev, const uint8_t *frames_dev, con
                         const uint8_t *mission_dev, const uint8_t *prev_age_dev, const uint8_t *prev_done_dev,
                         uint8_t *age_out_dev, uint8_t *start_out_dev, uint8_t *action_dev, float *logp_dev,
                         float *value_dev, float *logits_dev, int num_envs, int time_index, uint64_t seed,
-                        uint64_t env_id_base, uint32_t step, void *stream);
+                        uint64_t env_id_base, uint32_t step, int flags, void *stream);
 const char *mgrl_policy_last_error(void);
 
 /* ---- host-buffer drop-in path (what B200VecEnv.reset/step with numpy arrays calls) --- */

@@ -55,6 +55,7 @@ struct PolicyArgs {
     int n, b;
     uint64_t seed, env_id_base;
     uint32_t step;           // sampling counter (global step index)
+    int deterministic;       // 1: action = argmax(logits) (evaluate_policy / test(), ppo.py:161,174-292)
 };
 
 __device__ __forceinline__ void philox_u01(uint64_t seed, uint64_t env, uint32_t step, float& u) {
@@ -277,7 +278,8 @@ __global__ void __launch_bounds__(NT, 3) policy_forward_kernel(const PolicyArgs 
 #pragma unroll
         for (int a = 0; a < 7; ++a) {
             c += expf(lg[a] - lse);
-            if (!found && u < c) { act = a; chosen = lg[a]; found = true; }
+            const bool take = p.deterministic ? (lg[a] == m) : (u < c);   // argmax: first maximum, like torch.argmax
+            if (!found && take) { act = a; chosen = lg[a]; found = true; }
         }
         p.action[i] = (uint8_t)act;
         if (p.logp) p.logp[i] = chosen - lse;
@@ -296,7 +298,7 @@ int mgrl_policy_forward(const float* weights_dev, const uint8_t* frames_dev, con
                         const uint8_t* mission_dev, const uint8_t* prev_age_dev, const uint8_t* prev_done_dev,
                         uint8_t* age_out_dev, uint8_t* start_out_dev, uint8_t* action_dev, float* logp_dev,
                         float* value_dev, float* logits_dev, int num_envs, int time_index, uint64_t seed,
-                        uint64_t env_id_base, uint32_t step, void* stream) {
+                        uint64_t env_id_base, uint32_t step, int flags, void* stream) {
     if (!weights_dev || !frames_dev || !dirs_dev || !mission_dev || !age_out_dev || !value_dev || num_envs <= 0 ||
         time_index < 3) {
         snprintf(g_perr, sizeof g_perr, "mgrl_policy_forward: null argument, empty batch or time_index < 3");
@@ -307,6 +309,7 @@ int mgrl_policy_forward(const float* weights_dev, const uint8_t* frames_dev, con
     a.prev_age = prev_age_dev; a.prev_done = prev_done_dev; a.age_out = age_out_dev; a.start_out = start_out_dev;
     a.action = action_dev; a.logp = logp_dev; a.value = value_dev; a.logits = logits_dev;
     a.n = num_envs; a.b = time_index; a.seed = seed; a.env_id_base = env_id_base; a.step = step;
+    a.deterministic = (flags & MGRL_POLICY_DETERMINISTIC) ? 1 : 0;
     const size_t smem = (size_t)OB * PITCH * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {

@@ -224,7 +224,7 @@ class Policy:
         self._packed = None
 
     def forward_rollout(self, frames, dirs, mission, time_index, prev_age, prev_done, age_out, value, action=None,
-                        logp=None, logits=None, start_out=None, seed=0, env_id_base=0, step=0):
+                        logp=None, logits=None, start_out=None, seed=0, env_id_base=0, step=0, deterministic=False):
         """launch mgrl_policy_forward on the current stream (frames [B,N,148] u8, dirs [B,N] u8, mission [N] u8)"""
         torch = self.torch
         n = int(mission.shape[0])
@@ -232,5 +232,6 @@ class Policy:
         s = C.c_void_p(torch.cuda.current_stream(frames.device).cuda_stream)
         nat.check(nat.lib().mgrl_policy_forward(
             p(self.packed()), p(frames), p(dirs), p(mission), p(prev_age), p(prev_done), p(age_out), p(start_out),
-            p(action), p(logp), p(value), p(logits), n, int(time_index), int(seed), int(env_id_base), int(step), s),
+            p(action), p(logp), p(value), p(logits), n, int(time_index), int(seed), int(env_id_base), int(step),
+            1 if deterministic else 0, s),
             "mgrl_policy_forward")

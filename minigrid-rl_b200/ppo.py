@@ -186,7 +186,7 @@ class RolloutEngine:
         self.prev_done.fill_(1); self.prev_age.zero_()
         self.launches += 1
 
-    def collect(self):
+    def collect(self, deterministic: bool = False):
         """One rollout of T steps: 2 launches per step, everything stays on the device."""
         b, T, env, pol = self.buf, self.T, self.env, self.policy
         pol.packed()
@@ -194,7 +194,7 @@ class RolloutEngine:
             k = t + 3
             pol.forward_rollout(b["frames"], b["dirs"], b["mission"][k], k, self.prev_age, self.prev_done, b["age"][t],
                                 b["values"][t], b["actions"][t], b["logp"][t], start_out=b["start"][t], seed=self.seed,
-                                env_id_base=self.env_id_base, step=self.global_step)
+                                env_id_base=self.env_id_base, step=self.global_step, deterministic=deterministic)
             env.step(b["actions"][t], b["frames"][k + 1], b["dirs"][k + 1], b["mission"][k + 1], b["rewards"][t],
                      b["term"][t], b["trunc"][t], b["ep_len"][t],
                      term_image=None if self.term_frames is None else self.term_frames[t],
@@ -255,6 +255,25 @@ class RolloutEngine:
                                        b["adv"][t, i], b["ret"][t, i])
                 n_mb += 1
         return n_mb
+
+    def evaluate(self, n_rollouts: int = 1, deterministic: bool = True):
+        """`evaluate_policy` / `test()` of the reference (ppo.py:161, 174-292) on the device: run the policy without
+        learning and summarise the episodes that finished: count, mean reward, success rate (reward > 0), mean length.
+        With several ranks the sums are all-reduced."""
+        torch = self.torch
+        tot = torch.zeros(4, dtype=torch.float64, device=self.buf["rewards"].device)
+        for _ in range(n_rollouts):
+            self.collect(deterministic=deterministic)
+            b = self.buf
+            done = b["ep_len"] != 0
+            r = b["rewards"][done].double()
+            tot += torch.stack([done.sum().double(), r.sum(), (r > 0).sum().double(), b["ep_len"][done].double().sum()])
+            self.shift()
+        if self.dist is not None and self.dist.get_world_size() > 1:
+            self.dist.all_reduce(tot)
+        n = max(float(tot[0]), 1.0)
+        return {"episodes": int(tot[0]), "mean_reward": float(tot[1]) / n, "success_rate": float(tot[2]) / n,
+                "mean_length": float(tot[3]) / n}
 
     def shift(self):
         """the last 4 frame slots of this rollout become the first 4 of the next"""

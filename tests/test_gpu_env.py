@@ -309,3 +309,87 @@ def test_gae_bit_exact_vs_oracle():
                               c([[1], [0], [0]], torch.uint8), c([.5], torch.float32), c([1], torch.uint8), 0.9, 0.8)
     assert np.allclose(adv.cpu().numpy().ravel(), [0.1732, 0.31, 0.5], rtol=1e-6)
     assert np.allclose(ret.cpu().numpy().ravel(), [0.6732, 0.81, 1.0], rtol=1e-6)
+
+
+def scripted_actions(rs, st, S=11):
+    """Vectorised 'interact with what is in front of you' policy on the oracle's state: toggles doors and boxes, picks
+    up keys / balls / boxes, drops now and then, walks when the way is free -- so that every door / key / box
+    transition of the dynamics fires many times in a trace (BASELINE.json config 4)."""
+    n = st.shape[0]
+    d = st["agent_dir"].astype(np.int64)
+    fx = st["agent_x"].astype(np.int64) + (d == 0) - (d == 2)
+    fy = st["agent_y"].astype(np.int64) + (d == 1) - (d == 3)
+    k = st["grid"][np.arange(n), fy * S + fx].astype(np.int64)
+    is_door, is_box = (k >= 24) & (k < 48), k >= 64
+    pickable = ((k >= 8) & (k < 24)) | is_box
+    passable = (k == 0) | (k == 2) | (k == 3) | ((k >= 24) & (k < 32))
+    u = rs.rand(n)
+    a = np.where(passable & (u < 0.55), 2, rs.randint(0, 2, n))             # walk, else turn
+    a = np.where(is_door & (u < 0.6), 5, a)                                   # toggle doors (opens / closes / unlocks)
+    a = np.where(is_box & (u < 0.45), 5, a)                                   # open boxes
+    a = np.where(pickable & (st["carrying"] == 0) & (u > 0.55) & (u < 0.9), 3, a)
+    a = np.where((st["carrying"] != 0) & (k == 0) & (u > 0.97), 4, a)        # drop
+    a = np.where(rs.rand(n) < 0.01, 6, a)                                     # done
+    return a.astype(np.uint8)
+
+
+def test_tgl_replay_with_scripted_traces():
+    """BASELINE.json config 4: TGL, 1024 envs x 4096 steps of recorded traces (scripted interaction mixed with random
+    actions), replayed on the GPU in launches of 512 steps and compared after every step; the trace must contain every
+    door / key / box transition."""
+    n, T, CH = 1024, 4096, 512
+    kw = dict(problem="multi", mission=1)
+    o = orc.OracleVecEnv(orc.make_config(**kw), n, seed=2024, nthreads=8)
+    o.reset()
+    init = o.states.copy()
+    rs = np.random.RandomState(4)
+    acts = np.empty((T, n), np.uint8)
+    want = {k: [] for k in ("obs", "reward", "term", "trunc", "ep_len", "dir", "mission")}
+    ev = dict(unlock=0, open_close=0, box_key=0, box_empty=0, pickup_key=0, key_used=0, drop=0, success=0, trunc=0,
+              carried_shown=0)
+    for t in range(T):
+        a = scripted_actions(rs, o.states) if t % 8 else rs.randint(0, 7, n).astype(np.uint8)
+        acts[t] = a
+        pre = o.states.copy()
+        d = pre["agent_dir"].astype(np.int64)
+        fidx = (pre["agent_y"].astype(np.int64) + (d == 1) - (d == 3)) * 11 + pre["agent_x"].astype(np.int64) + (d == 0) - (d == 2)
+        k0 = pre["grid"][np.arange(n), fidx].astype(np.int64)
+        o.step(a, want_term_obs=False)
+        alive = ~((o.term | o.trunc).astype(bool))
+        k1 = o.states["grid"][np.arange(n), fidx].astype(np.int64)
+        tog = (a == 5) & alive
+        ev["unlock"] += int((tog & (k0 >= 40) & (k0 < 48) & (k1 >= 24) & (k1 < 32)).sum())
+        ev["open_close"] += int((tog & (k0 >= 24) & (k0 < 40) & (k1 != k0)).sum())
+        ev["box_key"] += int((tog & (k0 >= 72) & (k1 >= 8) & (k1 < 16)).sum())
+        ev["box_empty"] += int((tog & (k0 >= 64) & (k0 < 72) & (k1 == 0)).sum())
+        ev["pickup_key"] += int(((a == 3) & alive & (k0 >= 8) & (k0 < 16) & (o.states["carrying"] == k0)).sum())
+        ev["key_used"] += int((tog & (pre["carrying"] != 0) & (o.states["carrying"] == 0)).sum())
+        ev["drop"] += int(((a == 4) & alive & (pre["carrying"] != 0) & (o.states["carrying"] == 0)).sum())
+        ev["success"] += int((o.reward > 0).sum()); ev["trunc"] += int(o.trunc.sum())
+        ev["carried_shown"] += int((o.obs[:, 3, 6, 0] != 1).sum())
+        for key, val in (("obs", o.obs), ("reward", o.reward), ("term", o.term), ("trunc", o.trunc), ("ep_len", o.ep_len),
+                         ("dir", o.dir), ("mission", o.mission)):
+            want[key].append(val.copy())
+    assert all(v > 0 for v in ev.values()), ev
+
+    env = mg.DeviceEnv(mg.EnvConfig(**kw), num_envs=n, seed=2024, layout="hwc148")
+    env.reset()
+    assert np.array_equal(env.get_state_numpy()["grid"], init["grid"])
+    u8 = dict(dtype=torch.uint8, device="cuda")
+    image = torch.empty((CH, n, 148), **u8); dirs = torch.empty((CH, n), **u8); mis = torch.empty((CH, n), **u8)
+    rew = torch.empty((CH, n), dtype=torch.float32, device="cuda")
+    term = torch.empty((CH, n), **u8); trunc = torch.empty((CH, n), **u8); eplen = torch.empty((CH, n), **u8)
+    for c in range(0, T, CH):
+        env.step_many(torch.from_numpy(acts[c:c + CH]).cuda(), image, dirs, mis, rew, term, trunc, eplen)
+        got = {"obs": image.cpu().numpy()[:, :, :147].reshape(CH, n, 7, 7, 3), "reward": rew.cpu().numpy(),
+               "term": term.cpu().numpy(), "trunc": trunc.cpu().numpy(), "ep_len": eplen.cpu().numpy(),
+               "dir": dirs.cpu().numpy(), "mission": mis.cpu().numpy()}
+        for key in got:
+            w = np.stack(want[key][c:c + CH])
+            if key == "reward":
+                assert np.array_equal(got[key].view(np.uint32), w.view(np.uint32)), (key, c)
+            else:
+                assert np.array_equal(got[key], w), (key, c)
+    assert_state_equal(env, o, "tgl replay final")
+    assert env.error_flags() == 0
+    env.close()

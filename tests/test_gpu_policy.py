@@ -190,3 +190,21 @@ def test_one_ppo_iteration_updates_the_policy_and_matches_cpu_update():
         assert torch.isfinite(v).all()
     assert eng.env.error_flags() == 0
     eng.env.close()
+
+
+def test_deterministic_evaluation_takes_the_argmax():
+    n, T = 512, 12
+    eng, o = make_engine(n, T)
+    stats = eng.evaluate(1, deterministic=True)          # evaluate() shifts the buffers: recompute from the shifted rows
+    assert stats["episodes"] >= 0 and 0.0 <= stats["success_rate"] <= 1.0
+    eng.collect(deterministic=True)
+    b = eng.buf
+    logits = torch.zeros((n, 7), device="cuda"); val = torch.zeros(n, device="cuda")
+    age = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    for t in (1, 5, T - 1):
+        eng.policy.forward_rollout(b["frames"], b["dirs"], b["mission"][t + 3], t + 3, b["age"][t - 1], b["ep_len"][t - 1], age,
+                                   val, logits=logits)
+        assert torch.equal(b["actions"][t].long(), logits.argmax(1))
+        lsm = torch.log_softmax(logits, 1).gather(1, b["actions"][t].long()[:, None])[:, 0]
+        assert torch.allclose(b["logp"][t], lsm, rtol=1e-5, atol=1e-6)
+    eng.env.close()
