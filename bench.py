@@ -299,7 +299,7 @@ def main():
         del image, dirs, mis, rew, term, trunc, eplen, actions
         torch.cuda.empty_cache()
         penv = mg.DeviceEnv(cfg, num_envs=n, seed=SEED, env_id_base=rank * n, layout="hwc148")
-        pcfg = mg.PPOConfig(n_steps=T, batch_size=n * T // 32, n_epochs=4)
+        pcfg = mg.PPOConfig(n_steps=T, batch_size=n * T // 32, n_epochs=4, update_tf32=True)
         eng = mg.RolloutEngine(penv, mg.Policy(dev, seed=SEED), pcfg, dist=dist if world > 1 else None, seed=SEED)
         eng.iteration(1.0)                                   # warm-up: cuDNN autotune, allocator, layouts in L2
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -327,7 +327,8 @@ def main():
                     "config": {"n_steps": T, "n_envs_per_gpu": n, "batch_size_per_gpu": pcfg.batch_size, "n_epochs": 4,
                                "minibatches_per_iteration": n_mb, "policy": "CustomPPOPolicy 110216 params, fp32",
                                "rollout": "mgrl_policy_forward + mgrl_step per step (hand-written kernels)",
-                               "update": "torch autograd on library kernels (cuDNN/cuBLAS, TF32 off)",
+                               "update": "torch autograd on library kernels; matmuls may use TF32 like the reference (ppo.py:29-32), the "
+                                         "rollout kernels are fp32",
                                "all_reduces_per_optimizer_step": 2 if world > 1 else 0},
                     "env_error_flags": penv.error_flags()}
         env = penv

@@ -40,6 +40,7 @@ class PPOConfig:                      # hydra_configs/algorithm/ppo.yaml:9-40
     initial_learning_rate: float = 3e-4
     final_learning_rate: float = 3e-6
     optim_eps: float = 1e-8           # single.yaml:31
+    update_tf32: bool = False         # True: the update's library GEMMs may use TF32 like the reference (ppo.py:29-32)
     total_timesteps: float = 2e7
 
 
@@ -138,12 +139,18 @@ class Updater:
         self.policy.invalidate()
 
     def minibatch(self, image, onehot, mrow, actions, old_values, old_logp, adv, returns):
+        torch = self.torch
         stats = None
         if self.world > 1 and self.cfg.normalize_advantage:
             stats = self.global_adv_stats(adv)
-        loss, parts = ppo_minibatch_loss(self.policy, self.cfg, image, onehot, mrow, actions, old_values, old_logp, adv,
-                                         returns, stats)
-        self.step(loss)
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = bool(self.cfg.update_tf32)
+        try:
+            loss, parts = ppo_minibatch_loss(self.policy, self.cfg, image, onehot, mrow, actions, old_values, old_logp, adv,
+                                             returns, stats)
+            self.step(loss)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
         return loss.detach(), parts
 
 
