@@ -121,6 +121,27 @@ class Policy:
                 v.copy_(torch.as_tensor(sd[k]).to(v.device, v.dtype).reshape(v.shape))
         self._packed = None
 
+    # ---------------------------------------------------------------- SB3 checkpoint interop (ppo.py:128-132, 145-150)
+    def sb3_state_dict(self):
+        """The tensors under every key SB3's `policy.state_dict()` has for CustomPPOPolicy with a shared features
+        extractor: SB3 also exposes the extractor as `pi_features_extractor.*` and `vf_features_extractor.*` (aliases)."""
+        sd = self.state_dict()
+        for k in list(sd):
+            if k.startswith("features_extractor."):
+                sd["pi_" + k] = sd[k]
+                sd["vf_" + k] = sd[k]
+        return sd
+
+    def save(self, path: str):
+        """torch.save of the SB3-named state dict: the `policy.pth` member of an SB3 zip, loadable with
+        `model.policy.load_state_dict(torch.load(path))` in the reference."""
+        self.torch.save({k: v.cpu() for k, v in self.sb3_state_dict().items()}, path)
+
+    def load(self, path: str):
+        """accepts this class's own files and an SB3 `policy.pth` (aliases and optimizer entries are ignored)"""
+        sd = self.torch.load(path, map_location="cpu")
+        self.load_state_dict({k: sd[k] for k in self.params})
+
     def load_oracle(self, oracle_policy):
         """copy the weights of an oracle.policy_oracle.OraclePolicy (tests)"""
         o = oracle_policy

@@ -47,6 +47,20 @@ def test_parameter_count_and_names():
     assert "mlp_extractor.policy_net.0.weight" in p.state_dict() and "action_net.weight" in p.state_dict()
 
 
+def test_sb3_named_checkpoint_round_trip(tmp_path):
+    o, p = make_pair()
+    path = str(tmp_path / "policy.pth")
+    p.save(path)
+    sd = torch.load(path)
+    assert "pi_features_extractor.extractors.image.image_Conv2d_0.weight" in sd       # SB3's aliases of the shared extractor
+    assert "vf_features_extractor.extractors.mission.mission_GRU_1.weight_hh_l0" in sd
+    q = pol.Policy("cpu", seed=99)
+    q.load(path)
+    img, d, mis, mrow = random_stacked_obs(32, 2)
+    a, b = p.evaluate(img, d, mrow), q.evaluate(img, d, mrow)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
 def test_lut_network_equals_full_gru_oracle():
     o, p = make_pair()
     img, d, mis, mrow = random_stacked_obs(256, 0)
