@@ -5,6 +5,7 @@
 //   step_kernel<LAYOUT,SEE>      K1+K2  T >= 1 steps per launch: step -> mission bookkeeping -> reward/done ->
 //                                       auto-reset by adopting a prepared layout -> 7x7x3 encode; the same
 //                                       warps build new layouts in dense batches of 32 between steps
+//   generate_kernel              K2     dense rebuild of the layouts that one-step launches used up (every kDepth steps)
 //   reset_kernel                 K2     fresh environments + kDepth prepared layouts each (also after set_state)
 //   gae_kernel                   K4     SB3 GAE reverse scan
 //   stack_push_kernel                   VecFrameStack + Discrete2Box + TokenizeVocab gathers
@@ -35,7 +36,7 @@ using namespace mgrl;
 namespace {
 
 constexpr int STATE_WORDS = 35;           // sizeof(EnvState) / 4
-constexpr int kDepth = 3;                 // layouts prepared ahead of time per environment
+constexpr int kDepth = 4;                 // layouts prepared ahead of time per environment
 constexpr int kQueueCap = 512;            // >= TILE * kDepth requests can be outstanding per tile
 constexpr uint32_t kNoEntry = 0xFFFFu;
 constexpr unsigned FULL = 0xffffffffu;
@@ -54,6 +55,9 @@ struct EnvParams {
                               //   episode word (the tag, written last) reads E + 1
     uint16_t* qsave;          // [tiles][kQueueCap] generation requests left over by the previous launch
     uint32_t* qcount;         // [tiles]
+    uint32_t* glist;          // [kDepth * n] deferred requests of one-step launches: env * kDepth + slot
+    uint32_t* gcount;         // [1]
+    int defer;                // 1: this launch only records its requests in glist (generate_kernel builds them later)
     const uint32_t* tasks;    // [kTaskEntries][kTaskWords] (build_task_table)
     const uint32_t* prefix;   // [kTaskWords] (build_task_prefix)
     const uint32_t* empty;    // [kGridWords] (build_empty_grid)
@@ -215,6 +219,15 @@ __device__ __forceinline__ void push_requests(TileSmem<TILE, NB>& sm, unsigned m
     }
 }
 
+// the step kernel's single out-of-line copy of the generator
+__device__ __noinline__ void generate_layout(uint32_t* sc, const EnvCfg& cfg, uint64_t seed, uint64_t env_id, uint32_t episode,
+                                             uint32_t* draws, const uint32_t* tasks, const uint32_t* prefix, const uint32_t* empty) {
+    sc[32] = 0u; sc[34] = 0u;
+    GenIO io;
+    io.draws = draws; io.stride = 32; io.tasks = tasks; io.prefix = prefix; io.empty = empty;
+    generate(*reinterpret_cast<EnvState*>(sc), cfg, seed, env_id, episode, io);
+}
+
 // Take up to 32 requests off the tile's queue and build their layouts, one lane each (dense
 // generation).  A full batch is required unless `partial` (the caller is waiting for a layout).
 // Returns false when there was nothing to take or no draw buffer was free.  Call converged.
@@ -248,10 +261,8 @@ __device__ __noinline__ bool serve_queue(TileSmem<TILE, NB>& sm, const EnvParams
         uint32_t* slot = reinterpret_cast<uint32_t*>(p.slots + (size_t)j * p.n + tile0 + e);
         const uint32_t episode = __ldcg(slot + 33) - 1u + kDepth;   // the slot's old layout was adopted
         uint32_t* sc = reinterpret_cast<uint32_t*>(sm.obs[warp]) + lane * STATE_WORDS;
-        sc[32] = 0u; sc[34] = 0u;
-        GenIO io;
-        io.draws = sm.draws[b] + lane; io.stride = 32; io.tasks = p.tasks; io.prefix = sm.prefix; io.empty = sm.empty;
-        generate(*reinterpret_cast<EnvState*>(sc), p.cfg, p.seed, p.env_id_base + (uint64_t)(tile0 + e), episode, io);
+        generate_layout(sc, p.cfg, p.seed, p.env_id_base + (uint64_t)(tile0 + e), episode, sm.draws[b] + lane, p.tasks,
+                        sm.prefix, sm.empty);
 #pragma unroll
         for (int i = 0; i < STATE_WORDS; ++i) __stcg(slot + i, sc[i]);
         // hand-off inside the CTA: layout (global) -> fence -> tag byte (shared); the adopting lane
@@ -279,8 +290,16 @@ __global__ void __launch_bounds__(TILE, TILE == 128 ? 4 : 7) step_kernel(const E
     coop_copy<TILE>(sm.state, p.states + tile0, nv * (int)sizeof(EnvState), tid);
     tile_prologue<TILE, NB>(sm, p, tid);
     {   // requests the previous launch left behind
-        const uint32_t nq = p.qcount[blockIdx.x];
+        uint32_t nq = p.qcount[blockIdx.x];
         const uint16_t* qs = p.qsave + (size_t)blockIdx.x * kQueueCap;
+        if (p.defer && nq) {   // a one-step launch does not build layouts: hand the leftovers to generate_kernel
+            __shared__ uint32_t gbase;
+            if (tid == 0) gbase = atomicAdd(p.gcount, nq);
+            __syncthreads();
+            for (uint32_t i = tid; i < nq; i += TILE)
+                p.glist[gbase + i] = (uint32_t)(tile0 + (qs[i] & 0xFFu)) * kDepth + (uint32_t)(qs[i] >> 8);
+            nq = 0u;
+        }
         for (int i = tid; i < kQueueCap; i += TILE) sm.queue[i] = (uint32_t)i < nq ? qs[i] : (uint16_t)kNoEntry;
         if (tid == 0) { sm.q_head = 0u; sm.q_tail = nq; }
         if (tid < NB) sm.lock[tid] = 0;
@@ -339,8 +358,41 @@ __global__ void __launch_bounds__(TILE, TILE == 128 ? 4 : 7) step_kernel(const E
                     adopt_layout(cur, w);
                     ready = true; pending = false; carry = 0;
                 }
-                push_requests<TILE, NB>(sm, __ballot_sync(FULL, ready), entry, lane);
+                const unsigned rm = __ballot_sync(FULL, ready);
+                if (!p.defer) {
+                    push_requests<TILE, NB>(sm, rm, entry, lane);
+                } else if (rm) {   // one-step launch: record the request for generate_kernel (warp-aggregated)
+                    const int leader = __ffs(rm) - 1;
+                    uint32_t base = 0;
+                    if (lane == leader) base = atomicAdd(p.gcount, (uint32_t)__popc(rm));
+                    base = __shfl_sync(FULL, base, leader);
+                    if (ready) p.glist[base + (uint32_t)__popc(rm & ((1u << lane) - 1u))] = (uint32_t)(tile0 + tid) * kDepth + (uint32_t)j;
+                }
                 if (!__any_sync(FULL, pending)) break;
+                if (p.defer) {
+                    // One-step launches do not serve requests.  generate_kernel refills every slot at least every kDepth
+                    // steps, so this is only reached right after a switch from multi-step launches whose leftover requests
+                    // covered all slots of an environment: build the layout here and leave the slot's pending request to
+                    // produce the episode after it (the tag says "adopted").
+                    int b = -1;
+                    if (lane == 0)
+                        while (b < 0)
+                            for (int i = 0; i < NB && b < 0; ++i)
+                                if (atomicCAS(&sm.lock[i], 0, 1) == 0) b = i;
+                    b = __shfl_sync(FULL, b, 0);
+                    if (pending) {
+                        uint32_t* sc = reinterpret_cast<uint32_t*>(sm.obs[warp]) + lane * STATE_WORDS;
+                        generate_layout(sc, p.cfg, p.seed, p.env_id_base + (uint64_t)(tile0 + tid), E, sm.draws[b] + lane, p.tasks,
+                                        sm.prefix, sm.empty);
+                        adopt_layout(cur, sc);
+                        __stcg(const_cast<uint32_t*>(slot) + 33, E + 1u);
+                        *const_cast<volatile uint8_t*>(tag) = (uint8_t)(E + 1u);
+                        pending = false; carry = 0;
+                    }
+                    __syncwarp();
+                    if (lane == 0) atomicExch(&sm.lock[b], 0);
+                    break;
+                }
                 // a layout is not there yet: serve the queue ourselves (any batch size), else back off
                 if (!serve_queue<TILE, NB>(sm, p, tile0, warp, lane, true)) __nanosleep(200);
                 if (++spins > kSpinLimit) {
@@ -373,10 +425,10 @@ __global__ void __launch_bounds__(TILE, TILE == 128 ? 4 : 7) step_kernel(const E
         bool lead = true;
 #pragma unroll
         for (int w2 = 0; w2 < NW; ++w2) lead = lead && warp_t[w2] <= t + 1;
-        if (lead) serve_queue<TILE, NB>(sm, p, tile0, warp, lane, false);
+        if (lead && !p.defer) serve_queue<TILE, NB>(sm, p, tile0, warp, lane, false);
     }
     // keep serving full batches until every warp of the tile has finished its steps
-    for (int spins = 0; spins < kSpinLimit; ++spins) {
+    for (int spins = 0; spins < kSpinLimit && !p.defer; ++spins) {
         bool all = true;
 #pragma unroll
         for (int w2 = 0; w2 < NW; ++w2) all = all && warp_t[w2] >= p.T;
@@ -390,6 +442,45 @@ __global__ void __launch_bounds__(TILE, TILE == 128 ? 4 : 7) step_kernel(const E
         uint16_t* qs = p.qsave + (size_t)blockIdx.x * kQueueCap;
         for (uint32_t i = tid; i < nq; i += TILE) qs[i] = sm.queue[(head + i) & (kQueueCap - 1)];
         if (tid == 0) p.qcount[blockIdx.x] = nq;
+    }
+}
+
+// Dense layout generation for the requests recorded by one-step launches: every warp takes batches of 32 entries of
+// the global list (grid-stride), one lane per layout, all lanes busy.
+template <int NWARPS>
+struct GenSmem {
+    alignas(16) uint32_t scratch[NWARPS][32 * STATE_WORDS];
+    alignas(16) uint32_t draws[NWARPS][kDrawBuf * 32];
+    uint32_t empty[kGridWords];
+    uint32_t prefix[kTaskWords];
+};
+
+template <int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32) generate_kernel(const EnvParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GenSmem<NWARPS>& sm = *reinterpret_cast<GenSmem<NWARPS>*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < kGridWords; i += NWARPS * 32) sm.empty[i] = p.empty[i];
+    for (int i = tid; i < kTaskWords; i += NWARPS * 32) sm.prefix[i] = p.prefix[i];
+    __syncthreads();
+    const uint32_t count = *p.gcount;
+    const uint32_t nwarps = gridDim.x * NWARPS;
+    for (uint32_t b = blockIdx.x * NWARPS + warp; b * 32u < count; b += nwarps) {
+        const uint32_t r = b * 32u + (uint32_t)lane;
+        if (r < count) {
+            const uint32_t ent = p.glist[r];
+            const uint32_t env = ent / kDepth, j = ent % kDepth;
+            uint32_t* slot = reinterpret_cast<uint32_t*>(p.slots + (size_t)j * p.n + env);
+            const uint32_t episode = slot[33] - 1u + kDepth;   // the slot's old layout was adopted
+            uint32_t* sc = sm.scratch[warp] + lane * STATE_WORDS;
+            sc[32] = 0u; sc[34] = 0u;
+            GenIO io;
+            io.draws = sm.draws[warp] + lane; io.stride = 32; io.tasks = p.tasks; io.prefix = sm.prefix; io.empty = sm.empty;
+            generate(*reinterpret_cast<EnvState*>(sc), p.cfg, p.seed, p.env_id_base + (uint64_t)env, episode, io);
+#pragma unroll
+            for (int i = 0; i < STATE_WORDS; ++i) slot[i] = sc[i];
+        }
+        __syncwarp();
     }
 }
 
@@ -591,6 +682,9 @@ struct mgrl_env {
     EnvState* slots;     // [kDepth][N]
     uint16_t* qsave;     // [tiles(64)][kQueueCap]
     uint32_t* qcount;    // [tiles(64)]
+    uint32_t* glist;     // [kDepth * N] deferred requests of one-step launches
+    uint32_t* gcount;    // [1]
+    int deferred_steps;  // one-step launches since generate_kernel last ran
     uint32_t* tasks;
     uint32_t* prefix;
     uint32_t* empty;
@@ -618,6 +712,8 @@ EnvParams make_params(const mgrl_env* e) {
     p.slots = e->slots;
     p.qsave = e->qsave;
     p.qcount = e->qcount;
+    p.glist = e->glist;
+    p.gcount = e->gcount;
     p.tasks = e->tasks;
     p.prefix = e->prefix;
     p.empty = e->empty;
@@ -665,6 +761,24 @@ int launch_env(const mgrl_env* e, int mode, const EnvParams& p, cudaStream_t s) 
     default:
         return see ? launch_layout<OBS_HWC, true>(e, mode, p, s) : launch_layout<OBS_HWC, false>(e, mode, p, s);
     }
+}
+
+// build the layouts requested by the one-step launches since the last flush (dense generate_kernel)
+int flush_deferred(mgrl_env* e, cudaStream_t s) {
+    if (e->deferred_steps == 0) return MGRL_OK;
+    constexpr int NWARPS = 4;
+    const EnvParams p = make_params(e);
+    // sized for a quarter of the environments finishing on every step; the kernel strides over anything beyond that
+    long long batches = ((long long)e->cfg.num_envs * e->deferred_steps / 4 + 31) / 32;
+    int grid = (int)((batches + NWARPS - 1) / NWARPS);
+    grid = grid < 1 ? 1 : (grid > 148 * 4 ? 148 * 4 : grid);
+    const size_t smem = sizeof(GenSmem<NWARPS>);
+    CUDA_TRY(cudaFuncSetAttribute(generate_kernel<NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    generate_kernel<NWARPS><<<grid, NWARPS * 32, smem, s>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemsetAsync(e->gcount, 0, sizeof(uint32_t), s));
+    e->deferred_steps = 0;
+    return MGRL_OK;
 }
 
 int ensure_host_buffers(mgrl_env* e) {
@@ -769,6 +883,9 @@ int mgrl_create(const mgrl_config* cfg, int device, mgrl_env** out) {
     if (err == cudaSuccess) err = cudaMalloc(&e->qsave, n_tiles * kQueueCap * sizeof(uint16_t));
     if (err == cudaSuccess) err = cudaMalloc(&e->qcount, n_tiles * sizeof(uint32_t));
     if (err == cudaSuccess) err = cudaMemset(e->qcount, 0, n_tiles * sizeof(uint32_t));
+    if (err == cudaSuccess) err = cudaMalloc(&e->glist, (size_t)kDepth * cfg->num_envs * sizeof(uint32_t));
+    if (err == cudaSuccess) err = cudaMalloc(&e->gcount, sizeof(uint32_t));
+    if (err == cudaSuccess) err = cudaMemset(e->gcount, 0, sizeof(uint32_t));
     if (err == cudaSuccess) err = cudaMalloc(&e->tasks, sizeof tasks);
     if (err == cudaSuccess) err = cudaMemcpy(e->tasks, tasks, sizeof tasks, cudaMemcpyHostToDevice);
     if (err == cudaSuccess) err = cudaMalloc(&e->prefix, sizeof prefix);
@@ -790,7 +907,7 @@ int mgrl_create(const mgrl_config* cfg, int device, mgrl_env** out) {
 int mgrl_destroy(mgrl_env* e) {
     if (!e) return MGRL_OK;
     DeviceGuard guard(e->device);
-    void* bufs[] = {e->states, e->slots, e->qsave, e->qcount, e->tasks, e->prefix, e->empty, e->lut, e->err_flags, e->h_actions, e->h_image, e->h_dir, e->h_mission, e->h_term,
+    void* bufs[] = {e->states, e->slots, e->qsave, e->qcount, e->glist, e->gcount, e->tasks, e->prefix, e->empty, e->lut, e->err_flags, e->h_actions, e->h_image, e->h_dir, e->h_mission, e->h_term,
                     e->h_trunc, e->h_eplen, e->h_termimg, e->h_termdir, e->h_reward, e->h_stack_img, e->h_stack_dir,
                     e->h_stack_mis, e->h_table};
     for (void* b : bufs)
@@ -813,6 +930,8 @@ int mgrl_reset(mgrl_env* e, uint64_t seed, uint8_t* image, uint8_t* dir, uint8_t
     if (!e) return fail(MGRL_ERR_INVALID, "mgrl_reset: null handle%s");
     DeviceGuard guard(e->device);
     e->seed = seed;
+    e->deferred_steps = 0;
+    CUDA_TRY(cudaMemsetAsync(e->gcount, 0, sizeof(uint32_t), (cudaStream_t)stream));
     EnvParams p = make_params(e);
     p.image = image; p.dir = dir; p.mission = mission;
     return launch_env(e, MODE_RESET, p, (cudaStream_t)stream);
@@ -827,7 +946,13 @@ int mgrl_step(mgrl_env* e, const uint8_t* actions, uint8_t* image, uint8_t* dir,
     EnvParams p = make_params(e);
     p.actions = actions; p.image = image; p.dir = dir; p.mission = mission; p.reward = reward;
     p.term = term; p.trunc = trunc; p.ep_len = ep_len; p.term_image = term_image; p.term_dir = term_dir;
-    return launch_env(e, MODE_STEP, p, (cudaStream_t)stream);
+    // a one-step launch only records which layouts it used up; generate_kernel rebuilds them, densely, every
+    // kDepth steps (an environment cannot use more than kDepth layouts in between)
+    p.defer = 1;
+    int rc = launch_env(e, MODE_STEP, p, (cudaStream_t)stream);
+    if (rc) return rc;
+    if (++e->deferred_steps >= kDepth) rc = flush_deferred(e, (cudaStream_t)stream);
+    return rc;
 }
 
 int mgrl_step_many(mgrl_env* e, int T, const uint8_t* actions, uint8_t* image, uint8_t* dir, uint8_t* mission,
@@ -836,6 +961,8 @@ int mgrl_step_many(mgrl_env* e, int T, const uint8_t* actions, uint8_t* image, u
     if (T <= 0 || !actions || !reward || !term || !trunc)
         return fail(MGRL_ERR_INVALID, "mgrl_step_many: T>0, actions, reward, term and trunc are required%s");
     DeviceGuard guard(e->device);
+    int rc = flush_deferred(e, (cudaStream_t)stream);   // layouts owed to earlier one-step launches first
+    if (rc) return rc;
     EnvParams p = make_params(e);
     p.T = T;
     p.actions = actions; p.image = image; p.dir = dir; p.mission = mission; p.reward = reward;
@@ -864,6 +991,8 @@ int mgrl_set_state(mgrl_env* e, const void* src, size_t bytes, uint64_t seed, vo
     if (bytes != (size_t)e->cfg.num_envs * sizeof(EnvState)) return fail(MGRL_ERR_INVALID, "mgrl_set_state: bad size%s");
     DeviceGuard guard(e->device);
     e->seed = seed;
+    e->deferred_steps = 0;
+    CUDA_TRY(cudaMemsetAsync(e->gcount, 0, sizeof(uint32_t), (cudaStream_t)stream));
     CUDA_TRY(cudaMemcpyAsync(e->states, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return launch_env(e, MODE_PRIME, make_params(e), (cudaStream_t)stream);   // layouts of the next episodes
 }
@@ -884,6 +1013,8 @@ int mgrl_set_state_host(mgrl_env* e, const void* src, size_t bytes, uint64_t see
         return fail(MGRL_ERR_INVALID, "mgrl_set_state_host: bad size%s");
     DeviceGuard guard(e->device);
     e->seed = seed;
+    e->deferred_steps = 0;
+    CUDA_TRY(cudaMemsetAsync(e->gcount, 0, sizeof(uint32_t), (cudaStream_t)stream));
     CUDA_TRY(cudaMemcpyAsync(e->states, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     const int rc = launch_env(e, MODE_PRIME, make_params(e), (cudaStream_t)stream);
     if (rc) return rc;

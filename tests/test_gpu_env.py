@@ -393,3 +393,56 @@ def test_tgl_replay_with_scripted_traces():
     assert_state_equal(env, o, "tgl replay final")
     assert env.error_flags() == 0
     env.close()
+
+
+def test_mixed_single_and_multi_step_launches_match_oracle():
+    """One-step launches defer layout generation to generate_kernel (every 4 steps); multi-step launches build layouts
+    inside the kernel.  Interleave both on one handle, with uniform random actions (an episode ends every ~7 steps, so
+    environments regularly use several prepared layouts in a row), and compare every step with the oracle."""
+    kw = dict(problem="multi", mission=None)
+    n = 5000
+    env = mg.DeviceEnv(mg.EnvConfig(**kw), num_envs=n, seed=31, env_id_base=7, layout="hwc148")
+    o = orc.OracleVecEnv(orc.make_config(**kw), n, seed=31, env_id_base=7, nthreads=8)
+    env.reset(); o.reset()
+    rs = np.random.RandomState(12)
+    u8 = dict(dtype=torch.uint8, device="cuda")
+
+    def check(img, rew, term, trunc, ctx):
+        assert np.array_equal(img.cpu().numpy()[:, :147].reshape(n, 7, 7, 3), o.obs), ctx
+        assert np.array_equal(rew.cpu().numpy().view(np.uint32), o.reward.view(np.uint32)), ctx
+        assert np.array_equal(term.cpu().numpy(), o.term) and np.array_equal(trunc.cpu().numpy(), o.trunc), ctx
+
+    step_no = 0
+    for kind, count in [("one", 3), ("many", 5), ("one", 2), ("many", 37), ("one", 9), ("many", 1), ("one", 1), ("many", 64),
+                        ("one", 23), ("many", 3), ("one", 6)]:
+        if kind == "one":
+            for _ in range(count):
+                a = rs.randint(0, 7, n).astype(np.uint8)
+                env.step(torch.from_numpy(a).cuda())
+                o.step(a)
+                check(env.image, env.reward, env.term, env.trunc, (kind, step_no))
+                step_no += 1
+        else:
+            acts = rs.randint(0, 7, (count, n)).astype(np.uint8)
+            image = torch.empty((count, n, 148), **u8)
+            rew = torch.empty((count, n), dtype=torch.float32, device="cuda")
+            term = torch.empty((count, n), **u8); trunc = torch.empty((count, n), **u8)
+            env.step_many(torch.from_numpy(acts).cuda(), image, None, None, rew, term, trunc, None)
+            for t in range(count):
+                o.step(acts[t])
+                check(image[t], rew[t], term[t], trunc[t], (kind, step_no))
+                step_no += 1
+    assert_state_equal(env, o, "mixed final")
+    # a state restore in the middle of deferred bookkeeping
+    snap = env.get_state_numpy().copy()
+    for _ in range(2):
+        a = rs.randint(0, 7, n).astype(np.uint8)
+        env.step(torch.from_numpy(a).cuda()); o.step(a)
+    env.set_state_numpy(snap, seed=31)
+    o.states[:] = snap
+    for t in range(11):
+        a = rs.randint(0, 7, n).astype(np.uint8)
+        env.step(torch.from_numpy(a).cuda()); o.step(a)
+        check(env.image, env.reward, env.term, env.trunc, ("restored", t))
+    assert env.error_flags() == 0
+    env.close()
