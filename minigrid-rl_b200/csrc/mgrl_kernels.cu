@@ -53,6 +53,7 @@ struct EnvParams {
     EnvState* states;         // [n] current state of every environment
     EnvState* slots;          // [kDepth][n] prepared layouts: slot (E % kDepth) holds episode E once its
                               //   episode word (the tag, written last) reads E + 1
+    uint8_t* tags;            // [kDepth][n] low byte of every slot's tag, compact copy for the coalesced prologue load
     uint16_t* qsave;          // [tiles][kQueueCap] generation requests left over by the previous launch
     uint32_t* qcount;         // [tiles]
     uint32_t* glist;          // [kDepth * n] deferred requests of one-step launches: env * kDepth + slot
@@ -267,6 +268,7 @@ __device__ __noinline__ bool serve_queue(TileSmem<TILE, NB>& sm, const EnvParams
         for (int i = 0; i < STATE_WORDS; ++i) __stcg(slot + i, sc[i]);
         // hand-off inside the CTA: layout (global) -> fence -> tag byte (shared); the adopting lane
         // reads the tag byte, fences, then reads the layout
+        p.tags[(size_t)j * p.n + tile0 + e] = (uint8_t)sc[33];
         __threadfence_block();
         *reinterpret_cast<volatile uint8_t*>(&sm.ready[j][e]) = (uint8_t)sc[33];
     }
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(TILE, TILE == 128 ? 4 : 7) step_kernel(const E
         if (tid < NW) sm.warp_t[tid] = 0;
 #pragma unroll
         for (int j = 0; j < kDepth; ++j)
-            sm.ready[j][tid] = tid < nv ? (uint8_t)reinterpret_cast<const uint32_t*>(p.slots + (size_t)j * p.n + tile0 + tid)[33] : (uint8_t)0;
+            sm.ready[j][tid] = tid < nv ? p.tags[(size_t)j * p.n + tile0 + tid] : (uint8_t)0;
     }
     __syncthreads();
 
@@ -386,6 +388,7 @@ __global__ void __launch_bounds__(TILE, TILE == 128 ? 4 : 7) step_kernel(const E
                                         sm.prefix, sm.empty);
                         adopt_layout(cur, sc);
                         __stcg(const_cast<uint32_t*>(slot) + 33, E + 1u);
+                        p.tags[(size_t)j * p.n + tile0 + tid] = (uint8_t)(E + 1u);
                         *const_cast<volatile uint8_t*>(tag) = (uint8_t)(E + 1u);
                         pending = false; carry = 0;
                     }
@@ -479,6 +482,7 @@ __global__ void __launch_bounds__(NWARPS * 32) generate_kernel(const EnvParams p
             generate(*reinterpret_cast<EnvState*>(sc), p.cfg, p.seed, p.env_id_base + (uint64_t)env, episode, io);
 #pragma unroll
             for (int i = 0; i < STATE_WORDS; ++i) slot[i] = sc[i];
+            p.tags[(size_t)j * p.n + env] = (uint8_t)sc[33];
         }
         __syncwarp();
     }
@@ -531,6 +535,7 @@ __global__ void __launch_bounds__(TILE) reset_kernel(const EnvParams p) {
             uint32_t* slot = reinterpret_cast<uint32_t*>(p.slots + (size_t)(episode % kDepth) * p.n + tile0 + tid);
 #pragma unroll
             for (int i = 0; i < STATE_WORDS; ++i) slot[i] = sc[i];
+            p.tags[(size_t)(episode % kDepth) * p.n + tile0 + tid] = (uint8_t)sc[33];
         }
     }
     if (PRIME) return;
@@ -680,6 +685,7 @@ struct mgrl_env {
     uint64_t seed;
     EnvState* states;
     EnvState* slots;     // [kDepth][N]
+    uint8_t* tags;       // [kDepth][N]
     uint16_t* qsave;     // [tiles(64)][kQueueCap]
     uint32_t* qcount;    // [tiles(64)]
     uint32_t* glist;     // [kDepth * N] deferred requests of one-step launches
@@ -710,6 +716,7 @@ EnvParams make_params(const mgrl_env* e) {
     p.T = 1;
     p.states = e->states;
     p.slots = e->slots;
+    p.tags = e->tags;
     p.qsave = e->qsave;
     p.qcount = e->qcount;
     p.glist = e->glist;
@@ -880,6 +887,8 @@ int mgrl_create(const mgrl_config* cfg, int device, mgrl_env** out) {
     if (err == cudaSuccess) err = cudaMemset(e->states, 0, (size_t)cfg->num_envs * sizeof(EnvState));
     if (err == cudaSuccess) err = cudaMalloc(&e->slots, (size_t)kDepth * cfg->num_envs * sizeof(EnvState));
     if (err == cudaSuccess) err = cudaMemset(e->slots, 0, (size_t)kDepth * cfg->num_envs * sizeof(EnvState));
+    if (err == cudaSuccess) err = cudaMalloc(&e->tags, (size_t)kDepth * cfg->num_envs);
+    if (err == cudaSuccess) err = cudaMemset(e->tags, 0, (size_t)kDepth * cfg->num_envs);
     if (err == cudaSuccess) err = cudaMalloc(&e->qsave, n_tiles * kQueueCap * sizeof(uint16_t));
     if (err == cudaSuccess) err = cudaMalloc(&e->qcount, n_tiles * sizeof(uint32_t));
     if (err == cudaSuccess) err = cudaMemset(e->qcount, 0, n_tiles * sizeof(uint32_t));
@@ -907,7 +916,7 @@ int mgrl_create(const mgrl_config* cfg, int device, mgrl_env** out) {
 int mgrl_destroy(mgrl_env* e) {
     if (!e) return MGRL_OK;
     DeviceGuard guard(e->device);
-    void* bufs[] = {e->states, e->slots, e->qsave, e->qcount, e->glist, e->gcount, e->tasks, e->prefix, e->empty, e->lut, e->err_flags, e->h_actions, e->h_image, e->h_dir, e->h_mission, e->h_term,
+    void* bufs[] = {e->states, e->slots, e->tags, e->qsave, e->qcount, e->glist, e->gcount, e->tasks, e->prefix, e->empty, e->lut, e->err_flags, e->h_actions, e->h_image, e->h_dir, e->h_mission, e->h_term,
                     e->h_trunc, e->h_eplen, e->h_termimg, e->h_termdir, e->h_reward, e->h_stack_img, e->h_stack_dir,
                     e->h_stack_mis, e->h_table};
     for (void* b : bufs)
