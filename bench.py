@@ -139,8 +139,10 @@ def run_reference(args):
         "impl": "reference", "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * N_ENVS * T_ROLLOUT / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"{TASK} multi-room 11x11, {N_ENVS} envs/GPU, rollout {T_ROLLOUT} steps",
-                   "note": "C oracle port of the reference CPU path (reference itself needs minigrid/SB3, absent)"},
+        "config": {"workload": f"{TASK} multi-room 11x11 (BASELINE configs[1]), {N_ENVS} envs/GPU, rollout {T_ROLLOUT} steps, "
+                               "uniform random u8 actions resident in HBM",
+                   "note": "C oracle port of the reference CPU path on the host cores (the reference itself needs minigrid / "
+                           "gymnasium / SB3, absent); outputs: un-stacked observation, reward, flags, like the GPU arm's e2e"},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": nthreads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
