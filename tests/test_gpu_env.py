@@ -446,3 +446,58 @@ def test_mixed_single_and_multi_step_launches_match_oracle():
         check(env.image, env.reward, env.term, env.trunc, ("restored", t))
     assert env.error_flags() == 0
     env.close()
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 127, 129, 257])
+def test_ragged_batch_sizes(n):
+    """tiles that are not full (and warps that are not full) in every kernel: reset, one-step, multi-step, deferred layouts"""
+    kw = dict(problem="multi", mission=None)
+    env = mg.DeviceEnv(mg.EnvConfig(**kw), num_envs=n, seed=3, env_id_base=11, layout="hwc148")
+    o = orc.OracleVecEnv(orc.make_config(**kw), n, seed=3, env_id_base=11)
+    env.reset(); o.reset()
+    rs = np.random.RandomState(n)
+    for t in range(30):
+        a = rs.randint(0, 7, n).astype(np.uint8)
+        env.step(torch.from_numpy(a).cuda()); o.step(a)
+        assert np.array_equal(env.image.cpu().numpy()[:, :147].reshape(n, 7, 7, 3), o.obs), t
+        assert np.array_equal(env.reward.cpu().numpy().view(np.uint32), o.reward.view(np.uint32)), t
+    T = 50
+    acts = rs.randint(0, 7, (T, n)).astype(np.uint8)
+    u8 = dict(dtype=torch.uint8, device="cuda")
+    image = torch.empty((T, n, 148), **u8); rew = torch.empty((T, n), dtype=torch.float32, device="cuda")
+    term = torch.empty((T, n), **u8); trunc = torch.empty((T, n), **u8)
+    env.step_many(torch.from_numpy(acts).cuda(), image, None, None, rew, term, trunc, None)
+    for t in range(T):
+        o.step(acts[t])
+        assert np.array_equal(image[t].cpu().numpy()[:, :147].reshape(n, 7, 7, 3), o.obs), t
+        assert np.array_equal(term[t].cpu().numpy(), o.term), t
+    assert_state_equal(env, o, f"ragged {n}")
+    assert env.error_flags() == 0
+    env.close()
+
+
+# (size 5 multi-room maps are left out on purpose: every interior cell is next to a door there, so the reference's
+#  "goal away from doors" loop never terminates; oracle and product both bound such loops at 1000 tries, but only
+#  terminating configurations are part of the parity contract -- DESIGN.md §2.)
+@pytest.mark.parametrize("kw", [dict(problem="multi", mission=0, size=7, num_objects=8),
+                                dict(problem="multi", mission=2, size=8, num_objects=0),
+                                dict(problem="gto", mission=None, size=6, num_objects=3),
+                                dict(problem="pkp", mission=None, size=11, num_objects=18),
+                                dict(problem="multi", mission=1, size=11, num_objects=16, all_doors_open=True)],
+                         ids=["s7_n8", "s8_n0", "gto_s6", "pkp_n18", "n16_open"])
+def test_size_and_object_count_extremes(kw):
+    n = 400
+    env = mg.DeviceEnv(mg.EnvConfig(**kw), num_envs=n, seed=21, layout="hwc")
+    o = orc.OracleVecEnv(orc.make_config(**kw), n, seed=21)
+    env.reset(); o.reset()
+    assert_state_equal(env, o, "reset")
+    rs = np.random.RandomState(2)
+    for t in range(60):
+        a = biased_actions(rs, n)
+        env.step(torch.from_numpy(a).cuda()); o.step(a)
+        assert np.array_equal(hwc(env.image, n), o.obs), t
+        assert np.array_equal(env.reward.cpu().numpy().view(np.uint32), o.reward.view(np.uint32)), t
+        assert np.array_equal(env.term.cpu().numpy(), o.term) and np.array_equal(env.trunc.cpu().numpy(), o.trunc), t
+    assert_state_equal(env, o, "final")
+    assert env.error_flags() == int(o.states["error"].max())
+    env.close()
