@@ -289,7 +289,20 @@ __global__ void __launch_bounds__(TILE, TILE == 128 ? 4 : 7) step_kernel(const E
     const int nv = min(TILE, p.n - tile0);
     const int S = p.cfg.size;
 
-    coop_copy<TILE>(sm.state, p.states + tile0, nv * (int)sizeof(EnvState), tid);
+    if (nv == TILE) {   // full tile: all 16-byte loads of a thread in flight together (the generic copy is rolled)
+        const uint4* g = reinterpret_cast<const uint4*>(p.states + tile0);
+        uint4* d = reinterpret_cast<uint4*>(sm.state);
+        constexpr int NV4 = TILE * (int)sizeof(EnvState) / 16;
+        uint4 v[(NV4 + TILE - 1) / TILE];
+#pragma unroll
+        for (int i = 0; i < (NV4 + TILE - 1) / TILE; ++i)
+            if (i * TILE + tid < NV4) v[i] = g[i * TILE + tid];
+#pragma unroll
+        for (int i = 0; i < (NV4 + TILE - 1) / TILE; ++i)
+            if (i * TILE + tid < NV4) d[i * TILE + tid] = v[i];
+    } else {
+        coop_copy<TILE>(sm.state, p.states + tile0, nv * (int)sizeof(EnvState), tid);
+    }
     tile_prologue<TILE, NB>(sm, p, tid);
     {   // requests the previous launch left behind
         uint32_t nq = p.qcount[blockIdx.x];
@@ -793,15 +806,14 @@ int ensure_host_buffers(mgrl_env* e) {
     const size_t n = (size_t)e->cfg.num_envs;
     CUDA_TRY(cudaMalloc(&e->h_actions, n));
     CUDA_TRY(cudaMalloc(&e->h_image, n * kObsPitch148));
-    CUDA_TRY(cudaMalloc(&e->h_dir, n));
-    CUDA_TRY(cudaMalloc(&e->h_mission, n));
-    CUDA_TRY(cudaMalloc(&e->h_term, n));
-    CUDA_TRY(cudaMalloc(&e->h_trunc, n));
-    CUDA_TRY(cudaMalloc(&e->h_eplen, n));
+    // the small per-step outputs live in one slab (reward | dir | mission | term | trunc | ep_len | term_dir) so that a
+    // caller whose host buffers are laid out the same way gets them with ONE device-to-host copy
+    CUDA_TRY(cudaMalloc(&e->h_reward, n * 10));
+    e->h_dir = reinterpret_cast<uint8_t*>(e->h_reward) + 4 * n;
+    e->h_mission = e->h_dir + n; e->h_term = e->h_mission + n; e->h_trunc = e->h_term + n; e->h_eplen = e->h_trunc + n;
+    e->h_termdir = e->h_eplen + n;
     CUDA_TRY(cudaMalloc(&e->h_termimg, n * kObsPitch148));
-    CUDA_TRY(cudaMalloc(&e->h_termdir, n));
     CUDA_TRY(cudaMemset(e->h_termdir, 0, n));
-    CUDA_TRY(cudaMalloc(&e->h_reward, n * sizeof(float)));
     CUDA_TRY(cudaMalloc(&e->h_stack_img, n * MGRL_FRAMES * kObsBytes));
     CUDA_TRY(cudaMalloc(&e->h_stack_dir, n * 16));
     CUDA_TRY(cudaMalloc(&e->h_stack_mis, n * MGRL_FRAMES * MGRL_MISSION_TOKENS * sizeof(int64_t)));
@@ -916,8 +928,8 @@ int mgrl_create(const mgrl_config* cfg, int device, mgrl_env** out) {
 int mgrl_destroy(mgrl_env* e) {
     if (!e) return MGRL_OK;
     DeviceGuard guard(e->device);
-    void* bufs[] = {e->states, e->slots, e->tags, e->qsave, e->qcount, e->glist, e->gcount, e->tasks, e->prefix, e->empty, e->lut, e->err_flags, e->h_actions, e->h_image, e->h_dir, e->h_mission, e->h_term,
-                    e->h_trunc, e->h_eplen, e->h_termimg, e->h_termdir, e->h_reward, e->h_stack_img, e->h_stack_dir,
+    void* bufs[] = {e->states, e->slots, e->tags, e->qsave, e->qcount, e->glist, e->gcount, e->tasks, e->prefix, e->empty, e->lut, e->err_flags, e->h_actions, e->h_image,
+                    e->h_termimg, e->h_reward, e->h_stack_img, e->h_stack_dir,
                     e->h_stack_mis, e->h_table};
     for (void* b : bufs)
         if (b) cudaFree(b);
@@ -1156,14 +1168,22 @@ int mgrl_vec_step_frames_host(mgrl_env* e, const uint8_t* actions_host, uint8_t*
                        e->h_eplen, term_image_host ? e->h_termimg : nullptr, term_dir_host ? e->h_termdir : nullptr, stream);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(image_host, e->h_image, n * pitch, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(dir_host, e->h_dir, n, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(mission_host, e->h_mission, n, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(reward_host, e->h_reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(term_host, e->h_term, n, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(trunc_host, e->h_trunc, n, cudaMemcpyDeviceToHost, s));
-    if (ep_len_host) CUDA_TRY(cudaMemcpyAsync(ep_len_host, e->h_eplen, n, cudaMemcpyDeviceToHost, s));
+    uint8_t* hb = reinterpret_cast<uint8_t*>(reward_host);
+    const bool slab = dir_host == hb + 4 * n && mission_host == dir_host + n && term_host == mission_host + n &&
+                      trunc_host == term_host + n && ep_len_host == trunc_host + n &&
+                      (!term_dir_host || term_dir_host == ep_len_host + n);
+    if (slab) {   // host buffers mirror the device slab: one copy for everything but the images
+        CUDA_TRY(cudaMemcpyAsync(reward_host, e->h_reward, n * (term_dir_host ? 10 : 9), cudaMemcpyDeviceToHost, s));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(dir_host, e->h_dir, n, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(mission_host, e->h_mission, n, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(reward_host, e->h_reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(term_host, e->h_term, n, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(trunc_host, e->h_trunc, n, cudaMemcpyDeviceToHost, s));
+        if (ep_len_host) CUDA_TRY(cudaMemcpyAsync(ep_len_host, e->h_eplen, n, cudaMemcpyDeviceToHost, s));
+        if (term_dir_host) CUDA_TRY(cudaMemcpyAsync(term_dir_host, e->h_termdir, n, cudaMemcpyDeviceToHost, s));
+    }
     if (term_image_host) CUDA_TRY(cudaMemcpyAsync(term_image_host, e->h_termimg, n * pitch, cudaMemcpyDeviceToHost, s));
-    if (term_dir_host) CUDA_TRY(cudaMemcpyAsync(term_dir_host, e->h_termdir, n, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return MGRL_OK;
 }

@@ -127,6 +127,19 @@ class _Pinned:
             self.ptr = C.c_void_p()
 
 
+class _View:
+    """typed window into a _Pinned slab"""
+
+    def __init__(self, slab, offset, shape, dtype):
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape))
+        self.ptr = C.c_void_p(slab.ptr.value + offset)
+        self.array = slab.array[offset:offset + count * dtype.itemsize].view(dtype).reshape(shape)
+
+    def free(self):
+        self.array = None
+
+
 _EMPTY_INFO: dict = {}
 
 
@@ -163,14 +176,19 @@ class B200VecEnv:
             "mission": _Pinned(lib, (n, 32 * FRAMES), np.int64),
         } for _ in range(2)]
         self._cur = 0
+        # the small per-step outputs share one pinned slab laid out like the library's device slab
+        # (reward | dir | mission | term | trunc | ep_len | term_dir), so step_frames gets them in one copy
+        self._slab = _Pinned(lib, (10 * n,), np.uint8)
         self._p = {
             "actions": _Pinned(lib, (n,), np.uint8),
-            "reward": _Pinned(lib, (n,), np.float32),
-            "term": _Pinned(lib, (n,), np.uint8),
-            "trunc": _Pinned(lib, (n,), np.uint8),
-            "ep_len": _Pinned(lib, (n,), np.uint8),
+            "reward": _View(self._slab, 0, (n,), np.float32),
+            "f_dir": _View(self._slab, 4 * n, (n,), np.uint8),
+            "f_mission": _View(self._slab, 5 * n, (n,), np.uint8),
+            "term": _View(self._slab, 6 * n, (n,), np.uint8),
+            "trunc": _View(self._slab, 7 * n, (n,), np.uint8),
+            "ep_len": _View(self._slab, 8 * n, (n,), np.uint8),
+            "term_dir": _View(self._slab, 9 * n, (n,), np.uint8),
             "term_image": _Pinned(lib, (n, 3, 7, 7), np.uint8),
-            "term_dir": _Pinned(lib, (n,), np.uint8),
         }
         self._frames = None
         self._actions = None
@@ -253,8 +271,8 @@ class B200VecEnv:
     def _frame_bufs(self):
         if self._frames is None:
             lib, n = self._h.lib, self.num_envs
-            self._frames = {"image": _Pinned(lib, (n, self.pitch), np.uint8), "dir": _Pinned(lib, (n,), np.uint8),
-                            "mission": _Pinned(lib, (n,), np.uint8), "term_image": _Pinned(lib, (n, self.pitch), np.uint8)}
+            self._frames = {"image": _Pinned(lib, (n, self.pitch), np.uint8), "dir": self._p["f_dir"],
+                            "mission": self._p["f_mission"], "term_image": _Pinned(lib, (n, self.pitch), np.uint8)}
         return self._frames
 
     def reset_frames(self):
@@ -283,6 +301,7 @@ class B200VecEnv:
                 v.free()
         for v in self._p.values():
             v.free()
+        self._slab.free()
         for b in self._obs_bufs:
             for v in b.values():
                 v.free()
