@@ -544,7 +544,10 @@ struct GenIO {
     const uint32_t* tasks;     // [kTaskEntries][kTaskWords] (build_task_table)
     const uint32_t* prefix;    // [kTaskWords] (build_task_prefix)
     const uint32_t* empty;     // [kGridWords] fresh grid
+    bool keep_marks = false;   // true: leave the next-to-a-door marks in the grid words; the caller strips them
+                               //   (word & kMarkMask) while it copies the layout out
 };
+constexpr uint32_t kMarkMask = 0x7F7F7F7Fu;
 
 // Builds the layout of `episode` into s: grid, agent, target, mission, carrying = 0, step_count = 0,
 // episode = episode + 1, reset_draws; ORs ERR_TRIES into s.error.  mission_done / latch_step are
@@ -658,7 +661,8 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
             const int i = (int)mulhi32(word, (uint32_t)popc32(pool)); ++nd;
             const int bit = nth_set_bit(pool, i);
             pool &= ~(1u << bit);
-            const int type = (int)((pool_types >> (3 * (bit / 6))) & 7u), colour = sorted_colour(bit % 6);
+            const int slot = (bit >= 6) + (bit >= 12) + (bit >= 18);       // bit / 6 for bit < 24
+            const int type = (int)((pool_types >> (3 * slot)) & 7u), colour = sorted_colour(bit - 6 * slot);
             kind = obj_kind(type, colour);
             objw = (uint32_t)(type | (colour << 3));
         } else if (stage == G_KEY) {
@@ -682,7 +686,14 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
     else { kind = K_GOAL; objw = T_GOAL; }
 
     while (task != 0u) {
-        const uint32_t d0 = draw(0), d1 = draw(1), d2 = draw(2), d3 = draw(3);
+        // the four draws an iteration can use: position x, y, then agent direction / next task's pool entry
+        uint32_t d0, d1, d2, d3;
+        if (nd + 4 <= kDrawBuf) {
+            const uint32_t* w = io.draws + nd * ds;
+            d0 = w[0]; d1 = w[ds]; d2 = w[2 * ds]; d3 = w[3 * ds];
+        } else {
+            d0 = draw(0); d1 = draw(1); d2 = draw(2); d3 = draw(3);
+        }
         const int x = (int)(task & 15u) + (int)mulhi32(d0, (task >> 4) & 15u);
         const int y = (int)((task >> 8) & 15u) + (int)mulhi32(d1, (task >> 12) & 15u);
         nd += 2;
@@ -690,10 +701,13 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
         const int cell = y * S + x;
         const uint32_t here = s.grid[cell];           // kind | kDoorFlag (flag only ever set on a multi map)
         const uint32_t mask = (task & TF_KEYMODE) ? kDoorFlag : (task & TF_AGENTMODE) ? 0x7Fu : 0xFFu;
-        bool bad = (here & mask) != 0u && !((task & TF_LAVA) && here == (uint32_t)K_LAVA);
-        bad = bad || ((task & TF_AGENT_CELL) && xy == agent_xy) || xy == goal_xy || xy == key_xy;
-        bad = bad || ((task & TF_MID) && (x == m || y == m));
-        if (bad && ++tries >= kMaxTries) { s.error |= ERR_TRIES; bad = false; }
+        // admissibility as one predicate expression (no short-circuit branches)
+        const bool occupied = ((here & mask) != 0u) & !(((task & TF_LAVA) != 0u) & (here == (uint32_t)K_LAVA));
+        const bool on_agent = ((task & TF_AGENT_CELL) != 0u) & (xy == agent_xy);
+        const bool on_mid = ((task & TF_MID) != 0u) & ((x == m) | (y == m));
+        bool bad = occupied | on_agent | (xy == goal_xy) | (xy == key_xy) | on_mid;
+        tries += bad;
+        if (tries >= kMaxTries) { s.error |= ERR_TRIES; bad = false; }
         if (!bad) {
             tries = 0;
             const int stage = (int)((task >> 16) & 7u);
@@ -720,9 +734,9 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
         }
     }
     s.agent_x = (uint8_t)(agent_xy & 0xFFu); s.agent_y = (uint8_t)(agent_xy >> 8);
-    if (multi) {  // drop the next-to-a-door marks
+    if (multi && !io.keep_marks) {  // drop the next-to-a-door marks
 #pragma unroll 4
-        for (int i = 0; i < kGridWords; ++i) gw[i] &= 0x7F7F7F7Fu;
+        for (int i = 0; i < kGridWords; ++i) gw[i] &= kMarkMask;
     }
 
     // ---- 4. target selection (:174-267)

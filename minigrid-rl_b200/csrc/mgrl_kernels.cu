@@ -221,11 +221,12 @@ __device__ __forceinline__ void push_requests(TileSmem<TILE, NB>& sm, unsigned m
 }
 
 // the step kernel's single out-of-line copy of the generator
+// (leaves the next-to-a-door marks in the grid words: strip them with kMarkMask on the way out)
 __device__ __noinline__ void generate_layout(uint32_t* sc, const EnvCfg& cfg, uint64_t seed, uint64_t env_id, uint32_t episode,
                                              uint32_t* draws, const uint32_t* tasks, const uint32_t* prefix, const uint32_t* empty) {
     sc[32] = 0u; sc[34] = 0u;
     GenIO io;
-    io.draws = draws; io.stride = 32; io.tasks = tasks; io.prefix = prefix; io.empty = empty;
+    io.draws = draws; io.stride = 32; io.tasks = tasks; io.prefix = prefix; io.empty = empty; io.keep_marks = true;
     generate(*reinterpret_cast<EnvState*>(sc), cfg, seed, env_id, episode, io);
 }
 
@@ -265,7 +266,7 @@ __device__ __noinline__ bool serve_queue(TileSmem<TILE, NB>& sm, const EnvParams
         generate_layout(sc, p.cfg, p.seed, p.env_id_base + (uint64_t)(tile0 + e), episode, sm.draws[b] + lane, p.tasks,
                         sm.prefix, sm.empty);
 #pragma unroll
-        for (int i = 0; i < STATE_WORDS; ++i) __stcg(slot + i, sc[i]);
+        for (int i = 0; i < STATE_WORDS; ++i) __stcg(slot + i, i < kGridWords ? sc[i] & kMarkMask : sc[i]);
         // hand-off inside the CTA: layout (global) -> fence -> tag byte (shared); the adopting lane
         // reads the tag byte, fences, then reads the layout
         p.tags[(size_t)j * p.n + tile0 + e] = (uint8_t)sc[33];
@@ -399,6 +400,8 @@ __global__ void __launch_bounds__(TILE, TILE == 128 ? 4 : 7) step_kernel(const E
                         uint32_t* sc = reinterpret_cast<uint32_t*>(sm.obs[warp]) + lane * STATE_WORDS;
                         generate_layout(sc, p.cfg, p.seed, p.env_id_base + (uint64_t)(tile0 + tid), E, sm.draws[b] + lane, p.tasks,
                                         sm.prefix, sm.empty);
+#pragma unroll 4
+                        for (int i = 0; i < kGridWords; ++i) sc[i] &= kMarkMask;
                         adopt_layout(cur, sc);
                         __stcg(const_cast<uint32_t*>(slot) + 33, E + 1u);
                         p.tags[(size_t)j * p.n + tile0 + tid] = (uint8_t)(E + 1u);
@@ -492,9 +495,10 @@ __global__ void __launch_bounds__(NWARPS * 32) generate_kernel(const EnvParams p
             sc[32] = 0u; sc[34] = 0u;
             GenIO io;
             io.draws = sm.draws[warp] + lane; io.stride = 32; io.tasks = p.tasks; io.prefix = sm.prefix; io.empty = sm.empty;
+            io.keep_marks = true;
             generate(*reinterpret_cast<EnvState*>(sc), p.cfg, p.seed, p.env_id_base + (uint64_t)env, episode, io);
 #pragma unroll
-            for (int i = 0; i < STATE_WORDS; ++i) slot[i] = sc[i];
+            for (int i = 0; i < STATE_WORDS; ++i) slot[i] = i < kGridWords ? sc[i] & kMarkMask : sc[i];
             p.tags[(size_t)j * p.n + env] = (uint8_t)sc[33];
         }
         __syncwarp();
@@ -544,7 +548,7 @@ __global__ void __launch_bounds__(TILE) reset_kernel(const EnvParams p) {
         for (int k = 0; k < kDepth; ++k) {
             const uint32_t episode = s.episode + (uint32_t)k;
             sc[32] = 0u; sc[34] = 0u;
-            generate(*reinterpret_cast<EnvState*>(sc), p.cfg, p.seed, env_id, episode, io);
+            generate(*reinterpret_cast<EnvState*>(sc), p.cfg, p.seed, env_id, episode, io);   // (marks stripped inside)
             uint32_t* slot = reinterpret_cast<uint32_t*>(p.slots + (size_t)(episode % kDepth) * p.n + tile0 + tid);
 #pragma unroll
             for (int i = 0; i < STATE_WORDS; ++i) slot[i] = sc[i];
