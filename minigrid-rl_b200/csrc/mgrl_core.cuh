@@ -599,8 +599,10 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
 
     // ---- 2. multi-room prologue (_generate_multi_map :601-611, doors :635-650, :880-929, :1324-1390)
     if (multi) {
-        if (cmd < 0) { cmd = (int)((0x5210u >> (4 * mulhi32(draw(0), 4))) & 0xFu); ++nd; }  // choice([0,1,2,5])
-        nrooms = 2 + (int)mulhi32(draw(0), 3); ++nd;                                         // randint(2,4)
+        // (at most 2 + 4*3 + 4*2 = 22 draws here: always inside the precomputed buffer)
+        auto pdraw = [&](int i) -> uint32_t { return io.draws[(nd + i) * ds]; };
+        if (cmd < 0) { cmd = (int)((0x5210u >> (4 * mulhi32(pdraw(0), 4))) & 0xFu); ++nd; }  // choice([0,1,2,5])
+        nrooms = 2 + (int)mulhi32(pdraw(0), 3); ++nd;                                         // randint(2,4)
         const int ndoors = nrooms == 2 ? 1 : nrooms;
         const int hi = nrooms == 3 ? m : S - 1;
         for (int i = 1; i < S - 1; ++i) {
@@ -611,13 +613,13 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
 #pragma unroll 1
         for (int d = 0; d < 4; ++d) {
             if (d < ndoors) {
-                const int i = (int)mulhi32(draw(0), (uint32_t)popc32(colours));
+                const int i = (int)mulhi32(pdraw(0), (uint32_t)popc32(colours));
                 const int bit = nth_set_bit(colours, i);
                 colours &= ~(1u << bit);
                 const int colour = sorted_colour(bit);
                 int used = 1;
-                const int locked = cfg.all_doors_open ? 0 : (mulhi32(draw(used++), 2) == 0);  // choice([True, False])
-                const int kib = mulhi32(draw(used++), 2) == 0;
+                const int locked = cfg.all_doors_open ? 0 : (mulhi32(pdraw(used++), 2) == 0);  // choice([True, False])
+                const int kib = mulhi32(pdraw(used++), 2) == 0;
                 nd += used;
                 if (locked) {  // obj_choice.remove(('key', c)) [, ('box', c)]: pool slots are key, ball, box
                     pool &= ~(1u << (0 * 6 + sorted_index(colour)));
@@ -634,9 +636,9 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
                 if (nrooms == 2) { horizontal = false; lo = 1; hi2 = S - 2; }
                 else if (nrooms == 3) { horizontal = d == 0; lo = d == 2 ? m + 1 : 1; hi2 = d == 2 ? S - 2 : m - 1; }
                 else { horizontal = d < 2; lo = (d & 1) ? m + 1 : 1; hi2 = (d & 1) ? S - 2 : m - 1; }
-                const int p = lo + (int)mulhi32(draw(0), (uint32_t)(hi2 - lo + 1)); ++nd;
+                const int p = lo + (int)mulhi32(pdraw(0), (uint32_t)(hi2 - lo + 1)); ++nd;
                 int is_open = 0;
-                if (cfg.all_doors_open) { is_open = mulhi32(draw(0), 2) == 0; ++nd; }
+                if (cfg.all_doors_open) { is_open = mulhi32(pdraw(0), 2) == 0; ++nd; }
                 const int props = (int)((doors >> (8 * d)) & 0xFFu);
                 const int colour = props & 7, state = is_open ? 0 : (((props >> 3) & 1) ? 2 : 1);
                 const int x = horizontal ? p : m, y = horizontal ? m : p;
