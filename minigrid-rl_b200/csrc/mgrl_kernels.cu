@@ -441,10 +441,16 @@ __global__ void __launch_bounds__(TILE, TILE == 128 ? 4 : 7) step_kernel(const E
         __syncwarp();
         // the warp that is furthest ahead builds the next batch of layouts
         if (lane == 0) warp_t[warp] = t + 1;
-        bool lead = true;
+        if (!p.defer) {
+            // cheap look before the call: is a full batch waiting, and is this warp (one of) the furthest ahead?
+            const uint32_t waiting = *reinterpret_cast<volatile uint32_t*>(&sm.q_tail) - *reinterpret_cast<volatile uint32_t*>(&sm.q_head);
+            if (waiting >= 32u) {
+                bool lead = true;
 #pragma unroll
-        for (int w2 = 0; w2 < NW; ++w2) lead = lead && warp_t[w2] <= t + 1;
-        if (lead && !p.defer) serve_queue<TILE, NB>(sm, p, tile0, warp, lane, false);
+                for (int w2 = 0; w2 < NW; ++w2) lead = lead && warp_t[w2] <= t + 1;
+                if (lead) serve_queue<TILE, NB>(sm, p, tile0, warp, lane, false);
+            }
+        }
     }
     // keep serving full batches until every warp of the tile has finished its steps
     for (int spins = 0; spins < kSpinLimit && !p.defer; ++spins) {
