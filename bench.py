@@ -358,7 +358,7 @@ def main():
                          # kernel at this shape (profiles/r1b_ncu_full_many.txt); algorithmic bytes = 158 * n * T
                          "traffic": 1.3598e9 if (n, T) == (N_ENVS, T_ROLLOUT) else None, "traffic_unit": "bytes/launch",
                          "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n * T,
-                         "kernel": "step_kernel<HWC148,see_through,128,2>", "peak_source": peak_src,
+                         "kernel": "step_kernel<HWC148,see_through,64,1>", "peak_source": peak_src,
                          "bytes_per_env_step": BYTES_PER_ENV_STEP, "us_per_launch": us_per_launch,
                          "env_steps_per_launch": n * T},
             "per_step_launch": {"value": steps_value, "unit": "env-steps/s", "ms_per_step": ms_steps / K,

@@ -876,8 +876,10 @@ int mgrl_create(const mgrl_config* cfg, int device, mgrl_env** out) {
     memset(e, 0, sizeof *e);
     e->cfg = *cfg;
     e->device = device;
-    e->tile = 128;
-    if (const char* t = getenv("MGRL_TILE")) e->tile = atoi(t) == 64 ? 64 : 128;
+    // 64 environments (2 warps, one draw buffer) per CTA: 7 CTAs per SM, so 65 536 environments spread evenly over the
+    // 148 SMs (6.9 tiles each); 128 per CTA (4 warps, two draw buffers) is the alternative shape (MGRL_TILE=128)
+    e->tile = 64;
+    if (const char* t = getenv("MGRL_TILE")) e->tile = atoi(t) == 128 ? 128 : 64;
     e->ecfg.size = cfg->size;
     e->ecfg.num_objects = cfg->num_objects;
     e->ecfg.problem = cfg->problem;
