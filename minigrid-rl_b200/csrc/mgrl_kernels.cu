@@ -37,6 +37,7 @@ namespace {
 
 constexpr int STATE_WORDS = 35;           // sizeof(EnvState) / 4
 constexpr int kDepth = 4;                 // layouts prepared ahead of time per environment
+constexpr int kSlotWords = 36;             // a prepared layout: the 35 state words + 1 pad word (16-byte aligned records)
 constexpr int kQueueCap = 512;            // >= TILE * kDepth requests can be outstanding per tile
 constexpr uint32_t kNoEntry = 0xFFFFu;
 constexpr unsigned FULL = 0xffffffffu;
@@ -51,8 +52,8 @@ struct EnvParams {
     int n;
     int T;                    // steps per launch
     EnvState* states;         // [n] current state of every environment
-    EnvState* slots;          // [kDepth][n] prepared layouts: slot (E % kDepth) holds episode E once its
-                              //   episode word (the tag, written last) reads E + 1
+    uint32_t* slots;          // [kDepth][n][kSlotWords] prepared layouts: slot (E % kDepth) holds episode E once its
+                              //   episode word (the tag) reads E + 1
     uint8_t* tags;            // [kDepth][n] low byte of every slot's tag, compact copy for the coalesced prologue load
     uint16_t* qsave;          // [tiles][kQueueCap] generation requests left over by the previous launch
     uint32_t* qcount;         // [tiles]
@@ -74,6 +75,10 @@ struct EnvParams {
     uint8_t* term_image;
     uint8_t* term_dir;
 };
+
+__device__ __forceinline__ uint32_t* slot_ptr(uint32_t* slots, int j, int n, int env) {
+    return slots + ((size_t)j * n + env) * kSlotWords;
+}
 
 // ---- cooperative copies (coalesced; 16-byte vectors when size and address allow) ------------
 template <int NTHREADS>
@@ -260,7 +265,7 @@ __device__ __noinline__ bool serve_queue(TileSmem<TILE, NB>& sm, const EnvParams
         while ((ent = *q) == kNoEntry) {}
         *q = (uint16_t)kNoEntry;
         const int e = (int)(ent & 0xFFu), j = (int)(ent >> 8);
-        uint32_t* slot = reinterpret_cast<uint32_t*>(p.slots + (size_t)j * p.n + tile0 + e);
+        uint32_t* slot = slot_ptr(p.slots, j, p.n, tile0 + e);
         const uint32_t episode = __ldcg(slot + 33) - 1u + kDepth;   // the slot's old layout was adopted
         uint32_t* sc = reinterpret_cast<uint32_t*>(sm.obs[warp]) + lane * STATE_WORDS;
         generate_layout(sc, p.cfg, p.seed, p.env_id_base + (uint64_t)(tile0 + e), episode, sm.draws[b] + lane, p.tasks,
@@ -342,6 +347,24 @@ __global__ void __launch_bounds__(TILE, TILE == 128 ? 4 : 7) step_kernel(const E
         int carry = 0;
         const int a = action;
         if (active && t + 1 < p.T) action = p.actions[gi + (size_t)p.n];   // next step's action, in flight during this one
+        // The `done` action always ends the episode (custom_env.py:319-328), so a lane that is about to take it knows
+        // now that it will adopt its next layout in this step: if that layout is ready, fetch it asynchronously
+        // (cp.async, 9 x 16 B, L2 -> the lane's row of the staging area) while the step itself is computed.
+        bool early = false;
+        if (active && a == A_DONE) {
+            const uint32_t E0 = s.episode;
+            const int j0 = (int)(E0 % kDepth);
+            if (*reinterpret_cast<const volatile uint8_t*>(&sm.ready[j0][tid]) == (uint8_t)(E0 + 1u)) {
+                __threadfence_block();
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(stage + lane * (kSlotWords * 4));
+                const uint32_t* src = slot_ptr(p.slots, j0, p.n, tile0 + tid);
+#pragma unroll
+                for (int i = 0; i < kSlotWords / 4; ++i)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + 4 * i) : "memory");
+                early = true;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
         if (active) {
             const StepOut o = env_step(s, a, S, p.cfg.max_steps, sm.lut);
             p.reward[gi] = o.reward;
@@ -360,13 +383,17 @@ __global__ void __launch_bounds__(TILE, TILE == 128 ? 4 : 7) step_kernel(const E
             bool pending = done;
             const uint32_t E = s.episode;
             const int j = (int)(E % kDepth);
-            const uint32_t* slot = reinterpret_cast<const uint32_t*>(p.slots + (size_t)j * p.n + tile0 + tid);
+            const uint32_t* slot = slot_ptr(p.slots, j, p.n, tile0 + tid);
             const uint32_t entry = (uint32_t)tid | ((uint32_t)j << 8);
             const volatile uint8_t* tag = &sm.ready[j][tid];
             int spins = 0;
             for (;;) {
                 bool ready = false;
-                if (pending && *tag == (uint8_t)(E + 1u)) {
+                if (pending && early) {          // the layout is already on its way into this lane's staging row
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    adopt_layout(cur, reinterpret_cast<const uint32_t*>(stage + lane * (kSlotWords * 4)));
+                    ready = true; pending = false; carry = 0;
+                } else if (pending && *tag == (uint8_t)(E + 1u)) {
                     __threadfence_block();
                     uint32_t w[STATE_WORDS];
 #pragma unroll
@@ -495,7 +522,7 @@ __global__ void __launch_bounds__(NWARPS * 32) generate_kernel(const EnvParams p
         if (r < count) {
             const uint32_t ent = p.glist[r];
             const uint32_t env = ent / kDepth, j = ent % kDepth;
-            uint32_t* slot = reinterpret_cast<uint32_t*>(p.slots + (size_t)j * p.n + env);
+            uint32_t* slot = slot_ptr(p.slots, (int)j, p.n, (int)env);
             const uint32_t episode = slot[33] - 1u + kDepth;   // the slot's old layout was adopted
             uint32_t* sc = sm.scratch[warp] + lane * STATE_WORDS;
             sc[32] = 0u; sc[34] = 0u;
@@ -555,7 +582,7 @@ __global__ void __launch_bounds__(TILE) reset_kernel(const EnvParams p) {
             const uint32_t episode = s.episode + (uint32_t)k;
             sc[32] = 0u; sc[34] = 0u;
             generate(*reinterpret_cast<EnvState*>(sc), p.cfg, p.seed, env_id, episode, io);   // (marks stripped inside)
-            uint32_t* slot = reinterpret_cast<uint32_t*>(p.slots + (size_t)(episode % kDepth) * p.n + tile0 + tid);
+            uint32_t* slot = slot_ptr(p.slots, (int)(episode % kDepth), p.n, tile0 + tid);
 #pragma unroll
             for (int i = 0; i < STATE_WORDS; ++i) slot[i] = sc[i];
             p.tags[(size_t)(episode % kDepth) * p.n + tile0 + tid] = (uint8_t)sc[33];
@@ -707,7 +734,7 @@ struct mgrl_env {
     int tile;    // environments per CTA (64 / 128)
     uint64_t seed;
     EnvState* states;
-    EnvState* slots;     // [kDepth][N]
+    uint32_t* slots;     // [kDepth][N][kSlotWords]
     uint8_t* tags;       // [kDepth][N]
     uint16_t* qsave;     // [tiles(64)][kQueueCap]
     uint32_t* qcount;    // [tiles(64)]
@@ -909,8 +936,8 @@ int mgrl_create(const mgrl_config* cfg, int device, mgrl_env** out) {
     const size_t n_tiles = ((size_t)cfg->num_envs + 63) / 64;
     cudaError_t err = cudaMalloc(&e->states, (size_t)cfg->num_envs * sizeof(EnvState));
     if (err == cudaSuccess) err = cudaMemset(e->states, 0, (size_t)cfg->num_envs * sizeof(EnvState));
-    if (err == cudaSuccess) err = cudaMalloc(&e->slots, (size_t)kDepth * cfg->num_envs * sizeof(EnvState));
-    if (err == cudaSuccess) err = cudaMemset(e->slots, 0, (size_t)kDepth * cfg->num_envs * sizeof(EnvState));
+    if (err == cudaSuccess) err = cudaMalloc(&e->slots, (size_t)kDepth * cfg->num_envs * kSlotWords * sizeof(uint32_t));
+    if (err == cudaSuccess) err = cudaMemset(e->slots, 0, (size_t)kDepth * cfg->num_envs * kSlotWords * sizeof(uint32_t));
     if (err == cudaSuccess) err = cudaMalloc(&e->tags, (size_t)kDepth * cfg->num_envs);
     if (err == cudaSuccess) err = cudaMemset(e->tags, 0, (size_t)kDepth * cfg->num_envs);
     if (err == cudaSuccess) err = cudaMalloc(&e->qsave, n_tiles * kQueueCap * sizeof(uint16_t));
