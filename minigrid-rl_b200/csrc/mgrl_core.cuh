@@ -516,6 +516,19 @@ inline void build_task_table(const EnvCfg& cfg, uint32_t* table) {
                 for (uint32_t l = 0; l < 16; ++l)
                     build_task_row(cfg, nrooms, a, g, l, table + (size_t)task_index(nrooms, a, g, l) * kTaskWords);
 }
+// Rows are mostly short (a dozen tasks at num_objects = 4): repack the table to the longest row so that it stays
+// L1-resident next to the kernels' shared memory (36 KB instead of 96 KB).  Returns the row pitch in words.
+inline int pack_task_table(const uint32_t* table, uint32_t* packed) {
+    int longest = 0;
+    for (int r = 0; r < kTaskEntries; ++r)
+        for (int i = 0; i < kTaskWords; ++i)
+            if (table[r * kTaskWords + i] != 0u && i + 1 > longest) longest = i + 1;
+    int pitch = (longest + 1 + 3) & ~3;
+    if (pitch > kTaskWords) pitch = kTaskWords;
+    for (int r = 0; r < kTaskEntries; ++r)
+        for (int i = 0; i < pitch; ++i) packed[r * pitch + i] = i < kTaskWords ? table[r * kTaskWords + i] : 0u;
+    return pitch;
+}
 // tasks up to and including the agent: single-room objects (:371-555), goal, agent
 inline void build_task_prefix(const EnvCfg& cfg, uint32_t* out /* [kTaskWords] */) {
     const int S = cfg.size;
@@ -541,7 +554,8 @@ inline void build_empty_grid(int S, uint32_t* words /* [kGridWords] */) {
 struct GenIO {
     uint32_t* draws;           // this lane's draw buffer: word i at draws[i * stride]
     int stride;                // 32 on the device (lane-interleaved shared memory), 1 on the host
-    const uint32_t* tasks;     // [kTaskEntries][kTaskWords] (build_task_table)
+    const uint32_t* tasks;     // [kTaskEntries][row_words] (build_task_table, then pack_task_table)
+    int row_words = kTaskWords;  // row pitch of `tasks`: the longest row + terminator, rounded up to 4 words
     const uint32_t* prefix;    // [kTaskWords] (build_task_prefix)
     const uint32_t* empty;     // [kGridWords] fresh grid
     bool keep_marks = false;   // true: leave the next-to-a-door marks in the grid words; the caller strips them
@@ -723,7 +737,7 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
                     const int gx = (int)(goal_xy & 0xFFu), gy = (int)(goal_xy >> 8);
                     row = task_index(nrooms, room_of(nrooms, m, x, y), room_of(nrooms, m, gx, gy), locked_mask);
                 }
-                list = io.tasks + (size_t)row * kTaskWords;
+                list = io.tasks + (size_t)row * io.row_words;
                 li = -1;
             } else {
                 s.grid[cell] = (uint8_t)((uint32_t)kind | (here & kDoorFlag));

@@ -36,7 +36,8 @@ using namespace mgrl;
 namespace {
 
 constexpr int STATE_WORDS = 35;           // sizeof(EnvState) / 4
-constexpr int kDepth = 4;                 // layouts prepared ahead of time per environment
+constexpr int kDepth = 4;                 // layouts prepared ahead of time per environment (a power of two)
+static_assert((kDepth & (kDepth - 1)) == 0, "kDepth must be a power of two");
 constexpr int kSlotWords = 36;             // a prepared layout: the 35 state words + 1 pad word (16-byte aligned records)
 constexpr int kQueueCap = 512;            // >= TILE * kDepth requests can be outstanding per tile
 constexpr uint32_t kNoEntry = 0xFFFFu;
@@ -60,7 +61,8 @@ struct EnvParams {
     uint32_t* glist;          // [kDepth * n] deferred requests of one-step launches: env * kDepth + slot
     uint32_t* gcount;         // [1]
     int defer;                // 1: this launch only records its requests in glist (generate_kernel builds them later)
-    const uint32_t* tasks;    // [kTaskEntries][kTaskWords] (build_task_table)
+    const uint32_t* tasks;    // [kTaskEntries][task_row_words] (build_task_table + pack_task_table)
+    int task_row_words;
     const uint32_t* prefix;   // [kTaskWords] (build_task_prefix)
     const uint32_t* empty;    // [kGridWords] (build_empty_grid)
     const float* reward_lut;  // [max_steps+1] device
@@ -228,10 +230,12 @@ __device__ __forceinline__ void push_requests(TileSmem<TILE, NB>& sm, unsigned m
 // the step kernel's single out-of-line copy of the generator
 // (leaves the next-to-a-door marks in the grid words: strip them with kMarkMask on the way out)
 __device__ __noinline__ void generate_layout(uint32_t* sc, const EnvCfg& cfg, uint64_t seed, uint64_t env_id, uint32_t episode,
-                                             uint32_t* draws, const uint32_t* tasks, const uint32_t* prefix, const uint32_t* empty) {
+                                             uint32_t* draws, const uint32_t* tasks, int row_words, const uint32_t* prefix,
+                                             const uint32_t* empty) {
     sc[32] = 0u; sc[34] = 0u;
     GenIO io;
-    io.draws = draws; io.stride = 32; io.tasks = tasks; io.prefix = prefix; io.empty = empty; io.keep_marks = true;
+    io.draws = draws; io.stride = 32; io.tasks = tasks; io.row_words = row_words; io.prefix = prefix; io.empty = empty;
+    io.keep_marks = true;
     generate(*reinterpret_cast<EnvState*>(sc), cfg, seed, env_id, episode, io);
 }
 
@@ -266,10 +270,14 @@ __device__ __noinline__ bool serve_queue(TileSmem<TILE, NB>& sm, const EnvParams
         *q = (uint16_t)kNoEntry;
         const int e = (int)(ent & 0xFFu), j = (int)(ent >> 8);
         uint32_t* slot = slot_ptr(p.slots, j, p.n, tile0 + e);
-        const uint32_t episode = __ldcg(slot + 33) - 1u + kDepth;   // the slot's old layout was adopted
+        // The slot's old layout was adopted, so it now gets the one episode in [E, E + kDepth) that maps to slot j, E being
+        // the environment's next episode.  (E may advance while we look: every value it can take gives the same answer,
+        // because the environment cannot adopt the layout we are about to build.)
+        const uint32_t E = *reinterpret_cast<const volatile uint32_t*>(&sm.state[e * STATE_WORDS + 33]);
+        const uint32_t episode = E + (((uint32_t)j - E) & (uint32_t)(kDepth - 1));
         uint32_t* sc = reinterpret_cast<uint32_t*>(sm.obs[warp]) + lane * STATE_WORDS;
         generate_layout(sc, p.cfg, p.seed, p.env_id_base + (uint64_t)(tile0 + e), episode, sm.draws[b] + lane, p.tasks,
-                        sm.prefix, sm.empty);
+                        p.task_row_words, sm.prefix, sm.empty);
 #pragma unroll
         for (int i = 0; i < STATE_WORDS; ++i) __stcg(slot + i, i < kGridWords ? sc[i] & kMarkMask : sc[i]);
         // hand-off inside the CTA: layout (global) -> fence -> tag byte (shared); the adopting lane
@@ -426,7 +434,7 @@ __global__ void __launch_bounds__(TILE, TILE == 128 ? 4 : 7) step_kernel(const E
                     if (pending) {
                         uint32_t* sc = reinterpret_cast<uint32_t*>(sm.obs[warp]) + lane * STATE_WORDS;
                         generate_layout(sc, p.cfg, p.seed, p.env_id_base + (uint64_t)(tile0 + tid), E, sm.draws[b] + lane, p.tasks,
-                                        sm.prefix, sm.empty);
+                                        p.task_row_words, sm.prefix, sm.empty);
 #pragma unroll 4
                         for (int i = 0; i < kGridWords; ++i) sc[i] &= kMarkMask;
                         adopt_layout(cur, sc);
@@ -527,8 +535,8 @@ __global__ void __launch_bounds__(NWARPS * 32) generate_kernel(const EnvParams p
             uint32_t* sc = sm.scratch[warp] + lane * STATE_WORDS;
             sc[32] = 0u; sc[34] = 0u;
             GenIO io;
-            io.draws = sm.draws[warp] + lane; io.stride = 32; io.tasks = p.tasks; io.prefix = sm.prefix; io.empty = sm.empty;
-            io.keep_marks = true;
+            io.draws = sm.draws[warp] + lane; io.stride = 32; io.tasks = p.tasks; io.row_words = p.task_row_words;
+            io.prefix = sm.prefix; io.empty = sm.empty; io.keep_marks = true;
             generate(*reinterpret_cast<EnvState*>(sc), p.cfg, p.seed, p.env_id_base + (uint64_t)env, episode, io);
 #pragma unroll
             for (int i = 0; i < STATE_WORDS; ++i) slot[i] = i < kGridWords ? sc[i] & kMarkMask : sc[i];
@@ -569,7 +577,8 @@ __global__ void __launch_bounds__(TILE) reset_kernel(const EnvParams p) {
     uint32_t* cur = sm.state + tid * STATE_WORDS;
     EnvState& s = *reinterpret_cast<EnvState*>(cur);
     GenIO io;
-    io.draws = sm.draws[warp] + lane; io.stride = 32; io.tasks = p.tasks; io.prefix = sm.prefix; io.empty = sm.empty;
+    io.draws = sm.draws[warp] + lane; io.stride = 32; io.tasks = p.tasks; io.row_words = p.task_row_words;
+    io.prefix = sm.prefix; io.empty = sm.empty;
     const uint64_t env_id = p.env_id_base + (uint64_t)(tile0 + tid);
     if (active) {
         if (!PRIME) {
@@ -742,6 +751,7 @@ struct mgrl_env {
     uint32_t* gcount;    // [1]
     int deferred_steps;  // one-step launches since generate_kernel last ran
     uint32_t* tasks;
+    int task_row_words;
     uint32_t* prefix;
     uint32_t* empty;
     float* lut;
@@ -772,6 +782,7 @@ EnvParams make_params(const mgrl_env* e) {
     p.glist = e->glist;
     p.gcount = e->gcount;
     p.tasks = e->tasks;
+    p.task_row_words = e->task_row_words;
     p.prefix = e->prefix;
     p.empty = e->empty;
     p.reward_lut = e->lut;
@@ -928,9 +939,10 @@ int mgrl_create(const mgrl_config* cfg, int device, mgrl_env** out) {
         lut[k] = (float)r;
     }
     // generator inputs: task strings of this num_objects and the fresh grid of this size
-    static thread_local uint32_t tasks[kTaskEntries * kTaskWords];
+    static thread_local uint32_t full_table[kTaskEntries * kTaskWords], tasks[kTaskEntries * kTaskWords];
     uint32_t empty[kGridWords], prefix[kTaskWords];
-    build_task_table(e->ecfg, tasks);
+    build_task_table(e->ecfg, full_table);
+    e->task_row_words = pack_task_table(full_table, tasks);
     build_task_prefix(e->ecfg, prefix);
     build_empty_grid(cfg->size, empty);
     const size_t n_tiles = ((size_t)cfg->num_envs + 63) / 64;

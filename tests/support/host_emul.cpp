@@ -17,13 +17,15 @@ static const uint32_t* host_lut() {
 
 // generation inputs the kernels keep in device memory: task strings and the fresh grid of the configuration
 struct HostGen {
+    uint32_t full[kTaskEntries * kTaskWords];
     uint32_t tasks[kTaskEntries * kTaskWords];
     uint32_t prefix[kTaskWords];
     uint32_t empty[kGridWords];
     uint32_t draws[kDrawBuf];
     GenIO io;
     explicit HostGen(const EnvCfg& cfg) {
-        build_task_table(cfg, tasks);
+        build_task_table(cfg, full);
+        io.row_words = pack_task_table(full, tasks);
         build_task_prefix(cfg, prefix);
         build_empty_grid(cfg.size, empty);
         io.draws = draws; io.stride = 1; io.tasks = tasks; io.prefix = prefix; io.empty = empty;
