@@ -447,10 +447,14 @@ MGRL_HD int obj_kind(int type, int colour) {
 enum GenStage : int { G_OBJ = 1, G_GOAL, G_AGENT, G_KEY, G_DIST, G_OBST };
 constexpr uint32_t TF_MID = 1u << 24, TF_LAVA = 1u << 25, TF_KEYMODE = 1u << 26, TF_AGENTMODE = 1u << 27, TF_AGENT_CELL = 1u << 28;
 constexpr int kTaskWords = 32;            // words per table row / prefix list, zero terminated
-constexpr int kTaskEntries = 3 * 4 * 4 * 16;
+// rows exist for the valid combinations only: 2 rooms: 2 x 2 x 2 lock states of its one door; 3 rooms: 3 x 3 x 8;
+// 4 rooms: 4 x 4 x 16  ->  8 + 72 + 256 rows
+constexpr int kTaskEntries = 8 + 72 + 256;
 
 MGRL_HD int task_index(int nrooms, int agent_room, int goal_room, uint32_t locked) {
-    return (((nrooms - 2) * 4 + agent_room) * 4 + goal_room) * 16 + (int)locked;
+    const int ndoors = nrooms == 2 ? 1 : nrooms;
+    const int base = nrooms == 2 ? 0 : nrooms == 3 ? 8 : 80;
+    return base + (((agent_room * nrooms + goal_room) << ndoors) | (int)locked);
 }
 inline uint32_t task_word(int stage, int x0, int x1, int y0, int y1, uint32_t flags, int room = 0, int door = 0, int second = 0) {
     return (uint32_t)x0 | ((uint32_t)(x1 - x0 + 1) << 4) | ((uint32_t)y0 << 8) | ((uint32_t)(y1 - y0 + 1) << 12) |
@@ -511,9 +515,9 @@ inline void build_task_table(const EnvCfg& cfg, uint32_t* table) {
         return;
     }
     for (int nrooms = 2; nrooms <= 4; ++nrooms)
-        for (int a = 0; a < 4; ++a)
-            for (int g = 0; g < 4; ++g)
-                for (uint32_t l = 0; l < 16; ++l)
+        for (int a = 0; a < nrooms; ++a)
+            for (int g = 0; g < nrooms; ++g)
+                for (uint32_t l = 0; l < (1u << (nrooms == 2 ? 1 : nrooms)); ++l)
                     build_task_row(cfg, nrooms, a, g, l, table + (size_t)task_index(nrooms, a, g, l) * kTaskWords);
 }
 // Rows are mostly short (a dozen tasks at num_objects = 4): repack the table to the longest row so that it stays
