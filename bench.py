@@ -356,7 +356,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this
                          # kernel at this shape (profiles/r1b_ncu_full_many.txt); algorithmic bytes = 158 * n * T
-                         "traffic": 1.3598e9 if (n, T) == (N_ENVS, T_ROLLOUT) else None, "traffic_unit": "bytes/launch",
+                         "traffic": 1.4008e9 if (n, T) == (N_ENVS, T_ROLLOUT) else None, "traffic_unit": "bytes/launch",
                          "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n * T,
                          "kernel": "step_kernel<HWC148,see_through,64,1>", "peak_source": peak_src,
                          "bytes_per_env_step": BYTES_PER_ENV_STEP, "us_per_launch": us_per_launch,
