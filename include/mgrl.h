@@ -180,6 +180,20 @@ int mgrl_policy_forward(const float *weights_dev, const uint8_t *frames_dev, con
                         uint64_t env_id_base, uint32_t step, int flags, void *stream);
 const char *mgrl_policy_last_error(void);
 
+/* PPO update, first stage of the image extractor (Conv2d(12,16,2) + ReLU + MaxPool2d(2): policies.py:59 over
+ * single.yaml:44-47, inside SB3's PPO.train) for the minibatch samples (t_dev[b], i_dev[b]) of a rollout, read
+ * straight from the un-stacked frame buffer (frames_dev [time, N, 148] u8; the newest frame of sample b is record
+ * t+3, frames older than the episode - age_dev[b] = 0..3 frames of history - are zero):
+ *   forward : w1_dev [16,12,2,2] f32 (torch layout), b1_dev [16] -> pooled_dev [B,9,16] f32 (cell = qh*3+qw, after
+ *             bias and ReLU) and arg_dev [B,9,16] u8 (position of the maximum | 4 if positive);
+ *   backward: dpooled_dev [B,9,16] -> dw1_dev [16,48] f32, db1_dev [16] (overwritten). */
+int mgrl_conv1_pool_forward(const uint8_t *frames_dev, int num_envs, const int32_t *t_dev, const int32_t *i_dev,
+                            const uint8_t *age_dev, int batch, const float *w1_dev, const float *b1_dev,
+                            float *pooled_dev, uint8_t *arg_dev, void *stream);
+int mgrl_conv1_pool_backward(const uint8_t *frames_dev, int num_envs, const int32_t *t_dev, const int32_t *i_dev,
+                             const uint8_t *age_dev, int batch, const uint8_t *arg_dev, const float *dpooled_dev,
+                             float *dw1_dev, float *db1_dev, void *stream);
+
 /* ---- host-buffer drop-in path (what B200VecEnv.reset/step with numpy arrays calls) --- */
 
 /* VecEnv.reset(): stacked observation dict into host buffers; synchronous.

@@ -324,3 +324,210 @@ int mgrl_policy_forward(const float* weights_dev, const uint8_t* frames_dev, con
 }
 
 }  // extern "C"
+
+// ================================================================================================================
+// PPO update, first stage of the image extractor by hand: Conv2d(12,16,2) + ReLU + MaxPool2d(2) forward, and the
+// gradient of its weight / bias (the input is an observation: it needs no gradient).  In the library formulation
+// this stage alone is ~45 % of a minibatch update (1.8 GB of float patches written and re-read); here the frames are
+// read as bytes straight from the rollout buffer (the (t, env) samples of the minibatch are gathered on the fly,
+// frames older than the episode zero-filled), and only the pooled 3x3x16 activations leave the kernel.
+// Replaces, inside PPO.train ([UPSTREAM] SB3, driven from /root/reference/src/ppo.py:159), the first three modules of
+// CustomExtractor's image branch (policies.py:59, hydra_configs/single.yaml:44-47) and their autograd.
+namespace {
+
+constexpr int C1_OB = 64;        // samples per CTA (forward)
+constexpr int C1_PITCH = 149;    // words per staged sample: 4 frames x 37 words, odd pitch
+
+struct Conv1Args {
+    const uint8_t* frames;   // [time, n, 148]
+    const int32_t* t;        // [B] time index of the sample (its newest frame is record t + 3)
+    const int32_t* i;        // [B] environment
+    const uint8_t* age;      // [B] frames of history available (0..3)
+    const float* w1;         // [16][12][2][2] (torch layout)
+    const float* b1;         // [16]
+    float* pooled;           // [B][9][16] post bias + ReLU, pooled cell q = qh * 3 + qw
+    uint8_t* arg;            // [B][9][16] position of the maximum (0..3) | 4 if the output is positive
+    const float* dpooled;    // backward: [B][9][16]
+    float* dw1;              // backward: [16][48] accumulated with atomics (caller zeroes)
+    float* db1;              // backward: [16]
+    int n, B;
+};
+
+// stage the 4-frame stacks of samples [s0, s0 + count) into shared memory, PITCH words per sample
+__device__ __forceinline__ void stage_samples(const Conv1Args& p, int s0, int count, uint32_t* blocks, int pitch, int tid,
+                                              int nthreads) {
+    for (int e = tid; e < count * 4 * FRAME_WORDS; e += nthreads) {
+        const int o = e / (4 * FRAME_WORDS), r = e - o * (4 * FRAME_WORDS);
+        const int f = r / FRAME_WORDS, j = r - f * FRAME_WORDS;
+        const int s = s0 + o;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(p.frames + ((size_t)(p.t[s] + f) * p.n + p.i[s]) * 148);
+        blocks[o * pitch + f * FRAME_WORDS + j] = (3 - f) <= (int)p.age[s] ? __ldg(src + j) : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(C1_OB * 4) conv1_pool_fwd_kernel(const Conv1Args p) {
+    extern __shared__ __align__(16) uint32_t c1_smem[];
+    float* w1t = reinterpret_cast<float*>(c1_smem + C1_OB * C1_PITCH);   // [48][16]
+    float* div255 = w1t + 768;                                           // byte -> float(byte) / 255 (preprocess_obs, exact)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int part = warp >> 1, ob = (warp & 1) * 32 + lane;
+    const int s0 = blockIdx.x * C1_OB;
+    const int count = min(C1_OB, p.B - s0);
+    div255[tid] = (float)tid / 255.0f;
+    for (int e = tid; e < 768; e += C1_OB * 4) {   // [co][j] -> [j][co]
+        const int co = e / 48, j = e - co * 48;
+        w1t[j * 16 + co] = p.w1[e];
+    }
+    stage_samples(p, s0, count, c1_smem, C1_PITCH, tid, C1_OB * 4);
+    __syncthreads();
+    if (ob >= count) return;
+    const uint8_t* px = reinterpret_cast<const uint8_t*>(c1_smem + ob * C1_PITCH);
+    const size_t s = (size_t)(s0 + ob);
+    for (int q = part; q < 9; q += 4) {
+        const int qh = q / 3, qw = q - qh * 3;
+        float best[16];
+        int pos[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { best[c] = -3.0e38f; pos[c] = 0; }
+        for (int sp = 0; sp < 4; ++sp) {
+            const int ph = 2 * qh + (sp >> 1), pw = 2 * qw + (sp & 1);
+            float acc[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[c] = 0.0f;
+            for (int f = 0; f < 4; ++f) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const uint8_t* b = px + f * 148 + ((ph + (kk >> 1)) * 7 + pw + (kk & 1)) * 3;
+#pragma unroll
+                    for (int c3 = 0; c3 < 3; ++c3) {
+                        const float x = div255[b[c3]];
+                        const float4* w4 = reinterpret_cast<const float4*>(w1t + ((f * 3 + c3) * 4 + kk) * 16);
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const float4 w = w4[v];
+                            acc[4 * v + 0] = fmaf(x, w.x, acc[4 * v + 0]); acc[4 * v + 1] = fmaf(x, w.y, acc[4 * v + 1]);
+                            acc[4 * v + 2] = fmaf(x, w.z, acc[4 * v + 2]); acc[4 * v + 3] = fmaf(x, w.w, acc[4 * v + 3]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+                if (acc[c] > best[c]) { best[c] = acc[c]; pos[c] = sp; }   // first maximum wins, like max_pool2d
+        }
+        float* out = p.pooled + (s * 9 + q) * 16;
+        uint8_t* ao = p.arg + (s * 9 + q) * 16;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float v = best[c] + __ldg(p.b1 + c);
+            out[c] = fmaxf(v, 0.0f);
+            ao[c] = (uint8_t)(pos[c] | (v > 0.0f ? 4 : 0));
+        }
+    }
+}
+
+// weight / bias gradient: thread = (input index j of 48, channel quad cq of 4), accumulating over every sample of the
+// CTA's chunks in registers, one atomic per weight per CTA at the end
+constexpr int C1B_CHUNK = 32;
+__global__ void __launch_bounds__(192) conv1_pool_bwd_kernel(const Conv1Args p) {
+    extern __shared__ __align__(16) uint32_t c1_smem[];
+    uint32_t* blocks = c1_smem;                                                        // [32][149] frames
+    float* dz = reinterpret_cast<float*>(c1_smem + C1B_CHUNK * C1_PITCH);              // [32][9][16] masked gradient
+    uint32_t* arg = reinterpret_cast<uint32_t*>(dz + C1B_CHUNK * 144);                 // [32][9][4] words of 4 positions
+    float* div255 = reinterpret_cast<float*>(arg + C1B_CHUNK * 36);                    // byte -> float(byte) / 255
+    const int tid = threadIdx.x;
+    for (int e = tid; e < 256; e += 192) div255[e] = (float)e / 255.0f;
+    const int j = tid % 48, cq = tid / 48;
+    const int f = j / 12, c3 = (j / 4) % 3, kk = j & 3;                                // j = (f*3 + c3)*4 + kk
+    const int joff = f * 148 + ((kk >> 1) * 7 + (kk & 1)) * 3 + c3;                    // byte offset of input j at position (0,0)
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    float bacc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    const int nchunks = (p.B + C1B_CHUNK - 1) / C1B_CHUNK;
+    for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        const int s0 = ch * C1B_CHUNK;
+        const int count = min(C1B_CHUNK, p.B - s0);
+        __syncthreads();
+        stage_samples(p, s0, count, blocks, C1_PITCH, tid, 192);
+        for (int e = tid; e < count * 144; e += 192) {
+            const uint8_t a = p.arg[(size_t)s0 * 144 + e];
+            dz[e] = (a & 4) ? p.dpooled[(size_t)s0 * 144 + e] : 0.0f;
+            reinterpret_cast<uint8_t*>(arg)[e] = a & 3;
+        }
+        __syncthreads();
+        for (int o = 0; o < count; ++o) {
+            const uint8_t* px = reinterpret_cast<const uint8_t*>(blocks + o * C1_PITCH) + joff;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                const int qh = q / 3, qw = q - qh * 3;
+                const uint8_t* b = px + ((2 * qh) * 7 + 2 * qw) * 3;
+                // the four candidate positions of this pooled cell: (0,0) (0,1) (1,0) (1,1)
+                const uint32_t x4 = (uint32_t)b[0] | ((uint32_t)b[3] << 8) | ((uint32_t)b[21] << 16) | ((uint32_t)b[24] << 24);
+                const uint32_t pos4 = arg[(o * 9 + q) * 4 + cq];
+                const float4 g = *reinterpret_cast<const float4*>(dz + (o * 9 + q) * 16 + cq * 4);
+                const float gs[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t x = (x4 >> (8 * ((pos4 >> (8 * c)) & 3u))) & 0xFFu;
+                    acc[c] = fmaf(div255[x], gs[c], acc[c]);
+                    bacc[c] += gs[c];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        atomicAdd(p.dw1 + (cq * 4 + c) * 48 + j, acc[c]);
+        if (j == 0) atomicAdd(p.db1 + cq * 4 + c, bacc[c]);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int mgrl_conv1_pool_forward(const uint8_t* frames_dev, int num_envs, const int32_t* t_dev, const int32_t* i_dev,
+                            const uint8_t* age_dev, int batch, const float* w1_dev, const float* b1_dev, float* pooled_dev,
+                            uint8_t* arg_dev, void* stream) {
+    if (!frames_dev || !t_dev || !i_dev || !age_dev || !w1_dev || !b1_dev || !pooled_dev || !arg_dev || batch <= 0 || num_envs <= 0) {
+        snprintf(g_perr, sizeof g_perr, "mgrl_conv1_pool_forward: null argument or empty batch");
+        return MGRL_ERR_INVALID;
+    }
+    Conv1Args a = {};
+    a.frames = frames_dev; a.t = t_dev; a.i = i_dev; a.age = age_dev; a.w1 = w1_dev; a.b1 = b1_dev; a.pooled = pooled_dev;
+    a.arg = arg_dev; a.n = num_envs; a.B = batch;
+    const size_t smem = (size_t)(C1_OB * C1_PITCH + 768 + 256) * 4;
+    cudaError_t e = cudaFuncSetAttribute(conv1_pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+        conv1_pool_fwd_kernel<<<(batch + C1_OB - 1) / C1_OB, C1_OB * 4, smem, (cudaStream_t)stream>>>(a);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) { snprintf(g_perr, sizeof g_perr, "mgrl_conv1_pool_forward: %s", cudaGetErrorString(e)); return MGRL_ERR_CUDA; }
+    return MGRL_OK;
+}
+
+int mgrl_conv1_pool_backward(const uint8_t* frames_dev, int num_envs, const int32_t* t_dev, const int32_t* i_dev,
+                             const uint8_t* age_dev, int batch, const uint8_t* arg_dev, const float* dpooled_dev, float* dw1_dev,
+                             float* db1_dev, void* stream) {
+    if (!frames_dev || !t_dev || !i_dev || !age_dev || !arg_dev || !dpooled_dev || !dw1_dev || !db1_dev || batch <= 0 || num_envs <= 0) {
+        snprintf(g_perr, sizeof g_perr, "mgrl_conv1_pool_backward: null argument or empty batch");
+        return MGRL_ERR_INVALID;
+    }
+    Conv1Args a = {};
+    a.frames = frames_dev; a.t = t_dev; a.i = i_dev; a.age = age_dev; a.arg = const_cast<uint8_t*>(arg_dev); a.dpooled = dpooled_dev;
+    a.dw1 = dw1_dev; a.db1 = db1_dev; a.n = num_envs; a.B = batch;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(dw1_dev, 0, 768 * sizeof(float), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(db1_dev, 0, 16 * sizeof(float), s);
+    const size_t smem = (size_t)(C1B_CHUNK * C1_PITCH) * 4 + (size_t)C1B_CHUNK * 144 * 4 + (size_t)C1B_CHUNK * 144 + 256 * 4;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv1_pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+        const int nchunks = (batch + C1B_CHUNK - 1) / C1B_CHUNK;
+        const int grid = nchunks < 148 * 4 ? nchunks : 148 * 4;
+        conv1_pool_bwd_kernel<<<grid, 192, smem, s>>>(a);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) { snprintf(g_perr, sizeof g_perr, "mgrl_conv1_pool_backward: %s", cudaGetErrorString(e)); return MGRL_ERR_CUDA; }
+    return MGRL_OK;
+}
+
+}  // extern "C"

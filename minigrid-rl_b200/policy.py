@@ -61,6 +61,45 @@ SHAPES = {
 N_PARAMS = sum(int(np.prod(s)) for s in SHAPES.values())      # 110 216
 
 
+_CONV1_POOL = None
+
+
+def _conv1_pool(torch):
+    """autograd wrapper of the hand-written first extractor stage (built lazily so the module imports without torch)"""
+    global _CONV1_POOL
+    if _CONV1_POOL is not None:
+        return _CONV1_POOL
+
+    class Conv1Pool(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, w1, b1, frames, t32, i32, age):
+            B, n = int(t32.numel()), int(frames.shape[1])
+            pooled = torch.empty((B, 9, 16), dtype=torch.float32, device=frames.device)
+            arg = torch.empty((B, 9, 16), dtype=torch.uint8, device=frames.device)
+            age = age.contiguous()
+            s = C.c_void_p(torch.cuda.current_stream(frames.device).cuda_stream)
+            p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+            nat.check(nat.lib().mgrl_conv1_pool_forward(p(frames), n, p(t32), p(i32), p(age), B, p(w1.detach().contiguous()),
+                                                        p(b1.detach().contiguous()), p(pooled), p(arg), s), "conv1_pool_forward")
+            ctx.save_for_backward(frames, t32, i32, age, arg)
+            return pooled
+
+        @staticmethod
+        def backward(ctx, g):
+            frames, t32, i32, age, arg = ctx.saved_tensors
+            B, n = int(t32.numel()), int(frames.shape[1])
+            dw1 = torch.empty((16, 48), dtype=torch.float32, device=frames.device)
+            db1 = torch.empty(16, dtype=torch.float32, device=frames.device)
+            s = C.c_void_p(torch.cuda.current_stream(frames.device).cuda_stream)
+            p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+            nat.check(nat.lib().mgrl_conv1_pool_backward(p(frames), n, p(t32), p(i32), p(age), B, p(arg), p(g.contiguous()),
+                                                         p(dw1), p(db1), s), "conv1_pool_backward")
+            return dw1.view(16, 12, 2, 2), db1, None, None, None, None
+
+    _CONV1_POOL = Conv1Pool.apply
+    return _CONV1_POOL
+
+
 class Policy:
     """Parameters + the two evaluation paths.  Works on any torch device for `evaluate` (the update's autograd
     path and the CPU tests of the data-parallel logic); `pack` / `forward_rollout` need CUDA."""
@@ -192,6 +231,13 @@ class Policy:
         p = x.unfold(2, 2, 1).unfold(3, 2, 1).permute(0, 2, 3, 1, 4, 5).reshape(B * 36, 48)          # (ci, kh, kw)
         h = torch.relu(F.linear(p, P[c + "0.weight"].reshape(16, 48), P[c + "0.bias"]))
         h = h.view(B, 3, 2, 3, 2, 16).amax(dim=(2, 4))                                                # MaxPool2d(2): 6x6 -> 3x3
+        return self._head(h, dir_onehot, mission_row, lut, F, P)
+
+    def _head(self, h, dir_onehot, mission_row, lut, F, P):
+        """everything after the first pooled convolution: h [B,3,3,16] (qh, qw, c)"""
+        torch = self.torch
+        B = h.shape[0]
+        c = _PREFIX + "image.image_Conv2d_"
         p = h.unfold(1, 2, 1).unfold(2, 2, 1).reshape(B * 4, 64)                                      # (ci, kh, kw)
         h = torch.relu(F.linear(p, P[c + "3.weight"].reshape(32, 64), P[c + "3.bias"])).view(B, 128)  # (oh, ow, c2)
         x = torch.relu(F.linear(h, P[c + "5.weight"].permute(0, 2, 3, 1).reshape(64, 128), P[c + "5.bias"]))
@@ -205,6 +251,25 @@ class Policy:
                         P["mlp_extractor.value_net.2.weight"], P["mlp_extractor.value_net.2.bias"]))
         return (F.linear(hp, P["action_net.weight"], P["action_net.bias"]),
                 F.linear(hv, P["value_net.weight"], P["value_net.bias"]).squeeze(-1))
+
+    def evaluate_samples(self, frames, dirs, mission, age, t, i, lut=None):
+        """`evaluate` for rollout samples (t, i) without materialising their stacked images: the first stage of the image
+        branch (Conv2d(12,16,2) + ReLU + MaxPool2d(2), forward and weight gradient) runs in the hand-written kernels
+        `mgrl_conv1_pool_forward/backward` straight off the frame buffer; the rest of the network is `_evaluate`'s."""
+        torch = self.torch
+        F = torch.nn.functional
+        P = self.params
+        c = _PREFIX + "image.image_Conv2d_"
+        lut = self.mission_lut() if lut is None else lut
+        a = age[t, i]
+        pooled = _conv1_pool(torch)(P[c + "0.weight"], P[c + "0.bias"], frames, t.to(torch.int32), i.to(torch.int32), a)
+        k = torch.arange(4, device=t.device)
+        valid = ((3 - k)[None, :] <= a.long()[:, None]).to(torch.uint8)
+        d = dirs[(t[:, None] + k[None, :]), i[:, None]].long()
+        onehot = (F.one_hot(d, 4).to(torch.uint8) * valid[:, :, None]).view(-1, 16)
+        mrow = mission[t + 3, i].long() * 4 + a.long()
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=not self.fp32_strict):
+            return self._head(pooled.view(-1, 3, 3, 16), onehot, mrow, lut, F, P)
 
     # ---------------------------------------------------------------- packed weights for the CUDA forward kernel
     def pack(self):

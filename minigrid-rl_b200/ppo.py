@@ -41,6 +41,7 @@ class PPOConfig:                      # hydra_configs/algorithm/ppo.yaml:9-40
     final_learning_rate: float = 3e-6
     optim_eps: float = 1e-8           # single.yaml:31
     update_tf32: bool = False         # True: the update's library GEMMs may use TF32 like the reference (ppo.py:29-32)
+    native_conv1: bool = True         # first extractor stage of the update in the hand-written kernels (CUDA only)
     total_timesteps: float = 2e7
 
 
@@ -67,11 +68,17 @@ def gather_minibatch(buf, t, i):
 
 
 def ppo_minibatch_loss(policy: Policy, cfg: PPOConfig, image, onehot, mrow, actions, old_values, old_logp, adv, returns,
-                       adv_stats=None):
-    """[UPSTREAM] PPO.train, one minibatch.  adv_stats = (mean, std) when they were computed over all ranks."""
+                       adv_stats=None, samples=None):
+    """[UPSTREAM] PPO.train, one minibatch.  adv_stats = (mean, std) when they were computed over all ranks.
+    samples = (buf, t, i): evaluate straight off the rollout buffer (hand-written first extractor stage) instead of the
+    gathered (image, onehot, mrow)."""
     import torch
     F = torch.nn.functional
-    logits, values = policy.evaluate(image, onehot, mrow)
+    if samples is not None:
+        buf, t, i = samples
+        logits, values = policy.evaluate_samples(buf["frames"], buf["dirs"], buf["mission"], buf["age"], t, i)
+    else:
+        logits, values = policy.evaluate(image, onehot, mrow)
     logp_all = F.log_softmax(logits, dim=1)
     logp = logp_all.gather(1, actions.long().view(-1, 1)).squeeze(1)
     entropy = -(logp_all.exp() * logp_all).sum(1)
@@ -138,7 +145,7 @@ class Updater:
         self.opt.step()
         self.policy.invalidate()
 
-    def minibatch(self, image, onehot, mrow, actions, old_values, old_logp, adv, returns):
+    def minibatch(self, image, onehot, mrow, actions, old_values, old_logp, adv, returns, samples=None):
         torch = self.torch
         stats = None
         if self.world > 1 and self.cfg.normalize_advantage:
@@ -147,7 +154,7 @@ class Updater:
         torch.backends.cuda.matmul.allow_tf32 = bool(self.cfg.update_tf32)
         try:
             loss, parts = ppo_minibatch_loss(self.policy, self.cfg, image, onehot, mrow, actions, old_values, old_logp, adv,
-                                             returns, stats)
+                                             returns, stats, samples)
             self.step(loss)
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
@@ -257,9 +264,12 @@ class RolloutEngine:
             for s in range(0, total - bs + 1, bs):
                 idx = perm[s:s + bs]
                 t, i = idx // N, idx % N
-                image, onehot, mrow = gather_minibatch(b, t, i)
-                self.updater.minibatch(image, onehot, mrow, b["actions"][t, i], b["values"][t, i], b["logp"][t, i],
-                                       b["adv"][t, i], b["ret"][t, i])
+                args = (b["actions"][t, i], b["values"][t, i], b["logp"][t, i], b["adv"][t, i], b["ret"][t, i])
+                if cfg.native_conv1 and b["frames"].is_cuda:
+                    self.updater.minibatch(None, None, None, *args, samples=(b, t, i))
+                else:
+                    image, onehot, mrow = gather_minibatch(b, t, i)
+                    self.updater.minibatch(image, onehot, mrow, *args)
                 n_mb += 1
         return n_mb
 

@@ -208,3 +208,33 @@ def test_deterministic_evaluation_takes_the_argmax():
         lsm = torch.log_softmax(logits, 1).gather(1, b["actions"][t].long()[:, None])[:, 0]
         assert torch.allclose(b["logp"][t], lsm, rtol=1e-5, atol=1e-6)
     eng.env.close()
+
+
+def test_native_conv1_stage_matches_library_path():
+    """mgrl_conv1_pool_forward / backward (first extractor stage of the update) against the torch expression: same
+    logits / values, same gradients for every parameter."""
+    n, T = 384, 12
+    eng, _ = make_engine(n, T)
+    eng.collect(); eng.compute_advantages()
+    b, pol_ = eng.buf, eng.policy
+    t = torch.arange(T, device="cuda").repeat_interleave(n)
+    i = torch.arange(n, device="cuda").repeat(T)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    sel = torch.randperm(T * n, device="cuda", generator=g)[:3000]          # 3000: a ragged last CTA / chunk
+    t, i = t[sel], i[sel]
+    image, onehot, mrow = ppo.gather_minibatch(b, t, i)
+    la, va = pol_.evaluate(image, onehot, mrow)
+    lb, vb = pol_.evaluate_samples(b["frames"], b["dirs"], b["mission"], b["age"], t, i)
+    assert close(lb, la, 2e-5) and close(vb, va, 2e-5)
+    wl, wv = torch.randn_like(la), torch.randn_like(va)
+    params = pol_.parameters()
+    ga = torch.autograd.grad((la * wl).sum() + (va * wv).sum(), params, allow_unused=True)
+    gb = torch.autograd.grad((lb * wl).sum() + (vb * wv).sum(), params, allow_unused=True)
+    for name, x, y in zip(pol_.params, ga, gb):
+        assert (x is None) == (y is None), name
+        if x is not None:
+            assert close(y, x, 2e-4), name
+    # and a whole iteration through the native stage
+    stats = eng.iteration(1.0)
+    assert stats["minibatches"] == 16 and eng.env.error_flags() == 0
+    eng.env.close()

@@ -17,7 +17,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "mgrl.h")).read()
-    declared = sorted(set(re.findall(r"\b(mgrl_[a-z_]+)\s*\(", hdr)))
+    declared = sorted(set(re.findall(r"\b(mgrl_[a-z0-9_]+)\s*\(", hdr)))
     assert len(declared) >= 20
     handle = C.CDLL(mg.library_path())
     for name in declared:
