@@ -329,8 +329,8 @@ def main():
                     "config": {"n_steps": T, "n_envs_per_gpu": n, "batch_size_per_gpu": pcfg.batch_size, "n_epochs": 4,
                                "minibatches_per_iteration": n_mb, "policy": "CustomPPOPolicy 110216 params, fp32",
                                "rollout": "mgrl_policy_forward + mgrl_step per step (hand-written kernels)",
-                               "update": "torch autograd on library kernels; matmuls may use TF32 like the reference (ppo.py:29-32), the "
-                                         "rollout kernels are fp32",
+                               "update": "first extractor stage hand-written (mgrl_conv1_pool_*), rest torch autograd on library kernels; "
+                                         "matmuls may use TF32 like the reference (ppo.py:29-32), the rollout kernels are fp32",
                                "all_reduces_per_optimizer_step": 2 if world > 1 else 0},
                     "env_error_flags": penv.error_flags()}
         env = penv

@@ -13,9 +13,9 @@ B = eng.buf
 idx = torch.randperm(n * T, device="cuda")[:cfg.batch_size]
 t, i = idx // n, idx % n
 def one():
-    image, onehot, mrow = ppo.gather_minibatch(B, t, i)
-    eng.updater.minibatch(image, onehot, mrow, B["actions"][t, i], B["values"][t, i], B["logp"][t, i], B["adv"][t, i], B["ret"][t, i])
+    eng.updater.minibatch(None, None, None, B["actions"][t, i], B["values"][t, i], B["logp"][t, i], B["adv"][t, i], B["ret"][t, i],
+                          samples=(B, t, i))
 one(); one(); torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     one(); torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=70))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=22, max_name_column_width=70))
