@@ -9,11 +9,12 @@
 // 128-float feature depends only on (mission id, frames in the stack) -> table [74*4][128] recomputed by the
 // host whenever the weights change.
 //
-// Mapping: 64 observations per CTA, 256 threads: a lane owns one observation (its activations live in a private
-// 293-word shared-memory block, odd pitch: conflict free) and FOUR warps share each group of 32 observations,
+// Mapping: 32 observations per CTA, 128 threads: a lane owns one observation (its activations live in a private
+// 293-word shared-memory block, odd pitch: conflict free) and the CTA's FOUR warps share the 32 observations,
 // splitting every layer by output (pooled cells for conv1, output positions for conv2, 16 of the 64 channels for
-// conv3 and the hidden layers).  All weight reads are therefore warp-uniform 16-byte read-only loads (one
-// transaction broadcast to the warp); with 24 warps per SM their L2 latency is covered by the other warps.
+// conv3 and the hidden layers).  Weights are staged layer by layer (16 KB chunks) through shared memory by the whole
+// CTA, so every weight read in the inner loops is a warp-uniform 16-byte shared-memory broadcast instead of an L2
+// round trip; 4 CTAs per SM overlap one CTA's staging with the others' arithmetic.
 // fp32 FMA throughout (single-pass TF32 would miss the 1e-5 parity bar).
 #include <cuda_runtime.h>
 
@@ -24,7 +25,7 @@
 
 namespace {
 
-constexpr int OB = 64;             // observations per CTA
+constexpr int OB = 32;             // observations per CTA
 constexpr int PITCH = 293;         // words of shared memory per observation
 constexpr int FRAME_WORDS = 37;    // 148-byte frame record
 constexpr int POOL_OFF = 148;      // pooled conv1 output: 9 cells x 16 channels
@@ -85,33 +86,64 @@ __device__ __forceinline__ void fma_row(float* acc, float x, const float* __rest
     }
 }
 
-constexpr int PARTS = 4;           // warps sharing one group of 32 observations
+constexpr int PARTS = 4;           // warps sharing the CTA's 32 observations
 constexpr int NT = OB * PARTS;     // threads per CTA
+constexpr int WBUF = 4096;         // floats of weights staged in shared memory at a time (16 KB)
 
-// 16 of the 64 outputs of two hidden layers at once (policy and value net read the same input):
-// acc_a += in_a[k] * wa[k][c0..c0+16), acc_b += in_b[k] * wb[k][c0..c0+16)
+// acc[0..NOUT) += x * w[0..NOUT) with w in shared memory (the same address in every lane: one broadcast per 16 bytes)
+template <int NOUT>
+__device__ __forceinline__ void fma_row_s(float* acc, float x, const float* w) {
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+#pragma unroll
+    for (int i = 0; i < NOUT / 4; ++i) {
+        const float4 v = w4[i];
+        acc[4 * i + 0] = fmaf(x, v.x, acc[4 * i + 0]);
+        acc[4 * i + 1] = fmaf(x, v.y, acc[4 * i + 1]);
+        acc[4 * i + 2] = fmaf(x, v.z, acc[4 * i + 2]);
+        acc[4 * i + 3] = fmaf(x, v.w, acc[4 * i + 3]);
+    }
+}
+
+// the CTA copies `nfloats` (a multiple of 4, 16-byte aligned source) of the packed weights into the staging buffer
+__device__ __forceinline__ void stage_weights(float* wbuf, const float* __restrict__ src, int nfloats, int tid) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(wbuf);
+    for (int e = tid; e < nfloats / 4; e += NT) d4[e] = __ldg(s4 + e);
+}
+
+// two 64-wide layers at once (policy and value net), K inputs each, weights streamed through the staging buffer in
+// chunks of 32 rows per net; this thread owns outputs [c0, c0 + 16) of both
 template <int K>
-__device__ __forceinline__ void dense16x2(const float* __restrict__ wa, const float* __restrict__ ba, const float* in_a,
-                                          const float* __restrict__ wb, const float* __restrict__ bb, const float* in_b,
-                                          int c0, float* acc_a, float* acc_b) {
+__device__ __forceinline__ void dense16x2(float* wbuf, const float* __restrict__ wa, const float* __restrict__ ba,
+                                          const float* in_a, const float* __restrict__ wb, const float* __restrict__ bb,
+                                          const float* in_b, int c0, float* acc_a, float* acc_b, int tid, bool valid) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) { acc_a[i] = __ldg(ba + c0 + i); acc_b[i] = __ldg(bb + c0 + i); }
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        const int rows = min(32, K - k0);
+        __syncthreads();                                   // the previous chunk (or layer) is done with the buffer
+        stage_weights(wbuf, wa + k0 * 64, rows * 64, tid);
+        stage_weights(wbuf + 2048, wb + k0 * 64, rows * 64, tid);
+        __syncthreads();
+        if (valid) {
 #pragma unroll 4
-    for (int k = 0; k < K; ++k) {
-        fma_row<16>(acc_a, in_a[k], wa + k * 64 + c0);
-        fma_row<16>(acc_b, in_b[k], wb + k * 64 + c0);
+            for (int k = 0; k < rows; ++k) {
+                fma_row_s<16>(acc_a, in_a[k0 + k], wbuf + k * 64 + c0);
+                fma_row_s<16>(acc_b, in_b[k0 + k], wbuf + 2048 + k * 64 + c0);
+            }
+        }
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) { acc_a[i] = tanhf(acc_a[i]); acc_b[i] = tanhf(acc_b[i]); }
 }
 
-__global__ void __launch_bounds__(NT, 3) policy_forward_kernel(const PolicyArgs p) {
+__global__ void __launch_bounds__(NT, 4) policy_forward_kernel(const PolicyArgs p) {
     extern __shared__ __align__(16) float smem[];
     __shared__ uint8_t s_age[OB];
+    float* wbuf = smem + OB * PITCH;             // 16-byte aligned: OB * PITCH * 4 = 37 504
     const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int part = warp >> 1;                 // 0..3: which slice of every layer this warp computes
-    const int ob = (warp & 1) * 32 + lane;      // observation of this lane within the CTA
+    const int lane = tid & 31, part = tid >> 5;  // part 0..3: which slice of every layer this warp computes
+    const int ob = lane;                         // observation of this lane within the CTA
     const int i0 = blockIdx.x * OB;
     const int i = i0 + ob;
     const int nv = min(OB, p.n - i0);
@@ -130,6 +162,7 @@ __global__ void __launch_bounds__(NT, 3) policy_forward_kernel(const PolicyArgs 
         }
         s_age[tid] = (uint8_t)a;
     }
+    stage_weights(wbuf, w + W1, 768 + 16, tid);  // conv1 weights + bias
     __syncthreads();
     const int age = s_age[ob];
 
@@ -166,40 +199,46 @@ __global__ void __launch_bounds__(NT, 3) policy_forward_kernel(const PolicyArgs 
                         const uint8_t* b = px + f * 148 + cell * 3;
 #pragma unroll
                         for (int c = 0; c < 3; ++c)
-                            fma_row<16>(acc, (float)b[c] * (1.0f / 255.0f), w + W1 + (((f * 3 + c) * 4 + kk) * 16));
+                            fma_row_s<16>(acc, (float)b[c] * (1.0f / 255.0f), wbuf + (((f * 3 + c) * 4 + kk) * 16));
                     }
                 }
 #pragma unroll
                 for (int c = 0; c < 16; ++c) pooled[c] = fmaxf(pooled[c], acc[c]);
             }
 #pragma unroll
-            for (int c = 0; c < 16; ++c) blk[POOL_OFF + q * 16 + c] = fmaxf(pooled[c] + __ldg(w + B1 + c), 0.0f);
+            for (int c = 0; c < 16; ++c) blk[POOL_OFF + q * 16 + c] = fmaxf(pooled[c] + wbuf[768 + c], 0.0f);
         }
     }
+    __syncthreads();
+    stage_weights(wbuf, w + W2, 2048 + 32, tid);   // conv2 weights + bias
     __syncthreads();
     // ---- Conv2d(16,32,2) + ReLU  (3x3 -> 2x2): output position o = part, at words [o*32 + c2] over the consumed frames
     if (valid) {
         const int o = part;
         float acc[32];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c] = __ldg(w + B2 + c);
+        for (int c = 0; c < 32; ++c) acc[c] = wbuf[2048 + c];
         for (int kk = 0; kk < 4; ++kk) {
             const int q = ((o >> 1) + (kk >> 1)) * 3 + (o & 1) + (kk & 1);
 #pragma unroll 4
-            for (int c1 = 0; c1 < 16; ++c1) fma_row<32>(acc, blk[POOL_OFF + q * 16 + c1], w + W2 + (kk * 16 + c1) * 32);
+            for (int c1 = 0; c1 < 16; ++c1) fma_row_s<32>(acc, blk[POOL_OFF + q * 16 + c1], wbuf + (kk * 16 + c1) * 32);
         }
 #pragma unroll
         for (int c = 0; c < 32; ++c) blk[o * 32 + c] = fmaxf(acc[c], 0.0f);
     }
-    __syncthreads();
-    // ---- Conv2d(32,64,2) + ReLU + Flatten  (2x2 -> 1x1): channels [16 part, 16 part + 16)
+    // ---- Conv2d(32,64,2) + ReLU + Flatten  (2x2 -> 1x1): channels [16 part, 16 part + 16), weights in two chunks of 64 rows
     const int c0 = part * 16;
     float fa[16], fb[16];
-    if (valid) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) fa[c] = __ldg(w + B3 + c0 + c);
+    for (int c = 0; c < 16; ++c) fa[c] = __ldg(w + B3 + c0 + c);
+    for (int j0 = 0; j0 < 128; j0 += 64) {
+        __syncthreads();
+        stage_weights(wbuf, w + W3 + j0 * 64, 64 * 64, tid);
+        __syncthreads();
+        if (valid) {
 #pragma unroll 4
-        for (int j = 0; j < 128; ++j) fma_row<16>(fa, blk[j], w + W3 + j * 64 + c0);
+            for (int j = 0; j < 64; ++j) fma_row_s<16>(fa, blk[j0 + j], wbuf + j * 64 + c0);
+        }
     }
     __syncthreads();          // conv2's output is consumed: the block becomes the 208 features
     if (valid) {
@@ -227,17 +266,15 @@ __global__ void __launch_bounds__(NT, 3) policy_forward_kernel(const PolicyArgs 
             d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
         }
     }
-    __syncthreads();
-    // ---- first hidden layer of the policy and the value net (208 -> 64 each, Tanh)
-    if (valid) dense16x2<208>(w + PI1, w + PI1B, blk, w + VF1, w + VF1B, blk, c0, fa, fb);
+    // ---- first hidden layer of the policy and the value net (208 -> 64 each, Tanh)  (the chunk loop starts with a barrier)
+    dense16x2<208>(wbuf, w + PI1, w + PI1B, blk, w + VF1, w + VF1B, blk, c0, fa, fb, tid, valid);
     __syncthreads();          // every part has read the features
     if (valid) {
 #pragma unroll
         for (int c = 0; c < 16; ++c) { blk[H_OFF + c0 + c] = fa[c]; blk[c0 + c] = fb[c]; }
     }
-    __syncthreads();
     // ---- second hidden layer (64 -> 64, Tanh): policy reads [208,272), value reads [0,64)
-    if (valid) dense16x2<64>(w + PI2, w + PI2B, blk + H_OFF, w + VF2, w + VF2B, blk, c0, fa, fb);
+    dense16x2<64>(wbuf, w + PI2, w + PI2B, blk + H_OFF, w + VF2, w + VF2B, blk, c0, fa, fb, tid, valid);
     __syncthreads();
     if (valid) {
 #pragma unroll
@@ -310,7 +347,7 @@ int mgrl_policy_forward(const float* weights_dev, const uint8_t* frames_dev, con
     a.action = action_dev; a.logp = logp_dev; a.value = value_dev; a.logits = logits_dev;
     a.n = num_envs; a.b = time_index; a.seed = seed; a.env_id_base = env_id_base; a.step = step;
     a.deterministic = (flags & MGRL_POLICY_DETERMINISTIC) ? 1 : 0;
-    const size_t smem = (size_t)OB * PITCH * sizeof(float);
+    const size_t smem = (size_t)(OB * PITCH + WBUF) * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
         policy_forward_kernel<<<(num_envs + OB - 1) / OB, NT, smem, (cudaStream_t)stream>>>(a);
