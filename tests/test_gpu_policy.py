@@ -238,3 +238,19 @@ def test_native_conv1_stage_matches_library_path():
     stats = eng.iteration(1.0)
     assert stats["minibatches"] == 16 and eng.env.error_flags() == 0
     eng.env.close()
+
+
+@pytest.mark.parametrize("n", [1, 33, 100])
+def test_forward_kernel_ragged_batches(n):
+    """batches that do not fill the last CTA (32 observations) of the policy kernel"""
+    eng, o = make_engine(n, 8)
+    eng.collect()
+    b = eng.buf
+    stacks = oracle_stacks(b, 8, n)
+    for t in (0, 3, 8):
+        img, d, mis = stacks[t]
+        with torch.no_grad():
+            _, vo = o({"direction": torch.from_numpy(d), "image": torch.from_numpy(img), "mission": torch.from_numpy(mis)})
+        got = b["values"][t].cpu()
+        assert close(got, vo, 2e-5) or float((got - vo).abs().max()) <= 5e-6, (n, t)   # a single small value: absolute floor
+    eng.env.close()
