@@ -212,6 +212,21 @@ class Policy:
             _, h = self._gru(x)
         return h[-1]
 
+    def _mission_lut_side_stream(self):
+        """The GRU over the 296 sequences is 128 dependent little steps (about 1.5 ms forward + backward, whatever the
+        minibatch size).  Run it on a side stream: autograd replays a node's backward on the stream of its forward, so
+        both passes overlap with the image branch instead of queueing behind it."""
+        torch = self.torch
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream(self.device)
+        self._side.wait_stream(main)              # the weights were last written (optimizer step) on the main stream
+        with torch.cuda.stream(self._side):
+            lut = self.mission_lut()
+        main.wait_stream(self._side)
+        lut.record_stream(main)                   # allocated on the side stream, consumed on the main one
+        return lut
+
     # ---------------------------------------------------------------- differentiable evaluation (PPO update)
     def evaluate(self, image_u8, dir_onehot, mission_row, lut=None):
         """image_u8 [B,12,7,7] (channels = frame*3 + c, H = view x, W = view y), dir_onehot [B,16], mission_row [B]
@@ -260,7 +275,8 @@ class Policy:
         F = torch.nn.functional
         P = self.params
         c = _PREFIX + "image.image_Conv2d_"
-        lut = self.mission_lut() if lut is None else lut
+        if lut is None:
+            lut = self._mission_lut_side_stream() if frames.is_cuda else self.mission_lut()
         a = age[t, i]
         pooled = _conv1_pool(torch)(P[c + "0.weight"], P[c + "0.bias"], frames, t.to(torch.int32), i.to(torch.int32), a)
         k = torch.arange(4, device=t.device)
