@@ -161,6 +161,9 @@ int mgrl_gae(const float *rewards_dev, const float *values_dev, const uint8_t *e
 /* ---- policy forward for the rollout (K3) ---------------------------------------------- */
 #define MGRL_POLICY_WEIGHTS 84940 /* floats in the packed weight buffer, layout in csrc/mgrl_policy.cu */
 #define MGRL_POLICY_DETERMINISTIC 1 /* flags: action = argmax(logits) instead of a sample (evaluate_policy, ppo.py:161) */
+#define MGRL_POLICY_TENSOR 2 /* flags: tensor-core kernel (split-TF32 mma, fp32-class results); the weight buffer then
+                              * holds MGRL_POLICY_WEIGHTS + MGRL_POLICY_FRAGMENTS floats, see mgrl_policy_pack_fragments */
+#define MGRL_POLICY_FRAGMENTS 93696 /* floats of the per-lane mma fragment section behind the fp32 weights */
 
 /* replaces CustomPPOPolicy.forward (policies.py:227-244, CustomExtractor policies.py:21-120) together with
  * the VecFrameStack(4,'first') / VecTransposeImage it reads through (ppo.py:124-126), for the rollout:
@@ -178,6 +181,11 @@ int mgrl_policy_forward(const float *weights_dev, const uint8_t *frames_dev, con
                         uint8_t *age_out_dev, uint8_t *start_out_dev, uint8_t *action_dev, float *logp_dev,
                         float *value_dev, float *logits_dev, int num_envs, int time_index, uint64_t seed,
                         uint64_t env_id_base, uint32_t step, int flags, void *stream);
+/* Fills the fragment section (floats [MGRL_POLICY_WEIGHTS, MGRL_POLICY_WEIGHTS + MGRL_POLICY_FRAGMENTS) of
+ * weights_dev, 16-byte aligned) from the fp32 weights in front of it: every convolution / linear layer of
+ * CustomExtractor + MlpExtractor + heads (policies.py:21-120,227-244) as tf32 hi/lo B fragments of mma.m16n8k8.
+ * Call after every weight change, before mgrl_policy_forward with MGRL_POLICY_TENSOR. */
+int mgrl_policy_pack_fragments(float *weights_dev, void *stream);
 const char *mgrl_policy_last_error(void);
 
 /* PPO update, first stage of the image extractor (Conv2d(12,16,2) + ReLU + MaxPool2d(2): policies.py:59 over

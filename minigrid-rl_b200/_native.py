@@ -66,6 +66,7 @@ _SIGNATURES = {
     "mgrl_vec_reset_frames_host": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp]),
     "mgrl_vec_step_frames_host": (C.c_int, [vp] * 12),
     "mgrl_policy_forward": (C.c_int, [vp] * 12 + [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, vp]),
+    "mgrl_policy_pack_fragments": (C.c_int, [vp, vp]),
     "mgrl_policy_last_error": (C.c_char_p, []),
     "mgrl_conv1_pool_forward": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp]),
     "mgrl_conv1_pool_backward": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp]),

@@ -8,5 +8,5 @@ mkdir -p "$OUT"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 "$NVCC" -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo \
     -Xcompiler -fPIC -shared -I "$ROOT/include" -I "$HERE" \
-    -o "$OUT/libmgrl.so" "$HERE/mgrl_kernels.cu" "$HERE/mgrl_policy.cu" "$@"
+    -o "$OUT/libmgrl.so" "$HERE/mgrl_kernels.cu" "$HERE/mgrl_policy.cu" "$HERE/mgrl_policy_tc.cu" "$@"
 echo "built $OUT/libmgrl.so"

@@ -22,6 +22,9 @@
 #include <cstdio>
 
 #include "mgrl.h"
+#include "mgrl_policy_layout.cuh"
+
+using namespace mgrl_policy;
 
 namespace {
 
@@ -30,47 +33,6 @@ constexpr int PITCH = 293;         // words of shared memory per observation
 constexpr int FRAME_WORDS = 37;    // 148-byte frame record
 constexpr int POOL_OFF = 148;      // pooled conv1 output: 9 cells x 16 channels
 constexpr int H_OFF = 208;         // hidden layer scratch (64 floats) behind the 208 features
-
-// float offsets into the packed weight buffer (mirrored in minigrid-rl_b200/policy.py: WEIGHT_LAYOUT)
-constexpr int W1 = 0, B1 = W1 + 48 * 16, W2 = B1 + 16, B2 = W2 + 64 * 32, W3 = B2 + 32, B3 = W3 + 128 * 64;
-constexpr int WD = B3 + 64, BD = WD + 16 * 16;
-constexpr int PI1 = BD + 16, PI1B = PI1 + 208 * 64, PI2 = PI1B + 64, PI2B = PI2 + 64 * 64;
-constexpr int VF1 = PI2B + 64, VF1B = VF1 + 208 * 64, VF2 = VF1B + 64, VF2B = VF2 + 64 * 64;
-constexpr int WA = VF2B + 64, BA = WA + 64 * 8, WV = BA + 8, BV = WV + 64, LUT = BV + 4;
-constexpr int N_WEIGHTS = LUT + MGRL_N_MISSIONS * 4 * 128;
-static_assert(N_WEIGHTS == MGRL_POLICY_WEIGHTS, "weight layout");
-
-struct PolicyArgs {
-    const float* w;
-    const uint8_t* frames;   // record of (time b, env i) at frames + (b * n + i) * 148; the kernel reads b-3..b
-    const uint8_t* dirs;     // (b * n + i)
-    const uint8_t* mission;  // [n] mission id at time b
-    const uint8_t* prev_age; // [n] or null (= first observation after a reset)
-    const uint8_t* prev_done;// [n] done flag of the step that produced this observation, or null
-    uint8_t* age_out;        // [n] frames of history available for this observation, 0..3
-    uint8_t* start_out;      // [n] or null: episode_start flag
-    uint8_t* action;         // [n] or null
-    float* logp;             // [n] or null
-    float* value;            // [n]
-    float* logits;           // [n,7] or null
-    int n, b;
-    uint64_t seed, env_id_base;
-    uint32_t step;           // sampling counter (global step index)
-    int deterministic;       // 1: action = argmax(logits) (evaluate_policy / test(), ppo.py:161,174-292)
-};
-
-__device__ __forceinline__ void philox_u01(uint64_t seed, uint64_t env, uint32_t step, float& u) {
-    uint32_t c0 = step, c1 = 0x504F4C49u /* "POLI" */, c2 = (uint32_t)env, c3 = (uint32_t)(env >> 32);
-    uint32_t ka = (uint32_t)seed, kb = (uint32_t)(seed >> 32);
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
-        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
-        c0 = h1 ^ c1 ^ ka; c1 = l1; c2 = h0 ^ c3 ^ kb; c3 = l0;
-        ka += 0x9E3779B9u; kb += 0xBB67AE85u;
-    }
-    u = (float)(c0 >> 8) * (1.0f / 16777216.0f);
-}
 
 // acc[0..NOUT) += x * w[0..NOUT), w 16-byte aligned and the same address in every lane
 template <int NOUT>
@@ -347,14 +309,32 @@ int mgrl_policy_forward(const float* weights_dev, const uint8_t* frames_dev, con
     a.action = action_dev; a.logp = logp_dev; a.value = value_dev; a.logits = logits_dev;
     a.n = num_envs; a.b = time_index; a.seed = seed; a.env_id_base = env_id_base; a.step = step;
     a.deterministic = (flags & MGRL_POLICY_DETERMINISTIC) ? 1 : 0;
-    const size_t smem = (size_t)(OB * PITCH + WBUF) * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) {
-        policy_forward_kernel<<<(num_envs + OB - 1) / OB, NT, smem, (cudaStream_t)stream>>>(a);
-        e = cudaGetLastError();
+    cudaError_t e;
+    if (flags & MGRL_POLICY_TENSOR) {       // tensor-core kernel: the buffer carries the fragment section
+        e = launch_policy_forward_tc(a, (cudaStream_t)stream);
+    } else {
+        const size_t smem = (size_t)(OB * PITCH + WBUF) * sizeof(float);
+        e = cudaFuncSetAttribute(policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) {
+            policy_forward_kernel<<<(num_envs + OB - 1) / OB, NT, smem, (cudaStream_t)stream>>>(a);
+            e = cudaGetLastError();
+        }
     }
     if (e != cudaSuccess) {
         snprintf(g_perr, sizeof g_perr, "mgrl_policy_forward: %s", cudaGetErrorString(e));
+        return MGRL_ERR_CUDA;
+    }
+    return MGRL_OK;
+}
+
+int mgrl_policy_pack_fragments(float* weights_dev, void* stream) {
+    if (!weights_dev) {
+        snprintf(g_perr, sizeof g_perr, "mgrl_policy_pack_fragments: null argument");
+        return MGRL_ERR_INVALID;
+    }
+    const cudaError_t e = launch_pack_fragments(weights_dev, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        snprintf(g_perr, sizeof g_perr, "mgrl_policy_pack_fragments: %s", cudaGetErrorString(e));
         return MGRL_ERR_CUDA;
     }
     return MGRL_OK;

@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import numpy as np
 
@@ -24,6 +25,8 @@ from .missions import N_MISSIONS, token_table
 
 N_ACTIONS = 7
 N_WEIGHTS = 84940
+N_FRAGMENTS = 93696            # MGRL_POLICY_FRAGMENTS: tf32 hi/lo mma fragments of the tensor-core forward kernel
+FLAG_DETERMINISTIC, FLAG_TENSOR = 1, 2
 # float offsets of the packed buffer, identical to csrc/mgrl_policy.cu
 _L = {}
 _off = 0
@@ -108,6 +111,9 @@ class Policy:
         import torch
         self.torch = torch
         self.fp32_strict = fp32_strict      # False = allow TF32 in the library kernels of the update, like ppo.py:29-32
+        # rollout forward: split-TF32 tensor-core kernel (fp32-class results); MGRL_POLICY_SIMT=1 selects the fp32
+        # CUDA-core kernel it replaced (kept for A/B measurements)
+        self.tensor_cores = os.environ.get("MGRL_POLICY_SIMT", "0") != "1"
         self.device = torch.device(device)
         g = torch.Generator().manual_seed(seed)
         self.params = {}
@@ -291,7 +297,9 @@ class Policy:
     def pack(self):
         torch = self.torch
         P = {k: v.detach() for k, v in self.params.items()}
-        out = torch.zeros(N_WEIGHTS, dtype=torch.float32, device=self.device)
+        # fp32 weights, then (CUDA) the fragment section that mgrl_policy_pack_fragments derives from them
+        cuda = self.device.type == "cuda"
+        out = torch.zeros(N_WEIGHTS + (N_FRAGMENTS if cuda else 0), dtype=torch.float32, device=self.device)
 
         def put(name, t):
             o, n = WEIGHT_LAYOUT[name]
@@ -317,6 +325,9 @@ class Policy:
         with torch.no_grad():
             put("LUT", self.mission_lut())
         self._packed = out.contiguous()
+        if cuda:
+            s = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            nat.check(nat.lib().mgrl_policy_pack_fragments(C.c_void_p(self._packed.data_ptr()), s), "mgrl_policy_pack_fragments")
         return self._packed
 
     def packed(self):
@@ -335,5 +346,5 @@ class Policy:
         nat.check(nat.lib().mgrl_policy_forward(
             p(self.packed()), p(frames), p(dirs), p(mission), p(prev_age), p(prev_done), p(age_out), p(start_out),
             p(action), p(logp), p(value), p(logits), n, int(time_index), int(seed), int(env_id_base), int(step),
-            1 if deterministic else 0, s),
+            (FLAG_DETERMINISTIC if deterministic else 0) | (FLAG_TENSOR if self.tensor_cores else 0), s),
             "mgrl_policy_forward")

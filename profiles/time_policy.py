@@ -12,4 +12,4 @@ a.record()
 for rep in range(3):
     for t in range(T):
         eng.policy.forward_rollout(B["frames"], B["dirs"], B["mission"][t + 3], t + 3, eng.prev_age, eng.prev_done, B["age"][t], B["values"][t], B["actions"][t], B["logp"][t])
-b.record(); torch.cuda.synchronize(); print("carveout", os.environ.get("MGRL_POLICY_CARVEOUT"), "policy kernel us/step %.1f" % (1000 * a.elapsed_time(b) / (3 * T)))
+b.record(); torch.cuda.synchronize(); print("simt", os.environ.get("MGRL_POLICY_SIMT"), "occ", os.environ.get("MGRL_TC_OCC"), "policy kernel us/step %.1f" % (1000 * a.elapsed_time(b) / (3 * T)))

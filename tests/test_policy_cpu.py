@@ -105,8 +105,11 @@ def test_ppo_loss_and_gradients_match_oracle():
 def test_packed_weight_layout_matches_header_and_kernel_source():
     hdr = open(os.path.join(ROOT, "include", "mgrl.h")).read()
     assert int(re.search(r"#define MGRL_POLICY_WEIGHTS (\d+)", hdr).group(1)) == pol.N_WEIGHTS
-    src = open(os.path.join(ROOT, "minigrid-rl_b200", "csrc", "mgrl_policy.cu")).read()
+    assert int(re.search(r"#define MGRL_POLICY_FRAGMENTS (\d+)", hdr).group(1)) == pol.N_FRAGMENTS
+    src = open(os.path.join(ROOT, "minigrid-rl_b200", "csrc", "mgrl_policy_layout.cuh")).read()
     assert "N_WEIGHTS == MGRL_POLICY_WEIGHTS" in src
+    assert "F_END * 4 == MGRL_POLICY_FRAGMENTS" in open(os.path.join(ROOT, "minigrid-rl_b200", "csrc", "mgrl_policy_tc.cu")).read()
+    assert pol.N_WEIGHTS % 4 == 0                   # the fragment section behind the weights is 16-byte aligned
     off = 0
     for name, (o, n) in pol.WEIGHT_LAYOUT.items():
         assert o == off and o % 4 == 0, name        # 16-byte aligned rows for the float4 weight loads
