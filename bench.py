@@ -322,13 +322,30 @@ def main():
         if dist is not None:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_roll, t_upd = float(tt[0]), float(tt[1])
+        # the rollout's policy kernel alone (K3): T launches over the collected frames, CUDA events on the launching stream
+        B = eng.buf
+        kev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        kev[0].record()
+        for t in range(T):
+            eng.policy.forward_rollout(B["frames"], B["dirs"], B["mission"][t + 3], t + 3, eng.prev_age, eng.prev_done,
+                                       B["age"][t], B["values"][t], B["actions"][t], B["logp"][t])
+        kev[1].record()
+        torch.cuda.synchronize()
+        k3_us = 1000.0 * kev[0].elapsed_time(kev[1]) / T
+        k3_flop = 2.0 * 79616 * n      # MACs / observation: conv 27 648 + 8 192 + 8 192, direction 256, MLPs 26 624 + 8 192, heads 512
         frames = world * n * T * args.ppo_iters
         ppo_line = {"value": frames / ((t_roll + t_upd) / 1000.0), "unit": "frames/s",
+                    "policy_kernel": {"us_per_launch": k3_us, "observations_per_launch": n,
+                                      "kernel": "policy_forward_tc_kernel (mma.sync m16n8k8 TF32, three-term split, fp32 accumulate)"
+                                                if eng.policy.tensor_cores else "policy_forward_kernel (fp32 CUDA cores)",
+                                      "algorithmic_tflops": k3_flop / (k3_us * 1e-6) / 1e12,
+                                      "tensor_tflops_issued": (3312 * 2048.0 * (n / 16.0)) / (k3_us * 1e-6) / 1e12
+                                                              if eng.policy.tensor_cores else 0.0},
                     "rollout_env_steps_per_s": frames / (t_roll / 1000.0), "rollout_ms": t_roll / args.ppo_iters,
                     "update_ms": t_upd / args.ppo_iters, "iterations": args.ppo_iters,
                     "config": {"n_steps": T, "n_envs_per_gpu": n, "batch_size_per_gpu": pcfg.batch_size, "n_epochs": 4,
                                "minibatches_per_iteration": n_mb, "policy": "CustomPPOPolicy 110216 params, fp32",
-                               "rollout": "mgrl_policy_forward + mgrl_step per step (hand-written kernels)",
+                               "rollout": "mgrl_policy_forward (tensor cores, split TF32 = fp32-class) + mgrl_step per step (hand-written kernels)",
                                "update": "first extractor stage hand-written (mgrl_conv1_pool_*), rest torch autograd on library kernels; "
                                          "matmuls may use TF32 like the reference (ppo.py:29-32), the rollout kernels are fp32",
                                "all_reduces_per_optimizer_step": 2 if world > 1 else 0},
