@@ -207,7 +207,11 @@ __global__ void __launch_bounds__(NT, MINB) policy_forward_tc_kernel(const Polic
         // Conv2d(12,16,2) at the four positions of pooled cell q, running maximum (MaxPool2d(2)), then bias + ReLU
         float best[2][4];
 #pragma unroll
-        for (int sp = 0; sp < 4; ++sp) {
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) best[nt][r] = -3.0e38f;
+#pragma unroll 1
+        for (int sp = 0; sp < 4; ++sp) {      // rolled: the fully unrolled network does not fit the instruction cache
             const int cell = ((2 * qh + (sp >> 1)) * 7 + 2 * qw + (sp & 1)) * 3 + tap;
             float cur[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
@@ -227,7 +231,7 @@ __global__ void __launch_bounds__(NT, MINB) policy_forward_tc_kernel(const Polic
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-                for (int r = 0; r < 4; ++r) best[nt][r] = sp == 0 ? cur[nt][r] : fmaxf(best[nt][r], cur[nt][r]);
+                for (int r = 0; r < 4; ++r) best[nt][r] = fmaxf(best[nt][r], cur[nt][r]);
         }
         AFrag pa[2];
         {

@@ -230,19 +230,21 @@ class RolloutEngine:
         if idx.numel() == 0:
             return 0
         t, i = idx[:, 0], idx[:, 1]
-        age = torch.clamp(b["age"][t, i].long() + 1, max=3)           # the terminal frame extends the same episode
+        # The terminal observation extends the finished episode by one frame: stack = buffer slots of times t-2..t + the
+        # terminal frame, the old mission, age = min(age + 1, 3).  Valued by the rollout's own forward kernel (the same
+        # numbers the rollout would have produced, and no library kernels whose first call on a new batch size costs
+        # tens of milliseconds): the M samples are gathered into a small [4, M, 148] frame buffer.
         k = torch.arange(3, device=t.device)
-        valid = (3 - k)[None, :] <= age[:, None]
-        hist = b["frames"][(t[:, None] + 1 + k[None, :]), i[:, None]]    # slots of times t-2..t
-        hist = hist * valid[:, :, None].to(torch.uint8)
-        fr = torch.cat([hist, self.term_frames[t, i][:, None]], dim=1)[:, :, :147]
-        image = fr.reshape(-1, 4, 7, 7, 3).permute(0, 1, 4, 2, 3).reshape(-1, 12, 7, 7)
-        d = torch.cat([b["dirs"][(t[:, None] + 1 + k[None, :]), i[:, None]], self.term_dirs[t, i][:, None]], dim=1).long()
-        valid4 = torch.cat([valid, torch.ones_like(valid[:, :1])], dim=1)
-        onehot = (torch.nn.functional.one_hot(d, 4).to(torch.uint8) * valid4[:, :, None].to(torch.uint8)).view(-1, 16)
-        mrow = b["mission"][t + 3, i].long() * 4 + age               # the terminal observation keeps the old mission
-        with torch.no_grad():
-            _, v = self.policy.evaluate(image, onehot, mrow)
+        hist = b["frames"][(t[:, None] + 1 + k[None, :]), i[:, None]]                       # [M,3,148]
+        frames4 = torch.cat([hist, self.term_frames[t, i][:, None]], dim=1).permute(1, 0, 2).contiguous()
+        dirs4 = torch.cat([b["dirs"][(t[:, None] + 1 + k[None, :]), i[:, None]], self.term_dirs[t, i][:, None]],
+                          dim=1).t().contiguous()
+        m = int(t.numel())
+        v = torch.empty(m, dtype=torch.float32, device=t.device)
+        age_out = torch.empty(m, dtype=torch.uint8, device=t.device)
+        self.policy.forward_rollout(frames4, dirs4, b["mission"][t + 3, i].contiguous(), 3, b["age"][t, i].contiguous(),
+                                    torch.zeros(m, dtype=torch.uint8, device=t.device), age_out, v)
+        self.launches += 1
         b["rewards"][t, i] += self.cfg.gamma * v
         return int(idx.shape[0])
 
