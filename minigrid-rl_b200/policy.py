@@ -103,6 +103,37 @@ def _conv1_pool(torch):
     return _CONV1_POOL
 
 
+_SPLITK_LINEAR = None
+
+
+def _linear(torch, x, w, b):
+    """F.linear whose weight gradient is a split-K batched GEMM.  The update's minibatches are 10^5..10^6 rows deep and
+    the layers at most 208 x 128 wide: as ONE `dz.T @ x` GEMM the weight gradient has a handful of output tiles and the
+    library runs it on a few CTAs of a 148-SM GPU (1.4 ms of an 8 ms minibatch); cut into 64 row blocks it is a batched
+    GEMM that fills the machine, plus a sum over 64 small partial results."""
+    if not x.is_cuda or x.shape[0] < 16384 or x.shape[0] % 64 != 0 or not torch.is_grad_enabled():
+        return torch.nn.functional.linear(x, w, b)
+    global _SPLITK_LINEAR
+    if _SPLITK_LINEAR is None:
+        class SplitKLinear(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, x, w, b):
+                ctx.save_for_backward(x, w)
+                return torch.addmm(b, x, w.t())
+
+            @staticmethod
+            def backward(ctx, g):
+                x, w = ctx.saved_tensors
+                g = g.contiguous()
+                m, s = g.shape[0], 64
+                dx = g @ w if ctx.needs_input_grad[0] else None
+                dw = torch.bmm(g.view(s, m // s, -1).transpose(1, 2), x.view(s, m // s, -1)).sum(0)
+                return dx, dw, g.sum(0)
+
+        _SPLITK_LINEAR = SplitKLinear.apply
+    return _SPLITK_LINEAR(x.contiguous(), w, b)
+
+
 class Policy:
     """Parameters + the two evaluation paths.  Works on any torch device for `evaluate` (the update's autograd
     path and the CPU tests of the data-parallel logic); `pack` / `forward_rollout` need CUDA."""
@@ -258,20 +289,24 @@ class Policy:
         """everything after the first pooled convolution: h [B,3,3,16] (qh, qw, c)"""
         torch = self.torch
         B = h.shape[0]
+
+        def lin(x, w, b):
+            return _linear(torch, x, w, b)
+
         c = _PREFIX + "image.image_Conv2d_"
         p = h.unfold(1, 2, 1).unfold(2, 2, 1).reshape(B * 4, 64)                                      # (ci, kh, kw)
-        h = torch.relu(F.linear(p, P[c + "3.weight"].reshape(32, 64), P[c + "3.bias"])).view(B, 128)  # (oh, ow, c2)
-        x = torch.relu(F.linear(h, P[c + "5.weight"].permute(0, 2, 3, 1).reshape(64, 128), P[c + "5.bias"]))
-        d = F.linear(dir_onehot.float(), P[_PREFIX + "direction.direction_Linear_0.weight"],
+        h = torch.relu(lin(p, P[c + "3.weight"].reshape(32, 64), P[c + "3.bias"])).view(B, 128)  # (oh, ow, c2)
+        x = torch.relu(lin(h, P[c + "5.weight"].permute(0, 2, 3, 1).reshape(64, 128), P[c + "5.bias"]))
+        d = lin(dir_onehot.float(), P[_PREFIX + "direction.direction_Linear_0.weight"],
                      P[_PREFIX + "direction.direction_Linear_0.bias"])
         f = torch.cat([d, x, F.embedding(mission_row.long(), lut)], dim=1)
         t = torch.tanh
-        hp = t(F.linear(t(F.linear(f, P["mlp_extractor.policy_net.0.weight"], P["mlp_extractor.policy_net.0.bias"])),
+        hp = t(lin(t(lin(f, P["mlp_extractor.policy_net.0.weight"], P["mlp_extractor.policy_net.0.bias"])),
                         P["mlp_extractor.policy_net.2.weight"], P["mlp_extractor.policy_net.2.bias"]))
-        hv = t(F.linear(t(F.linear(f, P["mlp_extractor.value_net.0.weight"], P["mlp_extractor.value_net.0.bias"])),
+        hv = t(lin(t(lin(f, P["mlp_extractor.value_net.0.weight"], P["mlp_extractor.value_net.0.bias"])),
                         P["mlp_extractor.value_net.2.weight"], P["mlp_extractor.value_net.2.bias"]))
-        return (F.linear(hp, P["action_net.weight"], P["action_net.bias"]),
-                F.linear(hv, P["value_net.weight"], P["value_net.bias"]).squeeze(-1))
+        return (lin(hp, P["action_net.weight"], P["action_net.bias"]),
+                lin(hv, P["value_net.weight"], P["value_net.bias"]).squeeze(-1))
 
     def evaluate_samples(self, frames, dirs, mission, age, t, i, lut=None):
         """`evaluate` for rollout samples (t, i) without materialising their stacked images: the first stage of the image
