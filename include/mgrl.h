@@ -202,6 +202,13 @@ int mgrl_conv1_pool_backward(const uint8_t *frames_dev, int num_envs, const int3
                              const uint8_t *age_dev, int batch, const uint8_t *arg_dev, const float *dpooled_dev,
                              float *dw1_dev, float *db1_dev, void *stream);
 
+/* PPO update, input patches of the second convolution (Conv2d(16,32,2), policies.py:59 over single.yaml:48) and their
+ * adjoint: patches_dev [B,4,64] f32 with patches[b][o][kk*16+ci] = pooled[b][q(o,kk)][ci] (o = oh*2+ow, kk = kh*2+kw,
+ * q = (oh+kh)*3 + ow+kw) from pooled_dev [B,9,16]; backward sums dpatches_dev [B,4,64] into dpooled_dev [B,9,16]
+ * (overwritten).  16-byte aligned buffers. */
+int mgrl_patch2x2_forward(const float *pooled_dev, int batch, float *patches_dev, void *stream);
+int mgrl_patch2x2_backward(const float *dpatches_dev, int batch, float *dpooled_dev, void *stream);
+
 /* ---- host-buffer drop-in path (what B200VecEnv.reset/step with numpy arrays calls) --- */
 
 /* VecEnv.reset(): stacked observation dict into host buffers; synchronous.

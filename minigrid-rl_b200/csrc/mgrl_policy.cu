@@ -500,6 +500,40 @@ __global__ void __launch_bounds__(192) conv1_pool_bwd_kernel(const Conv1Args p) 
 
 }  // namespace
 
+// PPO update, input patches of the second convolution (Conv2d(16,32,2) on the pooled 3x3x16 map, policies.py:59 over
+// single.yaml:48): patches[b][o][kk * 16 + ci] = pooled[b][q(o, kk)][ci], o = oh * 2 + ow, kk = kh * 2 + kw,
+// q = (oh + kh) * 3 + ow + kw, and its adjoint.  The library formulation (two unfolds + reshape) spends 0.74 ms of a
+// 262 144-sample minibatch in unfold_backward alone; these are two float4 copy kernels.
+namespace {
+
+__global__ void patch2x2_fwd_kernel(const float4* __restrict__ pooled, float4* __restrict__ patches, int batch) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // (b, o, kk, ci / 4)
+    if (e >= (size_t)batch * 64) return;
+    const int c4 = (int)(e & 3), kk = (int)((e >> 2) & 3), o = (int)((e >> 4) & 3);
+    const size_t b = e >> 6;
+    const int q = ((o >> 1) + (kk >> 1)) * 3 + (o & 1) + (kk & 1);
+    patches[e] = __ldg(pooled + (b * 9 + q) * 4 + c4);
+}
+
+__global__ void patch2x2_bwd_kernel(const float4* __restrict__ dpatches, float4* __restrict__ dpooled, int batch) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // (b, q, ci / 4)
+    if (e >= (size_t)batch * 36) return;
+    const size_t b = e / 36;
+    const int r = (int)(e - b * 36), q = r >> 2, c4 = r & 3;
+    const int qh = q / 3, qw = q - qh * 3;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        const int oh = qh - (kk >> 1), ow = qw - (kk & 1);
+        if (oh < 0 || oh > 1 || ow < 0 || ow > 1) continue;
+        const float4 v = __ldg(dpatches + (b * 4 + oh * 2 + ow) * 16 + kk * 4 + c4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    dpooled[e] = acc;
+}
+
+}  // namespace
+
 extern "C" {
 
 int mgrl_conv1_pool_forward(const uint8_t* frames_dev, int num_envs, const int32_t* t_dev, const int32_t* i_dev,
@@ -544,6 +578,32 @@ int mgrl_conv1_pool_backward(const uint8_t* frames_dev, int num_envs, const int3
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) { snprintf(g_perr, sizeof g_perr, "mgrl_conv1_pool_backward: %s", cudaGetErrorString(e)); return MGRL_ERR_CUDA; }
+    return MGRL_OK;
+}
+
+int mgrl_patch2x2_forward(const float* pooled_dev, int batch, float* patches_dev, void* stream) {
+    if (!pooled_dev || !patches_dev || batch <= 0) {
+        snprintf(g_perr, sizeof g_perr, "mgrl_patch2x2_forward: null argument or empty batch");
+        return MGRL_ERR_INVALID;
+    }
+    const size_t total = (size_t)batch * 64;
+    patch2x2_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(pooled_dev), reinterpret_cast<float4*>(patches_dev), batch);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(g_perr, sizeof g_perr, "mgrl_patch2x2_forward: %s", cudaGetErrorString(e)); return MGRL_ERR_CUDA; }
+    return MGRL_OK;
+}
+
+int mgrl_patch2x2_backward(const float* dpatches_dev, int batch, float* dpooled_dev, void* stream) {
+    if (!dpatches_dev || !dpooled_dev || batch <= 0) {
+        snprintf(g_perr, sizeof g_perr, "mgrl_patch2x2_backward: null argument or empty batch");
+        return MGRL_ERR_INVALID;
+    }
+    const size_t total = (size_t)batch * 36;
+    patch2x2_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(dpatches_dev), reinterpret_cast<float4*>(dpooled_dev), batch);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(g_perr, sizeof g_perr, "mgrl_patch2x2_backward: %s", cudaGetErrorString(e)); return MGRL_ERR_CUDA; }
     return MGRL_OK;
 }
 

@@ -104,6 +104,39 @@ def _conv1_pool(torch):
 
 
 _SPLITK_LINEAR = None
+_PATCH2 = None
+
+
+def _patches2x2(torch, h):
+    """h [B,3,3,16] (qh, qw, c) -> conv2 input patches [B*4, 64] in (kh, kw, ci) order: hand-written gather and its adjoint
+    (mgrl_patch2x2_forward / backward) on CUDA, the same gather by slicing elsewhere."""
+    B = h.shape[0]
+    if not h.is_cuda:
+        return torch.stack([h[:, kh:kh + 2, kw:kw + 2, :] for kh in (0, 1) for kw in (0, 1)], dim=3).reshape(B * 4, 64)
+    global _PATCH2
+    if _PATCH2 is None:
+        class Patch2x2(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, pooled):
+                b = int(pooled.shape[0])
+                out = torch.empty((b * 4, 64), dtype=torch.float32, device=pooled.device)
+                s = C.c_void_p(torch.cuda.current_stream(pooled.device).cuda_stream)
+                nat.check(nat.lib().mgrl_patch2x2_forward(C.c_void_p(pooled.data_ptr()), b, C.c_void_p(out.data_ptr()), s),
+                          "mgrl_patch2x2_forward")
+                return out
+
+            @staticmethod
+            def backward(ctx, g):
+                g = g.contiguous()
+                b = int(g.shape[0]) // 4
+                d = torch.empty((b, 3, 3, 16), dtype=torch.float32, device=g.device)
+                s = C.c_void_p(torch.cuda.current_stream(g.device).cuda_stream)
+                nat.check(nat.lib().mgrl_patch2x2_backward(C.c_void_p(g.data_ptr()), b, C.c_void_p(d.data_ptr()), s),
+                          "mgrl_patch2x2_backward")
+                return d
+
+        _PATCH2 = Patch2x2.apply
+    return _PATCH2(h.contiguous().float())
 
 
 def _linear(torch, x, w, b):
@@ -294,8 +327,8 @@ class Policy:
             return _linear(torch, x, w, b)
 
         c = _PREFIX + "image.image_Conv2d_"
-        p = h.unfold(1, 2, 1).unfold(2, 2, 1).reshape(B * 4, 64)                                      # (ci, kh, kw)
-        h = torch.relu(lin(p, P[c + "3.weight"].reshape(32, 64), P[c + "3.bias"])).view(B, 128)  # (oh, ow, c2)
+        p = _patches2x2(torch, h)                                                                     # (kh, kw, ci)
+        h = torch.relu(lin(p, P[c + "3.weight"].permute(0, 2, 3, 1).reshape(32, 64), P[c + "3.bias"])).view(B, 128)  # (oh, ow, c2)
         x = torch.relu(lin(h, P[c + "5.weight"].permute(0, 2, 3, 1).reshape(64, 128), P[c + "5.bias"]))
         d = lin(dir_onehot.float(), P[_PREFIX + "direction.direction_Linear_0.weight"],
                      P[_PREFIX + "direction.direction_Linear_0.bias"])
