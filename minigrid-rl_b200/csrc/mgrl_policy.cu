@@ -20,6 +20,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 #include "mgrl.h"
 #include "mgrl_policy_layout.cuh"
@@ -287,6 +288,12 @@ __global__ void __launch_bounds__(NT, 4) policy_forward_kernel(const PolicyArgs 
 
 thread_local char g_perr[256] = "";
 
+// MGRL_CONV1_SIMT=1 selects the CUDA-core kernels of the update's first stage (kept for A/B measurements)
+bool conv1_tensor_cores() {
+    static const bool simt = [] { const char* v = getenv("MGRL_CONV1_SIMT"); return v && atoi(v) != 0; }();
+    return !simt;
+}
+
 }  // namespace
 
 extern "C" {
@@ -354,21 +361,6 @@ namespace {
 
 constexpr int C1_OB = 64;        // samples per CTA (forward)
 constexpr int C1_PITCH = 149;    // words per staged sample: 4 frames x 37 words, odd pitch
-
-struct Conv1Args {
-    const uint8_t* frames;   // [time, n, 148]
-    const int32_t* t;        // [B] time index of the sample (its newest frame is record t + 3)
-    const int32_t* i;        // [B] environment
-    const uint8_t* age;      // [B] frames of history available (0..3)
-    const float* w1;         // [16][12][2][2] (torch layout)
-    const float* b1;         // [16]
-    float* pooled;           // [B][9][16] post bias + ReLU, pooled cell q = qh * 3 + qw
-    uint8_t* arg;            // [B][9][16] position of the maximum (0..3) | 4 if the output is positive
-    const float* dpooled;    // backward: [B][9][16]
-    float* dw1;              // backward: [16][48] accumulated with atomics (caller zeroes)
-    float* db1;              // backward: [16]
-    int n, B;
-};
 
 // stage the 4-frame stacks of samples [s0, s0 + count) into shared memory, PITCH words per sample
 __device__ __forceinline__ void stage_samples(const Conv1Args& p, int s0, int count, uint32_t* blocks, int pitch, int tid,
@@ -546,11 +538,16 @@ int mgrl_conv1_pool_forward(const uint8_t* frames_dev, int num_envs, const int32
     Conv1Args a = {};
     a.frames = frames_dev; a.t = t_dev; a.i = i_dev; a.age = age_dev; a.w1 = w1_dev; a.b1 = b1_dev; a.pooled = pooled_dev;
     a.arg = arg_dev; a.n = num_envs; a.B = batch;
-    const size_t smem = (size_t)(C1_OB * C1_PITCH + 768 + 256) * 4;
-    cudaError_t e = cudaFuncSetAttribute(conv1_pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) {
-        conv1_pool_fwd_kernel<<<(batch + C1_OB - 1) / C1_OB, C1_OB * 4, smem, (cudaStream_t)stream>>>(a);
-        e = cudaGetLastError();
+    cudaError_t e;
+    if (conv1_tensor_cores()) {
+        e = launch_conv1_pool_fwd_tc(a, (cudaStream_t)stream);
+    } else {
+        const size_t smem = (size_t)(C1_OB * C1_PITCH + 768 + 256) * 4;
+        e = cudaFuncSetAttribute(conv1_pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) {
+            conv1_pool_fwd_kernel<<<(batch + C1_OB - 1) / C1_OB, C1_OB * 4, smem, (cudaStream_t)stream>>>(a);
+            e = cudaGetLastError();
+        }
     }
     if (e != cudaSuccess) { snprintf(g_perr, sizeof g_perr, "mgrl_conv1_pool_forward: %s", cudaGetErrorString(e)); return MGRL_ERR_CUDA; }
     return MGRL_OK;
@@ -569,13 +566,17 @@ int mgrl_conv1_pool_backward(const uint8_t* frames_dev, int num_envs, const int3
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(dw1_dev, 0, 768 * sizeof(float), s);
     if (e == cudaSuccess) e = cudaMemsetAsync(db1_dev, 0, 16 * sizeof(float), s);
-    const size_t smem = (size_t)(C1B_CHUNK * C1_PITCH) * 4 + (size_t)C1B_CHUNK * 144 * 4 + (size_t)C1B_CHUNK * 144 + 256 * 4;
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv1_pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) {
-        const int nchunks = (batch + C1B_CHUNK - 1) / C1B_CHUNK;
-        const int grid = nchunks < 148 * 4 ? nchunks : 148 * 4;
-        conv1_pool_bwd_kernel<<<grid, 192, smem, s>>>(a);
-        e = cudaGetLastError();
+    if (e == cudaSuccess && conv1_tensor_cores()) {
+        e = launch_conv1_pool_bwd_tc(a, s);
+    } else if (e == cudaSuccess) {
+        const size_t smem = (size_t)(C1B_CHUNK * C1_PITCH) * 4 + (size_t)C1B_CHUNK * 144 * 4 + (size_t)C1B_CHUNK * 144 + 256 * 4;
+        e = cudaFuncSetAttribute(conv1_pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) {
+            const int nchunks = (batch + C1B_CHUNK - 1) / C1B_CHUNK;
+            const int grid = nchunks < 148 * 4 ? nchunks : 148 * 4;
+            conv1_pool_bwd_kernel<<<grid, 192, smem, s>>>(a);
+            e = cudaGetLastError();
+        }
     }
     if (e != cudaSuccess) { snprintf(g_perr, sizeof g_perr, "mgrl_conv1_pool_backward: %s", cudaGetErrorString(e)); return MGRL_ERR_CUDA; }
     return MGRL_OK;

@@ -52,9 +52,27 @@ __device__ __forceinline__ void philox_u01(uint64_t seed, uint64_t env, uint32_t
 }
 
 
+struct Conv1Args {
+    const uint8_t* frames;   // [time, n, 148]
+    const int32_t* t;        // [B] time index of the sample (its newest frame is record t + 3)
+    const int32_t* i;        // [B] environment
+    const uint8_t* age;      // [B] frames of history available (0..3)
+    const float* w1;         // [16][12][2][2] (torch layout)
+    const float* b1;         // [16]
+    float* pooled;           // [B][9][16] post bias + ReLU, pooled cell q = qh * 3 + qw
+    uint8_t* arg;            // [B][9][16] position of the maximum (0..3) | 4 if the output is positive
+    const float* dpooled;    // backward: [B][9][16]
+    float* dw1;              // backward: [16][48] accumulated with atomics (caller zeroes)
+    float* db1;              // backward: [16]
+    int n, B;
+};
+
 // mgrl_policy_tc.cu: the tensor-core forward and the fragment packing of its weights (section of MGRL_POLICY_FRAGMENTS
 // floats behind the N_WEIGHTS fp32 weights of the same buffer)
 cudaError_t launch_policy_forward_tc(const PolicyArgs& a, cudaStream_t stream);
 cudaError_t launch_pack_fragments(float* weights_dev, cudaStream_t stream);
+// mgrl_policy_tc.cu: first extractor stage of the PPO update on the tensor cores
+cudaError_t launch_conv1_pool_fwd_tc(const Conv1Args& a, cudaStream_t stream);
+cudaError_t launch_conv1_pool_bwd_tc(const Conv1Args& a, cudaStream_t stream);
 
 }  // namespace mgrl_policy

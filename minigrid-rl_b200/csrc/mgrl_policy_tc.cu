@@ -472,6 +472,182 @@ __global__ void pack_fragments_kernel(const float* __restrict__ w, float4* __res
     frag[e] = make_float4(h0, h1, __uint_as_float(to_tf32(b0 - h0)), __uint_as_float(to_tf32(b1 - h1)));
 }
 
+
+// ================================================================================================================
+// PPO update, first extractor stage (Conv2d(12,16,2) + ReLU + MaxPool2d(2): policies.py:59 over single.yaml:44-47,
+// inside SB3's PPO.train driven from ppo.py:159) on the tensor cores.  Same contracts as the CUDA-core kernels of
+// mgrl_policy.cu (mgrl_conv1_pool_forward / backward): the minibatch samples (t, env) are read as bytes straight off
+// the rollout's frame buffer, only the pooled 3x3x16 activations and a byte of arg-max per output leave the forward.
+//   forward : the rollout kernel's first stage on gathered samples, plus the arg-max bookkeeping; two-term split
+//             (bytes are exact in TF32), so the result is fp32-class whatever precision the rest of the update runs in;
+//   backward: dW1[co][k] = sum over (sample, cell, position) of [arg-max == position, output > 0] * dpooled * x(k):
+//             a GEMM whose reduction dimension is the sample axis.  A k-tile is 8 samples at one position; A = masked
+//             gradient (row = channel), B = the bytes of the patch (column = input index), a 7th n-tile of ones yields the
+//             bias gradient; a warp keeps its 16 x 56 accumulators for every sample it sees and the CTA adds them to
+//             global memory once.
+constexpr int SAMPLE_BYTES = 4 * 148;     // staged 4-frame stack of one sample
+
+// gather the 4-frame stacks of samples [s0, s0 + 64) (4-byte cp.async, all in flight; frames older than the episode
+// and rows past the batch are zero-filled by the copy)
+__device__ __forceinline__ void stage_samples_async(const Conv1Args& p, int s0, uint8_t* smem, int tid) {
+    for (int e = tid; e < OBC * 4 * FRAME_WORDS; e += NT) {
+        const int o = e / (4 * FRAME_WORDS), r = e - o * (4 * FRAME_WORDS);
+        const int f = r / FRAME_WORDS, j = r - f * FRAME_WORDS;
+        const int s = s0 + o;
+        const bool live = s < p.B && (3 - f) <= (int)p.age[s];
+        const uint8_t* src = live ? p.frames + ((size_t)(p.t[s] + f) * p.n + p.i[s]) * 148 + j * 4 : p.frames;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem + o * SAMPLE_BYTES + r * 4);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(live ? 4 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(NT, 4) conv1_pool_fwd_tc_kernel(const Conv1Args p) {
+    __shared__ __align__(16) uint8_t s_px[OBC * SAMPLE_BYTES];
+    __shared__ __align__(16) float4 s_c1[6 * 2 * 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int s0 = blockIdx.x * OBC;
+    stage_samples_async(p, s0, s_px, tid);
+    for (int e = tid; e < 6 * 2 * 32; e += NT) {   // B fragments of W1 / 255 (torch layout [co][k]), natural k order
+        const int l = e & 31, tile = e >> 5, kt = tile >> 1, nt = tile & 1;
+        const int n = nt * 8 + (l >> 2), k0 = kt * 8 + (l & 3), k1 = k0 + 4;
+        const float b0 = __ldg(p.w1 + n * 48 + k0) / 255.0f, b1 = __ldg(p.w1 + n * 48 + k1) / 255.0f;
+        const float h0 = __uint_as_float(to_tf32(b0)), h1 = __uint_as_float(to_tf32(b1));
+        s_c1[e] = make_float4(h0, h1, __uint_as_float(to_tf32(b0 - h0)), __uint_as_float(to_tf32(b1 - h1)));
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const int r0 = warp * 16 + g, r1 = r0 + 8;
+    const bool v0 = s0 + r0 < p.B, v1 = s0 + r1 < p.B;
+    const uint8_t* px0 = s_px + r0 * SAMPLE_BYTES;
+    const uint8_t* px1 = s_px + r1 * SAMPLE_BYTES;
+    const float2 b1a = __ldg(reinterpret_cast<const float2*>(p.b1) + t), b1b = __ldg(reinterpret_cast<const float2*>(p.b1 + 8) + t);
+    const int tap = ((t >> 1) * 7 + (t & 1)) * 3;
+#pragma unroll 1
+    for (int q = 0; q < 9; ++q) {
+        const int qh = q / 3, qw = q - qh * 3;
+        float best[2][4];
+        int pos[2][4];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { best[nt][r] = -3.0e38f; pos[nt][r] = 0; }
+#pragma unroll 1
+        for (int sp = 0; sp < 4; ++sp) {
+            const int cell = ((2 * qh + (sp >> 1)) * 7 + 2 * qw + (sp & 1)) * 3 + tap;
+            float cur[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+            for (int kt = 0; kt < 6; ++kt) {
+                const int oa = ((2 * kt) / 3) * 148 + (2 * kt) % 3, ob = ((2 * kt + 1) / 3) * 148 + (2 * kt + 1) % 3;
+                uint32_t a[4];
+                a[0] = byte_to_float_bits(px0[oa + cell]); a[1] = byte_to_float_bits(px1[oa + cell]);
+                a[2] = byte_to_float_bits(px0[ob + cell]); a[3] = byte_to_float_bits(px1[ob + cell]);
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    const float4 b = s_c1[(kt * 2 + nt) * 32 + lane];
+                    mma8(cur[nt], a, __float_as_uint(b.z), __float_as_uint(b.w));
+                    mma8(cur[nt], a, __float_as_uint(b.x), __float_as_uint(b.y));
+                }
+            }
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    if (cur[nt][r] > best[nt][r]) { best[nt][r] = cur[nt][r]; pos[nt][r] = sp; }   // first maximum wins, like max_pool2d
+        }
+        // accumulator (row g | g+8, columns 2t, 2t+1 of n-tile nt) -> pooled[s][q][nt*8 + 2t ..], arg likewise
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            const float2 bias = nt == 0 ? b1a : b1b;
+            const float x0 = best[nt][0] + bias.x, x1 = best[nt][1] + bias.y, x2 = best[nt][2] + bias.x, x3 = best[nt][3] + bias.y;
+            const int c = nt * 8 + 2 * t;
+            if (v0) {
+                const size_t o = ((size_t)(s0 + r0) * 9 + q) * 16 + c;
+                *reinterpret_cast<float2*>(p.pooled + o) = make_float2(fmaxf(x0, 0.f), fmaxf(x1, 0.f));
+                *reinterpret_cast<uint16_t*>(p.arg + o) = (uint16_t)((pos[nt][0] | (x0 > 0.f ? 4 : 0)) | ((pos[nt][1] | (x1 > 0.f ? 4 : 0)) << 8));
+            }
+            if (v1) {
+                const size_t o = ((size_t)(s0 + r1) * 9 + q) * 16 + c;
+                *reinterpret_cast<float2*>(p.pooled + o) = make_float2(fmaxf(x2, 0.f), fmaxf(x3, 0.f));
+                *reinterpret_cast<uint16_t*>(p.arg + o) = (uint16_t)((pos[nt][2] | (x2 > 0.f ? 4 : 0)) | ((pos[nt][3] | (x3 > 0.f ? 4 : 0)) << 8));
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NT, 4) conv1_pool_bwd_tc_kernel(const Conv1Args p) {
+    __shared__ __align__(16) uint8_t s_px[OBC * SAMPLE_BYTES];
+    __shared__ float s_acc[16 * 56];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    for (int e = tid; e < 16 * 56; e += NT) s_acc[e] = 0.f;
+    float acc[7][4];
+#pragma unroll
+    for (int nt = 0; nt < 7; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+    // B: column n = nt*8 + g is input index k = ci*4 + tap with ci = 2nt + (g >> 2), tap = g & 3
+    int koff[6];
+#pragma unroll
+    for (int nt = 0; nt < 6; ++nt) {
+        const int ci = 2 * nt + (g >> 2), tp = g & 3;
+        koff[nt] = (ci / 3) * 148 + ci % 3 + ((tp >> 1) * 7 + (tp & 1)) * 3;
+    }
+    const uint32_t one = g == 0 ? __float_as_uint(1.0f) : 0u;     // 7th n-tile: column 48 = ones (bias gradient)
+    const int nchunks = (p.B + OBC - 1) / OBC;
+    for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        const int s0 = ch * OBC;
+        __syncthreads();                                          // the previous chunk's bytes are consumed
+        stage_samples_async(p, s0, s_px, tid);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {                             // the warp's 16 samples = two k-tiles of 8
+            const int ja = warp * 16 + h * 8 + t, jb = ja + 4;    // samples of this lane's k-slots t and t+4
+            const bool va = s0 + ja < p.B, vb = s0 + jb < p.B;
+            const uint8_t* pa = s_px + ja * SAMPLE_BYTES;
+            const uint8_t* pb = s_px + jb * SAMPLE_BYTES;
+#pragma unroll 1
+            for (int q = 0; q < 9; ++q) {
+                const int qh = q / 3, qw = q - qh * 3;
+                // A: masked gradient of channels g / g+8 for samples ja / jb
+                const size_t oa = ((size_t)(s0 + ja) * 9 + q) * 16, ob = ((size_t)(s0 + jb) * 9 + q) * 16;
+                const float da0 = va ? __ldg(p.dpooled + oa + g) : 0.f, da1 = va ? __ldg(p.dpooled + oa + g + 8) : 0.f;
+                const float db0 = vb ? __ldg(p.dpooled + ob + g) : 0.f, db1 = vb ? __ldg(p.dpooled + ob + g + 8) : 0.f;
+                const int ga0 = va ? p.arg[oa + g] : 0, ga1 = va ? p.arg[oa + g + 8] : 0;
+                const int gb0 = vb ? p.arg[ob + g] : 0, gb1 = vb ? p.arg[ob + g + 8] : 0;
+#pragma unroll 1
+                for (int sp = 0; sp < 4; ++sp) {
+                    AFrag a;
+                    split(a, ga0 == (sp | 4) ? da0 : 0.f, ga1 == (sp | 4) ? da1 : 0.f, gb0 == (sp | 4) ? db0 : 0.f,
+                          gb1 == (sp | 4) ? db1 : 0.f);
+                    const int cell = ((2 * qh + (sp >> 1)) * 7 + 2 * qw + (sp & 1)) * 3;
+#pragma unroll
+                    for (int nt = 0; nt < 6; ++nt) {
+                        const uint32_t b0 = byte_to_float_bits(pa[koff[nt] + cell]), b1 = byte_to_float_bits(pb[koff[nt] + cell]);
+                        mma8(acc[nt], a.lo, b0, b1);
+                        mma8(acc[nt], a.hi, b0, b1);
+                    }
+                    mma8(acc[6], a.lo, one, one);
+                    mma8(acc[6], a.hi, one, one);
+                }
+            }
+        }
+    }
+    // warp accumulators (row co = g | g+8, columns 2t, 2t+1 of n-tile nt) -> CTA sum -> one atomic per weight per CTA
+#pragma unroll
+    for (int nt = 0; nt < 7; ++nt) {
+        atomicAdd(&s_acc[g * 56 + nt * 8 + 2 * t], acc[nt][0]); atomicAdd(&s_acc[g * 56 + nt * 8 + 2 * t + 1], acc[nt][1]);
+        atomicAdd(&s_acc[(g + 8) * 56 + nt * 8 + 2 * t], acc[nt][2]); atomicAdd(&s_acc[(g + 8) * 56 + nt * 8 + 2 * t + 1], acc[nt][3]);
+    }
+    __syncthreads();
+    for (int e = tid; e < 16 * 49; e += NT) {
+        const int co = e / 49, k = e - co * 49;
+        const float v = s_acc[co * 56 + k];
+        if (k < 48) atomicAdd(p.dw1 + co * 48 + k, v * (1.0f / 255.0f));
+        else atomicAdd(p.db1 + co, v);
+    }
+}
+
 }  // namespace
 
 namespace mgrl_policy {
@@ -485,6 +661,17 @@ cudaError_t launch_policy_forward_tc(const PolicyArgs& a, cudaStream_t stream) {
     static const int prec = [] { const char* v = getenv("MGRL_TC_PREC"); return v ? atoi(v) : 2; }();
     if (prec == 1) policy_forward_tc_kernel<2, 1><<<(a.n + OBC - 1) / OBC, NT, 0, stream>>>(a);
     else policy_forward_tc_kernel<2, 2><<<(a.n + OBC - 1) / OBC, NT, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_conv1_pool_fwd_tc(const Conv1Args& a, cudaStream_t stream) {
+    conv1_pool_fwd_tc_kernel<<<(a.B + OBC - 1) / OBC, NT, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_conv1_pool_bwd_tc(const Conv1Args& a, cudaStream_t stream) {   // dw1 / db1 zeroed by the caller
+    const int nchunks = (a.B + OBC - 1) / OBC;
+    conv1_pool_bwd_tc_kernel<<<nchunks < 148 * 4 ? nchunks : 148 * 4, NT, 0, stream>>>(a);
     return cudaGetLastError();
 }
 
