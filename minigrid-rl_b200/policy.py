@@ -14,6 +14,7 @@ sequences only (the mission is constant within an episode), never per observatio
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import math
 import os
@@ -178,6 +179,8 @@ class Policy:
         # rollout forward: split-TF32 tensor-core kernel (fp32-class results); MGRL_POLICY_SIMT=1 selects the fp32
         # CUDA-core kernel it replaced (kept for A/B measurements)
         self.tensor_cores = os.environ.get("MGRL_POLICY_SIMT", "0") != "1"
+        self.capturing = False              # set by the updater while it captures its optimizer step into a CUDA graph
+        self._leaves = None                 # see fresh_leaves()
         self.device = torch.device(device)
         g = torch.Generator().manual_seed(seed)
         self.params = {}
@@ -219,6 +222,22 @@ class Policy:
 
     def parameters(self):
         return list(self.params.values())
+
+    def _P(self):
+        return self._leaves if self._leaves is not None else self.params
+
+    @contextlib.contextmanager
+    def fresh_leaves(self):
+        """Evaluate through fresh autograd leaves that alias the parameters (same storage, same order as `parameters()`).
+        A parameter caches its AccumulateGrad node together with the stream it was created on; if an earlier evaluation
+        made it on the legacy default stream and anything keeps that graph alive, a backward pass inside a stream
+        capture would have to make the legacy stream wait on the capturing one, which CUDA refuses.  Fresh leaves have
+        no such history; their gradients are taken with autograd.grad."""
+        self._leaves = {k: v.detach().requires_grad_(True) for k, v in self.params.items()}
+        try:
+            yield self._leaves
+        finally:
+            self._leaves = None
 
     def state_dict(self):
         return {k: v.detach().clone() for k, v in self.params.items()}
@@ -273,13 +292,17 @@ class Policy:
     def mission_lut(self):
         """[74*4, 128]: GRU(Embedding(tokens)) final hidden state of every distinct stacked mission (differentiable)."""
         torch = self.torch
-        P = self.params
+        P = self._P()
         x = torch.nn.functional.embedding(self.sequences, P[_PREFIX + "mission.mission_Embedding_0.weight"])
-        if x.is_cuda:
+        if x.is_cuda and self._leaves is None:
             self._gru.flatten_parameters()
         # cuDNN would run the GRU in TF32 by default; the table feeds the fp32 rollout kernel (parity bar 1e-5)
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=not self.fp32_strict):
-            _, h = self._gru(x)
+            if self._leaves is None:
+                _, h = self._gru(x)
+            else:       # the module run on the aliases of its (flattened) weights
+                names = ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0")
+                _, h = torch.func.functional_call(self._gru, {n: P[_PREFIX + "mission.mission_GRU_1." + n] for n in names}, (x,))
         return h[-1]
 
     def _mission_lut_side_stream(self):
@@ -294,7 +317,8 @@ class Policy:
         with torch.cuda.stream(self._side):
             lut = self.mission_lut()
         main.wait_stream(self._side)
-        lut.record_stream(main)                   # allocated on the side stream, consumed on the main one
+        if not self.capturing:                    # (inside a CUDA graph the allocation belongs to the graph's pool)
+            lut.record_stream(main)               # allocated on the side stream, consumed on the main one
         return lut
 
     # ---------------------------------------------------------------- differentiable evaluation (PPO update)
@@ -302,7 +326,7 @@ class Policy:
         """image_u8 [B,12,7,7] (channels = frame*3 + c, H = view x, W = view y), dir_onehot [B,16], mission_row [B]
         (= mission*4 + age) -> logits [B,7], values [B]."""
         F = self.torch.nn.functional
-        P = self.params
+        P = self._P()
         lut = self.mission_lut() if lut is None else lut
         with self.torch.backends.cudnn.flags(enabled=True, allow_tf32=not self.fp32_strict):
             return self._evaluate(image_u8, dir_onehot, mission_row, lut, F, P)
@@ -347,7 +371,7 @@ class Policy:
         `mgrl_conv1_pool_forward/backward` straight off the frame buffer; the rest of the network is `_evaluate`'s."""
         torch = self.torch
         F = torch.nn.functional
-        P = self.params
+        P = self._P()
         c = _PREFIX + "image.image_Conv2d_"
         if lut is None:
             lut = self._mission_lut_side_stream() if frames.is_cuda else self.mission_lut()

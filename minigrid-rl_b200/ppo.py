@@ -42,6 +42,7 @@ class PPOConfig:                      # hydra_configs/algorithm/ppo.yaml:9-40
     optim_eps: float = 1e-8           # single.yaml:31
     update_tf32: bool = False         # True: the update's library GEMMs may use TF32 like the reference (ppo.py:29-32)
     native_conv1: bool = True         # first extractor stage of the update in the hand-written kernels (CUDA only)
+    cuda_graph: bool = True           # replay the optimizer step (forward + backward + clip + Adam) from a CUDA graph
     total_timesteps: float = 2e7
 
 
@@ -102,7 +103,15 @@ class Updater:
         self.torch, self.policy, self.cfg, self.dist = torch, policy, cfg, dist
         self.world = dist.get_world_size() if dist is not None else 1
         self.params = policy.parameters()
-        self.opt = torch.optim.Adam(self.params, lr=cfg.initial_learning_rate, eps=cfg.optim_eps)
+        # One optimizer step is ~150 small launches; issued from Python they take longer (5.1 ms) than the GPU needs to run
+        # them, so on one GPU the step is captured once into a CUDA graph and replayed (capturable Adam, lr in a tensor).
+        self.graphed = bool(cfg.cuda_graph and self.world == 1 and self.params[0].is_cuda and cfg.native_conv1)
+        if self.graphed:
+            self.opt = torch.optim.Adam(self.params, lr=torch.tensor(float(cfg.initial_learning_rate), device=self.params[0].device),
+                                        eps=cfg.optim_eps, capturable=True)
+        else:
+            self.opt = torch.optim.Adam(self.params, lr=cfg.initial_learning_rate, eps=cfg.optim_eps)
+        self._static = None
         self.schedule = linear_schedule(cfg.initial_learning_rate, cfg.final_learning_rate)
         self.n_all_reduces = 0
         if dist is not None and self.world > 1:       # identical weights everywhere (rank 0's)
@@ -113,7 +122,10 @@ class Updater:
     def set_progress(self, progress_remaining: float):
         lr = self.schedule(progress_remaining)
         for g in self.opt.param_groups:
-            g["lr"] = lr
+            if self.torch.is_tensor(g["lr"]):
+                g["lr"].fill_(lr)               # read by the captured Adam step
+            else:
+                g["lr"] = lr
 
     def global_adv_stats(self, adv):
         """mean and unbiased std of the minibatch advantages over ALL ranks: one small all-reduce"""
@@ -159,6 +171,60 @@ class Updater:
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
         return loss.detach(), parts
+
+
+    def minibatch_samples(self, buf, t, i):
+        """One optimizer step on the samples (t, i) of the rollout buffer `buf` (hand-written first stage).  With
+        `graphed`, the whole step - gathers, forward, loss, backward, gradient clip, Adam - is replayed from a CUDA graph
+        over static index tensors: three eager steps first (library workspaces, Adam state), then one capture."""
+        torch = self.torch
+
+        def body(tt, ii):
+            args = (buf["actions"][tt, ii], buf["values"][tt, ii], buf["logp"][tt, ii], buf["adv"][tt, ii], buf["ret"][tt, ii])
+            # fresh leaves + autograd.grad, not backward(): see Policy.fresh_leaves
+            with self.policy.fresh_leaves() as leaves:
+                loss, parts = ppo_minibatch_loss(self.policy, self.cfg, None, None, None, *args, None, (buf, tt, ii))
+                grads = torch.autograd.grad(loss, list(leaves.values()), allow_unused=True)
+            for p, g in zip(self.params, grads):
+                p.grad = g if g is not None else torch.zeros_like(p)
+            torch.nn.utils.clip_grad_norm_(self.params, self.cfg.max_grad_norm)
+            self.opt.step()
+            return loss.detach(), parts
+
+        if not self.graphed:
+            args = (buf["actions"][t, i], buf["values"][t, i], buf["logp"][t, i], buf["adv"][t, i], buf["ret"][t, i])
+            return self.minibatch(None, None, None, *args, samples=(buf, t, i))
+        st = self._static
+        if st is None or st["t"].shape != t.shape or st["frames"] is not buf["frames"]:
+            st = self._static = {"t": torch.empty_like(t), "i": torch.empty_like(i), "frames": buf["frames"], "graph": None,
+                                 "warm": 0, "out": None}
+        st["t"].copy_(t); st["i"].copy_(i)
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = bool(self.cfg.update_tf32)
+        try:
+            if st["graph"] is None and st["warm"] < 3:
+                side = torch.cuda.Stream(device=t.device)
+                side.wait_stream(torch.cuda.current_stream(t.device))
+                with torch.cuda.stream(side):
+                    out = body(st["t"], st["i"])
+                torch.cuda.current_stream(t.device).wait_stream(side)
+                st["warm"] += 1
+                self.policy.invalidate()
+                return out
+            if st["graph"] is None:
+                graph = torch.cuda.CUDAGraph()
+                self.policy.capturing = True
+                try:
+                    with torch.cuda.graph(graph):
+                        st["out"] = body(st["t"], st["i"])
+                finally:
+                    self.policy.capturing = False
+                st["graph"] = graph
+            st["graph"].replay()
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        self.policy.invalidate()
+        return st["out"]
 
 
 # ------------------------------------------------------------------------------------------- rollout (CUDA)
@@ -266,10 +332,10 @@ class RolloutEngine:
             for s in range(0, total - bs + 1, bs):
                 idx = perm[s:s + bs]
                 t, i = idx // N, idx % N
-                args = (b["actions"][t, i], b["values"][t, i], b["logp"][t, i], b["adv"][t, i], b["ret"][t, i])
                 if cfg.native_conv1 and b["frames"].is_cuda:
-                    self.updater.minibatch(None, None, None, *args, samples=(b, t, i))
+                    self.updater.minibatch_samples(b, t, i)
                 else:
+                    args = (b["actions"][t, i], b["values"][t, i], b["logp"][t, i], b["adv"][t, i], b["ret"][t, i])
                     image, onehot, mrow = gather_minibatch(b, t, i)
                     self.updater.minibatch(image, onehot, mrow, *args)
                 n_mb += 1

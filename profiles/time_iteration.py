@@ -17,3 +17,7 @@ for it in range(3):
     print("it %d: pack %.1f collect %.1f bootstrap %.1f (%d samples) gae %.2f update %.1f ms; episodes finished %d" %
           ((it,) + tuple(e[k].elapsed_time(e[k + 1]) for k in range(2)) + (e[2].elapsed_time(e[3]), nb, e[3].elapsed_time(e[4]),
            e[4].elapsed_time(e[5]), done)))
+# is the update bound by the host issuing its ~150 launches per minibatch?
+import time
+torch.cuda.synchronize(); t0 = time.perf_counter(); eng.update(); t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+print("update: host issue %.1f ms, wall %.1f ms" % (1e3 * (t1 - t0), 1e3 * (t2 - t0)))
