@@ -209,6 +209,11 @@ int mgrl_conv1_pool_backward(const uint8_t *frames_dev, int num_envs, const int3
 int mgrl_patch2x2_forward(const float *pooled_dev, int batch, float *patches_dev, void *stream);
 int mgrl_patch2x2_backward(const float *dpatches_dev, int batch, float *dpooled_dev, void *stream);
 
+/* PPO update, gradient of the mission look-up table (the table replaces the GRU of CustomExtractor's mission branch,
+ * policies.py:59 over single.yaml:52-56, for the (mission, age) pairs that exist): out_dev [n_rows,128] f32 =
+ * sum over b of d_dev [B,128] into row rows_dev[b] (int64, 0 <= row < n_rows <= 400); out_dev is overwritten. */
+int mgrl_lut_grad(const float *d_dev, const int64_t *rows_dev, int batch, int n_rows, float *out_dev, void *stream);
+
 /* ---- host-buffer drop-in path (what B200VecEnv.reset/step with numpy arrays calls) --- */
 
 /* VecEnv.reset(): stacked observation dict into host buffers; synchronous.

@@ -498,6 +498,34 @@ __global__ void __launch_bounds__(192) conv1_pool_bwd_kernel(const Conv1Args p) 
 // 262 144-sample minibatch in unfold_backward alone; these are two float4 copy kernels.
 namespace {
 
+// PPO update, gradient of the mission look-up table: out[row[b]][:] += d[b][:] over the minibatch (the adjoint of the
+// gather lut[mission * 4 + age] that stands in for the GRU).  A few dozen distinct rows receive 10^5..10^6
+// contributions: the library's embedding backward sorts the indices first (0.43 ms per 262 144 samples); here every CTA
+// sums its share of the samples into a shared-memory copy of the whole table (296 x 128 floats = 148 KB, conflict-free
+// column-interleaved rows, shared-memory float atomics) and adds the touched entries to global memory once.
+__global__ void __launch_bounds__(512) lut_grad_kernel(const float4* __restrict__ d, const long long* __restrict__ row, int batch,
+                                                       int n_rows, float* __restrict__ out) {
+    extern __shared__ float tab[];                 // [n_rows][4][32]: logical column lane * 4 + j at j * 32 + lane
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int e = tid; e < n_rows * 128; e += blockDim.x) tab[e] = 0.f;
+    __syncthreads();
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int b = (blockIdx.x * blockDim.x + tid) >> 5; b < batch; b += warps) {
+        const int r = (int)row[b];
+        const float4 v = __ldg(d + (size_t)b * 32 + lane);
+        float* t = tab + r * 128 + lane;
+        atomicAdd(t, v.x); atomicAdd(t + 32, v.y); atomicAdd(t + 64, v.z); atomicAdd(t + 96, v.w);
+    }
+    __syncthreads();
+    for (int e = tid; e < n_rows * 128; e += blockDim.x) {
+        const float v = tab[e];
+        if (v != 0.f) {
+            const int r = e >> 7, p = e & 127;
+            atomicAdd(out + r * 128 + (p & 31) * 4 + (p >> 5), v);
+        }
+    }
+}
+
 __global__ void patch2x2_fwd_kernel(const float4* __restrict__ pooled, float4* __restrict__ patches, int batch) {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // (b, o, kk, ci / 4)
     if (e >= (size_t)batch * 64) return;
@@ -605,6 +633,30 @@ int mgrl_patch2x2_backward(const float* dpatches_dev, int batch, float* dpooled_
         reinterpret_cast<const float4*>(dpatches_dev), reinterpret_cast<float4*>(dpooled_dev), batch);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(g_perr, sizeof g_perr, "mgrl_patch2x2_backward: %s", cudaGetErrorString(e)); return MGRL_ERR_CUDA; }
+    return MGRL_OK;
+}
+
+int mgrl_lut_grad(const float* d_dev, const int64_t* rows_dev, int batch, int n_rows, float* out_dev, void* stream) {
+    if (!d_dev || !rows_dev || !out_dev || batch <= 0 || n_rows <= 0 || n_rows > 400) {
+        snprintf(g_perr, sizeof g_perr, "mgrl_lut_grad: null argument, empty batch or more than 400 table rows");
+        return MGRL_ERR_INVALID;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t smem = (size_t)n_rows * 128 * sizeof(float);
+    static thread_local size_t opted = 0;          // the opt-in is not a stream operation: once, outside any capture
+    cudaError_t e = cudaSuccess;
+    if (smem > opted) {
+        e = cudaFuncSetAttribute(lut_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) opted = smem;
+    }
+    if (e == cudaSuccess) e = cudaMemsetAsync(out_dev, 0, smem, s);
+    if (e == cudaSuccess) {
+        const int grid = batch < 148 * 16 ? (batch + 15) / 16 : 148;
+        lut_grad_kernel<<<grid, 512, smem, s>>>(reinterpret_cast<const float4*>(d_dev), reinterpret_cast<const long long*>(rows_dev),
+                                               batch, n_rows, out_dev);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) { snprintf(g_perr, sizeof g_perr, "mgrl_lut_grad: %s", cudaGetErrorString(e)); return MGRL_ERR_CUDA; }
     return MGRL_OK;
 }
 

@@ -106,6 +106,35 @@ def _conv1_pool(torch):
 
 _SPLITK_LINEAR = None
 _PATCH2 = None
+_LUT_ROWS = None
+
+
+def _lut_rows(torch, lut, rows):
+    """lut[rows] whose backward is the hand-written segmented sum mgrl_lut_grad (CUDA, large minibatches); F.embedding
+    otherwise."""
+    if not lut.is_cuda or rows.numel() < 16384 or not torch.is_grad_enabled():
+        return torch.nn.functional.embedding(rows, lut)
+    global _LUT_ROWS
+    if _LUT_ROWS is None:
+        class LutRows(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, lut, rows):
+                ctx.save_for_backward(rows)
+                ctx.n_rows = int(lut.shape[0])
+                return lut.index_select(0, rows)
+
+            @staticmethod
+            def backward(ctx, g):
+                (rows,) = ctx.saved_tensors
+                g = g.contiguous()
+                out = torch.empty((ctx.n_rows, 128), dtype=torch.float32, device=g.device)
+                s = C.c_void_p(torch.cuda.current_stream(g.device).cuda_stream)
+                nat.check(nat.lib().mgrl_lut_grad(C.c_void_p(g.data_ptr()), C.c_void_p(rows.data_ptr()), int(g.shape[0]), ctx.n_rows,
+                                                  C.c_void_p(out.data_ptr()), s), "mgrl_lut_grad")
+                return out, None
+
+        _LUT_ROWS = LutRows.apply
+    return _LUT_ROWS(lut, rows.long().contiguous())
 
 
 def _patches2x2(torch, h):
@@ -356,7 +385,7 @@ class Policy:
         x = torch.relu(lin(h, P[c + "5.weight"].permute(0, 2, 3, 1).reshape(64, 128), P[c + "5.bias"]))
         d = lin(dir_onehot.float(), P[_PREFIX + "direction.direction_Linear_0.weight"],
                      P[_PREFIX + "direction.direction_Linear_0.bias"])
-        f = torch.cat([d, x, F.embedding(mission_row.long(), lut)], dim=1)
+        f = torch.cat([d, x, _lut_rows(torch, lut, mission_row.long())], dim=1)
         t = torch.tanh
         hp = t(lin(t(lin(f, P["mlp_extractor.policy_net.0.weight"], P["mlp_extractor.policy_net.0.bias"])),
                         P["mlp_extractor.policy_net.2.weight"], P["mlp_extractor.policy_net.2.bias"]))

@@ -108,7 +108,7 @@ class Updater:
         self.graphed = bool(cfg.cuda_graph and self.world == 1 and self.params[0].is_cuda and cfg.native_conv1)
         if self.graphed:
             self.opt = torch.optim.Adam(self.params, lr=torch.tensor(float(cfg.initial_learning_rate), device=self.params[0].device),
-                                        eps=cfg.optim_eps, capturable=True)
+                                        eps=cfg.optim_eps, capturable=True, fused=True)
         else:
             self.opt = torch.optim.Adam(self.params, lr=cfg.initial_learning_rate, eps=cfg.optim_eps)
         self._static = None
@@ -186,7 +186,7 @@ class Updater:
                 loss, parts = ppo_minibatch_loss(self.policy, self.cfg, None, None, None, *args, None, (buf, tt, ii))
                 grads = torch.autograd.grad(loss, list(leaves.values()), allow_unused=True)
             for p, g in zip(self.params, grads):
-                p.grad = g if g is not None else torch.zeros_like(p)
+                p.grad = g.contiguous() if g is not None else torch.zeros_like(p)   # (the fused Adam wants the parameter's layout)
             torch.nn.utils.clip_grad_norm_(self.params, self.cfg.max_grad_norm)
             self.opt.step()
             return loss.detach(), parts
