@@ -214,6 +214,10 @@ int mgrl_patch2x2_backward(const float *dpatches_dev, int batch, float *dpooled_
  * sum over b of d_dev [B,128] into row rows_dev[b] (int64, 0 <= row < n_rows <= 400); out_dev is overwritten. */
 int mgrl_lut_grad(const float *d_dev, const int64_t *rows_dev, int batch, int n_rows, float *out_dev, void *stream);
 
+/* PPO update, bias gradients of the convolution / linear layers (policies.py:59, SB3 MlpExtractor): out_dev [cols] f32 =
+ * column sums of the row-major g_dev [rows, cols] f32 (cols <= 128); out_dev is overwritten. */
+int mgrl_colsum(const float *g_dev, long long rows, int cols, float *out_dev, void *stream);
+
 /* ---- host-buffer drop-in path (what B200VecEnv.reset/step with numpy arrays calls) --- */
 
 /* VecEnv.reset(): stacked observation dict into host buffers; synchronous.

@@ -71,6 +71,7 @@ _SIGNATURES = {
     "mgrl_conv1_pool_forward": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp]),
     "mgrl_conv1_pool_backward": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp]),
     "mgrl_lut_grad": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp]),
+    "mgrl_colsum": (C.c_int, [vp, C.c_longlong, C.c_int, vp, vp]),
     "mgrl_patch2x2_forward": (C.c_int, [vp, C.c_int, vp, vp]),
     "mgrl_patch2x2_backward": (C.c_int, [vp, C.c_int, vp, vp]),
 }

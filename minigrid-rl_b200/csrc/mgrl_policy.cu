@@ -526,6 +526,34 @@ __global__ void __launch_bounds__(512) lut_grad_kernel(const float4* __restrict_
     }
 }
 
+// PPO update, bias gradients: out[c] = sum over rows of g[r][c] for a tall row-major matrix (rows = minibatch samples or
+// sample x position, cols <= 128).  One pass at streaming speed: a thread owns column (tid % cols) of every
+// (blockDim / cols)-th row of its CTA's slab, partial sums meet in shared memory, one atomic per column per CTA.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ g, long long rows, int cols, float* __restrict__ out) {
+    __shared__ float part[256];
+    const int tid = threadIdx.x;
+    const int groups = 256 / cols, grp = tid / cols, c = tid - grp * cols;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    if (grp < groups) {
+        const long long stride = (long long)gridDim.x * groups;
+        long long r = (long long)blockIdx.x * groups + grp;
+        for (; r + 3 * stride < rows; r += 4 * stride) {     // four independent loads in flight
+            acc0 += __ldg(g + r * cols + c);
+            acc1 += __ldg(g + (r + stride) * cols + c);
+            acc2 += __ldg(g + (r + 2 * stride) * cols + c);
+            acc3 += __ldg(g + (r + 3 * stride) * cols + c);
+        }
+        for (; r < rows; r += stride) acc0 += __ldg(g + r * cols + c);
+    }
+    part[tid] = (acc0 + acc1) + (acc2 + acc3);
+    __syncthreads();
+    if (tid < cols) {
+        float s = 0.f;
+        for (int k = 0; k < groups; ++k) s += part[k * cols + tid];
+        atomicAdd(out + tid, s);
+    }
+}
+
 __global__ void patch2x2_fwd_kernel(const float4* __restrict__ pooled, float4* __restrict__ patches, int batch) {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // (b, o, kk, ci / 4)
     if (e >= (size_t)batch * 64) return;
@@ -657,6 +685,24 @@ int mgrl_lut_grad(const float* d_dev, const int64_t* rows_dev, int batch, int n_
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) { snprintf(g_perr, sizeof g_perr, "mgrl_lut_grad: %s", cudaGetErrorString(e)); return MGRL_ERR_CUDA; }
+    return MGRL_OK;
+}
+
+int mgrl_colsum(const float* g_dev, long long rows, int cols, float* out_dev, void* stream) {
+    if (!g_dev || !out_dev || rows <= 0 || cols <= 0 || cols > 128) {
+        snprintf(g_perr, sizeof g_perr, "mgrl_colsum: null argument, empty matrix or more than 128 columns");
+        return MGRL_ERR_INVALID;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(out_dev, 0, (size_t)cols * sizeof(float), s);
+    if (e == cudaSuccess) {
+        const long long per = 256 / cols * 64;            // about 64 rows per thread
+        long long grid = (rows + per - 1) / per;
+        grid = grid < 1 ? 1 : (grid > 148 * 8 ? 148 * 8 : grid);
+        colsum_kernel<<<(unsigned)grid, 256, 0, s>>>(g_dev, rows, cols, out_dev);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) { snprintf(g_perr, sizeof g_perr, "mgrl_colsum: %s", cudaGetErrorString(e)); return MGRL_ERR_CUDA; }
     return MGRL_OK;
 }
 

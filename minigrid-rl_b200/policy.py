@@ -191,7 +191,10 @@ def _linear(torch, x, w, b):
                 m, s = g.shape[0], 64
                 dx = g @ w if ctx.needs_input_grad[0] else None
                 dw = torch.bmm(g.view(s, m // s, -1).transpose(1, 2), x.view(s, m // s, -1)).sum(0)
-                return dx, dw, g.sum(0)
+                db = torch.empty(g.shape[1], dtype=torch.float32, device=g.device)     # one streaming pass (mgrl_colsum)
+                nat.check(nat.lib().mgrl_colsum(C.c_void_p(g.data_ptr()), m, int(g.shape[1]), C.c_void_p(db.data_ptr()),
+                                                C.c_void_p(torch.cuda.current_stream(g.device).cuda_stream)), "mgrl_colsum")
+                return dx, dw, db
 
         _SPLITK_LINEAR = SplitKLinear.apply
     return _SPLITK_LINEAR(x.contiguous(), w, b)

@@ -105,7 +105,8 @@ class Updater:
         self.params = policy.parameters()
         # One optimizer step is ~150 small launches; issued from Python they take longer (5.1 ms) than the GPU needs to run
         # them, so on one GPU the step is captured once into a CUDA graph and replayed (capturable Adam, lr in a tensor).
-        self.graphed = bool(cfg.cuda_graph and self.world == 1 and self.params[0].is_cuda and cfg.native_conv1)
+        nccl = dist is not None and self.world > 1 and str(dist.get_backend()) == "nccl"   # NCCL collectives can be captured
+        self.graphed = bool(cfg.cuda_graph and (self.world == 1 or nccl) and self.params[0].is_cuda and cfg.native_conv1)
         if self.graphed:
             self.opt = torch.optim.Adam(self.params, lr=torch.tensor(float(cfg.initial_learning_rate), device=self.params[0].device),
                                         eps=cfg.optim_eps, capturable=True, fused=True)
@@ -130,8 +131,8 @@ class Updater:
     def global_adv_stats(self, adv):
         """mean and unbiased std of the minibatch advantages over ALL ranks: one small all-reduce"""
         torch = self.torch
-        s = torch.stack([adv.sum(dtype=torch.float64), (adv.double() ** 2).sum(), torch.tensor(float(adv.numel()),
-                        dtype=torch.float64, device=adv.device)])
+        s = torch.stack([adv.sum(dtype=torch.float64), (adv.double() ** 2).sum(),
+                         torch.full((), float(adv.numel()), dtype=torch.float64, device=adv.device)])
         self.dist.all_reduce(s)
         self.n_all_reduces += 1
         n = s[2]
@@ -181,12 +182,23 @@ class Updater:
 
         def body(tt, ii):
             args = (buf["actions"][tt, ii], buf["values"][tt, ii], buf["logp"][tt, ii], buf["adv"][tt, ii], buf["ret"][tt, ii])
+            stats = self.global_adv_stats(args[3]) if self.world > 1 and self.cfg.normalize_advantage else None
             # fresh leaves + autograd.grad, not backward(): see Policy.fresh_leaves
             with self.policy.fresh_leaves() as leaves:
-                loss, parts = ppo_minibatch_loss(self.policy, self.cfg, None, None, None, *args, None, (buf, tt, ii))
+                loss, parts = ppo_minibatch_loss(self.policy, self.cfg, None, None, None, *args, stats, (buf, tt, ii))
                 grads = torch.autograd.grad(loss, list(leaves.values()), allow_unused=True)
+            grads = [g if g is not None else torch.zeros_like(p) for p, g in zip(self.params, grads)]
+            if self.world > 1:                  # ONE all-reduce of the flat gradient buffer (441 KB), captured with the step
+                flat = torch.cat([g.reshape(-1) for g in grads])
+                self.dist.all_reduce(flat)
+                flat /= self.world
+                o, views = 0, []
+                for g in grads:
+                    views.append(flat[o:o + g.numel()].view(g.shape))
+                    o += g.numel()
+                grads = views
             for p, g in zip(self.params, grads):
-                p.grad = g.contiguous() if g is not None else torch.zeros_like(p)   # (the fused Adam wants the parameter's layout)
+                p.grad = g.contiguous()         # (the fused Adam wants the parameter's layout)
             torch.nn.utils.clip_grad_norm_(self.params, self.cfg.max_grad_norm)
             self.opt.step()
             return loss.detach(), parts
@@ -199,6 +211,7 @@ class Updater:
             st = self._static = {"t": torch.empty_like(t), "i": torch.empty_like(i), "frames": buf["frames"], "graph": None,
                                  "warm": 0, "out": None}
         st["t"].copy_(t); st["i"].copy_(i)
+        n_red = self.n_all_reduces + (0 if self.world == 1 else 1 + int(self.cfg.normalize_advantage))
         prev = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = bool(self.cfg.update_tf32)
         try:
@@ -209,6 +222,7 @@ class Updater:
                     out = body(st["t"], st["i"])
                 torch.cuda.current_stream(t.device).wait_stream(side)
                 st["warm"] += 1
+                self.n_all_reduces = n_red
                 self.policy.invalidate()
                 return out
             if st["graph"] is None:
@@ -223,6 +237,7 @@ class Updater:
             st["graph"].replay()
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
+        self.n_all_reduces = n_red
         self.policy.invalidate()
         return st["out"]
 
