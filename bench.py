@@ -391,6 +391,9 @@ def main():
         print(json.dumps(line))
     env.close()
     if dist is not None:
+        if not args.no_ppo:
+            eng.updater._static = None      # a captured optimizer step (opt-in with NCCL ranks) must not outlive the communicator
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 
