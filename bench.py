@@ -303,7 +303,8 @@ def main():
         penv = mg.DeviceEnv(cfg, num_envs=n, seed=SEED, env_id_base=rank * n, layout="hwc148")
         pcfg = mg.PPOConfig(n_steps=T, batch_size=n * T // 32, n_epochs=4, update_tf32=True)
         eng = mg.RolloutEngine(penv, mg.Policy(dev, seed=SEED), pcfg, dist=dist if world > 1 else None, seed=SEED)
-        eng.iteration(1.0)                                   # warm-up: cuDNN autotune, allocator, layouts in L2
+        for _ in range(2):                                   # warm-up: cuDNN autotune, allocator, layouts in L2, graph capture of
+            eng.iteration(1.0)                               # the optimizer step, first truncation bootstrap (lazy module loads)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         t_roll = t_upd = 0.0
         barrier()
