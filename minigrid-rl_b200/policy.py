@@ -107,12 +107,14 @@ def _conv1_pool(torch):
 _SPLITK_LINEAR = None
 _PATCH2 = None
 _LUT_ROWS = None
+NATIVE_MIN_ROWS = 16384        # minibatches at least this deep take the hand-written update kernels below (tests raise it
+                               # to get the pure library formulation of the same network as a reference)
 
 
 def _lut_rows(torch, lut, rows):
     """lut[rows] whose backward is the hand-written segmented sum mgrl_lut_grad (CUDA, large minibatches); F.embedding
     otherwise."""
-    if not lut.is_cuda or rows.numel() < 16384 or not torch.is_grad_enabled():
+    if not lut.is_cuda or rows.numel() < NATIVE_MIN_ROWS or not torch.is_grad_enabled():
         return torch.nn.functional.embedding(rows, lut)
     global _LUT_ROWS
     if _LUT_ROWS is None:
@@ -174,7 +176,7 @@ def _linear(torch, x, w, b):
     the layers at most 208 x 128 wide: as ONE `dz.T @ x` GEMM the weight gradient has a handful of output tiles and the
     library runs it on a few CTAs of a 148-SM GPU (1.4 ms of an 8 ms minibatch); cut into 64 row blocks it is a batched
     GEMM that fills the machine, plus a sum over 64 small partial results."""
-    if not x.is_cuda or x.shape[0] < 16384 or x.shape[0] % 64 != 0 or not torch.is_grad_enabled():
+    if not x.is_cuda or x.shape[0] < NATIVE_MIN_ROWS or x.shape[0] % 64 != 0 or not torch.is_grad_enabled():
         return torch.nn.functional.linear(x, w, b)
     global _SPLITK_LINEAR
     if _SPLITK_LINEAR is None:

@@ -254,3 +254,85 @@ def test_forward_kernel_ragged_batches(n):
         got = b["values"][t].cpu()
         assert close(got, vo, 2e-5) or float((got - vo).abs().max()) <= 5e-6, (n, t)   # a single small value: absolute floor
     eng.env.close()
+
+
+def test_update_kernels_match_torch_ops():
+    """The small hand-written kernels of the update, one by one, against the torch expression of the same thing:
+    mgrl_colsum (bias gradients), mgrl_lut_grad (mission-table gradient), mgrl_patch2x2_forward / backward (conv2 patches)."""
+    from minigrid_rl_b200 import _native as nat
+    lib, s = nat.lib(), C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for rows, cols in [(1, 1), (1000, 7), (70001, 16), (262144, 32), (50000, 64), (33333, 128), (5, 100)]:
+        x = torch.randn((rows, cols), device="cuda", generator=g)
+        out = torch.full((cols,), 7.0, device="cuda")
+        nat.check(lib.mgrl_colsum(p(x), rows, cols, p(out), s), "colsum")
+        want = x.double().sum(0)
+        assert float((out.double() - want).abs().max()) <= 2e-5 * max(1.0, float(x.abs().sum(0).max())), (rows, cols)
+    for batch in (1, 37, 4096, 100000):
+        d = torch.randn((batch, 128), device="cuda", generator=g)
+        rows = torch.randint(0, 296, (batch,), device="cuda", generator=g)
+        if batch == 100000:
+            rows = rows % 5 + 90                        # a handful of hot rows, like one task's missions
+        out = torch.full((296, 128), 3.0, device="cuda")
+        nat.check(lib.mgrl_lut_grad(p(d), p(rows), batch, 296, p(out), s), "lut_grad")
+        want = torch.zeros((296, 128), dtype=torch.float64, device="cuda").index_add_(0, rows, d.double())
+        assert float((out.double() - want).abs().max()) <= 1e-5 * max(1.0, float(want.abs().max())), batch
+    for batch in (1, 77, 5000):
+        h = torch.randn((batch, 3, 3, 16), device="cuda", generator=g)
+        patches = torch.empty((batch * 4, 64), device="cuda")
+        nat.check(lib.mgrl_patch2x2_forward(p(h), batch, p(patches), s), "patch fwd")
+        want = torch.stack([h[:, kh:kh + 2, kw:kw + 2, :] for kh in (0, 1) for kw in (0, 1)], dim=3).reshape(batch * 4, 64)
+        assert torch.equal(patches, want)
+        gp = torch.randn((batch * 4, 64), device="cuda", generator=g)
+        dh = torch.empty((batch, 3, 3, 16), device="cuda")
+        nat.check(lib.mgrl_patch2x2_backward(p(gp), batch, p(dh), s), "patch bwd")
+        hh = h.clone().requires_grad_(True)
+        w = torch.stack([hh[:, kh:kh + 2, kw:kw + 2, :] for kh in (0, 1) for kw in (0, 1)], dim=3).reshape(batch * 4, 64)
+        (w * gp).sum().backward()
+        assert torch.allclose(dh, hh.grad, rtol=1e-6, atol=1e-6)
+
+
+def test_large_minibatch_update_path_matches_library_formulation(monkeypatch):
+    """Minibatches of >= 16 384 samples take split-K weight gradients, mgrl_colsum and mgrl_lut_grad: same outputs and the
+    same gradient for every parameter as the library formulation of the network on the same samples."""
+    n, T = 1024, 32                                   # 32 768 samples
+    eng, _ = make_engine(n, T)
+    eng.collect()
+    b, pol_ = eng.buf, eng.policy
+    t = torch.arange(T, device="cuda").repeat_interleave(n)
+    i = torch.arange(n, device="cuda").repeat(T)
+    wl = torch.randn((n * T, 7), device="cuda") / (n * T)
+    wv = torch.randn(n * T, device="cuda") / (n * T)
+    params = pol_.parameters()
+
+    def grads():
+        lo, va = pol_.evaluate_samples(b["frames"], b["dirs"], b["mission"], b["age"], t, i)
+        return lo.detach(), va.detach(), torch.autograd.grad((lo * wl).sum() + (va * wv).sum(), params, allow_unused=True)
+
+    la, va, ga = grads()
+    monkeypatch.setattr(pol, "NATIVE_MIN_ROWS", 1 << 60)
+    lb, vb, gb = grads()
+    assert close(la, lb, 2e-6) and close(va, vb, 2e-6)
+    for name, x, y in zip(pol_.params, ga, gb):
+        assert (x is None) == (y is None), name
+        if x is not None:
+            assert close(x, y, 2e-4), name
+    eng.env.close()
+
+
+def test_graph_replayed_update_equals_eager_update():
+    """The optimizer step replayed from a CUDA graph (three eager steps, one capture, replays) leaves the same parameters
+    as the same minibatches stepped eagerly."""
+    out = []
+    for graph in (False, True):
+        eng, _ = make_engine(512, 32, n_epochs=1, cuda_graph=graph)
+        eng.cfg.batch_size = 2048                      # 8 optimizer steps
+        assert eng.updater.graphed == graph
+        eng.collect(); eng.compute_advantages()
+        gen = torch.Generator(device="cuda").manual_seed(5)
+        assert eng.update(generator=gen) == 8
+        out.append({k: v.detach().clone() for k, v in eng.policy.params.items()})
+        eng.env.close()
+    for k in out[0]:
+        assert torch.allclose(out[0][k], out[1][k], rtol=2e-3, atol=2e-5), k
