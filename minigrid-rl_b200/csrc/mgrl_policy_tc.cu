@@ -128,11 +128,16 @@ __device__ __forceinline__ void init_bias(float (&c)[4], const float* __restrict
     c[0] = b.x; c[1] = b.y; c[2] = b.x; c[3] = b.y;
 }
 
-template <int MINB, int PREC>
-__global__ void __launch_bounds__(NT, MINB) policy_forward_tc_kernel(const PolicyArgs p) {
-    __shared__ __align__(16) uint8_t s_frames[4 * SLAB];    // [frame][observation][148]
-    __shared__ __align__(16) float4 s_c1[6 * 2 * 32];      // conv1 fragments (reused by all 36 positions)
-    __shared__ uint8_t s_age[OBC];
+// W warps per CTA (16 observations each).  At N = 65 536 there are 4096 warp tiles: with 4 warps per CTA and 2 CTAs per
+// SM (255 registers) the 1184 resident warps need 4 rounds for 3.46 rounds of work; 5 warps per CTA (168 registers, 1480
+// resident warps) need 3 for 2.77 but each round is slower: no gain measured, 4 stays the default.
+template <int W, int PREC>
+__global__ void __launch_bounds__(32 * W, 2) policy_forward_tc_kernel(const PolicyArgs p) {
+    constexpr int OBC = 16 * W, NT = 32 * W, SLAB = OBC * 148;
+    extern __shared__ __align__(16) uint8_t tc_smem[];
+    uint8_t* s_frames = tc_smem;                                            // [frame][observation][148]
+    float4* s_c1 = reinterpret_cast<float4*>(tc_smem + 4 * SLAB);           // conv1 fragments (reused by all 36 positions)
+    uint8_t* s_age = tc_smem + 4 * SLAB + 6 * 2 * 32 * 16;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int i0 = blockIdx.x * OBC;
@@ -659,9 +664,18 @@ cudaError_t launch_policy_forward_tc(const PolicyArgs& a, cudaStream_t stream) {
     // tensor-core accumulator (15 % faster, 1.13e-5 / 9.7e-6).  A single accumulator measures 1.38e-5 / 1.18e-5: above
     // the 1e-5 bar, not built.
     static const int prec = [] { const char* v = getenv("MGRL_TC_PREC"); return v ? atoi(v) : 2; }();
-    if (prec == 1) policy_forward_tc_kernel<2, 1><<<(a.n + OBC - 1) / OBC, NT, 0, stream>>>(a);
-    else policy_forward_tc_kernel<2, 2><<<(a.n + OBC - 1) / OBC, NT, 0, stream>>>(a);
-    return cudaGetLastError();
+    // 4 warps per CTA by default; MGRL_TC_WARPS=5 measures the same (230 vs 234 us: three rounds of slower warps)
+    static const int warps = [] { const char* v = getenv("MGRL_TC_WARPS"); return v ? atoi(v) : 4; }();
+    auto launch = [&](auto kernel, int w) -> cudaError_t {
+        const int obc = 16 * w;
+        const size_t smem = (size_t)4 * obc * 148 + 6 * 2 * 32 * 16 + obc;
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kernel<<<(a.n + obc - 1) / obc, 32 * w, smem, stream>>>(a);
+        return cudaGetLastError();
+    };
+    if (warps == 4) return prec == 1 ? launch(policy_forward_tc_kernel<4, 1>, 4) : launch(policy_forward_tc_kernel<4, 2>, 4);
+    return prec == 1 ? launch(policy_forward_tc_kernel<5, 1>, 5) : launch(policy_forward_tc_kernel<5, 2>, 5);
 }
 
 cudaError_t launch_conv1_pool_fwd_tc(const Conv1Args& a, cudaStream_t stream) {
