@@ -106,12 +106,12 @@ class Updater:
         self.params = policy.parameters()
         # One optimizer step is ~150 small launches; issued from Python they take longer (5.1 ms) than the GPU needs to run
         # them, so on one GPU the step is captured once into a CUDA graph and replayed (capturable Adam, lr in a tensor).
-        # One rank only by default.  With NCCL ranks the two all-reduces are captured with the step and it runs as fast as
-        # on one GPU (measured at 2 GPUs: update 563 ms, 28.0 M frames/s), but the process then hung in
-        # destroy_process_group while the graph that holds the captured collectives was alive; until that teardown is
-        # sorted out the multi-rank graph is opt-in (MGRL_GRAPH_NCCL=1) and several ranks run the step eagerly.
-        nccl = (dist is not None and self.world > 1 and str(dist.get_backend()) == "nccl" and
-                os.environ.get("MGRL_GRAPH_NCCL", "0") == "1")
+        # One rank: the whole step is one graph.  NCCL ranks: two graphs around the eager gradient all-reduce.  With the two
+        # all-reduces captured as well (MGRL_GRAPH_NCCL=1) the step ran as fast as on one GPU (2 GPUs: update 563 ms,
+        # 28.0 M frames/s), but the process then hung in destroy_process_group while the graph that holds the captured
+        # collectives was alive; that mode stays opt-in until the teardown is sorted out.
+        nccl = dist is not None and self.world > 1 and str(dist.get_backend()) == "nccl"
+        self.graph_nccl = nccl and os.environ.get("MGRL_GRAPH_NCCL", "0") == "1"
         self.graphed = bool(cfg.cuda_graph and (self.world == 1 or nccl) and self.params[0].is_cuda and cfg.native_conv1)
         if self.graphed:
             self.opt = torch.optim.Adam(self.params, lr=torch.tensor(float(cfg.initial_learning_rate), device=self.params[0].device),
@@ -182,42 +182,65 @@ class Updater:
 
     def minibatch_samples(self, buf, t, i):
         """One optimizer step on the samples (t, i) of the rollout buffer `buf` (hand-written first stage).  With
-        `graphed`, the whole step - gathers, forward, loss, backward, gradient clip, Adam - is replayed from a CUDA graph
-        over static index tensors: three eager steps first (library workspaces, Adam state), then one capture."""
+        `graphed`, the step - gathers, forward, loss, backward, gradient clip, Adam - is replayed from CUDA graphs over
+        static index tensors: three eager steps first (library workspaces, Adam state), then the capture.  One rank: one
+        graph.  NCCL ranks: two graphs (gradients | clip + Adam) around the eager all-reduce of the flat gradient, the
+        advantage moments being all-reduced eagerly before the first; MGRL_GRAPH_NCCL=1 captures the collectives too."""
         torch = self.torch
+        multi = self.world > 1
+        norm = multi and self.cfg.normalize_advantage
 
-        def body(tt, ii):
+        def stats_part(tt, ii):                  # advantage moments over ALL ranks -> static tensor
+            if norm:
+                m, sd = self.global_adv_stats(buf["adv"][tt, ii])
+                st["stats"][0].copy_(m); st["stats"][1].copy_(sd)
+
+        def grads_part(tt, ii):
             args = (buf["actions"][tt, ii], buf["values"][tt, ii], buf["logp"][tt, ii], buf["adv"][tt, ii], buf["ret"][tt, ii])
-            stats = self.global_adv_stats(args[3]) if self.world > 1 and self.cfg.normalize_advantage else None
+            stats = (st["stats"][0], st["stats"][1]) if norm else None
             # fresh leaves + autograd.grad, not backward(): see Policy.fresh_leaves
             with self.policy.fresh_leaves() as leaves:
                 loss, parts = ppo_minibatch_loss(self.policy, self.cfg, None, None, None, *args, stats, (buf, tt, ii))
                 grads = torch.autograd.grad(loss, list(leaves.values()), allow_unused=True)
             grads = [g if g is not None else torch.zeros_like(p) for p, g in zip(self.params, grads)]
-            if self.world > 1:                  # ONE all-reduce of the flat gradient buffer (441 KB), captured with the step
-                flat = torch.cat([g.reshape(-1) for g in grads])
-                self.dist.all_reduce(flat)
-                flat /= self.world
-                o, views = 0, []
-                for g in grads:
-                    views.append(flat[o:o + g.numel()].view(g.shape))
-                    o += g.numel()
-                grads = views
-            for p, g in zip(self.params, grads):
-                p.grad = g.contiguous()         # (the fused Adam wants the parameter's layout)
+            if multi:                            # the flat gradient buffer (441 KB) that is all-reduced
+                torch.cat([g.reshape(-1) for g in grads], out=st["flat"])
+            else:
+                for p, g in zip(self.params, grads):
+                    p.grad = g.contiguous()      # (the fused Adam wants the parameter's layout)
+            return loss.detach(), parts
+
+        def step_part():
+            if multi:
+                st["flat"].div_(self.world)
+                o = 0
+                for p in self.params:
+                    p.grad = st["flat"][o:o + p.numel()].view(p.shape)
+                    o += p.numel()
             torch.nn.utils.clip_grad_norm_(self.params, self.cfg.max_grad_norm)
             self.opt.step()
-            return loss.detach(), parts
+
+        def full(tt, ii):
+            stats_part(tt, ii)
+            out = grads_part(tt, ii)
+            if multi:
+                self.dist.all_reduce(st["flat"])     # ONE all-reduce of the gradients per optimizer step
+            step_part()
+            return out
 
         if not self.graphed:
             args = (buf["actions"][t, i], buf["values"][t, i], buf["logp"][t, i], buf["adv"][t, i], buf["ret"][t, i])
             return self.minibatch(None, None, None, *args, samples=(buf, t, i))
         st = self._static
         if st is None or st["t"].shape != t.shape or st["frames"] is not buf["frames"]:
+            dev = t.device
             st = self._static = {"t": torch.empty_like(t), "i": torch.empty_like(i), "frames": buf["frames"], "graph": None,
-                                 "warm": 0, "out": None}
+                                 "graph_b": None, "warm": 0, "out": None,
+                                 "stats": torch.zeros(2, dtype=torch.float32, device=dev),
+                                 "flat": torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)}
         st["t"].copy_(t); st["i"].copy_(i)
-        n_red = self.n_all_reduces + (0 if self.world == 1 else 1 + int(self.cfg.normalize_advantage))
+        split = multi and not self.graph_nccl
+        n_red = self.n_all_reduces + (0 if not multi else 1 + int(self.cfg.normalize_advantage))
         prev = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = bool(self.cfg.update_tf32)
         try:
@@ -225,7 +248,7 @@ class Updater:
                 side = torch.cuda.Stream(device=t.device)
                 side.wait_stream(torch.cuda.current_stream(t.device))
                 with torch.cuda.stream(side):
-                    out = body(st["t"], st["i"])
+                    out = full(st["t"], st["i"])
                 torch.cuda.current_stream(t.device).wait_stream(side)
                 st["warm"] += 1
                 self.n_all_reduces = n_red
@@ -235,12 +258,25 @@ class Updater:
                 graph = torch.cuda.CUDAGraph()
                 self.policy.capturing = True
                 try:
-                    with torch.cuda.graph(graph):
-                        st["out"] = body(st["t"], st["i"])
+                    if split:
+                        stats_part(st["t"], st["i"])                 # eager: this step's moments
+                        with torch.cuda.graph(graph):
+                            st["out"] = grads_part(st["t"], st["i"])
+                        st["graph_b"] = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(st["graph_b"], pool=graph.pool()):
+                            step_part()
+                    else:
+                        with torch.cuda.graph(graph):
+                            st["out"] = full(st["t"], st["i"])
                 finally:
                     self.policy.capturing = False
                 st["graph"] = graph
+            elif split:
+                stats_part(st["t"], st["i"])
             st["graph"].replay()
+            if split:
+                self.dist.all_reduce(st["flat"])
+                st["graph_b"].replay()
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
         self.n_all_reduces = n_red
