@@ -669,8 +669,10 @@ cudaError_t launch_policy_forward_tc(const PolicyArgs& a, cudaStream_t stream) {
     auto launch = [&](auto kernel, int w) -> cudaError_t {
         const int obc = 16 * w;
         const size_t smem = (size_t)4 * obc * 148 + 6 * 2 * 32 * 16 + obc;
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+        if (smem > 48 * 1024) {    // 5 warps per CTA only (4 warps: 44 KB, no opt-in; keeps the default launch capturable)
+            const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
         kernel<<<(a.n + obc - 1) / obc, 32 * w, smem, stream>>>(a);
         return cudaGetLastError();
     };
