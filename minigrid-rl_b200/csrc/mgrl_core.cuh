@@ -706,7 +706,10 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
     else { kind = K_GOAL; objw = T_GOAL; }
 
     while (task != 0u) {
-        // the four draws an iteration can use: position x, y, then agent direction / next task's pool entry
+        // Two tries of the current task per iteration.  A try is two draws (x, y); the four draws in hand are try A and,
+        // should A be rejected, try B.  Both admissibility tests are independent (two grid bytes in flight, no state changes
+        // on a rejection), so a rejected try costs no extra round trip through the draw buffer and the grid.  When A is
+        // accepted, the third and fourth draw are what they were before: agent direction / next task's pool entry.
         uint32_t d0, d1, d2, d3;
         if (nd + 4 <= kDrawBuf) {
             const uint32_t* w = io.draws + nd * ds;
@@ -714,28 +717,43 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
         } else {
             d0 = draw(0); d1 = draw(1); d2 = draw(2); d3 = draw(3);
         }
-        const int x = (int)(task & 15u) + (int)mulhi32(d0, (task >> 4) & 15u);
-        const int y = (int)((task >> 8) & 15u) + (int)mulhi32(d1, (task >> 12) & 15u);
-        nd += 2;
-        const uint32_t xy = (uint32_t)x | ((uint32_t)y << 8);
-        const int cell = y * S + x;
-        const uint32_t here = s.grid[cell];           // kind | kDoorFlag (flag only ever set on a multi map)
+        const uint32_t rx0 = task & 15u, rw = (task >> 4) & 15u, ry0 = (task >> 8) & 15u, rh = (task >> 12) & 15u;
         const uint32_t mask = (task & TF_KEYMODE) ? kDoorFlag : (task & TF_AGENTMODE) ? 0x7Fu : 0xFFu;
-        // admissibility as one predicate expression (no short-circuit branches)
-        const bool occupied = ((here & mask) != 0u) & !(((task & TF_LAVA) != 0u) & (here == (uint32_t)K_LAVA));
-        const bool on_agent = ((task & TF_AGENT_CELL) != 0u) & (xy == agent_xy);
-        const bool on_mid = ((task & TF_MID) != 0u) & ((x == m) | (y == m));
-        bool bad = occupied | on_agent | (xy == goal_xy) | (xy == key_xy) | on_mid;
-        tries += bad;
+        const int xa = (int)rx0 + (int)mulhi32(d0, rw), ya = (int)ry0 + (int)mulhi32(d1, rh);
+        const int xb = (int)rx0 + (int)mulhi32(d2, rw), yb = (int)ry0 + (int)mulhi32(d3, rh);
+        const uint32_t herea = s.grid[ya * S + xa], hereb = s.grid[yb * S + xb];   // kind | kDoorFlag (flag only on a multi map)
+        const uint32_t xya = (uint32_t)xa | ((uint32_t)ya << 8), xyb = (uint32_t)xb | ((uint32_t)yb << 8);
+        // admissibility as one predicate expression per try (no short-circuit branches)
+        const bool lava_ok = (task & TF_LAVA) != 0u, own = (task & TF_AGENT_CELL) != 0u, mid = (task & TF_MID) != 0u;
+        const bool bada = (((herea & mask) != 0u) & !(lava_ok & (herea == (uint32_t)K_LAVA))) | (own & (xya == agent_xy)) |
+                          (xya == goal_xy) | (xya == key_xy) | (mid & ((xa == m) | (ya == m)));
+        const bool badb = (((hereb & mask) != 0u) & !(lava_ok & (hereb == (uint32_t)K_LAVA))) | (own & (xyb == agent_xy)) |
+                          (xyb == goal_xy) | (xyb == key_xy) | (mid & ((xb == m) | (yb == m)));
+        // try B counts only if A was rejected and the rejection bound is not reached by A alone
+        const bool second = bada & (tries + 1 < kMaxTries);
+        int x = xa, y = ya;
+        uint32_t xy = xya, here = herea;
+        bool bad = bada;
+        nd += 2;
+        tries += bada;
+        if (second) {
+            x = xb; y = yb; xy = xyb; here = hereb; bad = badb;
+            nd += 2;
+            tries += badb;
+        }
         if (tries >= kMaxTries) { s.error |= ERR_TRIES; bad = false; }
         if (!bad) {
             tries = 0;
+            const int cell = y * S + x;
             const int stage = (int)((task >> 16) & 7u);
-            uint32_t next_word = d2;
+            // the draws that follow the accepted position
+            uint32_t n0, n1;
+            if (second) { n0 = draw(0); n1 = draw(1); } else { n0 = d2; n1 = d3; }
+            uint32_t next_word = n0;
             if (stage == G_AGENT) {
                 agent_xy = xy;
-                s.agent_dir = (uint8_t)mulhi32(d2, 4); ++nd;
-                next_word = d3;
+                s.agent_dir = (uint8_t)mulhi32(n0, 4); ++nd;
+                next_word = n1;
                 int row = 0;
                 if (multi) {
                     const int gx = (int)(goal_xy & 0xFFu), gy = (int)(goal_xy >> 8);
