@@ -706,6 +706,8 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
     else { kind = K_GOAL; objw = T_GOAL; }
 
     while (task != 0u) {
+        // the task that follows in the current list, fetched now so that an accepted placement does not wait for it
+        const uint32_t task_after = list[li + 1];
         // Two tries of the current task per iteration.  A try is two draws (x, y); the four draws in hand are try A and,
         // should A be rejected, try B.  Both admissibility tests are independent (two grid bytes in flight, no state changes
         // on a rejection), so a rejected try costs no extra round trip through the draw buffer and the grid.  When A is
@@ -750,6 +752,7 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
             uint32_t n0, n1;
             if (second) { n0 = draw(0); n1 = draw(1); } else { n0 = d2; n1 = d3; }
             uint32_t next_word = n0;
+            uint32_t next_task = task_after;
             if (stage == G_AGENT) {
                 agent_xy = xy;
                 s.agent_dir = (uint8_t)mulhi32(n0, 4); ++nd;
@@ -761,13 +764,15 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
                 }
                 list = io.tasks + (size_t)row * io.row_words;
                 li = -1;
+                next_task = list[0];
             } else {
                 s.grid[cell] = (uint8_t)((uint32_t)kind | (here & kDoorFlag));
                 if (stage != G_OBST) { io.draws[nobjs * ds] = objw | ((uint32_t)x << 6) | ((uint32_t)y << 10); ++nobjs; }
                 if (stage == G_GOAL) goal_xy = xy;
                 if (stage == G_KEY && !(task & (1u << 21))) key_xy = xy;
             }
-            task = list[++li];
+            ++li;
+            task = next_task;
             start_task(task, next_word);
         }
     }
