@@ -35,6 +35,22 @@ BYTES_PER_ENV_STEP = 158
 BYTES_PER_ENV_STEP_STREAMED = 158 + 280
 
 
+def load_traffic(n, T):
+    """measured DRAM bytes per launch of step_kernel from the committed ncu summary of this build (None if absent / other
+    shape / another build of the kernel source)"""
+    import hashlib
+    try:
+        with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
+            rec = json.load(f)
+        src = b"".join(open(os.path.join(ROOT, "minigrid-rl_b200", "csrc", name), "rb").read()
+                       for name in ("mgrl_core.cuh", "mgrl_kernels.cu"))
+        if (rec["envs"], rec["steps"]) != (n, T) or rec["source_sha16"] != hashlib.sha256(src).hexdigest()[:16]:
+            return None
+        return float(rec["dram_bytes_read"]) + float(rec["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -160,6 +176,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ppo", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the PKP 32 768 / ALL 131 072 sub-records")
     ap.add_argument("--ppo-iters", type=int, default=2)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -182,24 +199,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     n, T = args.envs, T_ROLLOUT
+    if args.warmup < 3:
+        print(f"bench.py: warm-up raised from {args.warmup} to 3 (timing rules: W >= 3)", file=sys.stderr)
     W, K = max(args.warmup, 3), args.steps
-    cfg = mg.EnvConfig.for_task(TASK)
-    env = mg.DeviceEnv(cfg, num_envs=n, seed=SEED, env_id_base=rank * n, layout="hwc148")
-    env.reset()
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    actions = torch.randint(0, 7, (T, n), dtype=torch.uint8, device=dev, generator=g)
+    peak, peak_src = load_peaks()
     u8 = dict(dtype=torch.uint8, device=dev)
-    image = torch.empty((T, n, 148), **u8)        # 1.2 GB rollout buffer (> L2), 148-B packed HWC records
-    dirs = torch.empty((T, n), **u8); mis = torch.empty((T, n), **u8)
-    rew = torch.empty((T, n), dtype=torch.float32, device=dev)
-    term = torch.empty((T, n), **u8); trunc = torch.empty((T, n), **u8); eplen = torch.empty((T, n), **u8)
-
-    def rollout_many():  # the rollout as ONE launch: T steps per launch, state tile resident in shared memory
-        env.step_many(actions, image, dirs, mis, rew, term, trunc, eplen)
-
-    def rollout_steps():  # one launch per env step, the way a policy-in-the-loop rollout has to issue it
-        for t in range(T):
-            env.step(actions[t], image[t], dirs[t], mis[t], rew[t], term[t], trunc[t], eplen[t])
 
     def barrier():
         if dist is not None:
@@ -221,6 +225,39 @@ def main():
             ms = float(tmax.item())
         return ms
 
+    def make_rollout(task, n_envs):
+        """environments + synthetic actions + [T,N,...] output buffers of one K1 workload"""
+        e = mg.DeviceEnv(mg.EnvConfig.for_task(task), num_envs=n_envs, seed=SEED, env_id_base=rank * n_envs, layout="hwc148")
+        e.reset()
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+        acts = torch.randint(0, 7, (T, n_envs), dtype=torch.uint8, device=dev, generator=gen)
+        bufs = (torch.empty((T, n_envs, 148), **u8), torch.empty((T, n_envs), **u8), torch.empty((T, n_envs), **u8),
+                torch.empty((T, n_envs), dtype=torch.float32, device=dev), torch.empty((T, n_envs), **u8),
+                torch.empty((T, n_envs), **u8), torch.empty((T, n_envs), **u8))
+        return e, acts, bufs
+
+    def k1_record(task, n_envs, k, w):
+        """K1 (`mgrl_step_many`, one launch = one rollout of T steps) on `n_envs` environments of `task` per GPU"""
+        e, acts, bufs = make_rollout(task, n_envs)
+        for _ in range(w):
+            e.step_many(acts, *bufs)
+        t_ms = timed(lambda: e.step_many(acts, *bufs), k)
+        flags = e.error_flags()
+        e.close()
+        us = 1000.0 * t_ms / k
+        gbs = BYTES_PER_ENV_STEP * n_envs * T / (us * 1e-6) / 1e9
+        return {"task": task, "envs_per_gpu": n_envs, "value": world * n_envs * T * k / (t_ms / 1000.0), "unit": "env-steps/s",
+                "us_per_launch": us, "achieved_gbs": gbs, "frac": gbs / peak, "env_error_flags": flags}
+
+    env, actions, (image, dirs, mis, rew, term, trunc, eplen) = make_rollout(TASK, n)
+
+    def rollout_many():  # the rollout as ONE launch: T steps per launch, state tile resident in shared memory
+        env.step_many(actions, image, dirs, mis, rew, term, trunc, eplen)
+
+    def rollout_steps():  # one launch per env step, the way a policy-in-the-loop rollout has to issue it
+        for t in range(T):
+            env.step(actions[t], image[t], dirs[t], mis[t], rew[t], term[t], trunc[t], eplen[t])
+
     # W warm-up bench steps also de-synchronise the episode phases (SURVEY §8d: >= 121 env steps)
     with ClockSampler(local_rank) as clocks:
         for _ in range(W):
@@ -239,7 +276,6 @@ def main():
     value = total_env_steps / (ms / 1000.0)
     launches = K
     us_per_launch = 1000.0 * ms / launches
-    peak, peak_src = load_peaks()
     achieved = BYTES_PER_ENV_STEP * n * T / (us_per_launch * 1e-6) / 1e9
 
     # the same rollout issued as T one-step launches (what a policy in the loop needs)
@@ -295,24 +331,20 @@ def main():
 
     # PPO frames/sec (SB3 `time/fps`: env frames per wall second over rollout + update), BASELINE.json's second figure:
     # policy-in-the-loop rollout (2 launches per step) + GAE + n_epochs of minibatch updates, gradients all-reduced
-    ppo_line = None
-    if not args.no_ppo:
-        env.close()
-        del image, dirs, mis, rew, term, trunc, eplen, actions
-        torch.cuda.empty_cache()
-        penv = mg.DeviceEnv(cfg, num_envs=n, seed=SEED, env_id_base=rank * n, layout="hwc148")
-        pcfg = mg.PPOConfig(n_steps=T, batch_size=n * T // 32, n_epochs=4, update_tf32=True)
+    def ppo_record(task, n_envs, iters, with_kernel=False):
+        penv = mg.DeviceEnv(mg.EnvConfig.for_task(task), num_envs=n_envs, seed=SEED, env_id_base=rank * n_envs, layout="hwc148")
+        pcfg = mg.PPOConfig(n_steps=T, batch_size=n_envs * T // 32, n_epochs=4, update_tf32=True)
         eng = mg.RolloutEngine(penv, mg.Policy(dev, seed=SEED), pcfg, dist=dist if world > 1 else None, seed=SEED)
-        for _ in range(2):                                   # warm-up: cuDNN autotune, allocator, layouts in L2, graph capture of
-            eng.iteration(1.0)                               # the optimizer step, first truncation bootstrap (lazy module loads)
+        for _ in range(2):                                   # warm-up: allocator, layouts in L2, graph capture of the
+            eng.iteration(1.0)                               # optimizer step, first truncation bootstrap (lazy module loads)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         t_roll = t_upd = 0.0
         barrier()
-        for it in range(args.ppo_iters):
+        for it in range(iters):
             ev[0].record()
             eng.collect(); eng.bootstrap_truncated(); eng.compute_advantages()
             ev[1].record()
-            eng.updater.set_progress(1.0 - it / max(args.ppo_iters, 1))
+            eng.updater.set_progress(1.0 - it / max(iters, 1))
             n_mb = eng.update()
             eng.shift()
             ev[2].record()
@@ -323,35 +355,79 @@ def main():
         if dist is not None:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_roll, t_upd = float(tt[0]), float(tt[1])
-        # the rollout's policy kernel alone (K3): T launches over the collected frames, CUDA events on the launching stream
-        B = eng.buf
-        kev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        kev[0].record()
-        for t in range(T):
-            eng.policy.forward_rollout(B["frames"], B["dirs"], B["mission"][t + 3], t + 3, eng.prev_age, eng.prev_done,
-                                       B["age"][t], B["values"][t], B["actions"][t], B["logp"][t])
-        kev[1].record()
-        torch.cuda.synchronize()
-        k3_us = 1000.0 * kev[0].elapsed_time(kev[1]) / T
-        k3_flop = 2.0 * 79616 * n      # MACs / observation: conv 27 648 + 8 192 + 8 192, direction 256, MLPs 26 624 + 8 192, heads 512
-        frames = world * n * T * args.ppo_iters
-        ppo_line = {"value": frames / ((t_roll + t_upd) / 1000.0), "unit": "frames/s",
-                    "policy_kernel": {"us_per_launch": k3_us, "observations_per_launch": n,
-                                      "kernel": "policy_forward_tc_kernel (mma.sync m16n8k8 TF32, three-term split, fp32 accumulate)"
-                                                if eng.policy.tensor_cores else "policy_forward_kernel (fp32 CUDA cores)",
-                                      "algorithmic_tflops": k3_flop / (k3_us * 1e-6) / 1e12,
-                                      "tensor_tflops_issued": (3312 * 2048.0 * (n / 16.0)) / (k3_us * 1e-6) / 1e12
-                                                              if eng.policy.tensor_cores else 0.0},
-                    "rollout_env_steps_per_s": frames / (t_roll / 1000.0), "rollout_ms": t_roll / args.ppo_iters,
-                    "update_ms": t_upd / args.ppo_iters, "iterations": args.ppo_iters,
-                    "config": {"n_steps": T, "n_envs_per_gpu": n, "batch_size_per_gpu": pcfg.batch_size, "n_epochs": 4,
-                               "minibatches_per_iteration": n_mb, "policy": "CustomPPOPolicy 110216 params, fp32",
-                               "rollout": "mgrl_policy_forward (tensor cores, split TF32 = fp32-class) + mgrl_step per step (hand-written kernels)",
-                               "update": "first extractor stage hand-written (mgrl_conv1_pool_*), rest torch autograd on library kernels; "
-                                         "matmuls may use TF32 like the reference (ppo.py:29-32), the rollout kernels are fp32",
-                               "all_reduces_per_optimizer_step": 2 if world > 1 else 0},
-                    "env_error_flags": penv.error_flags()}
-        env = penv
+        frames = world * n_envs * T * iters
+        rec = {"value": frames / ((t_roll + t_upd) / 1000.0), "unit": "frames/s",
+               "rollout_env_steps_per_s": frames / (t_roll / 1000.0), "rollout_ms": t_roll / iters,
+               "update_ms": t_upd / iters, "iterations": iters,
+               "config": {"task": task, "n_steps": T, "n_envs_per_gpu": n_envs, "batch_size_per_gpu": pcfg.batch_size,
+                          "n_epochs": 4, "minibatches_per_iteration": n_mb, "policy": "CustomPPOPolicy 110216 params, fp32",
+                          "rollout": "mgrl_policy_forward + mgrl_step per step (hand-written kernels)",
+                          "update": eng.updater.describe(),
+                          "all_reduces_per_optimizer_step": eng.updater.all_reduces_per_step()},
+               "env_error_flags": penv.error_flags()}
+        if with_kernel:
+            # the rollout's policy kernel alone (K3): T launches over the collected frames, CUDA events on the launching stream
+            B = eng.buf
+            kev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            kev[0].record()
+            for t in range(T):
+                eng.policy.forward_rollout(B["frames"], B["dirs"], B["mission"][t + 3], t + 3, eng.prev_age, eng.prev_done,
+                                           B["age"][t], B["values"][t], B["actions"][t], B["logp"][t])
+            kev[1].record()
+            torch.cuda.synchronize()
+            k3_us = 1000.0 * kev[0].elapsed_time(kev[1]) / T
+            k3_flop = 2.0 * 79616 * n_envs   # MACs / observation: conv 27 648 + 8 192 + 8 192, direction 256, MLPs 26 624 + 8 192, heads 512
+            rec["policy_kernel"] = {"us_per_launch": k3_us, "observations_per_launch": n_envs,
+                                    "kernel": eng.policy.kernel_name(),
+                                    "algorithmic_tflops": k3_flop / (k3_us * 1e-6) / 1e12}
+        eng.updater.release()            # a captured optimizer step must not outlive the communicator
+        penv.close()
+        del eng
+        torch.cuda.empty_cache()
+        return rec
+
+    def gae_record():
+        """K4 (`mgrl_gae`) at the headline shape: T x N float32 rollouts, 17 algorithmic bytes per element (reward 4 + value 4
+        + episode start 1 read, advantage 4 + return 4 written).  Three buffer sets (3 x 142 MB > L2) are cycled."""
+        sets = []
+        for _ in range(3):
+            sets.append((torch.rand((T, n), device=dev), torch.randn((T, n), device=dev),
+                         (torch.rand((T, n), device=dev) < 0.14).to(torch.uint8), torch.randn(n, device=dev),
+                         torch.zeros(n, **u8), torch.empty((T, n), device=dev), torch.empty((T, n), device=dev)))
+        calls = [0]
+
+        def one():
+            r, v, st, lv, ld, adv, ret = sets[calls[0] % 3]
+            mg.vec_env.gae(r, v, st, lv, ld, 0.81, 0.945, adv, ret)
+            calls[0] += 1
+
+        for _ in range(3):
+            one()
+        reps = 30
+        t_ms = timed(one, reps)
+        us = 1000.0 * t_ms / reps
+        gbs = (17.0 * T * n + 5.0 * n) / (us * 1e-6) / 1e9
+        return {"kernel": "gae_kernel", "elements_per_launch": T * n, "bytes_per_element": 17, "us_per_launch": us,
+                "elements_per_s": world * T * n / (us * 1e-6), "achieved_gbs": gbs, "peak_gbs": peak, "frac": gbs / peak,
+                "l2": "three 142 MB buffer sets cycled (> 126 MB L2)"}
+
+    ppo_line = None
+    gae_line = None
+    cfg_lines = {}
+    env.close()
+    del image, dirs, mis, rew, term, trunc, eplen, actions
+    torch.cuda.empty_cache()
+    gae_line = gae_record()
+    if not args.no_ppo:
+        ppo_line = ppo_record(TASK, n, args.ppo_iters, with_kernel=True)
+    # BASELINE.json configs[2] (PKP, 262 144 envs over 8 GPUs = 32 768 per GPU) and configs[4] (ALL, 1 048 576 over 8 = 131 072
+    # per GPU, NCCL gradient all-reduce) at their per-GPU sizes: K1 alone and the PPO iteration
+    if not args.no_configs and n == N_ENVS:
+        for key, task, n_c in (("pkp_32768", "PKP", 32768), ("all_131072", "ALL", 131072)):
+            rec = k1_record(task, n_c, max(3, K // 2), 3)
+            if not args.no_ppo:
+                rec["ppo"] = ppo_record(task, n_c, args.ppo_iters)
+            cfg_lines[key] = rec
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -372,9 +448,10 @@ def main():
                              "in the algorithmic bytes",
                        "path": "mgrl_step_many: one launch = one rollout of T steps (actions known up front)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this
-                         # kernel at this shape (profiles/r1b_ncu_full_many.txt); algorithmic bytes = 158 * n * T
-                         "traffic": 1.4008e9 if (n, T) == (N_ENVS, T_ROLLOUT) else None, "traffic_unit": "bytes/launch",
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this shape, read from
+                         # the ncu --set full summary of the CURRENT build (profiles/k1_traffic.json, written by
+                         # profiles/ncu_summary.py); null when the shape differs or no capture of this build exists
+                         "traffic": load_traffic(n, T), "traffic_unit": "bytes/launch",
                          "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n * T,
                          "kernel": "step_kernel<HWC148,see_through,64,1>", "peak_source": peak_src,
                          "bytes_per_env_step": BYTES_PER_ENV_STEP, "us_per_launch": us_per_launch,
@@ -386,14 +463,15 @@ def main():
                                 "note": "mgrl_step x T: the same kernel with one step per launch, as a rollout with a "
                                         "policy in the loop issues it (latency-bound at this batch size)"},
             "ppo": ppo_line,
+            # PPO frames/s over all GPUs: the path that communicates (one gradient all-reduce per optimizer step)
+            "ppo_frames_per_s": None if ppo_line is None else ppo_line["value"],
+            "gae": gae_line,
+            "configs": cfg_lines,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clock_summary,
             "env_error_flags": err,
         }
         print(json.dumps(line))
-    env.close()
     if dist is not None:
-        if not args.no_ppo:
-            eng.updater._static = None      # a captured optimizer step (opt-in with NCCL ranks) must not outlive the communicator
         torch.cuda.synchronize()
         dist.destroy_process_group()
 

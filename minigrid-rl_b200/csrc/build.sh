@@ -1,12 +1,20 @@
 #!/bin/sh
-# Builds the C-ABI CUDA library in-tree for sm_100a (cross-compiles without a GPU).
+# Builds the C-ABI CUDA library in-tree for sm_100a (cross-compiles without a GPU).  The three translation units are
+# compiled in parallel, then linked.
 set -e
 HERE=$(cd "$(dirname "$0")" && pwd)
 ROOT=$(cd "$HERE/../.." && pwd)
 OUT="$HERE/../_lib"
-mkdir -p "$OUT"
+OBJ="$OUT/obj"
+mkdir -p "$OUT" "$OBJ"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-"$NVCC" -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo \
-    -Xcompiler -fPIC -shared -I "$ROOT/include" -I "$HERE" \
-    -o "$OUT/libmgrl.so" "$HERE/mgrl_kernels.cu" "$HERE/mgrl_policy.cu" "$HERE/mgrl_policy_tc.cu" "$@"
+FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -I $ROOT/include -I $HERE"
+pids=""
+for f in mgrl_kernels mgrl_policy mgrl_policy_tc $MGRL_EXTRA_UNITS; do
+    [ -f "$HERE/$f.cu" ] || continue
+    "$NVCC" $FLAGS "$@" -c -o "$OBJ/$f.o" "$HERE/$f.cu" &
+    pids="$pids $!"
+done
+for p in $pids; do wait "$p"; done
+"$NVCC" -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT/libmgrl.so" "$OBJ"/*.o
 echo "built $OUT/libmgrl.so"

@@ -110,9 +110,11 @@ MGRL_HD uint32_t kind_encode(int k) {
 
 // ---------------------------------------------------------------------------------- RNG
 // Philox4x32-10, key = seed, counter = (block, episode, env_lo, env_hi).  Draw d of an
-// episode is word d&3 of block d>>2; below(n) = mulhi32(word, n).  The generator computes the
-// first kDrawBuf draws of an episode up front (16 blocks, straight-line, all lanes converged)
-// into a lane-interleaved buffer and indexes it; draws beyond that (p < 0.5 %) are recomputed.
+// episode is word d&3 of block d>>2; below(n) = mulhi32(word, n).  The generator keeps a ring of
+// kRing draws per layout (lane-interleaved shared memory): kUpFront blocks before the straight-line
+// prologue, then one more block per placement iteration whenever the ring has room, so the Philox
+// rounds overlap the dependent load-compare chain of the placement loop; a draw the ring does not hold
+// (only if a lane consumed five draws per iteration for many iterations in a row) is recomputed.
 MGRL_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t ka, uint32_t kb, uint32_t* out) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
@@ -140,15 +142,37 @@ uint32_t philox_word(uint32_t idx, uint32_t episode, uint32_t e0, uint32_t e1, u
 struct StepOut {
     float reward;
     uint8_t terminated, truncated, carry_obs;
+    uint8_t step_count;   // steps of the episode including this one
+    uint8_t error;        // ERR_BAD_ACTION when the action was not a MiniGrid action (KEEP_IF_DONE only: not stored)
+    uint32_t w32;         // word 32 after the step (target_action, mission_id, mission_done, latch_step)
 };
 
 // [UPSTREAM] MiniGridEnv.step, then PlaygroundEnv.step's mission bookkeeping.
 // reward_lut[k] = float32(1 - 0.9*k/max_steps) computed in float64 on the host.
-MGRL_HD StepOut env_step(EnvState& s, int action, int S, int max_steps, const float* reward_lut) {
-    // the scalar fields travel as three words: 30 = grid[120], agent x, y, dir; 31 = carrying, step_count,
-    // target x, y; 32 = target_action, mission_id, mission_done, latch_step
+// KEEP_IF_DONE: when the step ends the episode nothing is written back to the state (the caller is about to
+// overwrite it with the layout of the next episode, possibly by an asynchronous copy that is already in flight);
+// the surviving fields (mission latch, error bit) are returned in the StepOut.
+// what a step reads from the state: the scalar fields travel as three words: 30 = grid[120], agent x, y, dir;
+// 31 = carrying, step_count, target x, y; 32 = target_action, mission_id, mission_done, latch_step; and the cell in front
+struct StepIn {
+    uint32_t w30, w31, w32;
+    int fidx, k;
+};
+MGRL_HD StepIn env_step_load(const EnvState& s, int S) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&s);
+    StepIn in;
+    in.w30 = w[30]; in.w31 = w[31]; in.w32 = w[32];
+    const int dir = (int)(in.w30 >> 24);
+    const int ax = (int)((in.w30 >> 8) & 0xFFu), ay = (int)((in.w30 >> 16) & 0xFFu);
+    in.fidx = (ay + (dir == 1) - (dir == 3)) * S + ax + (dir == 0) - (dir == 2);
+    in.k = s.grid[in.fidx];
+    return in;
+}
+
+template <bool KEEP_IF_DONE>
+MGRL_HD StepOut env_step_apply(EnvState& s, const StepIn& in, int action, int max_steps, const float* reward_lut) {
     uint32_t* w = reinterpret_cast<uint32_t*>(&s);
-    const uint32_t w30 = w[30], w31 = w[31], w32 = w[32];
+    const uint32_t w30 = in.w30, w31 = in.w31, w32 = in.w32;
     const int dir = (int)(w30 >> 24);
     int ax = (int)((w30 >> 8) & 0xFFu), ay = (int)((w30 >> 16) & 0xFFu);
     int carrying = (int)(w31 & 0xFFu);
@@ -157,12 +181,14 @@ MGRL_HD StepOut env_step(EnvState& s, int action, int S, int max_steps, const fl
     const int ta = (int)(w32 & 0xFFu), mission_id = (int)((w32 >> 8) & 0xFFu);
     int mdone = (int)((w32 >> 16) & 0xFFu), latch = (int)(w32 >> 24);
     const int dx = (dir == 0) - (dir == 2), dy = (dir == 1) - (dir == 3);
-    const int fidx = (ay + dy) * S + ax + dx;
-    const int k = s.grid[fidx];
+    const int fidx = in.fidx;
+    const int k = in.k;
     int nk = k;                // front cell after the action
     int ndir = dir;
     bool term = false;
     float r = 0.0f;
+    StepOut o;
+    o.error = 0;
 
     if (action == A_LEFT) ndir = (dir + 3) & 3;
     else if (action == A_RIGHT) ndir = (dir + 1) & 3;
@@ -184,11 +210,11 @@ MGRL_HD StepOut env_step(EnvState& s, int action, int S, int max_steps, const fl
             nk = m ? K_KEY + m - 1 : K_EMPTY;
         }
     } else if (action != A_DONE) {
-        s.error |= ERR_BAD_ACTION;  // upstream raises ValueError
+        if (KEEP_IF_DONE) o.error = ERR_BAD_ACTION;
+        else s.error |= ERR_BAD_ACTION;  // upstream raises ValueError
     }
-    if (nk != k) s.grid[fidx] = (uint8_t)nk;
-    StepOut o;
     o.truncated = step >= max_steps;
+    o.step_count = (uint8_t)step;
     o.carry_obs = (uint8_t)carrying;  // the observation is rendered here (custom_env.py:270)
 
     if (term) {  // custom_env.py:272-277
@@ -209,12 +235,21 @@ MGRL_HD StepOut env_step(EnvState& s, int action, int S, int max_steps, const fl
             term = true;
         }
     }
-    w[30] = (w30 & 0xFFu) | ((uint32_t)ax << 8) | ((uint32_t)ay << 16) | ((uint32_t)ndir << 24);
-    w[31] = (uint32_t)carrying | ((uint32_t)step << 8) | (w31 & 0xFFFF0000u);
-    w[32] = (w32 & 0xFFFFu) | ((uint32_t)mdone << 16) | ((uint32_t)latch << 24);
+    o.w32 = (w32 & 0xFFFFu) | ((uint32_t)mdone << 16) | ((uint32_t)latch << 24);
     o.reward = r;
     o.terminated = term;
+    if (!(KEEP_IF_DONE && (term || o.truncated))) {
+        if (nk != k) s.grid[fidx] = (uint8_t)nk;
+        w[30] = (w30 & 0xFFu) | ((uint32_t)ax << 8) | ((uint32_t)ay << 16) | ((uint32_t)ndir << 24);
+        w[31] = (uint32_t)carrying | ((uint32_t)step << 8) | (w31 & 0xFFFF0000u);
+        w[32] = o.w32;
+        if (KEEP_IF_DONE && o.error) s.error |= o.error;
+    }
     return o;
+}
+
+MGRL_HD StepOut env_step(EnvState& s, int action, int S, int max_steps, const float* reward_lut) {
+    return env_step_apply<false>(s, env_step_load(s, S), action, max_steps, reward_lut);
 }
 
 // -------------------------------------------------------------------------- observation
@@ -393,7 +428,11 @@ MGRL_HD void encode_full(const EnvState& s, int S, uint8_t* out) {
 //      next to a door" (next2door, :2036-2046) is one compare of the byte already loaded.
 // The draw order is the reference's; the CPU oracle consumes the same stream.
 constexpr int T_KEY = 0, T_BALL = 1, T_BOX = 2, T_DOOR = 3, T_GOAL = 4;
-constexpr int kDrawBuf = 64;            // draws precomputed per generation = 16 Philox blocks
+constexpr int kRing = 32;               // draws held per generation: a ring over the episode's Philox stream
+constexpr int kUpFront = 8;             // blocks computed before the prologue (it consumes at most 22 draws): the ring starts full
+constexpr int kObjWords = 14;           // the placed objects in insertion order, 16 bits each (<= 28 objects):
+                                        //   type | colour << 3 | cell << 6
+constexpr int kGenWords = kRing + kObjWords;   // words of generation scratch per layout besides the 35 state words
 constexpr int kGridWords = 31;          // words 0..30 of EnvState cover grid[121] + agent x/y/dir
 constexpr uint32_t kDoorFlag = 0x80u;   // "next to a door" mark on a grid byte (kinds are < 128)
 
@@ -556,7 +595,7 @@ inline void build_empty_grid(int S, uint32_t* words /* [kGridWords] */) {
 
 // what a generation reads besides the configuration
 struct GenIO {
-    uint32_t* draws;           // this lane's draw buffer: word i at draws[i * stride]
+    uint32_t* draws;           // this lane's generation scratch, word i at draws[i * stride]: kRing draws, then kObjWords
     int stride;                // 32 on the device (lane-interleaved shared memory), 1 on the host
     const uint32_t* tasks;     // [kTaskEntries][row_words] (build_task_table, then pack_task_table)
     int row_words = kTaskWords;  // row pitch of `tasks`: the longest row + terminator, rounded up to 4 words
@@ -577,23 +616,29 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
     const uint32_t e0 = (uint32_t)env_id, e1 = (uint32_t)(env_id >> 32);
     const int ds = io.stride;
 
-    // ---- 1. all draws of the episode
-#pragma unroll 1
-    for (int b = 0; b < kDrawBuf / 4; ++b) {
+    // ---- 1. the first draws of the episode (the ring is topped up inside the placement loop)
+    int filled = 0;  // Philox blocks produced so far: draws [0, 4 * filled) exist, the last kRing of them are in the ring
+    auto produce = [&]() {
         uint32_t w[4];
-        philox4x32_10((uint32_t)b, episode, e0, e1, k0, k1, w);
+        philox4x32_10((uint32_t)filled, episode, e0, e1, k0, k1, w);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) io.draws[(4 * b + j) * ds] = w[j];
-    }
+        for (int j = 0; j < 4; ++j) io.draws[((4 * filled + j) & (kRing - 1)) * ds] = w[j];
+        ++filled;
+    };
+#pragma unroll 1
+    for (int b = 0; b < kUpFront; ++b) produce();
     int nd = 0;  // draws consumed
     auto draw = [&](int i) -> uint32_t {  // word nd + i
         const int idx = nd + i;
-        if (idx < kDrawBuf) return io.draws[idx * ds];
+        if (idx < 4 * filled) return io.draws[(idx & (kRing - 1)) * ds];
         return philox_word((uint32_t)idx, episode, e0, e1, k0, k1);
     };
-    // placed objects, insertion order: type | colour<<3 | x<<6 | y<<10.  Entry i lives in draw slot i,
-    // which is dead by then (every object consumes at least one draw before it is recorded).
+    // placed objects, insertion order, 16 bits each behind the ring: type | colour << 3 | cell << 6
     int nobjs = 0;
+    auto record = [&](uint32_t tc, int cell) {
+        reinterpret_cast<uint16_t*>(io.draws + (kRing + (nobjs >> 1)) * ds)[nobjs & 1] = (uint16_t)(tc | ((uint32_t)cell << 6));
+        ++nobjs;
+    };
 
     // ---- fresh grid (Grid.wall_rect) and per-episode fields ([UPSTREAM] MiniGridEnv.reset, :125-127)
     uint32_t* gw = reinterpret_cast<uint32_t*>(&s);
@@ -617,7 +662,7 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
 
     // ---- 2. multi-room prologue (_generate_multi_map :601-611, doors :635-650, :880-929, :1324-1390)
     if (multi) {
-        // (at most 2 + 4*3 + 4*2 = 22 draws here: always inside the precomputed buffer)
+        // (at most 2 + 4*3 + 4*2 = 22 draws here: inside the kUpFront blocks, no ring wrap yet)
         auto pdraw = [&](int i) -> uint32_t { return io.draws[(nd + i) * ds]; };
         if (cmd < 0) { cmd = (int)((0x5210u >> (4 * mulhi32(pdraw(0), 4))) & 0xFu); ++nd; }  // choice([0,1,2,5])
         nrooms = 2 + (int)mulhi32(pdraw(0), 3); ++nd;                                         // randint(2,4)
@@ -664,8 +709,7 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
                 s.grid[c] = (uint8_t)(K_DOOR + 8 * state + colour);
                 s.grid[c - 1] |= kDoorFlag; s.grid[c + 1] |= kDoorFlag;
                 s.grid[c - S] |= kDoorFlag; s.grid[c + S] |= kDoorFlag;
-                io.draws[nobjs * ds] = (uint32_t)(T_DOOR | (colour << 3) | (x << 6) | (y << 10));
-                ++nobjs;
+                record((uint32_t)(T_DOOR | (colour << 3)), c);
             }
         }
     }
@@ -712,10 +756,13 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
         // should A be rejected, try B.  Both admissibility tests are independent (two grid bytes in flight, no state changes
         // on a rejection), so a rejected try costs no extra round trip through the draw buffer and the grid.  When A is
         // accepted, the third and fourth draw are what they were before: agent direction / next task's pool entry.
+        // top the ring up: a block whenever four slots are free (it never overwrites a draw that is still ahead:
+        // 4 * filled + 4 - nd <= kRing); an iteration consumes at most five draws
+        if (4 * filled - nd <= kRing - 4) produce();
         uint32_t d0, d1, d2, d3;
-        if (nd + 4 <= kDrawBuf) {
-            const uint32_t* w = io.draws + nd * ds;
-            d0 = w[0]; d1 = w[ds]; d2 = w[2 * ds]; d3 = w[3 * ds];
+        if (nd + 4 <= 4 * filled) {
+            d0 = io.draws[(nd & (kRing - 1)) * ds]; d1 = io.draws[((nd + 1) & (kRing - 1)) * ds];
+            d2 = io.draws[((nd + 2) & (kRing - 1)) * ds]; d3 = io.draws[((nd + 3) & (kRing - 1)) * ds];
         } else {
             d0 = draw(0); d1 = draw(1); d2 = draw(2); d3 = draw(3);
         }
@@ -767,7 +814,7 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
                 next_task = list[0];
             } else {
                 s.grid[cell] = (uint8_t)((uint32_t)kind | (here & kDoorFlag));
-                if (stage != G_OBST) { io.draws[nobjs * ds] = objw | ((uint32_t)x << 6) | ((uint32_t)y << 10); ++nobjs; }
+                if (stage != G_OBST) record(objw, cell);
                 if (stage == G_GOAL) goal_xy = xy;
                 if (stage == G_KEY && !(task & (1u << 21))) key_xy = xy;
             }
@@ -786,14 +833,16 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
     if (cmd <= 2) {
         const int n = nobjs;
         for (;;) {
-            const int o = (int)io.draws[(int)mulhi32(draw(0), (uint32_t)n) * ds]; ++nd;
+            const int oi = (int)mulhi32(draw(0), (uint32_t)n); ++nd;
+            const int o = reinterpret_cast<const uint16_t*>(io.draws + (kRing + (oi >> 1)) * ds)[oi & 1];
             const int t = o & 7;
             const bool ok = cmd == 0 ? t != T_GOAL : cmd == 1 ? (t == T_BOX || t == T_DOOR)
                                                               : (t == T_BOX || t == T_KEY || t == T_BALL);
             if (!ok && ++tries >= kMaxTries) s.error |= ERR_TRIES;
             if (ok || tries >= kMaxTries) {
+                const int cell = o >> 6, ty = cell / S;
                 s.mission_id = (uint8_t)(cmd * 24 + t * 6 + ((o >> 3) & 7));
-                s.target_x = (uint8_t)((o >> 6) & 15); s.target_y = (uint8_t)((o >> 10) & 15);
+                s.target_x = (uint8_t)(cell - ty * S); s.target_y = (uint8_t)ty;
                 s.target_action = (uint8_t)(cmd == 0 ? A_DONE : cmd == 1 ? A_TOGGLE : A_PICKUP);
                 break;
             }

@@ -192,7 +192,7 @@ template <int TILE, int NB>
 struct TileSmem {
     alignas(16) uint32_t state[TILE * STATE_WORDS];
     alignas(16) uint8_t obs[TILE / 32][32 * kObsPitch148];   // per warp: observation staging / layout scratch
-    alignas(16) uint32_t draws[NB][kDrawBuf * 32];            // lane-interleaved Philox draws of a serving warp
+    alignas(16) uint32_t draws[NB][kGenWords * 32];           // lane-interleaved draw ring + object list of a serving warp
     uint32_t kind_lut[128];
     float lut[kGridCells + 1];
     uint32_t empty[kGridWords];
@@ -505,12 +505,314 @@ __global__ void __launch_bounds__(TILE, TILE == 128 ? 4 : 7) step_kernel(const E
     }
 }
 
+// ======================================================================================= rollout_kernel
+// T > 1 steps per launch (mgrl_step_many): one big tile per SM, warp-specialised.
+//   * `sw` STEP warps, one lane per environment: step -> (adopt the prepared layout of the next episode) -> encode the
+//     observation into the warp's staging area -> ONE bulk copy (cp.async.bulk, TMA engine) of the 32 records to HBM;
+//   * `gw` GENERATOR warps that never step: they pop the tile's request queue in batches of 32 and build layouts
+//     densely (one lane per layout) into their own scratch rows, then write the 32 slot records with coalesced 16-byte
+//     stores and publish them through the tile's tag bytes.
+// The layout generator is ~44 % of the instructions of a uniform-random rollout; on its own warps it adds independent
+// warps per scheduler (22 instead of 14 per SM at 65 536 environments) instead of stalling the step warps.  Adoption is
+// nine 16-byte cp.async per finished lane straight from the slot record (L2) into the lane's state row: env_step_apply
+// <KEEP_IF_DONE> writes nothing when the episode ends, and for the `done` action (which always ends it,
+// custom_env.py:319-328) the copy is issued before the step is computed.  Every slot is full when a launch starts and
+// when it ends (the generator warps drain the queue), so launches leave no requests behind.
+constexpr int kRowWords = 36;        // state row pitch in shared memory: 144 B = 16-byte aligned cp.async destination
+constexpr int kScratchWords = 37;    // generator scratch row pitch (odd: lane-per-row accesses are conflict free)
+constexpr int kMaxStepWarps = 14, kMaxGenWarps = 8;
+constexpr uint32_t kEnvBits = 9;     // request = env-in-tile (9 bits, <= 448) | slot << 9
+
+struct RolloutSmem {                 // byte offsets into the dynamic shared memory of one tile
+    int state, stage, scratch, gen, queue, ready, kind_lut, lut, empty, prefix, ctrl, total, qcap;
+};
+__host__ __device__ inline RolloutSmem rollout_smem(int sw, int gw) {
+    RolloutSmem L;
+    int o = 0;
+    L.state = o; o += sw * 32 * kRowWords * 4;
+    L.stage = o; o += sw * 32 * kObsPitch148;
+    L.scratch = o; o += gw * 32 * kScratchWords * 4;
+    L.gen = o; o += gw * 32 * kGenWords * 4;
+    int qcap = 64;
+    while (qcap < sw * 32 * kDepth) qcap <<= 1;
+    L.qcap = qcap;
+    L.queue = o; o += qcap * 2;
+    L.ready = o; o += kDepth * sw * 32;
+    L.kind_lut = o; o += 128 * 4;
+    L.lut = o; o += 128 * 4;         // kGridCells + 1 = 122 floats
+    L.empty = o; o += 32 * 4;
+    L.prefix = o; o += kTaskWords * 4;
+    L.ctrl = o; o += 64;
+    L.total = o;
+    return L;
+}
+struct RolloutCtrl {
+    uint32_t q_head, q_tail;
+    int finished;        // step warps that have done their T steps
+    int starve;          // a step lane is waiting for a layout: generator warps take partial batches
+};
+
+__device__ __forceinline__ void fetch_layout(uint32_t row_sa, const uint32_t* slot) {
+#pragma unroll
+    for (int i = 0; i < kSlotWords / 4; ++i)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(row_sa + 16u * i), "l"(slot + 4 * i) : "memory");
+}
+
+template <int LAYOUT, bool SEE>
+__global__ void __launch_bounds__((kMaxStepWarps + kMaxGenWarps) * 32, 1) rollout_kernel(const EnvParams p, int sw, int gw) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int PITCH = obs_pitch(LAYOUT);
+    const RolloutSmem L = rollout_smem(sw, gw);
+    uint32_t* state = reinterpret_cast<uint32_t*>(smem_raw + L.state);
+    uint16_t* queue = reinterpret_cast<uint16_t*>(smem_raw + L.queue);
+    uint8_t* ready = smem_raw + L.ready;                                     // [kDepth][tile_envs]
+    uint32_t* kind_lut = reinterpret_cast<uint32_t*>(smem_raw + L.kind_lut);
+    float* lut = reinterpret_cast<float*>(smem_raw + L.lut);
+    uint32_t* empty = reinterpret_cast<uint32_t*>(smem_raw + L.empty);
+    uint32_t* prefix = reinterpret_cast<uint32_t*>(smem_raw + L.prefix);
+    RolloutCtrl& ctrl = *reinterpret_cast<RolloutCtrl*>(smem_raw + L.ctrl);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthreads = blockDim.x;
+    const int tile_envs = sw * 32;
+    const int tile0 = blockIdx.x * tile_envs;
+    const int nv = min(tile_envs, p.n - tile0);
+    const int S = p.cfg.size;
+    const uint32_t qmask = (uint32_t)L.qcap - 1u;
+
+    {   // ---- prologue: states [env][35 words] -> rows of kRowWords, constants, tags
+        const uint32_t* g = reinterpret_cast<const uint32_t*>(p.states + tile0);
+        for (int i = tid; i < nv * STATE_WORDS; i += nthreads) {
+            const int r = i / STATE_WORDS;
+            state[r * kRowWords + (i - r * STATE_WORDS)] = g[i];
+        }
+        for (int r = tid; r < tile_envs; r += nthreads) state[r * kRowWords + STATE_WORDS] = 0u;
+        fill_kind_lut(kind_lut, tid, nthreads);
+        for (int i = tid; i <= p.cfg.max_steps; i += nthreads) lut[i] = p.reward_lut[i];
+        for (int i = tid; i < kGridWords; i += nthreads) empty[i] = p.empty[i];
+        for (int i = tid; i < kTaskWords; i += nthreads) prefix[i] = p.prefix[i];
+        for (int i = tid; i < L.qcap; i += nthreads) queue[i] = (uint16_t)kNoEntry;
+        for (int i = tid; i < kDepth * tile_envs; i += nthreads) {
+            const int j = i / tile_envs, e = i - j * tile_envs;
+            ready[i] = e < nv ? p.tags[(size_t)j * p.n + tile0 + e] : (uint8_t)0;
+        }
+        if (tid == 0) { ctrl.q_head = 0u; ctrl.q_tail = 0u; ctrl.finished = 0; ctrl.starve = 0; }
+    }
+    __syncthreads();
+
+    if (warp < sw) {
+        // ================================================================ step warps
+        const int e = warp * 32 + lane;
+        const bool active = e < nv;
+        uint32_t* cur = state + e * kRowWords;
+        EnvState& s = *reinterpret_cast<EnvState*>(cur);
+        uint8_t* stage = smem_raw + L.stage + warp * (32 * kObsPitch148);
+        const int nvw = max(0, min(32, nv - warp * 32));
+        const uint32_t row_sa = (uint32_t)__cvta_generic_to_shared(cur);
+        const uint32_t stage_sa = (uint32_t)__cvta_generic_to_shared(stage);
+        __builtin_assume(__isShared(stage));
+        __builtin_assume(__isShared(cur));
+        uint64_t policy = 0;   // the records are not read again by this kernel: keep them from displacing the layouts in L2
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+        bool store_in_flight = false;   // (lane 0) a bulk copy may still be reading the staging area
+        int action = active ? p.actions[tile0 + e] : 0;
+        for (int t = 0; t < p.T; ++t) {
+            const size_t gi = (size_t)t * (size_t)p.n + (size_t)(tile0 + e);
+            const int a = action;
+            if (active && t + 1 < p.T) action = p.actions[gi + (size_t)p.n];   // next step's action, in flight during this one
+            bool done = false, fetched = false;
+            int carry = 0;
+            StepOut o;
+            o.w32 = 0u; o.error = 0;
+            uint32_t E = 0, old34 = 0;
+            int j = 0;
+            if (active) {
+                const StepIn in = env_step_load(s, S);
+                E = cur[33]; old34 = cur[34];
+                j = (int)(E & (uint32_t)(kDepth - 1));
+                const uint32_t* slot = slot_ptr(p.slots, j, p.n, tile0 + e);
+                // `done` always ends the episode: everything the step needs is in registers now, so the next layout can
+                // start to overwrite the row while the step is computed
+                if (a == A_DONE && *reinterpret_cast<const volatile uint8_t*>(&ready[j * tile_envs + e]) == (uint8_t)(E + 1u)) {
+                    __threadfence_block();
+                    fetch_layout(row_sa, slot);
+                    fetched = true;
+                }
+                o = env_step_apply<true>(s, in, a, p.cfg.max_steps, lut);
+                p.reward[gi] = o.reward;
+                p.term[gi] = o.terminated;
+                p.trunc[gi] = o.truncated;
+                done = o.terminated | o.truncated;
+                if (p.ep_len) p.ep_len[gi] = done ? o.step_count : (uint8_t)0;
+                carry = o.carry_obs;
+            }
+            if (__any_sync(FULL, done)) {
+                bool pending = done && !fetched;
+                const volatile uint8_t* tag = &ready[j * tile_envs + e];
+                for (int spins = 0; __any_sync(FULL, pending); ++spins) {
+                    if (pending && *tag == (uint8_t)(E + 1u)) {
+                        __threadfence_block();
+                        fetch_layout(row_sa, slot_ptr(p.slots, j, p.n, tile0 + e));
+                        fetched = true; pending = false;
+                    }
+                    if (pending) {   // the generator warps are behind: let them take what is queued, whatever the batch size
+                        *reinterpret_cast<volatile int*>(&ctrl.starve) = 1;
+                        __nanosleep(400);
+                        if (spins > kSpinLimit) { s.error |= ERR_SYNC; pending = false; }
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                const bool adopted = done && fetched;
+                if (adopted) {
+                    // what survives the reset: the mission latch (App. B Q1; zero after `done`) and the sticky error byte
+                    if (o.w32 & 0xFFFF0000u) cur[32] = (cur[32] & 0x0000FFFFu) | (o.w32 & 0xFFFF0000u);
+                    const uint32_t err = (old34 & 0x00FF0000u) | ((uint32_t)o.error << 16);
+                    if (err) cur[34] |= err;
+                    carry = 0;
+                }
+                const unsigned rm = __ballot_sync(FULL, adopted);
+                if (rm) {   // ask for the layout that will follow the one just adopted (warp-aggregated push)
+                    const int leader = __ffs(rm) - 1;
+                    uint32_t base = 0;
+                    if (lane == leader) base = atomicAdd(&ctrl.q_tail, (uint32_t)__popc(rm));
+                    base = __shfl_sync(FULL, base, leader);
+                    if (adopted) {
+                        const uint32_t pos = base + (uint32_t)__popc(rm & ((1u << lane) - 1u));
+                        *reinterpret_cast<volatile uint16_t*>(&queue[pos & qmask]) = (uint16_t)((uint32_t)e | ((uint32_t)j << kEnvBits));
+                    }
+                }
+            }
+            // the previous step's bulk copy must have read the staging area before it is rewritten
+            if (store_in_flight) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); store_in_flight = false; }
+            __syncwarp();
+            if (active) {
+                if (p.image) {
+                    if (LAYOUT == OBS_HWC148 && SEE) {
+                        asm volatile("" ::: "memory");   // the state bytes written above are read through asm loads
+                        encode_packed_smem(row_sa, s.agent_x, s.agent_y, s.agent_dir, (uint32_t)carry, S,
+                                           (uint32_t)__cvta_generic_to_shared(kind_lut), stage_sa + (uint32_t)(lane * PITCH));
+                        asm volatile("" ::: "memory");
+                    } else {
+                        encode_view<LAYOUT>(s, carry, S, SEE, kind_lut, stage + lane * PITCH);
+                    }
+                }
+                if (p.dir) p.dir[gi] = s.agent_dir;
+                if (p.mission) p.mission[gi] = s.mission_id;
+            }
+            if (p.image && nvw > 0) {
+                uint8_t* dst = p.image + ((size_t)t * (size_t)p.n + (size_t)(tile0 + warp * 32)) * PITCH;
+                if (nvw == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                    // generic-proxy writes of the staging area -> async proxy: fence by every writer, then one lane issues
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                                     ::"l"(dst), "r"(stage_sa), "r"(32 * PITCH), "l"(policy) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        store_in_flight = true;
+                    }
+                } else {
+                    __syncwarp();
+                    warp_copy_out<PITCH>(dst, stage, nvw, lane);
+                    __syncwarp();
+                }
+            }
+        }
+        if (store_in_flight) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); atomicAdd(&ctrl.finished, 1); }
+    } else {
+        // ================================================================ generator warps
+        const int g = warp - sw;
+        uint32_t* scratch = reinterpret_cast<uint32_t*>(smem_raw + L.scratch) + g * (32 * kScratchWords);
+        uint32_t* gen = reinterpret_cast<uint32_t*>(smem_raw + L.gen) + g * (32 * kGenWords);
+        int idle = 0;   // (lane 0) polls since this warp last had work
+        for (;;) {
+            int n_take = 0, h = 0;
+            if (lane == 0) {
+                const uint32_t head = *reinterpret_cast<volatile uint32_t*>(&ctrl.q_head);
+                const uint32_t avail = *reinterpret_cast<volatile uint32_t*>(&ctrl.q_tail) - head;
+                const bool fin = *reinterpret_cast<volatile int*>(&ctrl.finished) >= sw;
+                // a partial batch wastes lanes: only when the rollout is over, or when a step lane waits for a layout and no
+                // full batch has come together for a while (the whole tile may be waiting)
+                const bool starve = *reinterpret_cast<volatile int*>(&ctrl.starve) != 0 && idle >= 8;
+                n_take = avail >= 32u ? 32 : ((fin || starve) ? (int)avail : 0);
+                idle = n_take > 0 ? 0 : idle + 1;
+                if (n_take > 0) {
+                    if (atomicCAS(&ctrl.q_head, head, head + (uint32_t)n_take) != head) n_take = -1;   // another warp took them
+                    else { h = (int)head; if (n_take < 32) *reinterpret_cast<volatile int*>(&ctrl.starve) = 0; }
+                } else if (fin) {
+                    n_take = -2;   // every step warp is done and the queue is empty
+                }
+            }
+            n_take = __shfl_sync(FULL, n_take, 0);
+            if (n_take == -2) break;
+            if (n_take <= 0) { if (n_take == 0) __nanosleep(100); continue; }
+            h = __shfl_sync(FULL, h, 0);
+            int e = 0, j = 0;
+            uint32_t tagw = 0;
+            uint32_t* sc = scratch + lane * kScratchWords;
+            if (lane < n_take) {
+                volatile uint16_t* q = reinterpret_cast<volatile uint16_t*>(&queue[((uint32_t)h + (uint32_t)lane) & qmask]);
+                uint32_t ent;
+                while ((ent = *q) == kNoEntry) {}
+                *q = (uint16_t)kNoEntry;
+                e = (int)(ent & ((1u << kEnvBits) - 1u)); j = (int)(ent >> kEnvBits);
+                // The slot's old layout was adopted, so it gets the one episode in [E, E + kDepth) that maps to slot j, E being
+                // the environment's next episode (E may advance while we look: every value it can take gives the same answer,
+                // because the environment cannot adopt the layout we are about to build).
+                const uint32_t E = *reinterpret_cast<const volatile uint32_t*>(&state[e * kRowWords + 33]);
+                const uint32_t episode = E + (((uint32_t)j - E) & (uint32_t)(kDepth - 1));
+                generate_layout(sc, p.cfg, p.seed, p.env_id_base + (uint64_t)(tile0 + e), episode, gen + lane, p.tasks,
+                                p.task_row_words, prefix, empty);
+#pragma unroll
+                for (int i = 0; i < kGridWords; ++i) sc[i] &= kMarkMask;
+                sc[35] = 0u;
+                tagw = sc[33];
+            }
+            __syncwarp();
+            // write the n_take slot records (144 B each) with coalesced 16-byte stores: chunk c = record c / 9, part c % 9
+            const int chunks = n_take * (kSlotWords / 4);
+            for (int c0 = 0; c0 < chunks; c0 += 32) {
+                const int c = c0 + lane;
+                const bool valid = c < chunks;
+                const int r = valid ? c / (kSlotWords / 4) : 0;
+                const int q4 = c - r * (kSlotWords / 4);
+                const int er = __shfl_sync(FULL, e, r), jr = __shfl_sync(FULL, j, r);
+                if (valid) {
+                    const uint32_t* src = scratch + r * kScratchWords + 4 * q4;
+                    uint4 v;
+                    v.x = src[0]; v.y = src[1]; v.z = src[2]; v.w = src[3];
+                    __stcg(reinterpret_cast<uint4*>(slot_ptr(p.slots, jr, p.n, tile0 + er)) + q4, v);
+                }
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane < n_take) {
+                // hand-off inside the CTA: layout (global, L2) -> fence -> tag byte (shared); the adopting lane reads the
+                // tag byte, fences, then reads the layout
+                p.tags[(size_t)j * p.n + tile0 + e] = (uint8_t)tagw;
+                __threadfence_block();
+                *reinterpret_cast<volatile uint8_t*>(&ready[j * tile_envs + e]) = (uint8_t)tagw;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    {   // ---- epilogue: rows -> states
+        uint32_t* g = reinterpret_cast<uint32_t*>(p.states + tile0);
+        for (int i = tid; i < nv * STATE_WORDS; i += nthreads) {
+            const int r = i / STATE_WORDS;
+            g[i] = state[r * kRowWords + (i - r * STATE_WORDS)];
+        }
+    }
+}
+
 // Dense layout generation for the requests recorded by one-step launches: every warp takes batches of 32 entries of
 // the global list (grid-stride), one lane per layout, all lanes busy.
 template <int NWARPS>
 struct GenSmem {
     alignas(16) uint32_t scratch[NWARPS][32 * STATE_WORDS];
-    alignas(16) uint32_t draws[NWARPS][kDrawBuf * 32];
+    alignas(16) uint32_t draws[NWARPS][kGenWords * 32];
     uint32_t empty[kGridWords];
     uint32_t prefix[kTaskWords];
 };
@@ -552,7 +854,7 @@ template <int LAYOUT, bool SEE, bool PRIME, int TILE>
 struct ResetSmem {
     alignas(16) uint32_t state[TILE * STATE_WORDS];
     alignas(16) uint8_t obs[TILE / 32][32 * kObsPitch148];
-    alignas(16) uint32_t draws[TILE / 32][kDrawBuf * 32];
+    alignas(16) uint32_t draws[TILE / 32][kGenWords * 32];
     uint32_t kind_lut[128];
     uint32_t empty[kGridWords];
     uint32_t prefix[kTaskWords];
@@ -740,7 +1042,9 @@ struct mgrl_env {
     mgrl_config cfg;
     EnvCfg ecfg;
     int device;
-    int tile;    // environments per CTA (64 / 128)
+    int tile;    // environments per CTA (64 / 128) of the one-step kernel
+    int n_sms;   // multiprocessors of the device (tile shape of the rollout kernel)
+    int rollout; // 1: mgrl_step_many runs rollout_kernel; 0 (MGRL_ROLLOUT=0): the one-step kernel with T steps per launch
     uint64_t seed;
     EnvState* states;
     uint32_t* slots;     // [kDepth][N][kSlotWords]
@@ -831,6 +1135,44 @@ int launch_env(const mgrl_env* e, int mode, const EnvParams& p, cudaStream_t s) 
     }
 }
 
+// tile shape of the rollout kernel: one tile per SM when the environments fit one wave (14 step warps = 448 environments at
+// most), 4 generator warps per 7 step warps; MGRL_SW / MGRL_GW override (tuning)
+void rollout_shape(const mgrl_env* e, int* sw_out, int* gw_out) {
+    const int per_sm = (e->cfg.num_envs + e->n_sms - 1) / e->n_sms;
+    int sw = (per_sm + 31) / 32;
+    sw = sw < 1 ? 1 : (sw > kMaxStepWarps ? kMaxStepWarps : sw);
+    int gw = (sw * 4 + 6) / 7;
+    if (const char* v = getenv("MGRL_SW")) sw = atoi(v);
+    if (const char* v = getenv("MGRL_GW")) gw = atoi(v);
+    sw = sw < 1 ? 1 : (sw > kMaxStepWarps ? kMaxStepWarps : sw);
+    gw = gw < 1 ? 1 : (gw > kMaxGenWarps ? kMaxGenWarps : gw);
+    *sw_out = sw; *gw_out = gw;
+}
+
+template <int LAYOUT, bool SEE>
+int launch_rollout_t(const mgrl_env* e, const EnvParams& p, cudaStream_t s) {
+    int sw, gw;
+    rollout_shape(e, &sw, &gw);
+    const RolloutSmem L = rollout_smem(sw, gw);
+    const int grid = (p.n + sw * 32 - 1) / (sw * 32);
+    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<LAYOUT, SEE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    rollout_kernel<LAYOUT, SEE><<<grid, (sw + gw) * 32, L.total, s>>>(p, sw, gw);
+    CUDA_TRY(cudaGetLastError());
+    return MGRL_OK;
+}
+
+int launch_rollout(const mgrl_env* e, const EnvParams& p, cudaStream_t s) {
+    const bool see = e->ecfg.see_through_walls != 0;
+    switch (e->cfg.obs_layout) {
+    case MGRL_OBS_CHW:
+        return see ? launch_rollout_t<OBS_CHW, true>(e, p, s) : launch_rollout_t<OBS_CHW, false>(e, p, s);
+    case MGRL_OBS_HWC148:
+        return see ? launch_rollout_t<OBS_HWC148, true>(e, p, s) : launch_rollout_t<OBS_HWC148, false>(e, p, s);
+    default:
+        return see ? launch_rollout_t<OBS_HWC, true>(e, p, s) : launch_rollout_t<OBS_HWC, false>(e, p, s);
+    }
+}
+
 // build the layouts requested by the one-step launches since the last flush (dense generate_kernel)
 int flush_deferred(mgrl_env* e, cudaStream_t s) {
     if (e->deferred_steps == 0) return MGRL_OK;
@@ -918,6 +1260,10 @@ int mgrl_create(const mgrl_config* cfg, int device, mgrl_env** out) {
     // 148 SMs (6.9 tiles each); 128 per CTA (4 warps, two draw buffers) is the alternative shape (MGRL_TILE=128)
     e->tile = 64;
     if (const char* t = getenv("MGRL_TILE")) e->tile = atoi(t) == 128 ? 128 : 64;
+    e->n_sms = 148;
+    cudaDeviceGetAttribute(&e->n_sms, cudaDevAttrMultiProcessorCount, device);
+    e->rollout = 1;
+    if (const char* t = getenv("MGRL_ROLLOUT")) e->rollout = atoi(t) != 0;
     e->ecfg.size = cfg->size;
     e->ecfg.num_objects = cfg->num_objects;
     e->ecfg.problem = cfg->problem;
@@ -1039,6 +1385,7 @@ int mgrl_step_many(mgrl_env* e, int T, const uint8_t* actions, uint8_t* image, u
     p.T = T;
     p.actions = actions; p.image = image; p.dir = dir; p.mission = mission; p.reward = reward;
     p.term = term; p.trunc = trunc; p.ep_len = ep_len;
+    if (e->rollout) return launch_rollout(e, p, (cudaStream_t)stream);
     return launch_env(e, MODE_STEP, p, (cudaStream_t)stream);
 }
 

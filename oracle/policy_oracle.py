@@ -37,14 +37,22 @@ class OraclePolicy(nn.Module):
     def features(self, obs):
         """obs: direction (B,16) u8, image (B,12,7,7) u8, mission (B,128) i64; concat order direction, image, mission
         (policies.py:83-102 iterates the ModuleDict, whose keys follow the sorted observation space)."""
-        d = self.direction(obs["direction"].float())
-        im = self.image(obs["image"].float() / 255.0)          # [UPSTREAM] preprocess_obs, normalize_images=true
+        dt = self.direction[0].weight.dtype                     # float32; float64 for the `.double()` copy (tests)
+        d = self.direction(obs["direction"].to(dt))
+        im = self.image(obs["image"].to(dt) / 255.0)            # [UPSTREAM] preprocess_obs, normalize_images=true
         _, h = self.gru(self.embedding(obs["mission"].long()))  # policies.py:84-91
         return torch.cat([d, im, h[-1]], dim=1)
 
     def forward(self, obs):
         f = self.features(obs)
         return self.action_net(self.pi(f)), self.value_net(self.vf(f)).squeeze(-1)
+
+
+def double_copy(policy: OraclePolicy) -> OraclePolicy:
+    """The same network evaluated in float64: the yardstick of the 1e-5 bar (the float32 evaluation above carries
+    its own rounding error of the same size as the kernels')."""
+    import copy
+    return copy.deepcopy(policy).double()
 
 
 def init_reference(policy: OraclePolicy, seed: int) -> None:

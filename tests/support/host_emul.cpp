@@ -21,7 +21,7 @@ struct HostGen {
     uint32_t tasks[kTaskEntries * kTaskWords];
     uint32_t prefix[kTaskWords];
     uint32_t empty[kGridWords];
-    uint32_t draws[kDrawBuf];
+    uint32_t draws[kGenWords];
     GenIO io;
     explicit HostGen(const EnvCfg& cfg) {
         build_task_table(cfg, full);

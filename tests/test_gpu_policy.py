@@ -2,8 +2,11 @@
 fp32 oracle that sees SB3-style stacked observations, the sampling rule, the frame-stack gather across episode
 boundaries, truncation bootstrap, GAE on the rollout and one PPO iteration.  Tolerance for floating point
 (BASELINE.json north_star: 1e-5 relative in fp32): max |got - want| <= 1e-5 * max |want| over the batch, i.e. relative
-to the scale of the logits / values (an element-wise ratio is meaningless for logits that cross zero).  Measured on
-B200: 4.5e-6 for the logits, 5e-6 for the values."""
+to the scale of the logits / values (an element-wise ratio is meaningless for logits that cross zero).  `want` is the
+oracle network evaluated in FLOAT64 (policy_oracle.double_copy): the oracle's own float32 evaluation is itself up to
+~1e-5 away from it, so comparing two float32 evaluations with each other would measure the sum of two rounding errors.
+The bar is 1e-5 for every step and every batch size, with no exceptions (profiles/policy_error.py prints the measured
+errors of the kernel and of torch-CPU float32 against the same yardstick)."""
 import ctypes as C
 
 import numpy as np
@@ -17,9 +20,11 @@ from minigrid_rl_b200 import policy as pol, ppo  # noqa: E402
 from oracle import oracle as orc, policy_oracle as po, sb3_oracle  # noqa: E402
 
 REL = 1e-5
+VALUE_SCALE = 0.25      # typical max |V| of a batch under init_reference(seed 5) (printed by profiles/policy_error.py)
 
 
 def close(got, want, rel=REL):
+    got, want = got.double(), want.double()
     return float((got - want).abs().max()) <= rel * float(want.abs().max())
 
 
@@ -57,6 +62,7 @@ def oracle_stacks(buf, T, n):
 def test_forward_kernel_matches_oracle_on_a_rollout():
     n, T = 640, 20                       # 640 = 10 CTAs of 64 observations
     eng, o = make_engine(n, T)
+    o64 = po.double_copy(o)
     eng.collect()
     b = eng.buf
     stacks = oracle_stacks(b, T, n)
@@ -73,9 +79,9 @@ def test_forward_kernel_matches_oracle_on_a_rollout():
                                    logits=logits, seed=77, env_id_base=1000, step=t)
         img, d, mis = stacks[t]
         with torch.no_grad():
-            lo, vo = o({"direction": torch.from_numpy(d), "image": torch.from_numpy(img), "mission": torch.from_numpy(mis)})
+            lo, vo = o64({"direction": torch.from_numpy(d), "image": torch.from_numpy(img), "mission": torch.from_numpy(mis)})
         assert close(logits.cpu(), lo), t
-        assert close(val.cpu(), vo, 1.2e-5 if t == 0 else REL), t   # t = 0: all stacks hold one frame, values are small
+        assert close(val.cpu(), vo), t
         assert torch.equal(age, b["age"][t]) and torch.allclose(val, b["values"][t], rtol=0, atol=0)
         if t < T:   # the rollout stored exactly what this call recomputes (same Philox key: seed, env id, step)
             assert torch.equal(act, b["actions"][t]) and torch.equal(lp, b["logp"][t])
@@ -244,15 +250,18 @@ def test_native_conv1_stage_matches_library_path():
 def test_forward_kernel_ragged_batches(n):
     """batches that do not fill the last CTA (32 observations) of the policy kernel"""
     eng, o = make_engine(n, 8)
+    o64 = po.double_copy(o)
     eng.collect()
     b = eng.buf
     stacks = oracle_stacks(b, 8, n)
+    # the yardstick of the relative bar is the scale of the value head over a batch (a single observation whose value
+    # happens to sit near zero has no scale of its own): max |V| of the 100-env rollout of the same policy
     for t in (0, 3, 8):
         img, d, mis = stacks[t]
         with torch.no_grad():
-            _, vo = o({"direction": torch.from_numpy(d), "image": torch.from_numpy(img), "mission": torch.from_numpy(mis)})
-        got = b["values"][t].cpu()
-        assert close(got, vo, 2e-5) or float((got - vo).abs().max()) <= 5e-6, (n, t)   # a single small value: absolute floor
+            lo, vo = o64({"direction": torch.from_numpy(d), "image": torch.from_numpy(img), "mission": torch.from_numpy(mis)})
+        got = b["values"][t].cpu().double()
+        assert float((got - vo).abs().max()) <= REL * max(float(vo.abs().max()), VALUE_SCALE), (n, t)
     eng.env.close()
 
 
