@@ -118,8 +118,9 @@ MGRL_HD uint32_t kind_encode(int k) {
 MGRL_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t ka, uint32_t kb, uint32_t* out) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
-        const uint32_t h1 = mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;   // one wide multiply each
+        const uint32_t h0 = (uint32_t)(p0 >> 32), l0 = (uint32_t)p0;
+        const uint32_t h1 = (uint32_t)(p1 >> 32), l1 = (uint32_t)p1;
         c0 = h1 ^ c1 ^ ka; c1 = l1; c2 = h0 ^ c3 ^ kb; c3 = l0;
         ka += 0x9E3779B9u; kb += 0xBB67AE85u;
     }
@@ -428,8 +429,8 @@ MGRL_HD void encode_full(const EnvState& s, int S, uint8_t* out) {
 //      next to a door" (next2door, :2036-2046) is one compare of the byte already loaded.
 // The draw order is the reference's; the CPU oracle consumes the same stream.
 constexpr int T_KEY = 0, T_BALL = 1, T_BOX = 2, T_DOOR = 3, T_GOAL = 4;
-constexpr int kRing = 32;               // draws held per generation: a ring over the episode's Philox stream
-constexpr int kUpFront = 8;             // blocks computed before the prologue (it consumes at most 22 draws): the ring starts full
+constexpr int kRing = 16;               // draws held per generation: a ring over the episode's Philox stream
+constexpr int kUpFront = 4;             // blocks computed before the prologue: the ring starts full
 constexpr int kObjWords = 14;           // the placed objects in insertion order, 16 bits each (<= 28 objects):
                                         //   type | colour << 3 | cell << 6
 constexpr int kGenWords = kRing + kObjWords;   // words of generation scratch per layout besides the 35 state words
@@ -628,6 +629,9 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
 #pragma unroll 1
     for (int b = 0; b < kUpFront; ++b) produce();
     int nd = 0;  // draws consumed
+    // top the ring up: a block whenever four slots are free (it never overwrites a draw that is still ahead:
+    // 4 * filled + 4 - nd <= kRing)
+    auto topup = [&]() { if (4 * filled - nd <= kRing - 4) produce(); };
     auto draw = [&](int i) -> uint32_t {  // word nd + i
         const int idx = nd + i;
         if (idx < 4 * filled) return io.draws[(idx & (kRing - 1)) * ds];
@@ -662,8 +666,8 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
 
     // ---- 2. multi-room prologue (_generate_multi_map :601-611, doors :635-650, :880-929, :1324-1390)
     if (multi) {
-        // (at most 2 + 4*3 + 4*2 = 22 draws here: inside the kUpFront blocks, no ring wrap yet)
-        auto pdraw = [&](int i) -> uint32_t { return io.draws[(nd + i) * ds]; };
+        // (at most 2 + 4*3 + 4*2 = 22 draws here, at most 3 between two top-ups: always in the ring)
+        auto pdraw = [&](int i) -> uint32_t { return io.draws[((nd + i) & (kRing - 1)) * ds]; };
         if (cmd < 0) { cmd = (int)((0x5210u >> (4 * mulhi32(pdraw(0), 4))) & 0xFu); ++nd; }  // choice([0,1,2,5])
         nrooms = 2 + (int)mulhi32(pdraw(0), 3); ++nd;                                         // randint(2,4)
         const int ndoors = nrooms == 2 ? 1 : nrooms;
@@ -675,6 +679,7 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
         uint32_t colours = 0x3Fu;    // remaining door colours (sorted-name order)
 #pragma unroll 1
         for (int d = 0; d < 4; ++d) {
+            topup();
             if (d < ndoors) {
                 const int i = (int)mulhi32(pdraw(0), (uint32_t)popc32(colours));
                 const int bit = nth_set_bit(colours, i);
@@ -694,6 +699,7 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
         }
 #pragma unroll 1
         for (int d = 0; d < 4; ++d) {
+            topup();
             if (d < ndoors) {
                 bool horizontal; int lo, hi2;
                 if (nrooms == 2) { horizontal = false; lo = 1; hi2 = S - 2; }
@@ -756,9 +762,7 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
         // should A be rejected, try B.  Both admissibility tests are independent (two grid bytes in flight, no state changes
         // on a rejection), so a rejected try costs no extra round trip through the draw buffer and the grid.  When A is
         // accepted, the third and fourth draw are what they were before: agent direction / next task's pool entry.
-        // top the ring up: a block whenever four slots are free (it never overwrites a draw that is still ahead:
-        // 4 * filled + 4 - nd <= kRing); an iteration consumes at most five draws
-        if (4 * filled - nd <= kRing - 4) produce();
+        topup();   // an iteration consumes at most five draws
         uint32_t d0, d1, d2, d3;
         if (nd + 4 <= 4 * filled) {
             d0 = io.draws[(nd & (kRing - 1)) * ds]; d1 = io.draws[((nd + 1) & (kRing - 1)) * ds];

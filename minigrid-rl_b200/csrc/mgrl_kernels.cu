@@ -519,8 +519,8 @@ __global__ void __launch_bounds__(TILE, TILE == 128 ? 4 : 7) step_kernel(const E
 // custom_env.py:319-328) the copy is issued before the step is computed.  Every slot is full when a launch starts and
 // when it ends (the generator warps drain the queue), so launches leave no requests behind.
 constexpr int kRowWords = 36;        // state row pitch in shared memory: 144 B = 16-byte aligned cp.async destination
-constexpr int kScratchWords = 37;    // generator scratch row pitch (odd: lane-per-row accesses are conflict free)
-constexpr int kMaxStepWarps = 14, kMaxGenWarps = 8;
+constexpr int kScratchWords = 35;    // generator scratch row pitch (odd: lane-per-row accesses are conflict free)
+constexpr int kMaxStepWarps = 14, kMaxGenWarps = 10;
 constexpr uint32_t kEnvBits = 9;     // request = env-in-tile (9 bits, <= 448) | slot << 9
 
 struct RolloutSmem {                 // byte offsets into the dynamic shared memory of one tile
@@ -764,9 +764,6 @@ __global__ void __launch_bounds__((kMaxStepWarps + kMaxGenWarps) * 32, 1) rollou
                 const uint32_t episode = E + (((uint32_t)j - E) & (uint32_t)(kDepth - 1));
                 generate_layout(sc, p.cfg, p.seed, p.env_id_base + (uint64_t)(tile0 + e), episode, gen + lane, p.tasks,
                                 p.task_row_words, prefix, empty);
-#pragma unroll
-                for (int i = 0; i < kGridWords; ++i) sc[i] &= kMarkMask;
-                sc[35] = 0u;
                 tagw = sc[33];
             }
             __syncwarp();
@@ -779,9 +776,11 @@ __global__ void __launch_bounds__((kMaxStepWarps + kMaxGenWarps) * 32, 1) rollou
                 const int q4 = c - r * (kSlotWords / 4);
                 const int er = __shfl_sync(FULL, e, r), jr = __shfl_sync(FULL, j, r);
                 if (valid) {
+                    // the next-to-a-door marks are stripped on the way out (grid words 0..30); word 35 is the record's pad
                     const uint32_t* src = scratch + r * kScratchWords + 4 * q4;
                     uint4 v;
-                    v.x = src[0]; v.y = src[1]; v.z = src[2]; v.w = src[3];
+                    v.x = src[0]; v.y = src[1]; v.z = src[2]; v.w = q4 == 8 ? 0u : src[3];
+                    if (q4 < 8) { v.x &= kMarkMask; v.y &= kMarkMask; v.z &= kMarkMask; if (q4 < 7) v.w &= kMarkMask; }
                     __stcg(reinterpret_cast<uint4*>(slot_ptr(p.slots, jr, p.n, tile0 + er)) + q4, v);
                 }
             }
@@ -1136,12 +1135,12 @@ int launch_env(const mgrl_env* e, int mode, const EnvParams& p, cudaStream_t s) 
 }
 
 // tile shape of the rollout kernel: one tile per SM when the environments fit one wave (14 step warps = 448 environments at
-// most), 4 generator warps per 7 step warps; MGRL_SW / MGRL_GW override (tuning)
+// most), 5 generator warps per 7 step warps (what shared memory allows next to 14 step warps); MGRL_SW / MGRL_GW override
 void rollout_shape(const mgrl_env* e, int* sw_out, int* gw_out) {
     const int per_sm = (e->cfg.num_envs + e->n_sms - 1) / e->n_sms;
     int sw = (per_sm + 31) / 32;
     sw = sw < 1 ? 1 : (sw > kMaxStepWarps ? kMaxStepWarps : sw);
-    int gw = (sw * 4 + 6) / 7;
+    int gw = (sw * 5 + 6) / 7;
     if (const char* v = getenv("MGRL_SW")) sw = atoi(v);
     if (const char* v = getenv("MGRL_GW")) gw = atoi(v);
     sw = sw < 1 ? 1 : (sw > kMaxStepWarps ? kMaxStepWarps : sw);
