@@ -137,6 +137,9 @@ int mgrl_state_ptr(mgrl_env *env, void **state_dev);
 int mgrl_observe(mgrl_env *env, uint8_t *image_dev, uint8_t *dir_dev, uint8_t *mission_dev, void *stream);
 /* replaces minigrid FullyObsWrapper (experts_test.py:29): image [N,size,size,3], agent = (10,0,dir) */
 int mgrl_full_obs(mgrl_env *env, uint8_t *image_dev, void *stream);
+/* the same into a host buffer image_host [N,S,S,3] (device-to-host copy inside, synchronous): what
+ * FullyObsWrapper.observation returns per environment at experts_test.py:27-30,46 */
+int mgrl_full_obs_host(mgrl_env *env, uint8_t *image_host, void *stream);
 /* max over environments of the per-env error byte (synchronises the stream) */
 int mgrl_error_flags(mgrl_env *env, int *flags_out, void *stream);
 

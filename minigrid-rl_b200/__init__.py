@@ -6,12 +6,12 @@ over a C-ABI CUDA library of hand-written sm_100a kernels (include/mgrl.h).  The
 CPU implementation in this package: every op raises if the CUDA library or a GPU is missing.
 """
 from .config import EnvConfig
-from .missions import MISSIONS, mission_id, mission_string, token_table, tokenize
+from .missions import MISSIONS, expert_token_table, mission_id, mission_string, token_table, tokenize
 from ._native import NativeError, lib, build_library, library_path
 from .vec_env import B200VecEnv, DeviceEnv
 
 __all__ = [
-    "EnvConfig", "MISSIONS", "mission_id", "mission_string", "token_table", "tokenize",
+    "EnvConfig", "MISSIONS", "expert_token_table", "mission_id", "mission_string", "token_table", "tokenize",
     "NativeError", "lib", "build_library", "library_path", "B200VecEnv", "DeviceEnv",
 ]
 from .policy import Policy  # noqa: E402

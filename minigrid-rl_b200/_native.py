@@ -57,6 +57,7 @@ _SIGNATURES = {
     "mgrl_state_ptr": (C.c_int, [vp, C.POINTER(vp)]),
     "mgrl_observe": (C.c_int, [vp, vp, vp, vp, vp]),
     "mgrl_full_obs": (C.c_int, [vp, vp, vp]),
+    "mgrl_full_obs_host": (C.c_int, [vp, vp, vp]),
     "mgrl_error_flags": (C.c_int, [vp, C.POINTER(C.c_int), vp]),
     "mgrl_stack_push": (C.c_int, [C.c_int] + [vp] * 9),
     "mgrl_gae": (C.c_int, [vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp, vp]),

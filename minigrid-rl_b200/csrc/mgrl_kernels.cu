@@ -1037,6 +1037,9 @@ struct DeviceGuard {
 
 }  // namespace
 
+// the library's one thread-local error text, shared with the policy translation units
+char* mgrl_error_buffer() { return g_err; }
+
 struct mgrl_env {
     mgrl_config cfg;
     EnvCfg ecfg;
@@ -1064,6 +1067,7 @@ struct mgrl_env {
     uint8_t *h_actions, *h_image, *h_dir, *h_mission, *h_term, *h_trunc, *h_eplen, *h_termimg, *h_termdir, *h_stack_img, *h_stack_dir;
     float* h_reward;
     int64_t *h_stack_mis, *h_table;
+    uint8_t* h_full;     // full-grid observation staging of mgrl_full_obs_host
     bool table_set;
 };
 
@@ -1326,7 +1330,7 @@ int mgrl_destroy(mgrl_env* e) {
     DeviceGuard guard(e->device);
     void* bufs[] = {e->states, e->slots, e->tags, e->qsave, e->qcount, e->glist, e->gcount, e->tasks, e->prefix, e->empty, e->lut, e->err_flags, e->h_actions, e->h_image,
                     e->h_termimg, e->h_reward, e->h_stack_img, e->h_stack_dir,
-                    e->h_stack_mis, e->h_table};
+                    e->h_stack_mis, e->h_table, e->h_full};
     for (void* b : bufs)
         if (b) cudaFree(b);
     delete e;
@@ -1452,6 +1456,18 @@ int mgrl_full_obs(mgrl_env* e, uint8_t* image, void* stream) {
     const int n = e->cfg.num_envs;
     full_obs_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(e->states, n, e->ecfg.size, image);
     CUDA_TRY(cudaGetLastError());
+    return MGRL_OK;
+}
+
+int mgrl_full_obs_host(mgrl_env* e, uint8_t* image_host, void* stream) {
+    if (!e || !image_host) return fail(MGRL_ERR_INVALID, "mgrl_full_obs_host: null argument%s");
+    DeviceGuard guard(e->device);
+    const size_t bytes = (size_t)e->cfg.num_envs * e->ecfg.size * e->ecfg.size * 3;
+    if (!e->h_full) CUDA_TRY(cudaMalloc(&e->h_full, bytes));
+    const int rc = mgrl_full_obs(e, e->h_full, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(image_host, e->h_full, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     return MGRL_OK;
 }
 
@@ -1591,6 +1607,9 @@ int mgrl_vec_step_host(mgrl_env* e, const uint8_t* actions_host, uint8_t* image_
     if (!e || !actions_host || !reward_host || !term_host || !trunc_host)
         return fail(MGRL_ERR_INVALID, "mgrl_vec_step_host: null argument%s");
     if (!e->host_ready) return fail(MGRL_ERR_INVALID, "mgrl_vec_step_host: call mgrl_vec_reset_host first%s");
+    if (!e->table_set) return fail(MGRL_ERR_INVALID, "mgrl_vec_step_host: call mgrl_set_token_table first%s");
+    if (e->cfg.obs_layout == MGRL_OBS_HWC148)
+        return fail(MGRL_ERR_INVALID, "mgrl_vec_step_host: the host path needs a 147-byte layout (CHW or HWC)%s");
     DeviceGuard guard(e->device);
     cudaStream_t s = (cudaStream_t)stream;
     const size_t n = (size_t)e->cfg.num_envs;

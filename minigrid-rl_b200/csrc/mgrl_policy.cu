@@ -27,6 +27,9 @@
 
 using namespace mgrl_policy;
 
+// one error buffer for the whole library (mgrl_kernels.cu): mgrl_last_error() and mgrl_policy_last_error() read the same text
+char* mgrl_error_buffer();
+
 namespace {
 
 constexpr int OB = 32;             // observations per CTA
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__(NT, 4) policy_forward_kernel(const PolicyArgs 
     }
 }
 
-thread_local char g_perr[256] = "";
+constexpr size_t kErrBytes = 512;
 
 // MGRL_CONV1_SIMT=1 selects the CUDA-core kernels of the update's first stage (kept for A/B measurements)
 bool conv1_tensor_cores() {
@@ -298,7 +301,7 @@ bool conv1_tensor_cores() {
 
 extern "C" {
 
-const char* mgrl_policy_last_error(void) { return g_perr; }
+const char* mgrl_policy_last_error(void) { return mgrl_error_buffer(); }
 
 int mgrl_policy_forward(const float* weights_dev, const uint8_t* frames_dev, const uint8_t* dirs_dev,
                         const uint8_t* mission_dev, const uint8_t* prev_age_dev, const uint8_t* prev_done_dev,
@@ -307,7 +310,7 @@ int mgrl_policy_forward(const float* weights_dev, const uint8_t* frames_dev, con
                         uint64_t env_id_base, uint32_t step, int flags, void* stream) {
     if (!weights_dev || !frames_dev || !dirs_dev || !mission_dev || !age_out_dev || !value_dev || num_envs <= 0 ||
         time_index < 3) {
-        snprintf(g_perr, sizeof g_perr, "mgrl_policy_forward: null argument, empty batch or time_index < 3");
+        snprintf(mgrl_error_buffer(), kErrBytes, "mgrl_policy_forward: null argument, empty batch or time_index < 3");
         return MGRL_ERR_INVALID;
     }
     PolicyArgs a;
@@ -328,7 +331,7 @@ int mgrl_policy_forward(const float* weights_dev, const uint8_t* frames_dev, con
         }
     }
     if (e != cudaSuccess) {
-        snprintf(g_perr, sizeof g_perr, "mgrl_policy_forward: %s", cudaGetErrorString(e));
+        snprintf(mgrl_error_buffer(), kErrBytes, "mgrl_policy_forward: %s", cudaGetErrorString(e));
         return MGRL_ERR_CUDA;
     }
     return MGRL_OK;
@@ -336,12 +339,12 @@ int mgrl_policy_forward(const float* weights_dev, const uint8_t* frames_dev, con
 
 int mgrl_policy_pack_fragments(float* weights_dev, void* stream) {
     if (!weights_dev) {
-        snprintf(g_perr, sizeof g_perr, "mgrl_policy_pack_fragments: null argument");
+        snprintf(mgrl_error_buffer(), kErrBytes, "mgrl_policy_pack_fragments: null argument");
         return MGRL_ERR_INVALID;
     }
     const cudaError_t e = launch_pack_fragments(weights_dev, (cudaStream_t)stream);
     if (e != cudaSuccess) {
-        snprintf(g_perr, sizeof g_perr, "mgrl_policy_pack_fragments: %s", cudaGetErrorString(e));
+        snprintf(mgrl_error_buffer(), kErrBytes, "mgrl_policy_pack_fragments: %s", cudaGetErrorString(e));
         return MGRL_ERR_CUDA;
     }
     return MGRL_OK;
@@ -588,7 +591,7 @@ int mgrl_conv1_pool_forward(const uint8_t* frames_dev, int num_envs, const int32
                             const uint8_t* age_dev, int batch, const float* w1_dev, const float* b1_dev, float* pooled_dev,
                             uint8_t* arg_dev, void* stream) {
     if (!frames_dev || !t_dev || !i_dev || !age_dev || !w1_dev || !b1_dev || !pooled_dev || !arg_dev || batch <= 0 || num_envs <= 0) {
-        snprintf(g_perr, sizeof g_perr, "mgrl_conv1_pool_forward: null argument or empty batch");
+        snprintf(mgrl_error_buffer(), kErrBytes, "mgrl_conv1_pool_forward: null argument or empty batch");
         return MGRL_ERR_INVALID;
     }
     Conv1Args a = {};
@@ -605,7 +608,7 @@ int mgrl_conv1_pool_forward(const uint8_t* frames_dev, int num_envs, const int32
             e = cudaGetLastError();
         }
     }
-    if (e != cudaSuccess) { snprintf(g_perr, sizeof g_perr, "mgrl_conv1_pool_forward: %s", cudaGetErrorString(e)); return MGRL_ERR_CUDA; }
+    if (e != cudaSuccess) { snprintf(mgrl_error_buffer(), kErrBytes, "mgrl_conv1_pool_forward: %s", cudaGetErrorString(e)); return MGRL_ERR_CUDA; }
     return MGRL_OK;
 }
 
@@ -613,7 +616,7 @@ int mgrl_conv1_pool_backward(const uint8_t* frames_dev, int num_envs, const int3
                              const uint8_t* age_dev, int batch, const uint8_t* arg_dev, const float* dpooled_dev, float* dw1_dev,
                              float* db1_dev, void* stream) {
     if (!frames_dev || !t_dev || !i_dev || !age_dev || !arg_dev || !dpooled_dev || !dw1_dev || !db1_dev || batch <= 0 || num_envs <= 0) {
-        snprintf(g_perr, sizeof g_perr, "mgrl_conv1_pool_backward: null argument or empty batch");
+        snprintf(mgrl_error_buffer(), kErrBytes, "mgrl_conv1_pool_backward: null argument or empty batch");
         return MGRL_ERR_INVALID;
     }
     Conv1Args a = {};
@@ -634,39 +637,39 @@ int mgrl_conv1_pool_backward(const uint8_t* frames_dev, int num_envs, const int3
             e = cudaGetLastError();
         }
     }
-    if (e != cudaSuccess) { snprintf(g_perr, sizeof g_perr, "mgrl_conv1_pool_backward: %s", cudaGetErrorString(e)); return MGRL_ERR_CUDA; }
+    if (e != cudaSuccess) { snprintf(mgrl_error_buffer(), kErrBytes, "mgrl_conv1_pool_backward: %s", cudaGetErrorString(e)); return MGRL_ERR_CUDA; }
     return MGRL_OK;
 }
 
 int mgrl_patch2x2_forward(const float* pooled_dev, int batch, float* patches_dev, void* stream) {
     if (!pooled_dev || !patches_dev || batch <= 0) {
-        snprintf(g_perr, sizeof g_perr, "mgrl_patch2x2_forward: null argument or empty batch");
+        snprintf(mgrl_error_buffer(), kErrBytes, "mgrl_patch2x2_forward: null argument or empty batch");
         return MGRL_ERR_INVALID;
     }
     const size_t total = (size_t)batch * 64;
     patch2x2_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(pooled_dev), reinterpret_cast<float4*>(patches_dev), batch);
     const cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { snprintf(g_perr, sizeof g_perr, "mgrl_patch2x2_forward: %s", cudaGetErrorString(e)); return MGRL_ERR_CUDA; }
+    if (e != cudaSuccess) { snprintf(mgrl_error_buffer(), kErrBytes, "mgrl_patch2x2_forward: %s", cudaGetErrorString(e)); return MGRL_ERR_CUDA; }
     return MGRL_OK;
 }
 
 int mgrl_patch2x2_backward(const float* dpatches_dev, int batch, float* dpooled_dev, void* stream) {
     if (!dpatches_dev || !dpooled_dev || batch <= 0) {
-        snprintf(g_perr, sizeof g_perr, "mgrl_patch2x2_backward: null argument or empty batch");
+        snprintf(mgrl_error_buffer(), kErrBytes, "mgrl_patch2x2_backward: null argument or empty batch");
         return MGRL_ERR_INVALID;
     }
     const size_t total = (size_t)batch * 36;
     patch2x2_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(dpatches_dev), reinterpret_cast<float4*>(dpooled_dev), batch);
     const cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { snprintf(g_perr, sizeof g_perr, "mgrl_patch2x2_backward: %s", cudaGetErrorString(e)); return MGRL_ERR_CUDA; }
+    if (e != cudaSuccess) { snprintf(mgrl_error_buffer(), kErrBytes, "mgrl_patch2x2_backward: %s", cudaGetErrorString(e)); return MGRL_ERR_CUDA; }
     return MGRL_OK;
 }
 
 int mgrl_lut_grad(const float* d_dev, const int64_t* rows_dev, int batch, int n_rows, float* out_dev, void* stream) {
     if (!d_dev || !rows_dev || !out_dev || batch <= 0 || n_rows <= 0 || n_rows > 400) {
-        snprintf(g_perr, sizeof g_perr, "mgrl_lut_grad: null argument, empty batch or more than 400 table rows");
+        snprintf(mgrl_error_buffer(), kErrBytes, "mgrl_lut_grad: null argument, empty batch or more than 400 table rows");
         return MGRL_ERR_INVALID;
     }
     cudaStream_t s = (cudaStream_t)stream;
@@ -684,13 +687,13 @@ int mgrl_lut_grad(const float* d_dev, const int64_t* rows_dev, int batch, int n_
                                                batch, n_rows, out_dev);
         e = cudaGetLastError();
     }
-    if (e != cudaSuccess) { snprintf(g_perr, sizeof g_perr, "mgrl_lut_grad: %s", cudaGetErrorString(e)); return MGRL_ERR_CUDA; }
+    if (e != cudaSuccess) { snprintf(mgrl_error_buffer(), kErrBytes, "mgrl_lut_grad: %s", cudaGetErrorString(e)); return MGRL_ERR_CUDA; }
     return MGRL_OK;
 }
 
 int mgrl_colsum(const float* g_dev, long long rows, int cols, float* out_dev, void* stream) {
     if (!g_dev || !out_dev || rows <= 0 || cols <= 0 || cols > 128) {
-        snprintf(g_perr, sizeof g_perr, "mgrl_colsum: null argument, empty matrix or more than 128 columns");
+        snprintf(mgrl_error_buffer(), kErrBytes, "mgrl_colsum: null argument, empty matrix or more than 128 columns");
         return MGRL_ERR_INVALID;
     }
     cudaStream_t s = (cudaStream_t)stream;
@@ -702,7 +705,7 @@ int mgrl_colsum(const float* g_dev, long long rows, int cols, float* out_dev, vo
         colsum_kernel<<<(unsigned)grid, 256, 0, s>>>(g_dev, rows, cols, out_dev);
         e = cudaGetLastError();
     }
-    if (e != cudaSuccess) { snprintf(g_perr, sizeof g_perr, "mgrl_colsum: %s", cudaGetErrorString(e)); return MGRL_ERR_CUDA; }
+    if (e != cudaSuccess) { snprintf(mgrl_error_buffer(), kErrBytes, "mgrl_colsum: %s", cudaGetErrorString(e)); return MGRL_ERR_CUDA; }
     return MGRL_OK;
 }
 

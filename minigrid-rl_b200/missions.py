@@ -48,3 +48,16 @@ def tokenize(text: str) -> np.ndarray:
 def token_table() -> np.ndarray:
     """[74, 32] int64: row = mission id."""
     return np.stack([tokenize(s) for s in MISSIONS])
+
+
+EXPERT_VOCAB = [" "] + [chr(c) for c in range(ord("a"), ord("z") + 1)]     # /root/reference/src/experts.py:181-182
+
+
+def expert_token_table() -> np.ndarray:
+    """[74, 32] int64 in the 27-symbol vocabulary that Expert.decode_missions decodes with (it differs from
+    TokenizeVocabWrapper's 32-symbol one, environment.py:74-80: a reference inconsistency)."""
+    out = np.zeros((N_MISSIONS, MSN_LEN), np.int64)
+    for i, text in enumerate(MISSIONS):
+        for k, ch in enumerate(text):
+            out[i, k] = EXPERT_VOCAB.index(ch)
+    return out

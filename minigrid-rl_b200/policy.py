@@ -304,6 +304,42 @@ class Policy:
         sd = self.torch.load(path, map_location="cpu")
         self.load_state_dict({k: sd[k] for k in self.params})
 
+    def save_sb3_zip(self, path: str, data: dict | None = None):
+        """An SB3 model archive (`BaseAlgorithm.save`, used at ppo.py:145-150 through EvalCallback / `model.save`): a zip with
+        `policy.pth` (the state dict under SB3's names, extractor aliases included), `pytorch_variables.pth`, `data` (JSON:
+        plain hyper-parameters only - SB3 pickles its class objects there, which cannot be produced without SB3),
+        `_stable_baselines3_version` and `system_info.txt`.  The reference picks the weights up with
+        `model.set_parameters(path, exact_match=False)` or `model.policy.load_state_dict(th.load(<policy.pth>))`."""
+        import io
+        import json
+        import zipfile
+        torch = self.torch
+
+        def blob(obj):
+            f = io.BytesIO()
+            torch.save(obj, f)
+            return f.getvalue()
+
+        with zipfile.ZipFile(path, "w", zipfile.ZIP_DEFLATED) as z:
+            z.writestr("data", json.dumps({"policy_class_name": "CustomPPOPolicy", "n_parameters": N_PARAMS,
+                                           "written_by": "minigrid-rl_b200", **(data or {})}, indent=1))
+            z.writestr("policy.pth", blob({k: v.cpu() for k, v in self.sb3_state_dict().items()}))
+            z.writestr("pytorch_variables.pth", blob({}))
+            z.writestr("_stable_baselines3_version", "2.0.0")
+            z.writestr("system_info.txt", "minigrid-rl_b200 (B200 device path); weights only\n")
+
+    def load_sb3_zip(self, path: str):
+        """Weights of an SB3 model archive (`PPO.load` / `model.save`, ppo.py:128-132,145-150): reads `policy.pth` from the
+        zip; the optimizer state and SB3's pickled `data` are not needed for the forward / update paths here."""
+        import io
+        import zipfile
+        with zipfile.ZipFile(path) as z:
+            sd = self.torch.load(io.BytesIO(z.read("policy.pth")), map_location="cpu")
+        missing = [k for k in self.params if k not in sd]
+        if missing:
+            raise KeyError(f"{path}: policy.pth lacks {missing[:3]}... (not a CustomPPOPolicy checkpoint?)")
+        self.load_state_dict({k: sd[k] for k in self.params})
+
     def load_oracle(self, oracle_policy):
         """copy the weights of an oracle.policy_oracle.OraclePolicy (tests)"""
         o = oracle_policy
@@ -338,6 +374,21 @@ class Policy:
                 names = ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0")
                 _, h = torch.func.functional_call(self._gru, {n: P[_PREFIX + "mission.mission_GRU_1." + n] for n in names}, (x,))
         return h[-1]
+
+    def mission_lut_f64(self):
+        """The table for the ROLLOUT kernel, evaluated in float64 and rounded once to float32.  The 128-step recurrence in
+        float32 (cuDNN) is off by up to 6e-6 from the exact table - six times the rest of the forward kernel's error and most
+        of the 1e-5 parity budget - while the float64 recurrence costs nothing next to a rollout (296 sequences).  No
+        gradient flows through this copy; the update differentiates `mission_lut`."""
+        torch = self.torch
+        if getattr(self, "_gru64", None) is None:
+            self._gru64 = torch.nn.GRU(32, 128, 1, True, True).to(self.device).double()
+        with torch.no_grad():
+            for n in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"):
+                getattr(self._gru64, n).copy_(self.params[_PREFIX + "mission.mission_GRU_1." + n])
+            x = torch.nn.functional.embedding(self.sequences, self.params[_PREFIX + "mission.mission_Embedding_0.weight"].double())
+            _, h = self._gru64(x)
+        return h[-1].float()
 
     def _mission_lut_side_stream(self):
         """The GRU over the 296 sequences is 128 dependent little steps (about 1.5 ms forward + backward, whatever the
@@ -448,8 +499,7 @@ class Policy:
         ba = torch.zeros(8, device=self.device); ba[:7] = P["action_net.bias"]
         put("WA", wa); put("BA", ba)
         put("WV", P["value_net.weight"]); put("BV", P["value_net.bias"])
-        with torch.no_grad():
-            put("LUT", self.mission_lut())
+        put("LUT", self.mission_lut_f64())
         self._packed = out.contiguous()
         if cuda:
             s = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -461,6 +511,10 @@ class Policy:
 
     def invalidate(self):
         self._packed = None
+
+    def kernel_name(self) -> str:
+        return ("policy_forward_tc_kernel (mma.sync m16n8k8 TF32, three-term split, fp32 accumulate)" if self.tensor_cores
+                else "policy_forward_kernel (fp32 CUDA cores)")
 
     def forward_rollout(self, frames, dirs, mission, time_index, prev_age, prev_done, age_out, value, action=None,
                         logp=None, logits=None, start_out=None, seed=0, env_id_base=0, step=0, deterministic=False):

@@ -126,6 +126,18 @@ class Updater:
                 dist.broadcast(p.data, src=0)
             policy.invalidate()
 
+    def describe(self) -> str:
+        return ("first extractor stage hand-written (mgrl_conv1_pool_*), patch gather, table and bias gradients hand-written; "
+                "remaining GEMMs / GRU table / loss through torch autograd on library kernels"
+                + ("; optimizer step replayed from a CUDA graph" if self.graphed else ""))
+
+    def all_reduces_per_step(self) -> int:
+        return 0 if self.world == 1 else 1 + int(self.cfg.normalize_advantage)
+
+    def release(self):
+        """drop the captured optimizer step (it must not outlive a process group it captured collectives of)"""
+        self._static = None
+
     def set_progress(self, progress_remaining: float):
         lr = self.schedule(progress_remaining)
         for g in self.opt.param_groups:
@@ -180,8 +192,25 @@ class Updater:
         return loss.detach(), parts
 
 
-    def minibatch_samples(self, buf, t, i):
-        """One optimizer step on the samples (t, i) of the rollout buffer `buf` (hand-written first stage).  With
+    def gradients(self, buf, t, i):
+        """Loss and the gradient of every parameter for the minibatch samples (t, i), through the same evaluation path an
+        optimizer step takes (no step is made): what the parity tests compare with the torch-CPU oracle."""
+        torch = self.torch
+        args = (buf["actions"][t, i], buf["values"][t, i], buf["logp"][t, i], buf["adv"][t, i], buf["ret"][t, i])
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = bool(self.cfg.update_tf32)
+        try:
+            with self.policy.fresh_leaves() as leaves:
+                loss, _ = ppo_minibatch_loss(self.policy, self.cfg, None, None, None, *args, None, (buf, t, i))
+                grads = torch.autograd.grad(loss, list(leaves.values()), allow_unused=True)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        return loss.detach(), {k: (g if g is not None else torch.zeros_like(p))
+                               for (k, p), g in zip(self.policy.params.items(), grads)}
+
+    def minibatch_samples(self, buf, t, i, eager: bool = False):
+        """One optimizer step on the samples (t, i) of the rollout buffer `buf` (hand-written first stage).  `eager`: do not
+        use (or disturb) the captured step - for the trailing partial minibatch of an epoch, whose shape differs.  With
         `graphed`, the step - gathers, forward, loss, backward, gradient clip, Adam - is replayed from CUDA graphs over
         static index tensors: three eager steps first (library workspaces, Adam state), then the capture.  One rank: one
         graph.  NCCL ranks: two graphs (gradients | clip + Adam) around the eager all-reduce of the flat gradient, the
@@ -228,7 +257,7 @@ class Updater:
             step_part()
             return out
 
-        if not self.graphed:
+        if not self.graphed or eager:
             args = (buf["actions"][t, i], buf["values"][t, i], buf["logp"][t, i], buf["adv"][t, i], buf["ret"][t, i])
             return self.minibatch(None, None, None, *args, samples=(buf, t, i))
         st = self._static
@@ -312,6 +341,9 @@ class RolloutEngine:
         self.prev_done = torch.ones(N, **u8)
         self.prev_age = torch.zeros(N, **u8)
         self.global_step = 0
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.num_timesteps = 0            # SB3's counter: env steps of all environments (all ranks) collected so far
+        self.records_logits = None        # [T, N, 7] logits of the rollout, kept when records are being collected
         self.updater = Updater(policy, cfg, dist)
         self.launches = 0
         self.reset()
@@ -331,7 +363,8 @@ class RolloutEngine:
             k = t + 3
             pol.forward_rollout(b["frames"], b["dirs"], b["mission"][k], k, self.prev_age, self.prev_done, b["age"][t],
                                 b["values"][t], b["actions"][t], b["logp"][t], start_out=b["start"][t], seed=self.seed,
-                                env_id_base=self.env_id_base, step=self.global_step, deterministic=deterministic)
+                                env_id_base=self.env_id_base, step=self.global_step, deterministic=deterministic,
+                                logits=None if self.records_logits is None else self.records_logits[t])
             env.step(b["actions"][t], b["frames"][k + 1], b["dirs"][k + 1], b["mission"][k + 1], b["rewards"][t],
                      b["term"][t], b["trunc"][t], b["ep_len"][t],
                      term_image=None if self.term_frames is None else self.term_frames[t],
@@ -342,6 +375,7 @@ class RolloutEngine:
                             b["values"][T], start_out=b["start"][T], seed=self.seed, env_id_base=self.env_id_base,
                             step=self.global_step)
         self.launches += 2 * T + 1
+        self.num_timesteps += T * self.N * self.world
 
     def bootstrap_truncated(self):
         """[UPSTREAM] collect_rollouts: reward += gamma * V(terminal_observation) where truncated and not terminated."""
@@ -386,11 +420,11 @@ class RolloutEngine:
         n_mb = 0
         for _ in range(cfg.n_epochs):
             perm = torch.randperm(total, device=b["adv"].device, generator=generator)
-            for s in range(0, total - bs + 1, bs):
+            for s in range(0, total, bs):        # like RolloutBuffer.get: the trailing partial minibatch is trained on too
                 idx = perm[s:s + bs]
                 t, i = idx // N, idx % N
                 if cfg.native_conv1 and b["frames"].is_cuda:
-                    self.updater.minibatch_samples(b, t, i)
+                    self.updater.minibatch_samples(b, t, i, eager=int(idx.numel()) != bs)
                 else:
                     args = (b["actions"][t, i], b["values"][t, i], b["logp"][t, i], b["adv"][t, i], b["ret"][t, i])
                     image, onehot, mrow = gather_minibatch(b, t, i)
@@ -398,24 +432,120 @@ class RolloutEngine:
                 n_mb += 1
         return n_mb
 
-    def evaluate(self, n_rollouts: int = 1, deterministic: bool = True):
-        """`evaluate_policy` / `test()` of the reference (ppo.py:161, 174-292) on the device: run the policy without
-        learning and summarise the episodes that finished: count, mean reward, success rate (reward > 0), mean length.
-        With several ranks the sums are all-reduced."""
+    # ---------------------------------------------------------------- evaluation / record collection (ppo.py:161, 174-292)
+    def _snapshot(self):
+        b = self.buf
+        return {"state": self.env.get_state().clone(), "seed": self.env.seed, "prev_age": self.prev_age.clone(),
+                "prev_done": self.prev_done.clone(), "global_step": self.global_step, "num_timesteps": self.num_timesteps,
+                "head": {k: b[k][0:4].clone() for k in ("frames", "dirs", "mission")}}
+
+    def _restore(self, snap):
+        b = self.buf
+        self.env.set_state(snap["state"], snap["seed"])
+        self.prev_age, self.prev_done = snap["prev_age"], snap["prev_done"]
+        self.global_step, self.num_timesteps = snap["global_step"], snap["num_timesteps"]
+        for k, v in snap["head"].items():
+            b[k][0:4].copy_(v)
+
+    def _fresh_episodes(self, seed):
+        """reset for an evaluation: the evaluation's own Philox key, first observation into the buffer"""
+        b = self.buf
+        self.env.reset(seed)
+        b["frames"][3].copy_(self.env.image); b["dirs"][3].copy_(self.env.dir); b["mission"][3].copy_(self.env.mission)
+        self.prev_done = self.torch.ones_like(self.prev_done)
+        self.prev_age = self.torch.zeros_like(self.prev_age)
+
+    def evaluate(self, n_eval_episodes_per_env: int = 1, deterministic: bool = True, seed: int | None = None,
+                 max_rollouts: int = 64):
+        """SB3 `evaluate_policy` (ppo.py:161; `test()` ppo.py:174-292) on the device: every environment is reset, then its
+        FIRST `n_eval_episodes_per_env` episodes count - whatever their length, so long (timed-out) episodes are not
+        under-represented - and nothing of the training state moves: environments, frame history, step counters and the
+        environment seed are restored afterwards.  Returns episodes, mean reward, success rate (reward > 0), mean length;
+        with several ranks the sums are all-reduced."""
         torch = self.torch
-        tot = torch.zeros(4, dtype=torch.float64, device=self.buf["rewards"].device)
-        for _ in range(n_rollouts):
+        dev = self.buf["rewards"].device
+        snap = self._snapshot()
+        self._fresh_episodes(self.seed + 0x5EED if seed is None else seed)
+        tot = torch.zeros(4, dtype=torch.float64, device=dev)
+        seen = torch.zeros(self.N, dtype=torch.int64, device=dev)
+        for _ in range(max_rollouts):
             self.collect(deterministic=deterministic)
             b = self.buf
             done = b["ep_len"] != 0
-            r = b["rewards"][done].double()
-            tot += torch.stack([done.sum().double(), r.sum(), (r > 0).sum().double(), b["ep_len"][done].double().sum()])
+            order = torch.cumsum(done.long(), dim=0) + seen[None, :]          # 1-based index of each finished episode
+            take = done & (order <= n_eval_episodes_per_env)
+            r = b["rewards"][take].double()
+            tot += torch.stack([take.sum().double(), r.sum(), (r > 0).sum().double(), b["ep_len"][take].double().sum()])
+            seen += done.sum(0)
             self.shift()
+            if bool((seen >= n_eval_episodes_per_env).all()):
+                break
+        self._restore(snap)
         if self.dist is not None and self.dist.get_world_size() > 1:
             self.dist.all_reduce(tot)
         n = max(float(tot[0]), 1.0)
         return {"episodes": int(tot[0]), "mean_reward": float(tot[1]) / n, "success_rate": float(tot[2]) / n,
                 "mean_length": float(tot[3]) / n}
+
+    def collect_records(self, min_records: int = 1, deterministic: bool = True, seed: int | None = None,
+                        max_rollouts: int = 16):
+        """The rollout collection of `test()` with cfg.collect_rollouts (ppo.py:176-183, 214-262, 279-289): the policy acts
+        (argmax unless `deterministic=False`), and every step of every episode that ENDED WITH A REWARD contributes one
+        record `(image [12,7,7] u8, direction [16] u8, mission [128] i64, policy [7] f32)` - the stacked observation the
+        policy saw and the action probabilities it produced.  Episodes are taken after a reset and must lie inside one
+        rollout window.  Returns a dict of numpy arrays (+ `t`, `env`, `episode_return`); `records_as_list` gives the
+        reference's pickled list-of-dicts form.  The training state is restored afterwards."""
+        torch = self.torch
+        dev = self.buf["rewards"].device
+        snap = self._snapshot()
+        self._fresh_episodes(self.seed + 0xC011EC7 if seed is None else seed)
+        self.records_logits = torch.zeros((self.T, self.N, 7), dtype=torch.float32, device=dev)
+        out = {k: [] for k in ("image", "direction", "mission", "policy", "t", "env", "episode_return")}
+        total = 0
+        try:
+            for _ in range(max_rollouts):
+                self.collect(deterministic=deterministic)
+                b, T, N = self.buf, self.T, self.N
+                t_end, i_end = torch.nonzero((b["ep_len"] != 0) & (b["rewards"] != 0), as_tuple=True)
+                length = b["ep_len"][t_end, i_end].long()
+                inside = t_end - length + 1 >= 0                                   # the whole episode is in this window
+                t_end, i_end, length = t_end[inside], i_end[inside], length[inside]
+                if t_end.numel():
+                    # all (t, env) of those episodes: t in [t_end - length + 1, t_end]
+                    rep = torch.repeat_interleave(torch.arange(t_end.numel(), device=dev), length)
+                    first = torch.cumsum(length, 0) - length
+                    t = t_end[rep] - length[rep] + 1 + (torch.arange(rep.numel(), device=dev) - first[rep])
+                    i = i_end[rep]
+                    image, onehot, mrow = gather_minibatch(b, t, i)
+                    out["image"].append(image.cpu().numpy()); out["direction"].append(onehot.cpu().numpy())
+                    out["mission"].append(self.policy.sequences[mrow].cpu().numpy())
+                    out["policy"].append(torch.softmax(self.records_logits[t, i], dim=1).cpu().numpy())
+                    out["t"].append(t.cpu().numpy()); out["env"].append(i.cpu().numpy())
+                    out["episode_return"].append(b["rewards"][t_end, i_end][rep].cpu().numpy())
+                    total += int(rep.numel())
+                self.shift()
+                if total >= min_records:
+                    break
+        finally:
+            self.records_logits = None
+            self._restore(snap)
+        empty = {"image": (0, 12, 7, 7), "direction": (0, 16), "mission": (0, 128), "policy": (0, 7)}
+        return {k: (np.concatenate(v) if v else np.zeros(empty.get(k, (0,)))) for k, v in out.items()}
+
+    @staticmethod
+    def records_as_list(records):
+        """ppo.py:279-289: [{'image': ..., 'direction': ..., 'mission': ..., 'policy': ...}] of nested lists"""
+        return [{k: records[k][j].tolist() for k in ("image", "direction", "mission", "policy")}
+                for j in range(len(records["policy"]))]
+
+    @staticmethod
+    def save_records(records, path: str = "rollouts/data.pkl"):
+        """the pickle file `test()` writes (ppo.py:267-292) and the distillation path reads"""
+        import os
+        import pickle
+        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+        with open(path, "wb") as f:
+            pickle.dump(RolloutEngine.records_as_list(records), f)
 
     def shift(self):
         """the last 4 frame slots of this rollout become the first 4 of the next"""
@@ -423,10 +553,14 @@ class RolloutEngine:
         for key in ("frames", "dirs", "mission"):
             b[key][0:4].copy_(b[key][T:T + 4].clone())
 
-    def iteration(self, progress_remaining: float = 1.0):
+    def iteration(self, progress_remaining: float | None = None):
+        """One PPO iteration.  Like SB3 (`_update_current_progress_remaining` before every `train()`), the learning rate
+        follows `linear_schedule` of 1 - num_timesteps / total_timesteps AFTER the rollout; pass a value to override."""
         self.collect()
         n_boot = self.bootstrap_truncated()
         self.compute_advantages()
+        if progress_remaining is None:
+            progress_remaining = max(0.0, 1.0 - self.num_timesteps / float(self.cfg.total_timesteps))
         self.updater.set_progress(progress_remaining)
         n_mb = self.update()
         self.shift()

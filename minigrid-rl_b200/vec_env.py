@@ -1,11 +1,15 @@
 """Vector-environment front-ends over the C-ABI CUDA library.
 
-`B200VecEnv` duck-types the Stable-Baselines3 `VecEnv` that the reference builds at
+`B200VecEnv` is the Stable-Baselines3 `VecEnv` that the reference builds at
 /root/reference/src/ppo.py:118-126 (make_vec_env(make_env) -> VecTransposeImage ->
-VecFrameStack(4, channels_order='first')) and drives at ppo.py:159,210,242: numpy in, numpy
-out, same observation dict (`image` (N,12,7,7) u8, `direction` (N,16) u8, `mission` (N,128)
+VecFrameStack(4, channels_order='first')) and drives at ppo.py:134,145,159,161,210,242,265,292: numpy in,
+numpy out, same observation dict (`image` (N,12,7,7) u8, `direction` (N,16) u8, `mission` (N,128)
 i64), float32 rewards, bool dones and SB3-style infos (`terminal_observation`,
-`TimeLimit.truncated`, `episode`).  It needs neither SB3 nor gymnasium nor torch.
+`TimeLimit.truncated`, `episode`).  When `stable_baselines3` / `gymnasium` are importable the class
+derives from SB3's `VecEnv` and its spaces are `gymnasium.spaces` objects (SB3's `_wrap_env`,
+`get_obs_shape`, `preprocess_obs` and `DictRolloutBuffer` check with isinstance); without them the
+same class stands on `object` with the duck-typed spaces below, so the package needs neither.
+`obs_mode="full"` is the experts' surface (experts_test.py:27-47: FullyObsWrapper + tokens).
 
 `DeviceEnv` is the device-resident fast path used by the rollout engine and the benchmark:
 torch CUDA tensors in and out, nothing crosses PCIe.
@@ -19,7 +23,7 @@ import numpy as np
 
 from . import _native as nat
 from .config import EnvConfig, PROBLEMS
-from .missions import MISSIONS, token_table
+from .missions import MISSIONS, expert_token_table, token_table
 
 OBS_BYTES = 147
 STATE_BYTES = 140
@@ -70,7 +74,40 @@ class _Handle:
             pass
 
 
-# ----------------------------------------------------------------------------- spaces (duck types)
+# ----------------------------------------------------------------------------- optional upstream base classes
+def gym_spaces():
+    """`gymnasium.spaces` when importable (looked up on every construction: cheap, and test-friendly), else None."""
+    try:
+        from gymnasium import spaces
+        return spaces
+    except Exception:
+        return None
+
+
+def sb3_vecenv_base():
+    """SB3's abstract `VecEnv` when importable, else `object`."""
+    try:
+        from stable_baselines3.common.vec_env import VecEnv
+        return VecEnv
+    except Exception:
+        return object
+
+
+def make_spaces(obs_mode: str = "stacked", size: int = 11):
+    """(observation_space, action_space) of the reference's env stack: gymnasium objects when available.
+    stacked: ppo.py:118-126 (after VecTransposeImage + VecFrameStack(4,'first')); full: experts_test.py:27-30."""
+    sp = gym_spaces()
+    box = (lambda lo, hi, shape, dt: sp.Box(low=lo, high=hi, shape=shape, dtype=dt)) if sp else Box
+    if obs_mode == "full":
+        spaces = {"direction": (sp.Discrete(4) if sp else Discrete(4)), "image": box(0, 255, (size, size, 3), np.uint8),
+                  "mission": box(0, 32, (32,), np.int64)}
+    else:
+        spaces = {"direction": box(0, 1, (4 * FRAMES,), np.uint8), "image": box(0, 255, (3 * FRAMES, 7, 7), np.uint8),
+                  "mission": box(0, 32, (32 * FRAMES,), np.int64)}
+    return (sp.Dict(spaces) if sp else DictSpace(spaces)), (sp.Discrete(7) if sp else Discrete(7))
+
+
+# ----------------------------------------------------------------------------- spaces (duck types, no gymnasium)
 class Box:
     def __init__(self, low, high, shape, dtype):
         self.low, self.high, self.shape, self.dtype = low, high, tuple(shape), np.dtype(dtype)
@@ -140,33 +177,48 @@ class _View:
         self.array = None
 
 
-_EMPTY_INFO: dict = {}
+import types  # noqa: E402
+
+_EMPTY_INFO = types.MappingProxyType({})      # read-only info of an environment that did not finish (large batches)
+_FRESH_INFO_LIMIT = 4096                      # up to this many environments every info is its own (mutable) dict
 
 
-class B200VecEnv:
-    """Drop-in for the reference's stacked SB3 VecEnv (host numpy surface)."""
+class _B200VecEnvImpl:
+    """Drop-in for the reference's stacked SB3 VecEnv (host numpy surface).  `B200VecEnv` below is this class over
+    SB3's `VecEnv` when that is importable, over `object` otherwise (`bind_vecenv_base`)."""
 
     metadata = {"render_modes": []}
+    _vecenv_base = object
 
     def __init__(self, cfg: EnvConfig | None = None, num_envs: int = 16, seed: int | None = None,
-                 device: int = 0, env_id_base: int = 0, n_frames_stack: int = 4, layout: str = "chw"):
+                 device: int = 0, env_id_base: int = 0, n_frames_stack: int = 4, layout: str = "chw",
+                 obs_mode: str = "stacked", token_vocab: str = "reference"):
         if n_frames_stack != FRAMES:
             raise ValueError("only n_frames_stack == 4 is built (hydra_configs/algorithm/ppo.yaml:5)")
+        if obs_mode not in ("stacked", "full"):
+            raise ValueError("obs_mode must be 'stacked' (ppo.py:118-126) or 'full' (experts_test.py:27-30)")
         self.cfg = cfg or EnvConfig()
-        self.num_envs = int(num_envs)
+        self.obs_mode = obs_mode
+        obs_space, act_space = make_spaces(obs_mode, self.cfg.size)
+        if self._vecenv_base is not object:
+            # SB3's VecEnv.__init__: num_envs, spaces, reset_infos, _seeds, _options, render_mode (via get_attr)
+            self._vecenv_base.__init__(self, int(num_envs), obs_space, act_space)
+        else:
+            self.num_envs, self.observation_space, self.action_space = int(num_envs), obs_space, act_space
+            self.reset_infos = [dict() for _ in range(int(num_envs))]
+            self._seeds = [None] * int(num_envs)
+            self._options = [dict() for _ in range(int(num_envs))]
+            self.render_mode = None
         self._seed = 0 if seed is None else int(seed)
         self.layout, self.pitch = layout, LAYOUTS[layout][1]     # "hwc148" serves step_frames only (fast records)
         self._h = _Handle(self.cfg, self.num_envs, device, env_id_base, layout)
         lib = self._h.lib
         self._table = np.ascontiguousarray(token_table())
+        # full mode: tokens in the reference wrapper's vocabulary (environment.py:74-80) or in the one Expert.decode_missions
+        # decodes with (experts.py:181-182; the two differ in the reference)
+        self._full_table = np.ascontiguousarray(expert_token_table() if token_vocab == "expert" else token_table())
         nat.check(lib.mgrl_set_token_table(self._h.ptr, self._table.ctypes.data_as(C.c_void_p)), "set_token_table")
         n = self.num_envs
-        self.observation_space = DictSpace({
-            "direction": Box(0, 1, (4 * FRAMES,), np.uint8),
-            "image": Box(0, 255, (3 * FRAMES, 7, 7), np.uint8),
-            "mission": Box(0, 32, (32 * FRAMES,), np.int64),
-        })
-        self.action_space = Discrete(7)
         # the stacked observation is double-buffered in pinned memory: the arrays returned
         # by step t stay valid until step t+2, and step t+1 reads the history frames of
         # info['terminal_observation'] from them without copying
@@ -191,26 +243,44 @@ class B200VecEnv:
             "term_image": _Pinned(lib, (n, 3, 7, 7), np.uint8),
         }
         self._frames = None
+        self._full = None
         self._actions = None
         self._t0 = time.time()
-        self.reset_infos = [dict() for _ in range(n)]
-        self.render_mode = None
 
     # ------------------------------------------------------------------ VecEnv protocol
     def seed(self, seed=None):
+        """SB3 semantics: env i is seeded with seed + i at its next reset (ppo.py:134 -> set_random_seed -> env.seed).
+        Here the one seed keys the Philox streams of all environments by (seed, global env id, episode)."""
         if seed is not None:
             self._seed = int(seed)
-        return [self._seed + i for i in range(self.num_envs)]
+        self._seeds = [self._seed + i for i in range(self.num_envs)]
+        return list(self._seeds)
+
+    def set_options(self, options=None):
+        self._options = [dict() for _ in range(self.num_envs)]      # PlaygroundEnv.reset takes no options
 
     def _obs(self):
         b = self._obs_bufs[self._cur]
         return {"direction": b["direction"].array, "image": b["image"].array, "mission": b["mission"].array}
 
     def reset(self):
+        self.reset_infos = [dict() for _ in range(self.num_envs)]
+        if self.obs_mode == "full":
+            img, d, m = self.reset_frames()
+            return self._full_obs(d, m)
         b = self._obs_bufs[self._cur]
         nat.check(self._h.lib.mgrl_vec_reset_host(
             self._h.ptr, self._seed, b["image"].ptr, b["direction"].ptr, b["mission"].ptr, None), "vec_reset")
         return self._obs()
+
+    def _full_obs(self, d, m):
+        """experts_test.py:27-30: FullyObsWrapper image (S,S,3) with the agent cell (10, 0, dir), integer direction,
+        mission tokens."""
+        if self._full is None:
+            S = self.cfg.size
+            self._full = _Pinned(self._h.lib, (self.num_envs, S, S, 3), np.uint8)
+        nat.check(self._h.lib.mgrl_full_obs_host(self._h.ptr, self._full.ptr, None), "full_obs_host")
+        return {"direction": d.astype(np.int64), "image": self._full.array, "mission": self._full_table[m]}
 
     def step_async(self, actions):
         a = np.asarray(actions)
@@ -222,6 +292,8 @@ class B200VecEnv:
         self._actions = a
 
     def step_wait(self):
+        if self.obs_mode == "full":
+            return self._step_wait_full()
         p = self._p
         prev = self._obs()           # terminal_observation needs the three frames before the terminal one
         self._cur ^= 1
@@ -232,22 +304,38 @@ class B200VecEnv:
             p["term_dir"].ptr, None), "vec_step")
         term, trunc = p["term"].array, p["trunc"].array
         dones = (term | trunc).astype(bool)
-        infos = [_EMPTY_INFO] * self.num_envs
-        now = time.time()
-        for i in np.flatnonzero(dones):
-            tdir = np.zeros(4, np.uint8)
-            tdir[p["term_dir"].array[i]] = 1
-            infos[i] = {
-                "terminal_observation": {
-                    "direction": np.concatenate([prev["direction"][i, 4:], tdir]),
-                    "image": np.concatenate([prev["image"][i, 3:], p["term_image"].array[i]], axis=0),
-                    "mission": np.concatenate([prev["mission"][i, 32:], prev["mission"][i, 96:]]),
-                },
-                "TimeLimit.truncated": bool(trunc[i] and not term[i]),
-                "episode": {"r": float(p["reward"].array[i]), "l": int(p["ep_len"].array[i]),
-                            "t": round(now - self._t0, 6)},
-            }
-        return self._obs(), p["reward"].array, dones, infos
+        return self._obs(), p["reward"].array, dones, self._infos(dones, prev)
+
+    def _infos(self, dones, prev):
+        """SB3 infos: `terminal_observation` (the stacked observation the finished episode ended on), `TimeLimit.truncated`
+        and Monitor's `episode` for finished environments; gathered for all of them at once, one dict each."""
+        p, n = self._p, self.num_envs
+        infos = [dict() for _ in range(n)] if n <= _FRESH_INFO_LIMIT else [_EMPTY_INFO] * n
+        idx = np.flatnonzero(dones)
+        if idx.size == 0:
+            return infos
+        t = round(time.time() - self._t0, 6)
+        trunc_only = (p["trunc"].array[idx] != 0) & (p["term"].array[idx] == 0)
+        rew, length = p["reward"].array[idx].tolist(), p["ep_len"].array[idx].tolist()
+        if prev is None:             # full mode: no terminal observation (the full grid of the finished episode is gone)
+            for k, i in enumerate(idx.tolist()):
+                infos[i] = {"TimeLimit.truncated": bool(trunc_only[k]), "episode": {"r": rew[k], "l": length[k], "t": t}}
+            return infos
+        tdir = np.zeros((idx.size, 4), np.uint8)
+        tdir[np.arange(idx.size), p["term_dir"].array[idx]] = 1
+        t_dir = np.concatenate([prev["direction"][idx, 4:], tdir], axis=1)
+        t_img = np.concatenate([prev["image"][idx, 3:], p["term_image"].array[idx]], axis=1)
+        t_mis = np.concatenate([prev["mission"][idx, 32:], prev["mission"][idx, 96:]], axis=1)
+        for k, i in enumerate(idx.tolist()):
+            infos[i] = {"terminal_observation": {"direction": t_dir[k], "image": t_img[k], "mission": t_mis[k]},
+                        "TimeLimit.truncated": bool(trunc_only[k]), "episode": {"r": rew[k], "l": length[k], "t": t}}
+        return infos
+
+    def _step_wait_full(self):
+        out = self.step_frames(self._p["actions"].array)
+        _, d, m, rew, term, trunc, _ = out
+        dones = (term | trunc).astype(bool)
+        return self._full_obs(d, m), rew, dones, self._infos(dones, None)
 
     def step(self, actions):
         self.step_async(actions)
@@ -296,6 +384,8 @@ class B200VecEnv:
         return out + ((f["term_image"].array, p["term_dir"].array) if want_terminal else ())
 
     def close(self):
+        if self._full is not None:
+            self._full.free()
         if self._frames is not None:
             for v in self._frames.values():
                 v.free()
@@ -308,13 +398,30 @@ class B200VecEnv:
         self._h.close()
 
     def render(self, mode=None):
-        raise NotImplementedError("rendering is outside the hot path")
+        """ppo.py:265 calls vec_env.render() when cfg.render is set.  There is no renderer on the device path (rendering is
+        out of scope); like an SB3 VecEnv whose render_mode is None this returns None."""
+        return None
+
+    def get_images(self):
+        return [None for _ in range(self.num_envs)]
+
+    def _indices(self, indices):
+        if indices is None:
+            return range(self.num_envs)
+        return [int(i) for i in np.atleast_1d(indices)]
 
     def env_is_wrapped(self, wrapper_class, indices=None):
-        return [False] * self.num_envs
+        return [False for _ in self._indices(indices)]
 
     def get_attr(self, name, indices=None):
-        idx = range(self.num_envs) if indices is None else np.atleast_1d(indices)
+        idx = self._indices(indices)
+        if name == "render_mode":        # (SB3's VecEnv.__init__ asks before the device handle exists)
+            return [None for _ in idx]
+        if name == "llm_description":    # environment.py:190
+            return [None for _ in idx]
+        if name in ("size", "width", "height", "max_steps"):
+            v = self.cfg.max_steps if name == "max_steps" else self.cfg.size
+            return [v for _ in idx]
         if name == "mission":
             st = self.get_state()
             return [MISSIONS[int(st["mission_id"][i])] for i in idx]
@@ -323,15 +430,18 @@ class B200VecEnv:
             if name == "agent_pos":
                 return [(int(st["agent_x"][i]), int(st["agent_y"][i])) for i in idx]
             return [int(st[name][i]) for i in idx]
-        if name == "render_mode":
-            return [None for _ in idx]
         raise AttributeError(name)
 
     def set_attr(self, name, value, indices=None):
         raise AttributeError(f"attribute {name} cannot be set on device-resident environments")
 
-    def env_method(self, name, *a, indices=None, **k):
-        raise AttributeError(f"env_method({name}) is not available on device-resident environments")
+    def env_method(self, method_name, *method_args, indices=None, **method_kwargs):
+        """The per-environment methods SB3 and the reference reach through the vec-env: `render`/`close`/`seed` are
+        tolerated as no-ops (one simulator owns all environments); anything else has no per-environment object."""
+        idx = self._indices(indices)
+        if method_name in ("render", "close", "seed", "get_wrapper_attr"):
+            return [None for _ in idx]
+        raise AttributeError(f"env_method({method_name}) is not available on device-resident environments")
 
     # ------------------------------------------------------------------ extras
     def get_state(self) -> np.ndarray:
@@ -352,6 +462,18 @@ class B200VecEnv:
 
     def mission_strings(self):
         return self.get_attr("mission")
+
+
+def bind_vecenv_base(base=None):
+    """The drop-in class over `base` (SB3's `VecEnv` when importable): what `B200VecEnv` is.  Exposed so that the
+    binding can be exercised against a stand-in base class in tests."""
+    base = sb3_vecenv_base() if base is None else base
+    if base is object:
+        return type("B200VecEnv", (_B200VecEnvImpl,), {"__doc__": _B200VecEnvImpl.__doc__})
+    return type("B200VecEnv", (_B200VecEnvImpl, base), {"_vecenv_base": base, "__doc__": _B200VecEnvImpl.__doc__})
+
+
+B200VecEnv = bind_vecenv_base()
 
 
 # ================================================================================= device path

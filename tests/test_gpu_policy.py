@@ -198,11 +198,98 @@ def test_one_ppo_iteration_updates_the_policy_and_matches_cpu_update():
     eng.env.close()
 
 
+def test_evaluate_counts_the_first_episodes_of_every_env_and_restores_the_training_state():
+    """evaluate_policy semantics (ppo.py:161): after a reset, exactly the first k episodes of every environment count; the
+    training state (environments, frame history, counters) is untouched."""
+    n, T = 512, 24
+    eng, _ = make_engine(n, T)
+    eng.collect(); eng.shift()
+    before = (eng.env.get_state().clone(), eng.buf["frames"][0:4].clone(), eng.global_step, eng.num_timesteps, eng.env.seed,
+              eng.prev_age.clone())
+    stats = eng.evaluate(2, deterministic=False)
+    assert stats["episodes"] == 2 * n and 0.0 <= stats["success_rate"] <= 1.0 and 1.0 <= stats["mean_length"] <= 121.0
+    assert torch.equal(eng.env.get_state(), before[0]) and torch.equal(eng.buf["frames"][0:4], before[1])
+    assert (eng.global_step, eng.num_timesteps, eng.env.seed) == before[2:5] and torch.equal(eng.prev_age, before[5])
+    # the continued rollout is the one that would have been collected without the evaluation
+    eng2, _ = make_engine(n, T)
+    eng2.collect(); eng2.shift()
+    eng.collect(); eng2.collect()
+    for k in ("frames", "actions", "rewards", "ep_len"):
+        assert torch.equal(eng.buf[k], eng2.buf[k]), k
+    eng.env.close(); eng2.env.close()
+
+
+def test_collect_records_matches_the_reference_record_format():
+    """ppo.py:214-262,279-289: records = every step of the episodes that ended with a reward: the stacked observation the
+    policy saw (rebuilt independently with the numpy SB3 wrappers) and its action probabilities (float64 oracle, 1e-5)."""
+    n, T = 256, 40
+    eng, o = make_engine(n, T, task="GTO")
+    o64 = po.double_copy(o)
+    rec = eng.collect_records(min_records=50, deterministic=False, seed=123)
+    R = len(rec["policy"])
+    assert R >= 50 and rec["image"].shape == (R, 12, 7, 7) and rec["direction"].shape == (R, 16)
+    assert rec["mission"].shape == (R, 128) and rec["mission"].dtype == np.int64 and rec["policy"].shape == (R, 7)
+    assert np.allclose(rec["policy"].sum(1), 1.0, atol=1e-5) and (rec["episode_return"] != 0).all()
+    # the same rollout again, with the whole buffer at hand
+    eng._fresh_episodes(123)
+    eng.records_logits = torch.zeros((T, n, 7), device="cuda")
+    eng.collect(deterministic=False)
+    b = eng.buf
+    stacks = oracle_stacks(b, T, n)
+    ep_len, rew = b["ep_len"].cpu().numpy(), b["rewards"].cpu().numpy()
+    want = set()
+    for t_end, i in zip(*np.nonzero((ep_len != 0) & (rew != 0))):
+        if t_end - int(ep_len[t_end, i]) + 1 >= 0:
+            want |= {(t, i) for t in range(t_end - int(ep_len[t_end, i]) + 1, t_end + 1)}
+    first = rec["t"] < T       # (all records of the first window)
+    got = set(zip(rec["t"][:len(want)].tolist(), rec["env"][:len(want)].tolist()))
+    assert got == want and first[:len(want)].all()
+    for j in range(0, len(want), 7):
+        t, i = int(rec["t"][j]), int(rec["env"][j])
+        img, d, mis = stacks[t]
+        assert np.array_equal(rec["image"][j], img[i]) and np.array_equal(rec["direction"][j], d[i]) and np.array_equal(rec["mission"][j], mis[i])
+        with torch.no_grad():
+            lo, _ = o64({"direction": torch.from_numpy(d[i:i + 1]), "image": torch.from_numpy(img[i:i + 1]), "mission": torch.from_numpy(mis[i:i + 1])})
+        probs = torch.softmax(lo, 1)[0].numpy()
+        assert np.abs(rec["policy"][j] - probs).max() <= 1e-5
+    lst = eng.records_as_list({k: v[:3] for k, v in rec.items()})
+    assert sorted(lst[0]) == ["direction", "image", "mission", "policy"] and len(lst[0]["image"]) == 12 and len(lst[0]["policy"]) == 7
+    eng.records_logits = None
+    eng.env.close()
+
+
+def test_checkpoint_written_here_reproduces_the_kernel_logits_in_the_reference_network(tmp_path):
+    """f3: SB3 archive -> reference network (oracle, under SB3's names) -> the logits / values the rollout kernel computes."""
+    import io
+    import zipfile
+    from tests.test_policy_cpu import oracle_from_sb3_state_dict
+    n, T = 384, 6
+    eng, _ = make_engine(n, T)
+    eng.iteration()                                     # weights that are not the initial ones
+    path = str(tmp_path / "b200.zip")
+    eng.policy.save_sb3_zip(path)
+    with zipfile.ZipFile(path) as z:
+        sd = torch.load(io.BytesIO(z.read("policy.pth")), map_location="cpu")
+    o64 = po.double_copy(oracle_from_sb3_state_dict(sd))
+    eng.reset()                                         # (oracle_stacks rebuilds the stacks of a rollout that starts at a reset)
+    eng.collect()
+    b = eng.buf
+    stacks = oracle_stacks(b, T, n)
+    logits = torch.zeros((n, 7), device="cuda"); val = torch.zeros(n, device="cuda")
+    age = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    for t in (1, T):
+        eng.policy.forward_rollout(b["frames"], b["dirs"], b["mission"][t + 3], t + 3, b["age"][t - 1], b["ep_len"][t - 1], age,
+                                   val, logits=logits)
+        img, d, mis = stacks[t]
+        with torch.no_grad():
+            lo, vo = o64({"direction": torch.from_numpy(d), "image": torch.from_numpy(img), "mission": torch.from_numpy(mis)})
+        assert close(logits.cpu(), lo) and close(val.cpu(), vo), t
+    eng.env.close()
+
+
 def test_deterministic_evaluation_takes_the_argmax():
     n, T = 512, 12
     eng, o = make_engine(n, T)
-    stats = eng.evaluate(1, deterministic=True)          # evaluate() shifts the buffers: recompute from the shifted rows
-    assert stats["episodes"] >= 0 and 0.0 <= stats["success_rate"] <= 1.0
     eng.collect(deterministic=True)
     b = eng.buf
     logits = torch.zeros((n, 7), device="cuda"); val = torch.zeros(n, device="cuda")
@@ -345,3 +432,90 @@ def test_graph_replayed_update_equals_eager_update():
         eng.env.close()
     for k in out[0]:
         assert torch.allclose(out[0][k], out[1][k], rtol=2e-3, atol=2e-5), k
+
+
+def _oracle_minibatch_grads(o, eng, t, i, stacks):
+    """loss and gradients of the torch-CPU oracle network for the samples (t, i) of the engine's rollout"""
+    b, cfg = eng.buf, eng.cfg
+    tc, ic = t.cpu().numpy(), i.cpu().numpy()
+    obs = {"image": torch.from_numpy(np.stack([stacks[a][0][e] for a, e in zip(tc, ic)])),
+           "direction": torch.from_numpy(np.stack([stacks[a][1][e] for a, e in zip(tc, ic)])),
+           "mission": torch.from_numpy(np.stack([stacks[a][2][e] for a, e in zip(tc, ic)]))}
+    dt = next(o.parameters()).dtype
+    args = [b[k][t, i].cpu() for k in ("actions", "values", "logp", "adv", "ret")]
+    args = [args[0]] + [a.to(dt) for a in args[1:]]
+    for p_ in o.parameters():
+        p_.grad = None
+    loss, _ = po.ppo_loss(o, obs, *args, cfg.clip_range, cfg.clip_range_vf, cfg.ent_coef, cfg.vf_coef)
+    loss.backward()
+    pre = "features_extractor.extractors."
+    mods = {pre + "direction.direction_Linear_0": o.direction[0], pre + "image.image_Conv2d_0": o.image[0],
+            pre + "image.image_Conv2d_3": o.image[3], pre + "image.image_Conv2d_5": o.image[5],
+            "mlp_extractor.policy_net.0": o.pi[0], "mlp_extractor.policy_net.2": o.pi[2],
+            "mlp_extractor.value_net.0": o.vf[0], "mlp_extractor.value_net.2": o.vf[2],
+            "action_net": o.action_net, "value_net": o.value_net}
+    g = {}
+    for k, m in mods.items():
+        g[k + ".weight"], g[k + ".bias"] = m.weight.grad, m.bias.grad
+    g[pre + "mission.mission_Embedding_0.weight"] = o.embedding.weight.grad
+    for nme in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"):
+        g[pre + "mission.mission_GRU_1." + nme] = getattr(o.gru, nme).grad
+    return loss.detach(), g
+
+
+@pytest.mark.parametrize("tf32,bound,bound_gru", [(False, 1e-4, 1e-3), (True, 5e-3, 5e-3)], ids=["fp32", "tf32"])
+def test_bench_sized_update_gradients_match_the_cpu_oracle(tf32, bound, bound_gru):
+    """The update path that bench.py runs - minibatches of >= 16 384 samples (hand-written first stage, patch gather,
+    table and bias gradients, split weight gradients) - against the torch-CPU oracle network evaluated in FLOAT64, which
+    runs the GRU over every stacked mission: PPO loss and the gradient of EVERY parameter, max |got - want| <= bound *
+    max |want| per tensor.  fp32: 1e-4, and 1e-3 for the mission branch (Embedding + GRU), whose gradient goes back
+    through the 128-step recurrence in float32 (measured 2.7e-4).  update_tf32=True (the reference's own setting,
+    ppo.py:29-32: TF32 matmuls): 5e-3, the error of 10-bit-mantissa products in the GEMMs (measured 1.8e-3)."""
+    n, T = 512, 32                                      # 16 384 samples = one minibatch of the native path
+    eng, o = make_engine(n, T, update_tf32=tf32)
+    assert n * T >= pol.NATIVE_MIN_ROWS
+    eng.collect(); eng.bootstrap_truncated(); eng.compute_advantages()
+    t = torch.arange(T, device="cuda").repeat_interleave(n)
+    i = torch.arange(n, device="cuda").repeat(T)
+    loss, got = eng.updater.gradients(eng.buf, t, i)
+    stacks = oracle_stacks(eng.buf, T, n)
+    lo, want = _oracle_minibatch_grads(po.double_copy(o), eng, t, i, stacks)
+    assert abs(loss.item() - lo.item()) <= max(bound, 1e-4) * max(1.0, abs(lo.item()))
+    worst = {}
+    for k, w in want.items():
+        err = float((got[k].cpu().double() - w).abs().max()) / max(float(w.abs().max()), 1e-12)
+        group = "mission branch" if "mission" in k else "other"
+        worst[group] = max(worst.get(group, 0.0), err)
+        assert err <= (bound_gru if "mission" in k else bound), (k, err)
+    print(f"update gradients vs float64 CPU oracle (tf32={tf32}): worst relative error {worst}")
+    eng.env.close()
+
+
+def test_graph_replayed_bench_sized_steps_match_cpu_adam():
+    """Five optimizer steps of the captured step (three eager, capture, replay) on one 16 384-sample minibatch against five
+    steps of the torch-CPU oracle + torch.optim.Adam + clip_grad_norm_ on the same samples."""
+    n, T = 512, 32
+    eng, o = make_engine(n, T)
+    assert eng.updater.graphed
+    eng.collect(); eng.bootstrap_truncated(); eng.compute_advantages()
+    t = torch.arange(T, device="cuda").repeat_interleave(n)
+    i = torch.arange(n, device="cuda").repeat(T)
+    stacks = oracle_stacks(eng.buf, T, n)
+    cfg = eng.cfg
+    opt = torch.optim.Adam(o.parameters(), lr=cfg.initial_learning_rate, eps=cfg.optim_eps)
+    eng.updater.set_progress(1.0)
+    for _ in range(5):
+        eng.updater.minibatch_samples(eng.buf, t, i)
+        _oracle_minibatch_grads(o, eng, t, i, stacks)
+        torch.nn.utils.clip_grad_norm_(o.parameters(), cfg.max_grad_norm)
+        opt.step()
+    assert eng.updater._static is not None and eng.updater._static["graph"] is not None
+    P = eng.policy.params
+    pairs = {"mlp_extractor.policy_net.0.weight": o.pi[0].weight, "mlp_extractor.value_net.2.bias": o.vf[2].bias,
+             "features_extractor.extractors.image.image_Conv2d_0.weight": o.image[0].weight,
+             "features_extractor.extractors.image.image_Conv2d_5.bias": o.image[5].bias,
+             "features_extractor.extractors.mission.mission_GRU_1.weight_hh_l0": o.gru.weight_hh_l0,
+             "action_net.weight": o.action_net.weight}
+    for k, w in pairs.items():
+        assert torch.allclose(P[k].detach().cpu(), w.detach(), rtol=1e-3, atol=2e-5), k
+    eng.env.close()

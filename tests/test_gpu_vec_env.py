@@ -109,3 +109,93 @@ def test_step_frames_host_path_matches_oracle():
             done = (o.term | o.trunc).astype(bool)
             assert np.array_equal(timg[done][:, :147].reshape(-1, 7, 7, 3), o.term_obs[done]), t
         env.close()
+
+
+def test_sb3_vecenv_binding_drives_collect_rollouts():
+    """ppo.py:134,159: the class bound over SB3's VecEnv base (a faithful stand-in here, tests/support/fake_sb3.py) with
+    gymnasium-style spaces goes through OnPolicyAlgorithm.collect_rollouts' use of the environment - spaces -> buffers,
+    step, infos, truncation bootstrap - and fills the same buffers as the oracle env behind the numpy SB3-wrapper oracle."""
+    import os
+    import sys
+    from tests.support import fake_sb3
+    from minigrid_rl_b200 import vec_env as ve
+    shim = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "upstream_shim")
+    sys.path.insert(0, shim)
+    try:
+        import gymnasium
+        cls = ve.bind_vecenv_base(fake_sb3.VecEnv)
+        kw = dict(problem="multi", mission=5)
+        n, T, gamma = 96, 160, 0.81
+        env = cls(mg.EnvConfig(**kw), num_envs=n, seed=5)
+    finally:
+        sys.path.remove(shim)
+    assert isinstance(env, fake_sb3.VecEnv) and isinstance(env.observation_space, gymnasium.spaces.Dict)
+    assert isinstance(env.observation_space["image"], gymnasium.spaces.Box) and isinstance(env.action_space, gymnasium.spaces.Discrete)
+    assert env.render_mode is None and env.render() is None and env.env_method("render") == [None] * n
+    assert env.env_is_wrapped(object) == [False] * n and len(env.reset_infos) == n
+
+    rs = np.random.RandomState(11)
+    plan = np.stack([biased_actions(rs, n) for _ in range(T)])
+    plan[:, ::2] = np.where(plan[:, ::2] == 6, 2, plan[:, ::2])           # half of the envs never say done: truncations happen
+    value_of = lambda obs: float(obs["image"].astype(np.float64).sum() % 97) / 97.0    # noqa: E731  a deterministic critic
+    buf, ep_info, last = fake_sb3.collect_rollouts(env, T, lambda t, obs: plan[t], value_of, gamma, seed=5)
+
+    # the same loop on the oracle env + numpy wrapper stack
+    o = orc.OracleVecEnv(orc.make_config(**kw), n, seed=5)
+    table = mg.token_table()
+    fs = (sb3_oracle.FrameStack(n, (3, 7, 7), np.uint8), sb3_oracle.FrameStack(n, (4,), np.uint8),
+          sb3_oracle.FrameStack(n, (32,), np.int64))
+    o.reset()
+    cur = (fs[0].reset(o.obs.transpose(0, 3, 1, 2)), fs[1].reset(sb3_oracle.one_hot_dir(o.dir)), fs[2].reset(table[o.mission]))
+    lut = orc.reward_lut(121)
+    want_eps, n_boot = [], 0
+    starts = np.ones(n, bool)
+    for t in range(T):
+        assert np.array_equal(buf["image"][t], cur[0]) and np.array_equal(buf["direction"][t], cur[1]), t
+        assert np.array_equal(buf["mission"][t], cur[2]) and np.array_equal(buf["episode_starts"][t], starts.astype(np.float32)), t
+        a = plan[t]
+        pre_mission = o.mission.copy()
+        tdir = np.zeros(n, np.uint8)
+        for i in range(n):
+            s = o.states[i:i + 1].copy()
+            orc.step_one(o.cfg, lut, s, int(a[i]))
+            tdir[i] = s["agent_dir"][0]
+        o.step(a.astype(np.uint8))
+        done = (o.term | o.trunc).astype(bool)
+        img, timg = fs[0].update(o.obs.transpose(0, 3, 1, 2), done, o.term_obs.transpose(0, 3, 1, 2))
+        d, tdirs = fs[1].update(sb3_oracle.one_hot_dir(o.dir), done, sb3_oracle.one_hot_dir(tdir))
+        m, tmis = fs[2].update(table[o.mission], done, table[pre_mission])
+        r = o.reward.copy()
+        for i in np.flatnonzero(done):
+            want_eps.append((t, int(i), float(o.reward[i]), int(o.ep_len[i])))
+            if o.trunc[i] and not o.term[i]:
+                r[i] += np.float32(gamma) * np.float32(value_of({"image": timg[int(i)], "direction": tdirs[int(i)], "mission": tmis[int(i)]}))
+                n_boot += 1
+        assert np.array_equal(buf["rewards"][t].view(np.uint32), r.view(np.uint32)), t
+        cur, starts = (img, d, m), done
+    assert ep_info == want_eps and n_boot > 0 and len(want_eps) > 100
+    env.close()
+
+
+@pytest.mark.parametrize("name", ["single_gtg_obst", "multi_gtg", "multi_gto", "multi_pkp"])
+def test_full_obs_mode_replays_the_reference_expert(name):
+    """experts_test.py:27-47 on the device path: `obs_mode="full"` must show the unmodified reference Expert exactly the
+    observations it saw on the reference env (tests/golden/expert_*.npz, oracle/gen_expert_golden.py), so that it takes
+    the same actions; rewards and episode ends follow."""
+    import json
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"expert_{name}.npz"))
+    kw = json.loads(bytes(z["cfg_json"]).decode())
+    for vocab, key in (("expert", "tokens_expert"), ("reference", "tokens")):
+        env = mg.B200VecEnv(mg.EnvConfig(**kw), num_envs=1, seed=int(z["seed"]), obs_mode="full", token_vocab=vocab)
+        S = int(z["size"])
+        assert tuple(env.observation_space["image"].shape) == (S, S, 3)
+        obs = env.reset()
+        for t in range(len(z["action"])):
+            assert np.array_equal(obs["image"][0], z["image"][t]), (name, t)
+            assert int(obs["direction"][0]) == int(z["dir"][t]) and np.array_equal(obs["mission"][0], z[key][t]), (name, t)
+            obs, rew, dones, infos = env.step(np.array([z["action"][t]]))
+            assert np.float32(rew[0]) == z["reward"][t] and bool(dones[0]) == bool(z["term"][t] or z["trunc"][t]), (name, t)
+            if dones[0]:
+                assert infos[0]["episode"]["r"] == float(z["reward"][t])
+        env.close()

@@ -77,3 +77,47 @@ def test_frame_stack_oracle_known_answers():
     s, term = fs.update(np.array([[3], [50]]), np.array([False, True]), np.array([[0], [12]]))
     assert s.tolist() == [[0, 1, 2, 3], [0, 0, 0, 50]]
     assert term[1].tolist() == [0, 10, 11, 12]
+
+
+def test_spaces_are_gymnasium_objects_when_gymnasium_is_importable():
+    """ppo.py:134: SB3 isinstance-checks the spaces against gymnasium.spaces; without gymnasium the duck types stand in."""
+    import os
+    import sys
+    from minigrid_rl_b200 import vec_env as ve
+    obs, act = ve.make_spaces()
+    if ve.gym_spaces() is None:
+        assert isinstance(obs, ve.DictSpace) and isinstance(act, ve.Discrete)
+    assert list(obs.keys()) == ["direction", "image", "mission"] and act.n == 7
+    shim = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "upstream_shim")
+    sys.path.insert(0, shim)
+    try:
+        import gymnasium
+        obs, act = ve.make_spaces()
+        assert isinstance(obs, gymnasium.spaces.Dict) and isinstance(obs["image"], gymnasium.spaces.Box)
+        assert isinstance(act, gymnasium.spaces.Discrete) and act.n == 7
+        assert tuple(obs["image"].shape) == (12, 7, 7) and obs["mission"].dtype == np.int64 and tuple(obs["direction"].shape) == (16,)
+        full, _ = ve.make_spaces("full", 9)
+        assert tuple(full["image"].shape) == (9, 9, 3) and isinstance(full["direction"], gymnasium.spaces.Discrete)
+    finally:
+        sys.path.remove(shim)
+        for k in [k for k in sys.modules if k == "gymnasium" or k.startswith("gymnasium.")]:
+            if getattr(sys.modules[k], "__file__", "") and shim in (sys.modules[k].__file__ or ""):
+                del sys.modules[k]
+
+
+def test_vecenv_class_binds_over_the_sb3_base_class():
+    from tests.support import fake_sb3
+    from minigrid_rl_b200 import vec_env as ve
+    cls = ve.bind_vecenv_base(fake_sb3.VecEnv)
+    assert issubclass(cls, fake_sb3.VecEnv) and cls._vecenv_base is fake_sb3.VecEnv
+    assert not getattr(cls, "__abstractmethods__", None)          # every abstract method of the base is implemented
+    plain = ve.bind_vecenv_base(object)
+    assert plain.__mro__[1] is ve._B200VecEnvImpl and fake_sb3.VecEnv not in plain.__mro__
+
+
+def test_expert_vocabulary_round_trip():
+    import minigrid_rl_b200 as mg
+    tab = mg.expert_token_table()
+    vocab = [" "] + [chr(c) for c in range(ord("a"), ord("z") + 1)]
+    for i, text in enumerate(mg.MISSIONS):
+        assert "".join(vocab[k] for k in tab[i]).rstrip() == text

@@ -89,3 +89,25 @@ def test_layouts_bit_exact(path):
             assert nd == int(want[i, ep]["reset_draws"])
             _assert_states_equal(st[0], want[i, ep], f"layout env={i} ep={ep}")
             assert np.array_equal(orc.gen_obs(cfg, st), z["obs"][i, ep])
+
+
+EXPERTS = sorted(glob.glob(os.path.join(GOLDEN, "expert_*.npz")))
+
+
+@pytest.mark.parametrize("path", EXPERTS, ids=[os.path.basename(p)[7:-4] for p in EXPERTS])
+def test_full_observation_matches_the_reference_expert_fixture(path):
+    """`mg_full_obs` (FullyObsWrapper as the reference runs it, experts_test.py:27-30) and the step dynamics under the
+    actions the UNMODIFIED reference Expert took (oracle/gen_expert_golden.py): every full-grid image, direction, token row,
+    reward and episode end."""
+    from minigrid_rl_b200 import missions
+    z = np.load(path)
+    env = orc.OracleVecEnv(_cfg(z), 1, seed=int(z["seed"]))
+    env.reset()
+    table, table_x = missions.token_table(), missions.expert_token_table()
+    for t in range(len(z["action"])):
+        assert np.array_equal(env.full_obs()[0], z["image"][t]), t
+        assert int(env.dir[0]) == int(z["dir"][t]), t
+        assert np.array_equal(table[env.mission[0]], z["tokens"][t]) and np.array_equal(table_x[env.mission[0]], z["tokens_expert"][t]), t
+        env.step(np.array([z["action"][t]], np.uint8))
+        assert env.reward[0] == z["reward"][t] and env.term[0] == z["term"][t] and env.trunc[0] == z["trunc"][t], t
+    assert (z["returns"] > 0).sum() >= 3          # the expert solves episodes (README.md:84-95 style rewards)

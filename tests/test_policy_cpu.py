@@ -61,6 +61,57 @@ def test_sb3_named_checkpoint_round_trip(tmp_path):
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
 
 
+def oracle_from_sb3_state_dict(sd):
+    """An OraclePolicy carrying the weights of an SB3 `policy.state_dict()` (the names CustomPPOPolicy has in the reference:
+    policies.py:59 for the extractor, SB3's mlp_extractor / action_net / value_net)."""
+    o = po.OraclePolicy()
+    pre = "features_extractor.extractors."
+    m = {pre + "direction.direction_Linear_0": o.direction[0], pre + "image.image_Conv2d_0": o.image[0],
+         pre + "image.image_Conv2d_3": o.image[3], pre + "image.image_Conv2d_5": o.image[5],
+         "mlp_extractor.policy_net.0": o.pi[0], "mlp_extractor.policy_net.2": o.pi[2],
+         "mlp_extractor.value_net.0": o.vf[0], "mlp_extractor.value_net.2": o.vf[2],
+         "action_net": o.action_net, "value_net": o.value_net}
+    with torch.no_grad():
+        for k, mod in m.items():
+            mod.weight.copy_(sd[k + ".weight"]); mod.bias.copy_(sd[k + ".bias"])
+        o.embedding.weight.copy_(sd[pre + "mission.mission_Embedding_0.weight"])
+        for n in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"):
+            getattr(o.gru, n).copy_(sd[pre + "mission.mission_GRU_1." + n])
+    return o
+
+
+def test_sb3_zip_archive_round_trip(tmp_path):
+    """ppo.py:128-132,145-150: a model archive written here is read the way SB3's load_from_zip_file reads one (zip members
+    `data` JSON + `*.pth` through torch.load), its policy.pth loads into the reference network under SB3's names and gives
+    the same logits / values; and an archive loads back into a fresh Policy."""
+    import io
+    import json
+    import zipfile
+    _, p = make_pair(seed=8)
+    path = str(tmp_path / "model.zip")
+    p.save_sb3_zip(path, data={"gamma": 0.81})
+    with zipfile.ZipFile(path) as z:
+        names = set(z.namelist())
+        assert {"data", "policy.pth", "pytorch_variables.pth", "_stable_baselines3_version"} <= names
+        assert json.loads(z.read("data").decode())["gamma"] == 0.81
+        params = {n[:-4]: torch.load(io.BytesIO(z.read(n)), map_location="cpu") for n in names if n.endswith(".pth")}
+    o = oracle_from_sb3_state_dict(params["policy"])
+    img, d, mis, mrow = random_stacked_obs(48, 4)
+    with torch.no_grad():
+        lo, vo = o({"image": img, "direction": d, "mission": mis})
+        lp, vp = p.evaluate(img, d, mrow)
+    assert torch.allclose(lp, lo, rtol=0, atol=2e-6) and torch.allclose(vp, vo, rtol=0, atol=2e-6)
+    q = pol.Policy("cpu", seed=123)
+    q.load_sb3_zip(path)
+    for k in p.params:
+        assert torch.equal(p.params[k].detach(), q.params[k].detach()), k
+    with pytest.raises(KeyError):
+        bad = str(tmp_path / "bad.zip")
+        with zipfile.ZipFile(bad, "w") as z:
+            f = io.BytesIO(); torch.save({"x": torch.zeros(1)}, f); z.writestr("policy.pth", f.getvalue())
+        q.load_sb3_zip(bad)
+
+
 def test_lut_network_equals_full_gru_oracle():
     o, p = make_pair()
     img, d, mis, mrow = random_stacked_obs(256, 0)
