@@ -311,6 +311,7 @@ def main():
                 el = float(tm.item())
             return world * n * e2e_steps / el
 
+        cfg = mg.EnvConfig.for_task(TASK)
         venv = mg.B200VecEnv(cfg, num_envs=n, seed=SEED, device=local_rank, env_id_base=rank * n, layout="hwc148")
         venv.reset_frames()
         v_frames = time_host(venv.step_frames)
@@ -318,6 +319,10 @@ def main():
         venv = mg.B200VecEnv(cfg, num_envs=n, seed=SEED, device=local_rank, env_id_base=rank * n)
         venv.reset()
         v_stacked = time_host(venv.step_arrays)
+        # the SB3 protocol itself: VecEnv.step with per-environment info dicts (terminal observations, Monitor episodes)
+        e2e_steps, saved = 8, e2e_steps
+        v_vecenv = time_host(lambda a: venv.step(a))
+        e2e_steps = saved
         venv.close()
         e2e = {"value": v_frames, "unit": "env-steps/s",
                "h2d_bytes_per_step": n * 1 * T, "d2h_bytes_per_step": n * (148 + 1 + 1 + 4 + 1 + 1 + 1) * T,
@@ -327,7 +332,10 @@ def main():
                "stacked": {"value": v_stacked, "unit": "env-steps/s",
                            "d2h_bytes_per_step": n * (4 * 147 + 16 + 128 * 8 + 4 + 1 + 1 + 1 + 147 + 1) * T,
                            "api": "B200VecEnv.step_arrays -> mgrl_vec_step_host (SB3 observation dict: 4-frame stack, "
-                                  "one-hot direction, int64 mission tokens)"}}
+                                  "one-hot direction, int64 mission tokens)"},
+               "vecenv_step": {"value": v_vecenv, "unit": "env-steps/s",
+                               "api": "B200VecEnv.step (the SB3 VecEnv protocol: stacked observation dict + one Python info dict "
+                                      "per finished environment); host-side Python, 8 vector steps"}}
 
     # PPO frames/sec (SB3 `time/fps`: env frames per wall second over rollout + update), BASELINE.json's second figure:
     # policy-in-the-loop rollout (2 launches per step) + GAE + n_epochs of minibatch updates, gradients all-reduced
