@@ -221,6 +221,60 @@ int mgrl_lut_grad(const float *d_dev, const int64_t *rows_dev, int batch, int n_
  * column sums of the row-major g_dev [rows, cols] f32 (cols <= 128); out_dev is overwritten. */
 int mgrl_colsum(const float *g_dev, long long rows, int cols, float *out_dev, void *stream);
 
+/* ---- PPO optimizer step, hand-written end to end (K5) --------------------------------- */
+/* Replaces SB3 `PPO.train` as the reference runs it (ppo.py:94-113,159 on CustomPPOPolicy, policies.py:21-120,227-257;
+ * hyper-parameters hydra_configs/algorithm/ppo.yaml:28-38): for one minibatch of rollout samples, the forward of
+ * extractor + MLPs + heads, the clipped-surrogate / clipped-value / entropy loss, every parameter gradient, the global-norm
+ * clip and the Adam step.  All kernels are in csrc/mgrl_update.cu (+ the first extractor stage of mgrl_policy_tc.cu); no
+ * library kernel runs inside these calls.
+ *   Parameters, gradients and Adam moments are caller-owned flat float buffers of MGRL_PPO_PARAMS entries in the order
+ *   of SB3's state dict as listed in minigrid-rl_b200/policy.py SHAPES (direction Linear, the three convolutions,
+ *   Embedding, GRU, policy_net, value_net, action_net, value_net).  sequences_dev [num_sequences,128] u8 are the
+ *   stacked mission token sequences (row = mission*4 + age). */
+#define MGRL_PPO_PARAMS 110216
+typedef struct mgrl_ppo mgrl_ppo;
+typedef struct {
+    const uint8_t *frames;   /* [T+4, N, 148] u8 un-stacked frame records (newest frame of sample (t, i) is record t+3) */
+    const uint8_t *dirs;     /* [T+4, N] */
+    const uint8_t *mission;  /* [T+4, N] mission ids */
+    const uint8_t *age;      /* [T+1, N] frames of history available (0..3) */
+    const uint8_t *actions;  /* [T, N] */
+    const float *values;     /* [T, N] old values */
+    const float *logp;       /* [T, N] old log-probabilities */
+    const float *adv;        /* [T, N] advantages (mgrl_gae) */
+    const float *ret;        /* [T, N] returns */
+    int num_envs;            /* N */
+} mgrl_rollout_view;
+typedef struct {
+    float clip_range, clip_range_vf /* < 0: no value clipping */, ent_coef, vf_coef;
+    int normalize_advantage; /* (adv - mean) / (std + 1e-8) with the minibatch moments of adv_sums_dev */
+    int strict_fp32;         /* 1: three-term split TF32 (fp32-class results); 0: one TF32 pass like ppo.py:29-32 */
+} mgrl_ppo_hyper;
+int mgrl_ppo_create(int device, int max_batch, int num_sequences, mgrl_ppo **out);
+int mgrl_ppo_destroy(mgrl_ppo *ctx);
+int mgrl_ppo_bind(mgrl_ppo *ctx, float *params_dev, float *grads_dev, float *adam_m_dev, float *adam_v_dev,
+                  const uint8_t *sequences_dev);
+/* GRU(Embedding(tokens)) final hidden state of every sequence -> lut_out_dev [num_sequences,128] (policies.py:61-67,87-93) */
+int mgrl_ppo_mission_table(mgrl_ppo *ctx, float *lut_out_dev, void *stream);
+/* (sum, sum of squares, count) in double of adv_dev[idx_dev[..]] for every consecutive minibatch of `batch` entries of
+ * idx_dev [total] -> sums_dev [ceil(total/batch)][3]: what the per-minibatch advantage normalisation needs; summed over
+ * ranks by the caller (one all-reduce per epoch). */
+int mgrl_ppo_moments(const float *adv_dev, const int32_t *idx_dev, int batch, long long total, double *sums_dev,
+                     void *stream);
+/* forward + loss + backward of the minibatch idx_dev [batch] (flat indices t*N + i): the flat gradient buffer is overwritten;
+ * loss_out_dev [4] (optional) = sums over the minibatch of policy loss, value loss and -entropy terms (divide by batch);
+ * logits_out_dev [batch,7] / values_out_dev [batch] optional. */
+int mgrl_ppo_gradients(mgrl_ppo *ctx, const mgrl_rollout_view *rollout, const int32_t *idx_dev, int batch,
+                       const double *adv_sums_dev, const mgrl_ppo_hyper *hyper, float *loss_out_dev,
+                       float *logits_out_dev, float *values_out_dev, void *stream);
+/* clip_grad_norm_(max_grad_norm) + Adam step number `step` (1-based) on the bound buffers; gradients are multiplied by
+ * grad_scale first (1 / world size after an all-reduce).  norm_out_dev (optional) receives the gradient norm. */
+int mgrl_ppo_apply(mgrl_ppo *ctx, float lr, float max_grad_norm, float grad_scale, float beta1, float beta2, float eps,
+                   int step, float *norm_out_dev, void *stream);
+/* device pointer of an internal activation buffer of the last mgrl_ppo_gradients call (tests): "pooled", "h2", "f", "a1",
+ * "a2", "dz2", "dz1", "df", "dh2", "dpooled", "lut", "dlut", "stats" */
+int mgrl_ppo_debug_buffer(mgrl_ppo *ctx, const char *name, void **out);
+
 /* ---- host-buffer drop-in path (what B200VecEnv.reset/step with numpy arrays calls) --- */
 
 /* VecEnv.reset(): stacked observation dict into host buffers; synchronous.

@@ -22,6 +22,16 @@ class Config(C.Structure):
                 ("obs_layout", C.c_int32), ("env_id_base", C.c_uint64)]
 
 
+class RolloutView(C.Structure):          # mgrl_rollout_view
+    _fields_ = [(n, C.c_void_p) for n in ("frames", "dirs", "mission", "age", "actions", "values", "logp", "adv", "ret")] + [
+        ("num_envs", C.c_int)]
+
+
+class PPOHyper(C.Structure):             # mgrl_ppo_hyper
+    _fields_ = [("clip_range", C.c_float), ("clip_range_vf", C.c_float), ("ent_coef", C.c_float), ("vf_coef", C.c_float),
+                ("normalize_advantage", C.c_int), ("strict_fp32", C.c_int)]
+
+
 def library_path() -> str:
     return _LIB
 
@@ -75,6 +85,14 @@ _SIGNATURES = {
     "mgrl_colsum": (C.c_int, [vp, C.c_longlong, C.c_int, vp, vp]),
     "mgrl_patch2x2_forward": (C.c_int, [vp, C.c_int, vp, vp]),
     "mgrl_patch2x2_backward": (C.c_int, [vp, C.c_int, vp, vp]),
+    "mgrl_ppo_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "mgrl_ppo_destroy": (C.c_int, [vp]),
+    "mgrl_ppo_bind": (C.c_int, [vp] * 6),
+    "mgrl_ppo_mission_table": (C.c_int, [vp, vp, vp]),
+    "mgrl_ppo_moments": (C.c_int, [vp, vp, C.c_int, C.c_longlong, vp, vp]),
+    "mgrl_ppo_gradients": (C.c_int, [vp, C.POINTER(RolloutView), vp, C.c_int, vp, C.POINTER(PPOHyper), vp, vp, vp, vp]),
+    "mgrl_ppo_apply": (C.c_int, [vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, vp, vp]),
+    "mgrl_ppo_debug_buffer": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
 }
 EXPORTS = sorted(_SIGNATURES)
 

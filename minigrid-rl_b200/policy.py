@@ -236,6 +236,23 @@ class Policy:
                 seq[age::4, f * 32:(f + 1) * 32] = tt
         self.sequences = seq.to(self.device)
         self._packed = None
+        self.flat = None                    # see flatten()
+
+    def flatten(self):
+        """Re-home every parameter as a view of ONE flat float32 buffer (order = SHAPES = `parameters()`), the layout the
+        hand-written optimizer step (csrc/mgrl_update.cu, MGRL_PPO_PARAMS) reads and writes.  The tensors in `params`
+        keep their identity, names and shapes."""
+        if self.flat is None:
+            torch = self.torch
+            flat = torch.empty(N_PARAMS, dtype=torch.float32, device=self.device)
+            o = 0
+            for v in self.params.values():
+                n = v.numel()
+                flat[o:o + n].copy_(v.detach().reshape(-1))
+                v.data = flat[o:o + n].view(v.shape)
+                o += n
+            self.flat = flat
+        return self.flat
 
     # ---------------------------------------------------------------- init (policies.py:246-257 + torch defaults)
     def _init(self, name, shape, g):
@@ -364,7 +381,7 @@ class Policy:
         torch = self.torch
         P = self._P()
         x = torch.nn.functional.embedding(self.sequences, P[_PREFIX + "mission.mission_Embedding_0.weight"])
-        if x.is_cuda and self._leaves is None:
+        if x.is_cuda and self._leaves is None and self.flat is None:   # (flatten_parameters would re-home the weights)
             self._gru.flatten_parameters()
         # cuDNN would run the GRU in TF32 by default; the table feeds the fp32 rollout kernel (parity bar 1e-5)
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=not self.fp32_strict):

@@ -44,6 +44,7 @@ class PPOConfig:                      # hydra_configs/algorithm/ppo.yaml:9-40
     update_tf32: bool = False         # True: the update's library GEMMs may use TF32 like the reference (ppo.py:29-32)
     native_conv1: bool = True         # first extractor stage of the update in the hand-written kernels (CUDA only)
     cuda_graph: bool = True           # replay the optimizer step (forward + backward + clip + Adam) from a CUDA graph
+    native_update: bool = True        # the whole optimizer step in hand-written kernels (csrc/mgrl_update.cu; CUDA only)
     total_timesteps: float = 2e7
 
 
@@ -313,6 +314,168 @@ class Updater:
         return st["out"]
 
 
+class NativeUpdater:
+    """The PPO optimizer step in hand-written kernels only (include/mgrl.h `mgrl_ppo_*`, csrc/mgrl_update.cu): forward of
+    extractor + MLPs + heads, loss, every gradient, global-norm clip and Adam for one minibatch of rollout samples, issued
+    as ~30 launches of this library on the current stream - no cuBLAS / cuDNN / torch kernel in between.  Parameters,
+    gradients and Adam moments live in flat buffers (`Policy.flatten`).  Data parallel: per epoch ONE all-reduce of the
+    advantage moments of all its minibatches, per optimizer step ONE all-reduce of the flat gradient."""
+
+    def __init__(self, policy: Policy, cfg: PPOConfig, dist=None, max_batch: int | None = None):
+        import ctypes as C
+        import torch
+        from . import _native as nat
+        self.torch, self.policy, self.cfg, self.dist, self.nat, self.C = torch, policy, cfg, dist, nat, C
+        self.world = dist.get_world_size() if dist is not None else 1
+        dev = policy.device
+        assert dev.type == "cuda", "the hand-written optimizer step needs CUDA (there is no CPU path)"
+        self.P = policy.flatten()
+        self.params = policy.parameters()
+        if dist is not None and self.world > 1:       # identical weights everywhere (rank 0's)
+            dist.broadcast(self.P, src=0)
+            policy.invalidate()
+        self.G = torch.zeros_like(self.P)
+        self.M = torch.zeros_like(self.P)
+        self.V = torch.zeros_like(self.P)
+        self.seq = policy.sequences.to(torch.uint8).contiguous()
+        self.max_batch, self._h = 0, None
+        self._ensure(int(max_batch or cfg.batch_size))
+        self.hyper = nat.PPOHyper(float(cfg.clip_range), float(-1.0 if cfg.clip_range_vf is None else cfg.clip_range_vf),
+                                  float(cfg.ent_coef), float(cfg.vf_coef), int(bool(cfg.normalize_advantage)),
+                                  int(not cfg.update_tf32))
+        self.schedule = linear_schedule(cfg.initial_learning_rate, cfg.final_learning_rate)
+        self.lr = float(cfg.initial_learning_rate)
+        self.steps = 0                      # Adam step counter
+        self.n_all_reduces = 0
+        self.graphed = False
+        self.stats = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.norm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.launches_per_step = 33
+
+    def _ensure(self, batch: int):
+        """(re)create the context so that its activation buffers hold `batch` samples (about 6.1 KB per sample)"""
+        if batch <= self.max_batch:
+            return
+        nat, C, torch = self.nat, self.C, self.torch
+        if self._h is not None:
+            torch.cuda.synchronize(self.policy.device)
+            nat.check(nat.lib().mgrl_ppo_destroy(self._h), "mgrl_ppo_destroy")
+            self._h = None
+        dev = self.policy.device
+        h = C.c_void_p()
+        index = dev.index if dev.index is not None else torch.cuda.current_device()
+        nat.check(nat.lib().mgrl_ppo_create(int(index), int(batch), int(self.seq.shape[0]), C.byref(h)), "mgrl_ppo_create")
+        self._h, self.max_batch = h, int(batch)
+        p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        nat.check(nat.lib().mgrl_ppo_bind(h, p(self.P), p(self.G), p(self.M), p(self.V), p(self.seq)), "mgrl_ppo_bind")
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h is not None:
+            try:
+                self.nat.lib().mgrl_ppo_destroy(h)
+            except Exception:
+                pass
+
+    def describe(self) -> str:
+        return ("hand-written end to end (mgrl_ppo_gradients + mgrl_ppo_apply: mma.sync TF32 GEMM kernels with fused epilogues, "
+                "register-resident GRU forward/backward, loss, clip + Adam; "
+                + ("three-term split, fp32-class" if self.hyper.strict_fp32 else "one TF32 pass like ppo.py:29-32") + ")")
+
+    def all_reduces_per_step(self) -> int:
+        return 0 if self.world == 1 else 1
+
+    def release(self):
+        pass
+
+    def set_progress(self, progress_remaining: float):
+        self.lr = float(self.schedule(progress_remaining))
+
+    def _stream(self):
+        return self.C.c_void_p(self.torch.cuda.current_stream(self.policy.device).cuda_stream)
+
+    def view(self, buf):
+        """mgrl_rollout_view of a RolloutEngine buffer dict"""
+        names = ("frames", "dirs", "mission", "age", "actions", "values", "logp", "adv", "ret")
+        for k in names:
+            assert buf[k].is_contiguous(), k
+        return self.nat.RolloutView(*[buf[k].data_ptr() for k in names], int(buf["frames"].shape[1]))
+
+    def moments(self, buf, idx32, batch: int):
+        """(sum, sum of squares, count) of the advantages of every consecutive minibatch of idx32, summed over all ranks"""
+        torch, C = self.torch, self.C
+        total = int(idx32.numel())
+        n_mb = (total + batch - 1) // batch
+        sums = torch.empty((n_mb, 3), dtype=torch.float64, device=idx32.device)
+        self.nat.check(self.nat.lib().mgrl_ppo_moments(C.c_void_p(buf["adv"].data_ptr()), C.c_void_p(idx32.data_ptr()), int(batch),
+                                                       total, C.c_void_p(sums.data_ptr()), self._stream()), "mgrl_ppo_moments")
+        if self.world > 1:
+            self.dist.all_reduce(sums)
+            self.n_all_reduces += 1
+        return sums
+
+    def gradients_native(self, view, idx32, sums_row, logits=None, values=None):
+        C = self.C
+        self._ensure(int(idx32.numel()))
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
+        self.nat.check(self.nat.lib().mgrl_ppo_gradients(self._h, C.byref(view), p(idx32), int(idx32.numel()), p(sums_row),
+                                                         C.byref(self.hyper), p(self.stats), p(logits), p(values), self._stream()),
+                       "mgrl_ppo_gradients")
+
+    def apply(self):
+        C = self.C
+        if self.world > 1:
+            self.dist.all_reduce(self.G)                 # ONE all-reduce of the gradients per optimizer step
+            self.n_all_reduces += 1
+        self.steps += 1
+        self.nat.check(self.nat.lib().mgrl_ppo_apply(self._h, self.lr, float(self.cfg.max_grad_norm), 1.0 / self.world, 0.9, 0.999,
+                                                     float(self.cfg.optim_eps), self.steps, C.c_void_p(self.norm.data_ptr()),
+                                                     self._stream()), "mgrl_ppo_apply")
+        self.policy.invalidate()
+
+    def minibatch_native(self, view, idx32, sums_row):
+        self.gradients_native(view, idx32, sums_row)
+        self.apply()
+
+    def loss_terms(self, batch: int):
+        """(loss, policy loss, value loss, -entropy) of the last minibatch, from the kernel's sums"""
+        s = self.stats / float(batch)
+        return s[0] + self.cfg.ent_coef * s[2] + self.cfg.vf_coef * s[1], (s[0], s[1], s[2])
+
+    def gradients(self, buf, t, i):
+        """Loss and the gradient of every parameter for the samples (t, i): what the parity tests compare with the oracle."""
+        torch = self.torch
+        N = int(buf["frames"].shape[1])
+        idx32 = (t.long() * N + i.long()).to(torch.int32).contiguous()
+        sums = self.moments(buf, idx32, int(idx32.numel())) if self.cfg.normalize_advantage else None
+        self.gradients_native(self.view(buf), idx32, None if sums is None else sums[0])
+        loss, _ = self.loss_terms(int(idx32.numel()))
+        out, o = {}, 0
+        for k, v in self.policy.params.items():
+            out[k] = self.G[o:o + v.numel()].view(v.shape).clone()
+            o += v.numel()
+        return loss.detach().clone(), out
+
+    def debug_buffer(self, name: str, shape, dtype=None):
+        """a copy of an internal activation buffer of the last gradients call (tests)"""
+        torch, C = self.torch, self.C
+        ptr = C.c_void_p()
+        self.nat.check(self.nat.lib().mgrl_ppo_debug_buffer(self._h, name.encode(), C.byref(ptr)), "mgrl_ppo_debug_buffer")
+        n = int(np.prod(shape))
+        out = torch.empty(n, dtype=torch.float32, device=self.policy.device)
+        torch.cuda.current_stream(self.policy.device).synchronize()
+        rc = torch.cuda.cudart().cudaMemcpy(out.data_ptr(), ptr.value, n * 4, 3)
+        assert int(rc) == 0, rc
+        return out.view(*shape)
+
+    def mission_table(self):
+        torch, C = self.torch, self.C
+        out = torch.empty((int(self.seq.shape[0]), 128), dtype=torch.float32, device=self.policy.device)
+        self.nat.check(self.nat.lib().mgrl_ppo_mission_table(self._h, C.c_void_p(out.data_ptr()), self._stream()),
+                       "mgrl_ppo_mission_table")
+        return out
+
+
 # ------------------------------------------------------------------------------------------- rollout (CUDA)
 class RolloutEngine:
     def __init__(self, env, policy: Policy, cfg: PPOConfig, dist=None, seed: int = 0, keep_terminal_frames: bool = True):
@@ -344,7 +507,9 @@ class RolloutEngine:
         self.world = dist.get_world_size() if dist is not None else 1
         self.num_timesteps = 0            # SB3's counter: env steps of all environments (all ranks) collected so far
         self.records_logits = None        # [T, N, 7] logits of the rollout, kept when records are being collected
-        self.updater = Updater(policy, cfg, dist)
+        self.native = bool(cfg.native_update and cfg.native_conv1 and dev.type == "cuda")
+        self.updater = (NativeUpdater(policy, cfg, dist, max_batch=min(cfg.batch_size, T * N)) if self.native
+                        else Updater(policy, cfg, dist))
         self.launches = 0
         self.reset()
 
@@ -418,6 +583,17 @@ class RolloutEngine:
         total = T * N
         bs = min(cfg.batch_size, total)
         n_mb = 0
+        if self.native:
+            up = self.updater
+            view = up.view(b)
+            for _ in range(cfg.n_epochs):
+                idx32 = torch.randperm(total, device=b["adv"].device, generator=generator).to(torch.int32)
+                sums = up.moments(b, idx32, bs) if cfg.normalize_advantage else None
+                for k, s in enumerate(range(0, total, bs)):      # the trailing partial minibatch is trained on too
+                    up.minibatch_native(view, idx32[s:s + bs], None if sums is None else sums[k])
+                    n_mb += 1
+            self.launches += n_mb * up.launches_per_step
+            return n_mb
         for _ in range(cfg.n_epochs):
             perm = torch.randperm(total, device=b["adv"].device, generator=generator)
             for s in range(0, total, bs):        # like RolloutBuffer.get: the trailing partial minibatch is trained on too

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Fixed launch sequence for ncu (deterministic -s/-c): reset, WARM rollout launches, then the launches to capture.
-   python profiles/prof_target.py many   -> step_kernel launches: 3 warm-up + 2 (T=128 steps per launch)
+   python profiles/prof_target.py many   -> rollout_kernel launches: 3 warm-up + 2 (T=128 steps per launch)
+   python profiles/prof_target.py gae    -> gae_kernel launches: 3 warm-up + 2 ([128, 65536] buffers)
    python profiles/prof_target.py step   -> step_kernel launches: 384 warm-up + 128 (one step per launch)
    python profiles/prof_target.py ppo    -> 2 rollouts of 32 steps: policy_forward_kernel + step_kernel per step"""
 import os
@@ -30,6 +31,12 @@ if mode == "ppo":      # policy_forward_kernel + step_kernel, two launches per r
                            keep_terminal_frames=False)
     for _ in range(2):
         eng.collect()
+elif mode == "gae":    # gae_kernel: 3 warm-up + 2 launches on bench-sized [T, N] buffers
+    r = torch.rand(T, n, device=dev); v = torch.randn(T, n, device=dev)
+    es = (torch.rand(T, n, device=dev) < 0.14).to(torch.uint8)
+    lv = torch.randn(n, device=dev); ld = torch.zeros(n, dtype=torch.uint8, device=dev)
+    for _ in range(5):
+        mg.vec_env.gae(r, v, es, lv, ld, 0.81, 0.945)
 elif mode == "many":
     for _ in range(5):
         env.step_many(actions, image, dirs, mis, rew, term, trunc, eplen)

@@ -11,10 +11,11 @@ $BENCH > gpurun_out/plain_bench_$TAG.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file gpurun_out/launches_bench_$TAG.csv $BENCH > gpurun_out/ncu_launches_bench_$TAG.log 2>&1
 echo "ncu launches bench rc=$?"
-for MODE in many step ppo; do
+for MODE in ${MODES:-many step ppo gae}; do
   python profiles/prof_target.py $MODE > gpurun_out/plain_${MODE}_$TAG.log 2>&1 || { echo "plain $MODE failed"; continue; }
   case $MODE in
-    many) K=step_kernel; SKIP=3; CNT=1;;
+    many) K=rollout_kernel; SKIP=3; CNT=1;;
+    gae)  K=gae_kernel; SKIP=3; CNT=1;;
     step) K=step_kernel; SKIP=400; CNT=1;;
     ppo)  K=policy_forward; SKIP=40; CNT=1;;
   esac

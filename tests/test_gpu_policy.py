@@ -163,7 +163,7 @@ def test_rollout_advantages_and_bootstrap_match_oracle():
 
 def test_one_ppo_iteration_updates_the_policy_and_matches_cpu_update():
     n, T = 256, 16
-    eng, o = make_engine(n, T, n_epochs=1)
+    eng, o = make_engine(n, T, n_epochs=1, native_update=False)
     before = {k: v.detach().clone() for k, v in eng.policy.params.items()}
     eng.collect(); eng.bootstrap_truncated(); eng.compute_advantages()
     # the same minibatch through the GPU updater and through the oracle network + torch.optim on the CPU
@@ -422,7 +422,7 @@ def test_graph_replayed_update_equals_eager_update():
     as the same minibatches stepped eagerly."""
     out = []
     for graph in (False, True):
-        eng, _ = make_engine(512, 32, n_epochs=1, cuda_graph=graph)
+        eng, _ = make_engine(512, 32, n_epochs=1, cuda_graph=graph, native_update=False)
         eng.cfg.batch_size = 2048                      # 8 optimizer steps
         assert eng.updater.graphed == graph
         eng.collect(); eng.compute_advantages()
@@ -463,8 +463,9 @@ def _oracle_minibatch_grads(o, eng, t, i, stacks):
     return loss.detach(), g
 
 
+@pytest.mark.parametrize("native", [True, False], ids=["handwritten", "autograd"])
 @pytest.mark.parametrize("tf32,bound,bound_gru", [(False, 1e-4, 1e-3), (True, 5e-3, 5e-3)], ids=["fp32", "tf32"])
-def test_bench_sized_update_gradients_match_the_cpu_oracle(tf32, bound, bound_gru):
+def test_bench_sized_update_gradients_match_the_cpu_oracle(tf32, bound, bound_gru, native):
     """The update path that bench.py runs - minibatches of >= 16 384 samples (hand-written first stage, patch gather,
     table and bias gradients, split weight gradients) - against the torch-CPU oracle network evaluated in FLOAT64, which
     runs the GRU over every stacked mission: PPO loss and the gradient of EVERY parameter, max |got - want| <= bound *
@@ -472,7 +473,8 @@ def test_bench_sized_update_gradients_match_the_cpu_oracle(tf32, bound, bound_gr
     through the 128-step recurrence in float32 (measured 2.7e-4).  update_tf32=True (the reference's own setting,
     ppo.py:29-32: TF32 matmuls): 5e-3, the error of 10-bit-mantissa products in the GEMMs (measured 1.8e-3)."""
     n, T = 512, 32                                      # 16 384 samples = one minibatch of the native path
-    eng, o = make_engine(n, T, update_tf32=tf32)
+    eng, o = make_engine(n, T, update_tf32=tf32, native_update=native)
+    assert isinstance(eng.updater, ppo.NativeUpdater) == native
     assert n * T >= pol.NATIVE_MIN_ROWS
     eng.collect(); eng.bootstrap_truncated(); eng.compute_advantages()
     t = torch.arange(T, device="cuda").repeat_interleave(n)
@@ -487,7 +489,7 @@ def test_bench_sized_update_gradients_match_the_cpu_oracle(tf32, bound, bound_gr
         group = "mission branch" if "mission" in k else "other"
         worst[group] = max(worst.get(group, 0.0), err)
         assert err <= (bound_gru if "mission" in k else bound), (k, err)
-    print(f"update gradients vs float64 CPU oracle (tf32={tf32}): worst relative error {worst}")
+    print(f"update gradients vs float64 CPU oracle (tf32={tf32}, hand-written step={native}): worst relative error {worst}")
     eng.env.close()
 
 
@@ -495,7 +497,7 @@ def test_graph_replayed_bench_sized_steps_match_cpu_adam():
     """Five optimizer steps of the captured step (three eager, capture, replay) on one 16 384-sample minibatch against five
     steps of the torch-CPU oracle + torch.optim.Adam + clip_grad_norm_ on the same samples."""
     n, T = 512, 32
-    eng, o = make_engine(n, T)
+    eng, o = make_engine(n, T, native_update=False)
     assert eng.updater.graphed
     eng.collect(); eng.bootstrap_truncated(); eng.compute_advantages()
     t = torch.arange(T, device="cuda").repeat_interleave(n)
@@ -518,4 +520,108 @@ def test_graph_replayed_bench_sized_steps_match_cpu_adam():
              "action_net.weight": o.action_net.weight}
     for k, w in pairs.items():
         assert torch.allclose(P[k].detach().cpu(), w.detach(), rtol=1e-3, atol=2e-5), k
+    eng.env.close()
+
+
+# ------------------------------------------------------------------------------ the hand-written optimizer step (K5)
+def test_handwritten_mission_table_matches_the_float64_gru():
+    """gru_fwd_kernel (W_hh in registers, two sequences per CTA) against torch's GRU evaluated in float64 on the 296 stacked
+    mission sequences: the table the update differentiates."""
+    eng, o = make_engine(64, 4)
+    assert isinstance(eng.updater, ppo.NativeUpdater)
+    got = eng.updater.mission_table().cpu().double()
+    want = eng.policy.mission_lut_f64().cpu().double()          # float64 recurrence, rounded once
+    err = float((got - want).abs().max()) / float(want.abs().max())
+    print(f"mission table vs float64 GRU: {err:.2e}")
+    assert err <= 1e-5
+    eng.env.close()
+
+
+@pytest.mark.parametrize("tf32,bound", [(False, 1e-5), (True, 3e-3)], ids=["fp32", "tf32"])
+def test_handwritten_update_forward_matches_the_cpu_oracle(tf32, bound):
+    """logits and values that the hand-written update computes for a minibatch (rows_gemm kernels + loss_kernel heads)
+    against the float64 oracle network on the SB3 stacks: 1e-5 with the three-term split, 3e-3 with one TF32 pass."""
+    n, T = 256, 16
+    eng, o = make_engine(n, T, update_tf32=tf32)
+    eng.collect(); eng.bootstrap_truncated(); eng.compute_advantages()
+    t = torch.arange(T, device="cuda").repeat_interleave(n)
+    i = torch.arange(n, device="cuda").repeat(T)
+    up = eng.updater
+    idx32 = (t * n + i).to(torch.int32)
+    logits = torch.empty((n * T, 7), device="cuda"); values = torch.empty(n * T, device="cuda")
+    sums = up.moments(eng.buf, idx32, n * T)
+    up.gradients_native(up.view(eng.buf), idx32, sums[0], logits, values)
+    stacks = oracle_stacks(eng.buf, T, n)
+    obs = {"direction": torch.from_numpy(np.concatenate([s[1] for s in stacks[:T]])),
+           "image": torch.from_numpy(np.concatenate([s[0] for s in stacks[:T]])),
+           "mission": torch.from_numpy(np.concatenate([s[2] for s in stacks[:T]]))}
+    with torch.no_grad():
+        wl, wv = po.double_copy(o)(obs)
+    el = float((logits.cpu().double() - wl).abs().max()) / float(wl.abs().max())
+    ev = float((values.cpu().double() - wv).abs().max()) / float(wv.abs().max())
+    print(f"hand-written update forward vs float64 oracle (tf32={tf32}): logits {el:.2e} values {ev:.2e}")
+    assert el <= bound and ev <= bound
+    # the minibatch advantage moments (double sums) against numpy
+    a = eng.buf["adv"].cpu().numpy().astype(np.float64).reshape(-1)
+    assert np.allclose(sums.cpu().numpy()[0], [a.sum(), (a * a).sum(), a.size], rtol=1e-12)
+    eng.env.close()
+
+
+def test_handwritten_steps_match_cpu_adam():
+    """Five optimizer steps of mgrl_ppo_gradients + mgrl_ppo_apply on one 16 384-sample minibatch against five steps of the
+    torch-CPU oracle + clip_grad_norm_ + torch.optim.Adam on the same samples."""
+    n, T = 512, 32
+    eng, o = make_engine(n, T)
+    up = eng.updater
+    assert isinstance(up, ppo.NativeUpdater)
+    eng.collect(); eng.bootstrap_truncated(); eng.compute_advantages()
+    t = torch.arange(T, device="cuda").repeat_interleave(n)
+    i = torch.arange(n, device="cuda").repeat(T)
+    idx32 = (t * n + i).to(torch.int32)
+    stacks = oracle_stacks(eng.buf, T, n)
+    cfg = eng.cfg
+    opt = torch.optim.Adam(o.parameters(), lr=cfg.initial_learning_rate, eps=cfg.optim_eps)
+    up.set_progress(1.0)
+    view = up.view(eng.buf)
+    sums = up.moments(eng.buf, idx32, n * T)
+    for _ in range(5):
+        up.minibatch_native(view, idx32, sums[0])
+        _oracle_minibatch_grads(o, eng, t, i, stacks)
+        torch.nn.utils.clip_grad_norm_(o.parameters(), cfg.max_grad_norm)
+        opt.step()
+    P = eng.policy.params
+    pairs = {"mlp_extractor.policy_net.0.weight": o.pi[0].weight, "mlp_extractor.value_net.2.bias": o.vf[2].bias,
+             "features_extractor.extractors.image.image_Conv2d_0.weight": o.image[0].weight,
+             "features_extractor.extractors.image.image_Conv2d_3.weight": o.image[3].weight,
+             "features_extractor.extractors.image.image_Conv2d_5.bias": o.image[5].bias,
+             "features_extractor.extractors.direction.direction_Linear_0.weight": o.direction[0].weight,
+             "features_extractor.extractors.mission.mission_Embedding_0.weight": o.embedding.weight,
+             "features_extractor.extractors.mission.mission_GRU_1.weight_hh_l0": o.gru.weight_hh_l0,
+             "features_extractor.extractors.mission.mission_GRU_1.weight_ih_l0": o.gru.weight_ih_l0,
+             "action_net.weight": o.action_net.weight, "value_net.bias": o.value_net.bias}
+    for k, w in pairs.items():
+        assert torch.allclose(P[k].detach().cpu(), w.detach(), rtol=1e-3, atol=2e-5), k
+    eng.env.close()
+
+
+def test_handwritten_iteration_runs_ragged_minibatches_and_keeps_parameter_views():
+    """A full iteration through RolloutEngine.update with a batch size that leaves a trailing partial minibatch; the
+    parameters stay views of the flat buffer (state-dict names and shapes unchanged) and the rollout kernel picks the new
+    weights up."""
+    n, T = 200, 12                                      # 2400 samples, minibatches of 1000 -> 1000, 1000, 400
+    eng, _ = make_engine(n, T, n_epochs=2)
+    eng.cfg.batch_size = 1000
+    before = eng.policy.flat.clone()
+    stats = eng.iteration(0.5)
+    assert stats["minibatches"] == 6
+    assert eng.updater.steps == 6
+    assert not torch.equal(before, eng.policy.flat)
+    o = 0
+    for k, v in eng.policy.params.items():
+        assert v.shape == torch.Size(pol.SHAPES[k]) and torch.isfinite(v).all(), k
+        assert v.data_ptr() == eng.policy.flat.data_ptr() + 4 * o, k
+        o += v.numel()
+    eng.collect()                                       # repacks the weights for the forward kernel
+    assert torch.isfinite(eng.buf["values"]).all()
+    assert eng.env.error_flags() == 0
     eng.env.close()
