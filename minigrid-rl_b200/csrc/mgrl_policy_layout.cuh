@@ -65,6 +65,7 @@ struct Conv1Args {
     float* dw1;              // backward: [16][48] accumulated with atomics (caller zeroes)
     float* db1;              // backward: [16]
     int n, B;
+    int onepass;             // tensor-core kernels: 1 = one TF32 pass instead of the two-term split (update_tf32)
 };
 
 // mgrl_policy_tc.cu: the tensor-core forward and the fragment packing of its weights (section of MGRL_POLICY_FRAGMENTS

@@ -507,6 +507,8 @@ __device__ __forceinline__ void stage_samples_async(const Conv1Args& p, int s0, 
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+// ONEPASS: one TF32 pass (weights rounded to TF32, the low term of the split dropped): what `update_tf32` asks for
+template <bool ONEPASS>
 __global__ void __launch_bounds__(NT, 4) conv1_pool_fwd_tc_kernel(const Conv1Args p) {
     __shared__ __align__(16) uint8_t s_px[OBC * SAMPLE_BYTES];
     __shared__ __align__(16) float4 s_c1[6 * 2 * 32];
@@ -551,7 +553,7 @@ __global__ void __launch_bounds__(NT, 4) conv1_pool_fwd_tc_kernel(const Conv1Arg
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt) {
                     const float4 b = s_c1[(kt * 2 + nt) * 32 + lane];
-                    mma8(cur[nt], a, __float_as_uint(b.z), __float_as_uint(b.w));
+                    if (!ONEPASS) mma8(cur[nt], a, __float_as_uint(b.z), __float_as_uint(b.w));
                     mma8(cur[nt], a, __float_as_uint(b.x), __float_as_uint(b.y));
                 }
             }
@@ -581,6 +583,7 @@ __global__ void __launch_bounds__(NT, 4) conv1_pool_fwd_tc_kernel(const Conv1Arg
     }
 }
 
+template <bool ONEPASS>
 __global__ void __launch_bounds__(NT, 4) conv1_pool_bwd_tc_kernel(const Conv1Args p) {
     __shared__ __align__(16) uint8_t s_px[OBC * SAMPLE_BYTES];
     __shared__ float s_acc[16 * 56];
@@ -629,10 +632,10 @@ __global__ void __launch_bounds__(NT, 4) conv1_pool_bwd_tc_kernel(const Conv1Arg
 #pragma unroll
                     for (int nt = 0; nt < 6; ++nt) {
                         const uint32_t b0 = byte_to_float_bits(pa[koff[nt] + cell]), b1 = byte_to_float_bits(pb[koff[nt] + cell]);
-                        mma8(acc[nt], a.lo, b0, b1);
+                        if (!ONEPASS) mma8(acc[nt], a.lo, b0, b1);
                         mma8(acc[nt], a.hi, b0, b1);
                     }
-                    mma8(acc[6], a.lo, one, one);
+                    if (!ONEPASS) mma8(acc[6], a.lo, one, one);
                     mma8(acc[6], a.hi, one, one);
                 }
             }
@@ -681,13 +684,16 @@ cudaError_t launch_policy_forward_tc(const PolicyArgs& a, cudaStream_t stream) {
 }
 
 cudaError_t launch_conv1_pool_fwd_tc(const Conv1Args& a, cudaStream_t stream) {
-    conv1_pool_fwd_tc_kernel<<<(a.B + OBC - 1) / OBC, NT, 0, stream>>>(a);
+    if (a.onepass) conv1_pool_fwd_tc_kernel<true><<<(a.B + OBC - 1) / OBC, NT, 0, stream>>>(a);
+    else conv1_pool_fwd_tc_kernel<false><<<(a.B + OBC - 1) / OBC, NT, 0, stream>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t launch_conv1_pool_bwd_tc(const Conv1Args& a, cudaStream_t stream) {   // dw1 / db1 zeroed by the caller
     const int nchunks = (a.B + OBC - 1) / OBC;
-    conv1_pool_bwd_tc_kernel<<<nchunks < 148 * 4 ? nchunks : 148 * 4, NT, 0, stream>>>(a);
+    const int grid = nchunks < 148 * 4 ? nchunks : 148 * 4;
+    if (a.onepass) conv1_pool_bwd_tc_kernel<true><<<grid, NT, 0, stream>>>(a);
+    else conv1_pool_bwd_tc_kernel<false><<<grid, NT, 0, stream>>>(a);
     return cudaGetLastError();
 }
 

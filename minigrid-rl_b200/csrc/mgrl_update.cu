@@ -85,9 +85,9 @@ struct PackDesc {
 };
 __host__ __device__ inline PackDesc pack_desc(int pk) {
     // entries per group = KT * NT * 32
-    const int g[PK_COUNT] = {1, 1, 2, 2, 2, 2, 2, 1};
+    const int g[PK_COUNT] = {1, 1, 1, 2, 2, 2, 1, 1};
     const int kt[PK_COUNT] = {8, 16, 26, 8, 8, 16, 8, 4};
-    const int nt[PK_COUNT] = {4, 8, 8, 8, 8, 13, 8, 8};
+    const int nt[PK_COUNT] = {4, 8, 16, 8, 8, 13, 16, 8};
     PackDesc d;
     int base = 0;
     for (int i = 0; i < pk; ++i) base += g[i] * kt[i] * nt[i] * 32;
@@ -103,11 +103,11 @@ __device__ __forceinline__ float pack_source(const float* __restrict__ P, int pk
     switch (pk) {
         case PK_C2F: { const int kk = k >> 4, ci = k & 15; return P[P_WC2 + n * 64 + ci * 4 + kk]; }            // k = kk*16+ci, n = co
         case PK_C3F: { const int kk = k >> 5, ci = k & 31; return P[P_WC3 + n * 128 + ci * 4 + kk]; }           // k = kk*32+ci, n = co
-        case PK_L1F: return P[(grp ? P_VF1 : P_PI1) + n * 208 + k];
+        case PK_L1F: return n < 64 ? P[P_PI1 + n * 208 + k] : P[P_VF1 + (n - 64) * 208 + k];                   // pi | vf side by side
         case PK_L2F: return P[(grp ? P_VF2 : P_PI2) + n * 64 + k];
         case PK_L2B: return P[(grp ? P_VF2 : P_PI2) + k * 64 + n];                                               // k = out j, n = in i
         case PK_L1B: { const int i = grp * 104 + n; return k < 64 ? P[P_PI1 + k * 208 + i] : P[P_VF1 + (k - 64) * 208 + i]; }
-        case PK_C3B: { const int i = grp * 64 + n, kk = i >> 5, ci = i & 31; return P[P_WC3 + k * 128 + ci * 4 + kk]; }   // k = co
+        case PK_C3B: { const int kk = n >> 5, ci = n & 31; return P[P_WC3 + k * 128 + ci * 4 + kk]; }           // k = co, n = kk*32+ci
         default:     { const int kk = n >> 4, ci = n & 15; return P[P_WC2 + k * 64 + ci * 4 + kk]; }                       // PK_C2B, k = co
     }
 }
@@ -167,13 +167,13 @@ __device__ __forceinline__ const float* patch_src(const float* pooled, long long
     return pooled + ((row >> 2) * 9 + q) * 16;
 }
 
-template <int K, int LOADER>
+template <int K, int LOADER, int C4_LO = 0, int C4_HI = K / 4>
 __device__ __forceinline__ void load_rows_tile(float* tile, const float* a, int lda, long long row0, long long rows, int nrows, int tid,
                                                int nthreads) {
-    constexpr int LD = K + 4, C4 = K / 4;
+    constexpr int LD = K + 4, C4 = C4_HI - C4_LO;
     const uint32_t sa = (uint32_t)__cvta_generic_to_shared(tile);
     for (int e = tid; e < nrows * C4; e += nthreads) {
-        const int r = e / C4, c4 = e - r * C4;
+        const int r = e / C4, c4 = C4_LO + e - r * C4;
         const long long row = row0 + r;
         const bool valid = row < rows;
         const float* src;
@@ -191,9 +191,13 @@ __global__ void __launch_bounds__(256, 2) rows_gemm_kernel(const GemmArgs p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int grp = blockIdx.y;
     const long long row0 = (long long)blockIdx.x * GM_ROWS;
-    load_rows_tile<K, LOADER>(tile, p.a + grp * p.a_col_step, p.lda, row0, p.rows, GM_ROWS, tid, 256);
+    // the tile arrives in two column halves: the k-loop starts on the first while the second is still in flight
+    constexpr int KT_A = (KT + 1) / 2;
+    load_rows_tile<K, LOADER, 0, KT_A * 2>(tile, p.a + grp * p.a_col_step, p.lda, row0, p.rows, GM_ROWS, tid, 256);
     cp_async_commit();
-    cp_async_wait<0>();
+    load_rows_tile<K, LOADER, KT_A * 2, K / 4>(tile, p.a + grp * p.a_col_step, p.lda, row0, p.rows, GM_ROWS, tid, 256);
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
 
     float acc[NT][4];
@@ -203,6 +207,7 @@ __global__ void __launch_bounds__(256, 2) rows_gemm_kernel(const GemmArgs p) {
     const size_t fbase = (size_t)grp * p.frag_step + lane;
 #pragma unroll 2
     for (int kt = 0; kt < KT; ++kt) {
+        if (kt == KT_A) { cp_async_wait<0>(); __syncthreads(); }
         const float v[4] = {ta[kt * 8], ta[kt * 8 + 8 * LD], ta[kt * 8 + 4], ta[kt * 8 + 8 * LD + 4]};
         AFrag af;
         make_afrag<STRICT>(af, v);
@@ -294,6 +299,7 @@ struct WgradArgs {
     const float* x; int ldx; int x_col_step;
     float* dw; int dw_step;       // [N][K] row-major (CONV: torch [co][ci][kh][kw] with k = kk*C + ci)
     float* db; int db_step;
+    float* dw_hi; float* db_hi; int split;   // split > 0: output rows >= split go to dw_hi / db_hi (row - split)
     long long rows;
     int stages_per_cta;
 };
@@ -364,18 +370,23 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const WgradArgs p) {
     for (int nt = 0; nt < NTW; ++nt) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int m = mt * 16 + g + (i >> 1) * 8;
+            int m = mt * 16 + g + (i >> 1) * 8;
             const int n = wg * (NTW * 8) + nt * 8 + 2 * t + (i & 1);
+            float* dst = dw;
+            if (p.split > 0 && m >= p.split) { dst = p.dw_hi; m -= p.split; }
             const int off = CONV ? m * K + (n % C) * 4 + n / C : m * K + n;
-            atomicAdd(dw + off, acc[nt][i]);
+            atomicAdd(dst + off, acc[nt][i]);
         }
     }
     if (wg == 0 && p.db) {
         bs0 += __shfl_xor_sync(0xffffffffu, bs0, 1); bs0 += __shfl_xor_sync(0xffffffffu, bs0, 2);
         bs1 += __shfl_xor_sync(0xffffffffu, bs1, 1); bs1 += __shfl_xor_sync(0xffffffffu, bs1, 2);
         if (t == 0) {
-            atomicAdd(p.db + grp * p.db_step + mt * 16 + g, bs0);
-            atomicAdd(p.db + grp * p.db_step + mt * 16 + g + 8, bs1);
+            float* db = p.db + grp * p.db_step;
+            int m = mt * 16 + g;
+            if (p.split > 0 && m >= p.split) { db = p.db_hi; m -= p.split; }     // (split is a multiple of 16)
+            atomicAdd(db + m, bs0);
+            atomicAdd(db + m + 8, bs1);
         }
     }
 }
@@ -454,25 +465,35 @@ __global__ void __launch_bounds__(256) assemble_kernel(const float* __restrict__
     *reinterpret_cast<float4*>(fr + 80 + lane * 4) = r;
 }
 
-// gradient of the direction Linear: dW[o][4k + dir_k] += df[b][o] for the frames k that exist, db[o] += df[b][o]
+// gradient of the direction Linear: dW[o][4k + dir_k] += df[b][o] for the frames k that exist, db[o] += df[b][o].  Thread =
+// (output o, row group): 17 register accumulators, one shared-memory reduction per CTA at the end.
 __global__ void __launch_bounds__(256) dir_grad_kernel(const float* __restrict__ df, const uint8_t* __restrict__ dcode, const uint8_t* __restrict__ age,
                                                        int B, float* __restrict__ G) {
-    __shared__ float acc[16 * 16 + 16];
-    for (int e = threadIdx.x; e < 272; e += 256) acc[e] = 0.f;
-    __syncthreads();
-    const int o = threadIdx.x & 15;
-    for (int b = blockIdx.x * 16 + (threadIdx.x >> 4); b < B; b += gridDim.x * 16) {
+    __shared__ float red[16][17 * 16 + 1];
+    const int o = threadIdx.x & 15, grp = threadIdx.x >> 4;
+    float acc[17];
+#pragma unroll
+    for (int e = 0; e < 17; ++e) acc[e] = 0.f;
+    for (int b = blockIdx.x * 16 + grp; b < B; b += gridDim.x * 16) {
         const float v = df[(size_t)b * 208 + o];
         const int dc = dcode[b], a = age[b];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (3 - k <= a) atomicAdd(&acc[o * 16 + 4 * k + ((dc >> (2 * k)) & 3)], v);
-        atomicAdd(&acc[256 + o], v);
+        for (int k = 0; k < 4; ++k) {
+            const int d = (dc >> (2 * k)) & 3;
+            const float vk = 3 - k <= a ? v : 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[4 * k + q] += d == q ? vk : 0.f;
+        }
+        acc[16] += v;
     }
+#pragma unroll
+    for (int e = 0; e < 17; ++e) red[grp][e * 16 + o] = acc[e];
     __syncthreads();
     for (int e = threadIdx.x; e < 272; e += 256) {
-        const float v = acc[e];
-        if (v != 0.f) atomicAdd(G + (e < 256 ? P_WD + e : P_BD + e - 256), v);
+        float v = 0.f;
+        for (int g2 = 0; g2 < 16; ++g2) v += red[g2][e];
+        const int in = e >> 4, oo = e & 15;            // e = in * 16 + o
+        if (v != 0.f) atomicAdd(G + (in < 16 ? P_WD + oo * 16 + in : P_BD + oo), v);
     }
 }
 
@@ -485,7 +506,22 @@ __global__ void __launch_bounds__(512) lut_grad_strided_kernel(const float* __re
     for (int e = tid; e < n_rows * 128; e += blockDim.x) tab[e] = 0.f;
     __syncthreads();
     const int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int b = (blockIdx.x * blockDim.x + tid) >> 5; b < batch; b += warps) {
+    int b = (blockIdx.x * blockDim.x + tid) >> 5;
+    for (; b + 3 * warps < batch; b += 4 * warps) {
+        float4 v[4];
+        int r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            r[u] = (int)row[b + u * warps];
+            v[u] = __ldg(reinterpret_cast<const float4*>(d + (size_t)(b + u * warps) * ld) + lane);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float* tp = tab + r[u] * 128 + lane;
+            atomicAdd(tp, v[u].x); atomicAdd(tp + 32, v[u].y); atomicAdd(tp + 64, v[u].z); atomicAdd(tp + 96, v[u].w);
+        }
+    }
+    for (; b < batch; b += warps) {
         const int r = (int)row[b];
         const float4 v = __ldg(reinterpret_cast<const float4*>(d + (size_t)b * ld) + lane);
         float* tp = tab + r * 128 + lane;
@@ -527,8 +563,10 @@ __global__ void __launch_bounds__(LS_ROWS) loss_kernel(const LossArgs p) {
     __shared__ float red[3][LS_ROWS / 32];
     const int tid = threadIdx.x;
     const long long row0 = (long long)blockIdx.x * LS_ROWS;
-    for (int e = tid; e < 448; e += LS_ROWS) wa[e] = p.P[P_WA + e];
-    for (int e = tid; e < 64; e += LS_ROWS) wa[448 + e] = p.P[P_WV + e];
+    for (int e = tid; e < 512; e += LS_ROWS) {            // wa[c][8] = action_net.weight[0..6][c], value_net.weight[c]
+        const int c = e >> 3, j = e & 7;
+        wa[e] = j < 7 ? p.P[P_WA + j * 64 + c] : p.P[P_WV + c];
+    }
     if (tid < 7) wa[512 + tid] = p.P[P_BA + tid];
     if (tid == 7) wa[512 + 7] = p.P[P_BV];
     for (int e = tid; e < LS_ROWS * 32; e += LS_ROWS) {
@@ -548,9 +586,10 @@ __global__ void __launch_bounds__(LS_ROWS) loss_kernel(const LossArgs p) {
     for (int j = 0; j < 7; ++j) lg[j] = wa[512 + j];
     for (int c = 0; c < 64; ++c) {
         const float hp = h[c], hv = h[64 + c];
-#pragma unroll
-        for (int j = 0; j < 7; ++j) lg[j] = fmaf(wa[j * 64 + c], hp, lg[j]);
-        val = fmaf(wa[448 + c], hv, val);
+        const float4 w0 = *reinterpret_cast<const float4*>(wa + c * 8), w1 = *reinterpret_cast<const float4*>(wa + c * 8 + 4);
+        lg[0] = fmaf(w0.x, hp, lg[0]); lg[1] = fmaf(w0.y, hp, lg[1]); lg[2] = fmaf(w0.z, hp, lg[2]); lg[3] = fmaf(w0.w, hp, lg[3]);
+        lg[4] = fmaf(w1.x, hp, lg[4]); lg[5] = fmaf(w1.y, hp, lg[5]); lg[6] = fmaf(w1.z, hp, lg[6]);
+        val = fmaf(w1.w, hv, val);
     }
     float s_pl = 0.f, s_vl = 0.f, s_el = 0.f;
     float dlg[7], dv = 0.f;
@@ -649,12 +688,13 @@ __global__ void __launch_bounds__(LS_ROWS) loss_kernel(const LossArgs p) {
     {
         float* hrow = tile + tid * LS_LD;
         for (int c = 0; c < 64; ++c) {
-            float dp = 0.f;
-#pragma unroll
-            for (int j = 0; j < 7; ++j) dp = fmaf(dlg[j], wa[j * 64 + c], dp);
+            const float4 w0 = *reinterpret_cast<const float4*>(wa + c * 8), w1 = *reinterpret_cast<const float4*>(wa + c * 8 + 4);
+            float dp = dlg[0] * w0.x;
+            dp = fmaf(dlg[1], w0.y, dp); dp = fmaf(dlg[2], w0.z, dp); dp = fmaf(dlg[3], w0.w, dp);
+            dp = fmaf(dlg[4], w1.x, dp); dp = fmaf(dlg[5], w1.y, dp); dp = fmaf(dlg[6], w1.z, dp);
             const float hp = hrow[c], hv = hrow[64 + c];
             hrow[c] = dp * (1.f - hp * hp);
-            hrow[64 + c] = dv * wa[448 + c] * (1.f - hv * hv);
+            hrow[64 + c] = dv * w1.w * (1.f - hv * hv);
         }
     }
     __syncthreads();
@@ -678,9 +718,20 @@ __global__ void gru_gi_kernel(const float* __restrict__ P, float* __restrict__ g
     gi[e] = s;
 }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// gate non-linearities on the exp2 / reciprocal units (a few ulp each): the 128-step recurrence is a latency chain, and the IEEE
+// divide + tanhf were half of a step
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_(float x) {
+    const float ax = fabsf(x);
+    const float e = __expf(-2.f * ax);                       // in (0, 1]: no overflow
+    const float r = __fdividef(1.f - e, 1.f + e);
+    return copysignf(r, x);
+}
 
-// Two sequences per CTA, 384 threads: thread j keeps row j of W_hh (128 floats) in registers for all 128 steps.
+// Two sequences per CTA, 384 threads, W_hh in REGISTERS for all 128 steps: thread (rq = tid / 4, ks = tid % 4) keeps rows
+// 4rq..4rq+3 x columns 32ks..32ks+31 (128 floats).  A step reads only the thread's quarter of the two hidden states from shared
+// memory (shared-memory wavefronts, not FMAs, bound the all-columns-per-thread layout: 3100 cycles per step against ~900 here);
+// the four partial dot products meet with two quad shuffles.
 // store: per (t, seq) the values the backward pass needs: r, z, n, gh_n, h_prev [5][128]; lut[seq] = final hidden state.
 struct GruArgs {
     const float* P;
@@ -695,43 +746,67 @@ struct GruArgs {
     float* dgh_rows;          // [128 * nseq][384]
     float* dgi_tab;           // [32][384] accumulated with atomics (caller zeroes)
 };
+constexpr int HS = 36;        // padded quarter of a hidden state: the four quarters of a quad's 16-byte reads fall on distinct banks
 
 __global__ void __launch_bounds__(384, 1) gru_fwd_kernel(const GruArgs p) {
-    __shared__ __align__(16) float h[2][HID];
+    extern __shared__ __align__(16) float gi_s[];      // [32][384] input halves of the gates per token (48 KB, dynamic)
+    __shared__ __align__(16) float h[2][4 * HS];
     __shared__ float gh[2][G3];
     __shared__ uint8_t tok[2][SEQ_LEN];
-    const int j = threadIdx.x;
-    float w[HID];
+    const int tid = threadIdx.x, ks = tid & 3, rq = tid >> 2;
+    float w[4][32];
 #pragma unroll
-    for (int k = 0; k < HID; ++k) w[k] = p.P[P_WHH + j * HID + k];
-    const float bhh = p.P[P_BHH + j];
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int kk = 0; kk < 32; ++kk) w[r][kk] = p.P[P_WHH + (4 * rq + r) * HID + ks * 32 + kk];
+    const float bhh = p.P[P_BHH + 4 * rq + ks];        // bias of the row this lane writes
     const int seq0 = blockIdx.x * 2;
-    for (int e = j; e < 2 * SEQ_LEN; e += 384) {
+    for (int e = tid; e < 2 * SEQ_LEN; e += 384) {
         const int s = e / SEQ_LEN, q = e - s * SEQ_LEN;
         tok[s][q] = seq0 + s < p.nseq ? p.tokens[(size_t)(seq0 + s) * SEQ_LEN + q] : (uint8_t)0;
     }
-    if (j < 2 * HID) (&h[0][0])[j] = 0.f;
+    if (tid < 2 * 4 * HS) (&h[0][0])[tid] = 0.f;
+    for (int e = tid; e < 32 * G3; e += 384) gi_s[e] = p.gi[e];
     __syncthreads();
     for (int t = 0; t < SEQ_LEN; ++t) {
-        float a0 = bhh, a1 = bhh;
+        float acc[4][2];
 #pragma unroll
-        for (int k4 = 0; k4 < HID / 4; ++k4) {
-            const float4 x0 = *reinterpret_cast<const float4*>(&h[0][k4 * 4]);
-            const float4 x1 = *reinterpret_cast<const float4*>(&h[1][k4 * 4]);
-            a0 = fmaf(w[k4 * 4], x0.x, a0); a0 = fmaf(w[k4 * 4 + 1], x0.y, a0); a0 = fmaf(w[k4 * 4 + 2], x0.z, a0); a0 = fmaf(w[k4 * 4 + 3], x0.w, a0);
-            a1 = fmaf(w[k4 * 4], x1.x, a1); a1 = fmaf(w[k4 * 4 + 1], x1.y, a1); a1 = fmaf(w[k4 * 4 + 2], x1.z, a1); a1 = fmaf(w[k4 * 4 + 3], x1.w, a1);
+        for (int r = 0; r < 4; ++r) acc[r][0] = acc[r][1] = 0.f;
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+            const float4 x0 = *reinterpret_cast<const float4*>(&h[0][ks * HS + k4 * 4]);
+            const float4 x1 = *reinterpret_cast<const float4*>(&h[1][ks * HS + k4 * 4]);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                acc[r][0] = fmaf(w[r][k4 * 4], x0.x, acc[r][0]); acc[r][0] = fmaf(w[r][k4 * 4 + 1], x0.y, acc[r][0]);
+                acc[r][0] = fmaf(w[r][k4 * 4 + 2], x0.z, acc[r][0]); acc[r][0] = fmaf(w[r][k4 * 4 + 3], x0.w, acc[r][0]);
+                acc[r][1] = fmaf(w[r][k4 * 4], x1.x, acc[r][1]); acc[r][1] = fmaf(w[r][k4 * 4 + 1], x1.y, acc[r][1]);
+                acc[r][1] = fmaf(w[r][k4 * 4 + 2], x1.z, acc[r][1]); acc[r][1] = fmaf(w[r][k4 * 4 + 3], x1.w, acc[r][1]);
+            }
         }
-        gh[0][j] = a0; gh[1][j] = a1;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                acc[r][s] += __shfl_xor_sync(0xffffffffu, acc[r][s], 1);
+                acc[r][s] += __shfl_xor_sync(0xffffffffu, acc[r][s], 2);
+            }
+        {   // lane ks writes row 4rq + ks
+            const float v0 = ks == 0 ? acc[0][0] : ks == 1 ? acc[1][0] : ks == 2 ? acc[2][0] : acc[3][0];
+            const float v1 = ks == 0 ? acc[0][1] : ks == 1 ? acc[1][1] : ks == 2 ? acc[2][1] : acc[3][1];
+            gh[0][4 * rq + ks] = v0 + bhh; gh[1][4 * rq + ks] = v1 + bhh;
+        }
         __syncthreads();
-        if (j < 2 * HID) {
-            const int s = j >> 7, c = j & (HID - 1);
+        if (tid < 2 * HID) {
+            const int s = tid >> 7, c = tid & (HID - 1);
             const int seq = seq0 + s;
-            const float* gi = p.gi + (int)tok[s][t] * G3;
+            const float* gi = gi_s + (int)tok[s][t] * G3;
             const float r = sigmoidf_(gi[c] + gh[s][c]);
             const float z = sigmoidf_(gi[HID + c] + gh[s][HID + c]);
             const float ghn = gh[s][2 * HID + c];
-            const float n = tanhf(gi[2 * HID + c] + r * ghn);
-            const float hp = h[s][c];
+            const float n = tanhf_(gi[2 * HID + c] + r * ghn);
+            float* hc = &h[s][(c >> 5) * HS + (c & 31)];
+            const float hp = *hc;
             const float hn = (1.f - z) * n + z * hp;
             if (seq < p.nseq) {
                 if (p.store) {
@@ -741,44 +816,57 @@ __global__ void __launch_bounds__(384, 1) gru_fwd_kernel(const GruArgs p) {
                 if (p.hprev_rows) p.hprev_rows[((size_t)t * p.nseq + seq) * HID + c] = hp;
                 if (t == SEQ_LEN - 1) p.lut[(size_t)seq * HID + c] = hn;
             }
-            h[s][c] = hn;          // (s, c) is read and written by this thread only in this phase
+            *hc = hn;              // (s, c) is read and written by this thread only in this phase
         }
         __syncthreads();
     }
 }
 
-// Backward through time.  Thread (q, k) keeps W_hh[q*128 .. q*128+127][k] in registers: dh_prev[k] += sum_j W[j][k] dgh[j] is a
-// sum of three partial sums (one per gate third).
+// Backward through time.  Thread (js = warp, kq = lane) keeps W_hh[32js .. 32js+31][4kq .. 4kq+3] in registers:
+// dh_prev[k] += sum_j W[j][k] dgh[j] is a sum of twelve partial sums (one per warp), which meet in shared memory.
 __global__ void __launch_bounds__(384, 1) gru_bwd_kernel(const GruArgs p) {
     extern __shared__ __align__(16) float dgi_acc[];   // [32][384] (48 KB, dynamic)
     __shared__ __align__(16) float dgh[2][G3];
-    __shared__ float dh[2][HID], part[3][2][HID];
+    __shared__ __align__(16) float part[12][2][HID];
+    __shared__ float dh[2][HID];
     __shared__ uint8_t tok[2][SEQ_LEN];
-    const int tid = threadIdx.x, q = tid >> 7, k = tid & (HID - 1);
-    float w[HID];
+    const int tid = threadIdx.x, kq = tid & 31, js = tid >> 5;
+    float w[4][32];                                    // w[kk][jj] = W_hh[32js + jj][4kq + kk]
 #pragma unroll
-    for (int jj = 0; jj < HID; ++jj) w[jj] = p.P[P_WHH + (q * HID + jj) * HID + k];
+    for (int jj = 0; jj < 32; ++jj) {
+        const float4 v = *reinterpret_cast<const float4*>(p.P + P_WHH + (js * 32 + jj) * HID + 4 * kq);
+        w[0][jj] = v.x; w[1][jj] = v.y; w[2][jj] = v.z; w[3][jj] = v.w;
+    }
     const int seq0 = blockIdx.x * 2;
     for (int e = tid; e < 32 * G3; e += 384) dgi_acc[e] = 0.f;
     for (int e = tid; e < 2 * SEQ_LEN; e += 384) {
         const int s = e / SEQ_LEN, qq = e - s * SEQ_LEN;
         tok[s][qq] = seq0 + s < p.nseq ? p.tokens[(size_t)(seq0 + s) * SEQ_LEN + qq] : (uint8_t)0;
     }
+    for (int e = tid; e < 12 * 2 * HID; e += 384) (&part[0][0][0])[e] = 0.f;
     if (tid < 2 * HID) {
         const int s = tid >> 7, c = tid & (HID - 1);
         dh[s][c] = seq0 + s < p.nseq ? p.dlut[(size_t)(seq0 + s) * HID + c] : 0.f;
-        part[0][s][c] = part[1][s][c] = part[2][s][c] = 0.f;
     }
     __syncthreads();
+    float pr = 0.f, pz = 0.f, pn = 0.f, pg = 0.f, ph = 0.f;      // r, z, n, gh_n, h_prev of the step about to be processed
+    auto fetch = [&](int t) {
+        if (tid < 2 * HID && seq0 + (tid >> 7) < p.nseq && t >= 0) {
+            const float* st = p.store + ((size_t)t * p.nseq + seq0 + (tid >> 7)) * 5 * HID + (tid & (HID - 1));
+            pr = __ldg(st); pz = __ldg(st + HID); pn = __ldg(st + 2 * HID); pg = __ldg(st + 3 * HID); ph = __ldg(st + 4 * HID);
+        }
+    };
+    fetch(SEQ_LEN - 1);
     for (int t = SEQ_LEN - 1; t >= 0; --t) {
         if (tid < 2 * HID) {
             const int s = tid >> 7, c = tid & (HID - 1);
             const int seq = seq0 + s;
-            const float d = dh[s][c] + part[0][s][c] + part[1][s][c] + part[2][s][c];
+            float d = dh[s][c];
+#pragma unroll
+            for (int q = 0; q < 12; ++q) d += part[q][s][c];
             float drp = 0.f, dzp = 0.f, dnp = 0.f, dghn = 0.f, dprev = 0.f;
             if (seq < p.nseq) {
-                const float* st = p.store + ((size_t)t * p.nseq + seq) * 5 * HID + c;
-                const float r = st[0], z = st[HID], n = st[2 * HID], ghn = st[3 * HID], hp = st[4 * HID];
+                const float r = pr, z = pz, n = pn, ghn = pg, hp = ph;
                 const float dn = d * (1.f - z);
                 dnp = dn * (1.f - n * n);
                 dzp = d * (hp - n) * z * (1.f - z);
@@ -793,16 +881,25 @@ __global__ void __launch_bounds__(384, 1) gru_bwd_kernel(const GruArgs p) {
             dgh[s][c] = drp; dgh[s][HID + c] = dzp; dgh[s][2 * HID + c] = dghn;
             dh[s][c] = dprev;
         }
+        fetch(t - 1);
         __syncthreads();
-        float a0 = 0.f, a1 = 0.f;
+        float acc[4][2];
 #pragma unroll
-        for (int j4 = 0; j4 < HID / 4; ++j4) {
-            const float4 x0 = *reinterpret_cast<const float4*>(&dgh[0][q * HID + j4 * 4]);
-            const float4 x1 = *reinterpret_cast<const float4*>(&dgh[1][q * HID + j4 * 4]);
-            a0 = fmaf(w[j4 * 4], x0.x, a0); a0 = fmaf(w[j4 * 4 + 1], x0.y, a0); a0 = fmaf(w[j4 * 4 + 2], x0.z, a0); a0 = fmaf(w[j4 * 4 + 3], x0.w, a0);
-            a1 = fmaf(w[j4 * 4], x1.x, a1); a1 = fmaf(w[j4 * 4 + 1], x1.y, a1); a1 = fmaf(w[j4 * 4 + 2], x1.z, a1); a1 = fmaf(w[j4 * 4 + 3], x1.w, a1);
+        for (int kk = 0; kk < 4; ++kk) acc[kk][0] = acc[kk][1] = 0.f;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 x0 = *reinterpret_cast<const float4*>(&dgh[0][js * 32 + j4 * 4]);
+            const float4 x1 = *reinterpret_cast<const float4*>(&dgh[1][js * 32 + j4 * 4]);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                acc[kk][0] = fmaf(w[kk][j4 * 4], x0.x, acc[kk][0]); acc[kk][0] = fmaf(w[kk][j4 * 4 + 1], x0.y, acc[kk][0]);
+                acc[kk][0] = fmaf(w[kk][j4 * 4 + 2], x0.z, acc[kk][0]); acc[kk][0] = fmaf(w[kk][j4 * 4 + 3], x0.w, acc[kk][0]);
+                acc[kk][1] = fmaf(w[kk][j4 * 4], x1.x, acc[kk][1]); acc[kk][1] = fmaf(w[kk][j4 * 4 + 1], x1.y, acc[kk][1]);
+                acc[kk][1] = fmaf(w[kk][j4 * 4 + 2], x1.z, acc[kk][1]); acc[kk][1] = fmaf(w[kk][j4 * 4 + 3], x1.w, acc[kk][1]);
+            }
         }
-        part[q][0][k] = a0; part[q][1][k] = a1;
+        *reinterpret_cast<float4*>(&part[js][0][4 * kq]) = make_float4(acc[0][0], acc[1][0], acc[2][0], acc[3][0]);
+        *reinterpret_cast<float4*>(&part[js][1][4 * kq]) = make_float4(acc[0][1], acc[1][1], acc[2][1], acc[3][1]);
         __syncthreads();
     }
     for (int e = tid; e < 32 * G3; e += 384) {
@@ -959,7 +1056,7 @@ int run_gru_forward(Ctx* c, bool keep, cudaStream_t s, const char* what) {
     gru_gi_kernel<<<(32 * G3 + 255) / 256, 256, 0, s>>>(c->P, c->gi);
     GruArgs g = gru_args(c);
     if (!keep) { g.store = nullptr; g.hprev_rows = nullptr; }
-    gru_fwd_kernel<<<(c->nseq + 1) / 2, 384, 0, s>>>(g);
+    gru_fwd_kernel<<<(c->nseq + 1) / 2, 384, 32 * G3 * sizeof(float), s>>>(g);
     UP_TRY(cudaGetLastError());
     return MGRL_OK;
 }
@@ -1004,6 +1101,7 @@ int mgrl_ppo_create(int device, int max_batch, int num_sequences, mgrl_ppo** out
     UP_TRY(cudaFuncSetAttribute(lut_grad_strided_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, num_sequences * 128 * 4));
     UP_TRY(cudaFuncSetAttribute(loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (LS_ROWS * LS_LD + LS_ROWS * 8 + 520) * 4));
     UP_TRY(cudaFuncSetAttribute(gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * G3 * 4));
+    UP_TRY(cudaFuncSetAttribute(gru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * G3 * 4));
     *out = h;
     return MGRL_OK;
 }
@@ -1077,7 +1175,7 @@ int mgrl_ppo_gradients(mgrl_ppo* h, const mgrl_rollout_view* rv, const int32_t* 
     UP_TRY(cudaGetLastError());
     Conv1Args ca = {};
     ca.frames = rv->frames; ca.t = c.t; ca.i = c.i; ca.age = c.age; ca.w1 = c.P + P_WC1; ca.b1 = c.P + P_BC1; ca.pooled = c.pooled; ca.arg = c.arg;
-    ca.n = rv->num_envs; ca.B = B;
+    ca.n = rv->num_envs; ca.B = B; ca.onepass = strict ? 0 : 1;
     UP_TRY(mgrl_policy::launch_conv1_pool_fwd_tc(ca, s));
     GemmArgs g = {};
     // conv2: patches [4B,64] -> h2 [4B,32] = [B,128] (oh, ow, c2)
@@ -1089,9 +1187,9 @@ int mgrl_ppo_gradients(mgrl_ppo* h, const mgrl_rollout_view* rv, const int32_t* 
     assemble_kernel<<<(unsigned)(((size_t)B * 32 + 255) / 256), 256, 0, s>>>(c.P, c.lut, c.dcode, c.age, c.mrow, B, c.f);
     UP_TRY(cudaGetLastError());
     // first MLP layer, pi | vf: f [B,208] -> a1 [B,128]
-    g = GemmArgs{}; g.a = c.f; g.lda = 208; g.frag = frag_ptr(&c, PK_L1F, strict); g.frag_step = frag_step(PK_L1F); g.bias = c.pbias + PB_L1; g.bias_step = 64;
-    g.out = c.a1; g.ldo = 128; g.out_col_step = 64; g.rows = B;
-    UP_TRY((launch_rows_gemm<208, 8, LD_PLAIN, EP_BIAS_TANH>(g, 2, strict, s)));
+    g = GemmArgs{}; g.a = c.f; g.lda = 208; g.frag = frag_ptr(&c, PK_L1F, strict); g.bias = c.pbias + PB_L1;
+    g.out = c.a1; g.ldo = 128; g.rows = B;
+    UP_TRY((launch_rows_gemm<208, 16, LD_PLAIN, EP_BIAS_TANH>(g, 1, strict, s)));
     // second MLP layer: a1[:, g*64 ..] -> a2[:, g*64 ..]
     g = GemmArgs{}; g.a = c.a1; g.lda = 128; g.a_col_step = 64; g.frag = frag_ptr(&c, PK_L2F, strict); g.frag_step = frag_step(PK_L2F);
     g.bias = c.pbias + PB_L2; g.bias_step = 64; g.out = c.a2; g.ldo = 128; g.out_col_step = 64; g.rows = B;
@@ -1116,9 +1214,9 @@ int mgrl_ppo_gradients(mgrl_ppo* h, const mgrl_rollout_view* rv, const int32_t* 
     g.y = c.a1; g.ldy = 128; g.y_col_step = 64; g.out = c.dz1; g.ldo = 128; g.out_col_step = 64; g.rows = B;
     UP_TRY((launch_rows_gemm<64, 8, LD_PLAIN, EP_GRAD_TANH>(g, 2, strict, s)));
     // first layer: dW = dz1[:, g*64..]^T f, df = dz1 [W_pi; W_vf] with ReLU' on the conv columns
-    w = WgradArgs{}; w.dz = c.dz1; w.ldz = 128; w.dz_col_step = 64; w.x = c.f; w.ldx = 208; w.dw = c.G + P_PI1; w.dw_step = P_VF1 - P_PI1;
-    w.db = c.G + P_PI1B; w.db_step = P_VF1B - P_PI1B; w.rows = B;
-    UP_TRY((launch_wgrad<64, 208, LD_PLAIN, false>(w, 2, strict, c.sms, s)));
+    w = WgradArgs{}; w.dz = c.dz1; w.ldz = 128; w.x = c.f; w.ldx = 208; w.dw = c.G + P_PI1; w.db = c.G + P_PI1B;
+    w.dw_hi = c.G + P_VF1; w.db_hi = c.G + P_VF1B; w.split = 64; w.rows = B;
+    UP_TRY((launch_wgrad<128, 208, LD_PLAIN, false>(w, 1, strict, c.sms, s)));
     g = GemmArgs{}; g.a = c.dz1; g.lda = 128; g.frag = frag_ptr(&c, PK_L1B, strict); g.frag_step = frag_step(PK_L1B);
     g.y = c.f; g.ldy = 208; g.y_col_step = 104; g.out = c.df; g.ldo = 208; g.out_col_step = 104; g.rows = B;
     UP_TRY((launch_rows_gemm<128, 13, LD_PLAIN, EP_GRAD_MIX>(g, 2, strict, s)));
@@ -1134,9 +1232,9 @@ int mgrl_ppo_gradients(mgrl_ppo* h, const mgrl_rollout_view* rv, const int32_t* 
     // conv3: dz3 = df[:, 16:80]; dW3 = dz3^T h2; dh2 = (dz3 W3) * (h2 > 0)
     w = WgradArgs{}; w.dz = c.df + 16; w.ldz = 208; w.x = c.h2; w.ldx = 128; w.dw = c.G + P_WC3; w.db = c.G + P_BC3; w.rows = B;
     UP_TRY((launch_wgrad<64, 128, LD_PLAIN, true>(w, 1, strict, c.sms, s)));
-    g = GemmArgs{}; g.a = c.df + 16; g.lda = 208; g.frag = frag_ptr(&c, PK_C3B, strict); g.frag_step = frag_step(PK_C3B);
-    g.y = c.h2; g.ldy = 128; g.y_col_step = 64; g.out = c.dh2; g.ldo = 128; g.out_col_step = 64; g.rows = B;
-    UP_TRY((launch_rows_gemm<64, 8, LD_PLAIN, EP_GRAD_RELU>(g, 2, strict, s)));
+    g = GemmArgs{}; g.a = c.df + 16; g.lda = 208; g.frag = frag_ptr(&c, PK_C3B, strict);
+    g.y = c.h2; g.ldy = 128; g.out = c.dh2; g.ldo = 128; g.rows = B;
+    UP_TRY((launch_rows_gemm<64, 16, LD_PLAIN, EP_GRAD_RELU>(g, 1, strict, s)));
     // conv2: dz2c = dh2 as [4B,32]; dW2 = dz2c^T patches; dpooled = adjoint gather of (dz2c W2)
     w = WgradArgs{}; w.dz = c.dh2; w.ldz = 32; w.x = c.pooled; w.dw = c.G + P_WC2; w.db = c.G + P_BC2; w.rows = 4LL * B;
     UP_TRY((launch_wgrad<32, 64, LD_PATCH, true>(w, 1, strict, c.sms, s)));
