@@ -324,10 +324,14 @@ def main():
         v_vecenv = time_host(lambda a: venv.step(a))
         e2e_steps = saved
         venv.close()
+        wire = os.environ.get("MGRL_WIRE", "1") != "0"
         e2e = {"value": v_frames, "unit": "env-steps/s",
-               "h2d_bytes_per_step": n * 1 * T, "d2h_bytes_per_step": n * (148 + 1 + 1 + 4 + 1 + 1 + 1) * T,
+               "h2d_bytes_per_step": n * 1 * T, "d2h_bytes_per_step": n * (64 if wire else 148 + 1 + 1 + 4 + 1 + 1 + 1) * T,
                "api": "B200VecEnv.step_frames -> mgrl_vec_step_frames_host (pinned numpy in/out, un-stacked observation: "
-                      "the outputs of the CPU arm's vector step)",
+                      "the outputs of the CPU arm's vector step)"
+                      + ("; PCIe wire format = one 64-byte record per environment (a code byte per view cell + the step's "
+                         "scalars), expanded into the 148-byte observation records, rewards and flags by the library's host "
+                         "threads while later chunks are in flight (format conversion only)" if wire else ""),
                "sample": f"{e2e_steps} vector steps of {n} envs per rank",
                "stacked": {"value": v_stacked, "unit": "env-steps/s",
                            "d2h_bytes_per_step": n * (4 * 147 + 16 + 128 * 8 + 4 + 1 + 1 + 1 + 147 + 1) * T,
@@ -359,6 +363,8 @@ def main():
             torch.cuda.synchronize()
             t_roll += ev[0].elapsed_time(ev[1]); t_upd += ev[1].elapsed_time(ev[2])
         barrier()
+        if os.environ.get("MGRL_BENCH_DEBUG"):
+            print(f"[rank {rank}] {task} {n_envs}: rollout {t_roll / iters:.2f} ms, update {t_upd / iters:.2f} ms", file=sys.stderr)
         tt = torch.tensor([t_roll, t_upd], device=dev)
         if dist is not None:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)

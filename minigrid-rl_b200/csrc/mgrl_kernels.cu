@@ -30,6 +30,7 @@
 
 #include "mgrl.h"
 #include "mgrl_core.cuh"
+#include "mgrl_wire.cuh"
 
 using namespace mgrl;
 
@@ -980,12 +981,14 @@ __global__ void stack_push_kernel(int n, const uint8_t* __restrict__ image, cons
     }
 }
 
-// SB3 GAE: one lane per environment walks the time axis backwards; the loads of a step do
-// not depend on the recurrence, so the unrolled loop keeps 16 steps of loads in flight.
-// __f*_rn intrinsics pin the float32 operation order (no FMA contraction) -> bit-exact, which is why the time
-// axis is not a parallel scan (a scan re-associates the sums).  Blocks of kGaeBlock environments: 65 536 environments are
-// 1024 blocks = 6.9 per SM (256-thread blocks left 256 blocks for 148 SMs: 1.7 waves).
+// SB3 GAE: one lane per environment walks the time axis backwards.  The loads of a step do not depend on the recurrence:
+// they are issued kGaeGroup steps at a time into register arrays (3 x 16 loads in flight per lane; left to the unroller
+// the compiler kept the loop at 32 registers and a couple of loads in flight: 0.41 of the HBM roofline), then the group's
+// recurrence runs on registers.  __f*_rn intrinsics pin the float32 operation order (no FMA contraction) -> bit-exact, which
+// is why the time axis is not a parallel scan (a scan re-associates the sums).  Blocks of kGaeBlock environments: 65 536
+// environments are 1024 blocks = 6.9 per SM.
 constexpr int kGaeBlock = 64;
+constexpr int kGaeGroup = 16;
 __global__ void __launch_bounds__(kGaeBlock) gae_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
                                                   const uint8_t* __restrict__ starts,
                                                   const float* __restrict__ last_values,
@@ -996,17 +999,28 @@ __global__ void __launch_bounds__(kGaeBlock) gae_kernel(const float* __restrict_
     float A = 0.0f;
     float nv = last_values[n];
     float nnt = 1.0f - (float)last_dones[n];
-#pragma unroll 16
-    for (int t = T - 1; t >= 0; --t) {
-        const size_t i = (size_t)t * N + n;
-        const float vt = values[i], rt = rewards[i];
-        const float st = (float)starts[i];
-        const float delta = __fsub_rn(__fadd_rn(rt, __fmul_rn(__fmul_rn(g, nv), nnt)), vt);
-        A = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, nnt), A));
-        adv[i] = A;
-        ret[i] = __fadd_rn(A, vt);
-        nv = vt;
-        nnt = 1.0f - st;
+    for (int t0 = T - 1; t0 >= 0; t0 -= kGaeGroup) {
+        float vt[kGaeGroup], rt[kGaeGroup];
+        uint8_t st[kGaeGroup];
+#pragma unroll
+        for (int u = 0; u < kGaeGroup; ++u) {
+            const int t = t0 - u;
+            const size_t i = (size_t)(t < 0 ? 0 : t) * N + n;
+            vt[u] = __ldcs(values + i); rt[u] = __ldcs(rewards + i); st[u] = __ldcs(starts + i);
+        }
+#pragma unroll
+        for (int u = 0; u < kGaeGroup; ++u) {
+            const int t = t0 - u;
+            if (t >= 0) {
+                const size_t i = (size_t)t * N + n;
+                const float delta = __fsub_rn(__fadd_rn(rt[u], __fmul_rn(__fmul_rn(g, nv), nnt)), vt[u]);
+                A = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, nnt), A));
+                __stcs(adv + i, A);
+                __stcs(ret + i, __fadd_rn(A, vt[u]));
+                nv = vt[u];
+                nnt = 1.0f - (float)st[u];
+            }
+        }
     }
 }
 
@@ -1072,6 +1086,7 @@ struct mgrl_env {
     int64_t *h_stack_mis, *h_table;
     uint8_t* h_full;     // full-grid observation staging of mgrl_full_obs_host
     bool table_set;
+    mgrl_wire::Path* wire;   // compact wire format + expansion pool of mgrl_vec_step_frames_host (mgrl_wire.cu), created on first use
 };
 
 namespace {
@@ -1336,6 +1351,7 @@ int mgrl_destroy(mgrl_env* e) {
                     e->h_stack_mis, e->h_table, e->h_full};
     for (void* b : bufs)
         if (b) cudaFree(b);
+    mgrl_wire::destroy(e->wire);
     delete e;
     return MGRL_OK;
 }
@@ -1583,6 +1599,26 @@ int mgrl_vec_step_frames_host(mgrl_env* e, const uint8_t* actions_host, uint8_t*
     int rc = mgrl_step(e, e->h_actions, e->h_image, e->h_dir, e->h_mission, e->h_reward, e->h_term, e->h_trunc,
                        e->h_eplen, term_image_host ? e->h_termimg : nullptr, term_dir_host ? e->h_termdir : nullptr, stream);
     if (rc) return rc;
+    // Default: the observation crosses PCIe as 64-byte records (one code byte per view cell + the step's scalars) and is
+    // expanded into the caller's arrays by the handle's host threads while later chunks are still in flight (mgrl_wire.cu);
+    // MGRL_WIRE=0 copies the full 148-byte records instead.
+    static const bool wire_on = [] { const char* v = getenv("MGRL_WIRE"); return !(v && v[0] == '0'); }();
+    if (wire_on) {
+        if (!e->wire) {
+            e->wire = mgrl_wire::create(e->cfg.num_envs);
+            if (!e->wire) return fail(MGRL_ERR_CUDA, "mgrl_vec_step_frames_host: wire staging allocation failed%s");
+        }
+        mgrl_wire::Outputs o = {};
+        o.layout = e->cfg.obs_layout; o.image_dev = e->h_image; o.image_host = image_host; o.reward_dev = e->h_reward; o.reward_host = reward_host;
+        o.dir_dev = e->h_dir; o.mission_dev = e->h_mission; o.term_dev = e->h_term; o.trunc_dev = e->h_trunc; o.eplen_dev = e->h_eplen;
+        o.tdir_dev = term_dir_host ? e->h_termdir : nullptr;
+        o.dir_host = dir_host; o.mission_host = mission_host; o.term_host = term_host; o.trunc_host = trunc_host; o.eplen_host = ep_len_host;
+        o.tdir_host = term_dir_host;
+        mgrl_wire::Outputs x = {};
+        x.layout = e->cfg.obs_layout; x.image_dev = e->h_termimg; x.image_host = term_image_host;
+        CUDA_TRY(mgrl_wire::step(e->wire, o, term_image_host ? &x : nullptr, s));
+        return MGRL_OK;
+    }
     CUDA_TRY(cudaMemcpyAsync(image_host, e->h_image, n * pitch, cudaMemcpyDeviceToHost, s));
     uint8_t* hb = reinterpret_cast<uint8_t*>(reward_host);
     const bool slab = dir_host == hb + 4 * n && mission_host == dir_host + n && term_host == mission_host + n &&

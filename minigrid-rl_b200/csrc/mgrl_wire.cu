@@ -1,0 +1,345 @@
+// mgrl_wire.cu — the PCIe wire format of the host-buffer drop-in path (mgrl_vec_step_frames_host / mgrl_vec_reset_frames_host).
+//
+// The host path of VecEnv.step (/root/reference/src/ppo.py:159,242 through SB3's VecEnv) is bound by the device-to-host copy
+// of the observation: 148 B of (type, colour, state) triples per environment and step.  A view cell has fewer than 256
+// distinct triples, so the device packs every cell into ONE code byte (49 B + the step's scalars = one 64-byte record per
+// environment), the records cross PCIe in ONE copy, and a small pool of host threads expands them into the caller's image /
+// reward / flag arrays while the copy is still in flight: a record is exactly one 64-byte cache line of pinned memory and
+// carries the step's tag byte, so a host thread knows that a record has landed by looking at the record itself (no events,
+// no chunked copies: splitting the copy in eight cost 60 us per step).  The expansion is a table look-up of the format
+// only; no environment logic runs on the CPU.
+//
+//   code = 128 | state << 3 | colour   for doors (type 4, the only objects with a state)
+//        = type << 3 | colour          otherwise (type <= 10, colour <= 5)
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "mgrl.h"
+#include "mgrl_wire.cuh"
+
+extern "C" int mgrl_wire_have_ssse3(void);                                              // mgrl_wire_host.cpp
+extern "C" void mgrl_wire_expand_hwc_ssse3(const uint8_t* rec, uint8_t* out, int pad148);
+extern "C" int mgrl_wire_expand_block_hwc_ssse3(const uint8_t* recs, int count, uint8_t* out, int pitch, uint8_t tag, int tag_offset,
+                                                const volatile int* abort_flag);
+
+namespace mgrl_wire {
+
+namespace {
+
+constexpr int kRec = 64;           // bytes per wire record
+constexpr int kCells = 49;
+// record layout: [0..48] cell codes, 49 dir, 50 mission, 51 terminated, 52 truncated, 53 episode length, 54 terminal dir,
+// 55 step tag (1..255, changes every step: "this cache line belongs to the current step"), [56..59] reward, [60..63] pad
+constexpr int O_DIR = 49, O_MIS = 50, O_TERM = 51, O_TRUNC = 52, O_EPLEN = 53, O_TDIR = 54, O_TAG = 55, O_REW = 56;
+constexpr int kBlock = 512;        // records per work item
+
+__device__ __forceinline__ uint32_t cell_code(uint32_t t, uint32_t c, uint32_t s) {
+    return t == 4u ? (128u | (s << 3) | c) : ((t << 3) | c);
+}
+
+struct PackArgs {
+    const uint8_t* image;    // [n][pitch] encoded observation
+    const float* reward;     // small outputs, any may be null (image-only job)
+    const uint8_t *dir, *mission, *term, *trunc, *eplen, *tdir;
+    uint8_t* wire;           // [n][64]
+    int n, layout;
+    uint32_t tag;
+};
+
+// 16 threads per environment: 12 x four cells, cell 48 + (dir, mission, terminated), (truncated, length, terminal dir), reward, pad
+__global__ void __launch_bounds__(256) pack_codes_kernel(const PackArgs p) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int env = gid >> 4, j = gid & 15;
+    if (env >= p.n) return;
+    uint32_t* out = reinterpret_cast<uint32_t*>(p.wire) + (size_t)env * 16 + j;
+    auto triple = [&](int cell, uint32_t& t, uint32_t& c, uint32_t& s) {
+        if (p.layout == MGRL_OBS_CHW) {
+            const uint8_t* b = p.image + (size_t)env * 147 + cell;
+            t = b[0]; c = b[49]; s = b[98];
+        } else {
+            const uint8_t* b = p.image + (size_t)env * (p.layout == MGRL_OBS_HWC148 ? 148 : 147) + 3 * cell;
+            t = b[0]; c = b[1]; s = b[2];
+        }
+    };
+    if (j < 12) {
+        uint32_t w = 0;
+        if (p.layout == MGRL_OBS_HWC148) {   // aligned words: cells 4j..4j+3 are bytes 12j..12j+11
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(p.image + (size_t)env * 148) + 3 * j;
+            const uint32_t a = src[0], b = src[1], c = src[2];
+            w = cell_code(a & 0xFF, (a >> 8) & 0xFF, (a >> 16) & 0xFF) |
+                cell_code(a >> 24, b & 0xFF, (b >> 8) & 0xFF) << 8 |
+                cell_code((b >> 16) & 0xFF, b >> 24, c & 0xFF) << 16 |
+                cell_code((c >> 8) & 0xFF, (c >> 16) & 0xFF, c >> 24) << 24;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t t, c, s;
+                triple(4 * j + q, t, c, s);
+                w |= cell_code(t, c, s) << (8 * q);
+            }
+        }
+        *out = w;
+    } else if (j == 12) {
+        uint32_t t, c, s;
+        triple(48, t, c, s);
+        uint32_t w = cell_code(t, c, s);
+        if (p.dir) w |= (uint32_t)p.dir[env] << 8;
+        if (p.mission) w |= (uint32_t)p.mission[env] << 16;
+        if (p.term) w |= (uint32_t)p.term[env] << 24;
+        *out = w;
+    } else if (j == 13) {
+        uint32_t w = 0;
+        if (p.trunc) w |= p.trunc[env];
+        if (p.eplen) w |= (uint32_t)p.eplen[env] << 8;
+        if (p.tdir) w |= (uint32_t)p.tdir[env] << 16;
+        *out = w | (p.tag << 24);
+    } else if (j == 14) {
+        *out = p.reward ? __float_as_uint(p.reward[env]) : 0u;
+    } else {
+        *out = 0u;
+    }
+}
+
+inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#else
+    std::this_thread::yield();
+#endif
+}
+
+}  // namespace
+
+struct Job {
+    const uint8_t* wire = nullptr;     // pinned host records of this job
+    uint8_t* image = nullptr;          // caller's image array [n][pitch]
+    int layout = 0;
+    uint8_t *dir = nullptr, *mission = nullptr, *term = nullptr, *trunc = nullptr, *eplen = nullptr, *tdir = nullptr;
+    float* reward = nullptr;
+    uint8_t tag = 0;
+};
+
+struct Path {
+    int n = 0;
+    uint8_t* wire_dev[2] = {nullptr, nullptr};
+    uint8_t* wire_host[2] = {nullptr, nullptr};
+    uint32_t lut[256];
+    // pool
+    std::vector<std::thread> threads;
+    std::mutex m;
+    std::condition_variable cv;
+    std::atomic<uint64_t> next{0};     // epoch << 32 | next item: a new epoch publishes a step's jobs; items are claimed by CAS so
+                                       // that a thread still leaving the previous step can never claim (or skip) one of this step
+    std::atomic<int> done{0};
+    uint32_t epoch = 0;
+    std::atomic<bool> stop{false};
+    volatile int abort_flag = 0;       // set when the step's copy failed: give up on records that will never land
+    Job jobs[2];
+    int njobs = 0, nitems = 0, blocks = 0;
+    bool ssse3 = false, stream_stores = true;
+    uint8_t tag[2] = {0, 0};           // per staging buffer: bumped whenever that buffer is used (1..255)
+
+    void expand(const Job& jb, int lo, int hi) const {
+        const int pitch = jb.layout == MGRL_OBS_HWC148 ? 148 : 147;
+        bool image_done = false;
+        if (ssse3 && stream_stores && jb.layout != MGRL_OBS_CHW && ((reinterpret_cast<uintptr_t>(jb.image) + (size_t)lo * pitch) & 15) == 0) {
+            // the whole block's images with aligned non-temporal stores (this also waits for every record of the block)
+            const int got = mgrl_wire_expand_block_hwc_ssse3(jb.wire + (size_t)lo * kRec, hi - lo, jb.image + (size_t)lo * pitch, pitch, jb.tag,
+                                                             O_TAG, &abort_flag);
+            if (got < hi - lo) return;
+            image_done = true;
+        }
+        for (int r = lo; r < hi; ++r) {
+            const uint8_t* rec = jb.wire + (size_t)r * kRec;
+            // the record is one cache line written by the copy engine: its tag says whether it is this step's
+            const volatile uint8_t* vt = rec + O_TAG;
+            while (*vt != jb.tag) {
+                if (abort_flag) return;
+                cpu_relax();
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+            uint8_t* o = jb.image + (size_t)r * pitch;
+            if (image_done) {
+            } else if (jb.layout == MGRL_OBS_CHW) {
+                for (int i = 0; i < kCells; ++i) {
+                    const uint32_t e = lut[rec[i]];
+                    o[i] = (uint8_t)e; o[49 + i] = (uint8_t)(e >> 8); o[98 + i] = (uint8_t)(e >> 16);
+                }
+            } else if (ssse3) {
+                mgrl_wire_expand_hwc_ssse3(rec, o, pitch == 148);
+            } else {
+                for (int i = 0; i < kCells - 1; ++i) {          // overlapping 4-byte stores, three bytes apart
+                    const uint32_t e = lut[rec[i]];
+                    memcpy(o + 3 * i, &e, 4);
+                }
+                const uint32_t e = lut[rec[kCells - 1]];
+                if (pitch == 148) memcpy(o + 144, &e, 4);       // cell 48 + the record's pad byte (0)
+                else { o[144] = (uint8_t)e; o[145] = (uint8_t)(e >> 8); o[146] = (uint8_t)(e >> 16); }
+            }
+            if (jb.dir) jb.dir[r] = rec[O_DIR];
+            if (jb.mission) jb.mission[r] = rec[O_MIS];
+            if (jb.term) jb.term[r] = rec[O_TERM];
+            if (jb.trunc) jb.trunc[r] = rec[O_TRUNC];
+            if (jb.eplen) jb.eplen[r] = rec[O_EPLEN];
+            if (jb.tdir) jb.tdir[r] = rec[O_TDIR];
+            if (jb.reward) memcpy(jb.reward + r, rec + O_REW, 4);
+        }
+    }
+
+    // item i = (job, block of kBlock records), in copy order
+    void run_items(uint32_t ep) {
+        for (;;) {
+            uint64_t v = next.load(std::memory_order_acquire);
+            int i;
+            for (;;) {
+                if ((uint32_t)(v >> 32) != ep) return;
+                i = (int)(uint32_t)v;
+                if (i >= nitems) return;
+                if (next.compare_exchange_weak(v, v + 1, std::memory_order_acq_rel, std::memory_order_acquire)) break;
+            }
+            const int job = i / blocks, b = i - job * blocks;
+            const int lo = b * kBlock, hi = lo + kBlock < n ? lo + kBlock : n;
+            expand(jobs[job], lo, hi);
+            done.fetch_add(1, std::memory_order_release);
+        }
+    }
+
+    uint32_t current_epoch() const { return (uint32_t)(next.load(std::memory_order_acquire) >> 32); }
+
+    void worker() {
+        uint32_t seen = 0;
+        while (!stop.load(std::memory_order_acquire)) {
+            // spin briefly for the next step (vector steps arrive back to back), then sleep
+            const auto t0 = std::chrono::steady_clock::now();
+            bool got = false;
+            for (int spins = 0;; ++spins) {
+                if (current_epoch() != seen) { got = true; break; }
+                if (stop.load(std::memory_order_acquire)) return;
+                cpu_relax();
+                if ((spins & 1023) == 1023 &&
+                    std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(2)) break;
+            }
+            if (!got) {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait_for(lk, std::chrono::milliseconds(50),
+                            [&] { return current_epoch() != seen || stop.load(std::memory_order_acquire); });
+                if (current_epoch() == seen) continue;
+            }
+            seen = current_epoch();
+            run_items(seen);
+        }
+    }
+};
+
+Path* create(int n) {
+    Path* p = new Path();
+    p->n = n;
+    p->blocks = (n + kBlock - 1) / kBlock;
+    p->ssse3 = mgrl_wire_have_ssse3() != 0 && !getenv("MGRL_WIRE_SCALAR");
+    p->stream_stores = !getenv("MGRL_WIRE_NO_STREAM");
+    for (int c = 0; c < 256; ++c) {
+        const uint32_t t = c >= 128 ? 4u : (uint32_t)(c >> 3), col = (uint32_t)(c & 7), s = c >= 128 ? (uint32_t)((c >> 3) & 3) : 0u;
+        p->lut[c] = t | (col << 8) | (s << 16);
+    }
+    bool ok = true;
+    for (int k = 0; k < 2 && ok; ++k) {
+        ok = cudaMalloc(&p->wire_dev[k], (size_t)n * kRec) == cudaSuccess &&
+             cudaHostAlloc(reinterpret_cast<void**>(&p->wire_host[k]), (size_t)n * kRec, cudaHostAllocDefault) == cudaSuccess;
+        if (ok) memset(p->wire_host[k], 0, (size_t)n * kRec);       // tag 0 = nothing has landed
+    }
+    if (!ok) { destroy(p); return nullptr; }
+    int nthreads = (int)std::thread::hardware_concurrency();
+    if (const char* v = getenv("LOCAL_WORLD_SIZE")) { const int w = atoi(v); if (w > 1) nthreads /= w; }
+    if (const char* v = getenv("MGRL_HOST_THREADS")) nthreads = atoi(v);
+    nthreads = nthreads < 1 ? 1 : (nthreads > 32 ? 32 : nthreads);
+    if (nthreads > p->blocks) nthreads = p->blocks;
+    for (int t = 0; t + 1 < nthreads; ++t) p->threads.emplace_back([p] { p->worker(); });   // the calling thread works too
+    return p;
+}
+
+void destroy(Path* p) {
+    if (!p) return;
+    p->stop.store(true, std::memory_order_release);
+    { std::lock_guard<std::mutex> lk(p->m); }
+    p->cv.notify_all();
+    for (auto& t : p->threads) t.join();
+    for (int k = 0; k < 2; ++k) {
+        if (p->wire_dev[k]) cudaFree(p->wire_dev[k]);
+        if (p->wire_host[k]) cudaFreeHost(p->wire_host[k]);
+    }
+    delete p;
+}
+
+int host_threads(const Path* p) { return p ? (int)p->threads.size() + 1 : 0; }
+
+cudaError_t step(Path* p, const Outputs& main, const Outputs* extra, cudaStream_t s) {
+    static const bool debug = getenv("MGRL_WIRE_DEBUG") != nullptr;
+    static double acc[2] = {0, 0};
+    static int nacc = 0;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto us_since = [&](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    };
+    const Outputs* outs[2] = {&main, extra};
+    const int njobs = extra ? 2 : 1;
+    const int n = p->n;
+    for (int k = 0; k < njobs; ++k) {
+        const Outputs& o = *outs[k];
+        p->tag[k] = (uint8_t)(p->tag[k] == 255 ? 1 : p->tag[k] + 1);
+        PackArgs a = {};
+        a.image = o.image_dev; a.reward = o.reward_dev; a.dir = o.dir_dev; a.mission = o.mission_dev; a.term = o.term_dev;
+        a.trunc = o.trunc_dev; a.eplen = o.eplen_dev; a.tdir = o.tdir_dev; a.wire = p->wire_dev[k]; a.n = n; a.layout = o.layout;
+        a.tag = p->tag[k];
+        pack_codes_kernel<<<(unsigned)(((size_t)n * 16 + 255) / 256), 256, 0, s>>>(a);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(p->wire_host[k], p->wire_dev[k], (size_t)n * kRec, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) return e;
+        Job& jb = p->jobs[k];
+        jb.wire = p->wire_host[k]; jb.image = o.image_host; jb.layout = o.layout; jb.dir = o.dir_host; jb.mission = o.mission_host;
+        jb.term = o.term_host; jb.trunc = o.trunc_host; jb.eplen = o.eplen_host; jb.tdir = o.tdir_host; jb.reward = o.reward_host;
+        jb.tag = p->tag[k];
+    }
+    // publish the step to the pool: the threads chase the copy, record by record
+    p->njobs = njobs;
+    p->nitems = njobs * p->blocks;
+    p->done.store(0, std::memory_order_relaxed);
+    p->abort_flag = 0;
+    p->epoch += 1;
+    p->next.store((uint64_t)p->epoch << 32, std::memory_order_release);
+    if (!p->threads.empty()) p->cv.notify_all();
+    const double t_issued = us_since(t_begin);
+    p->run_items(p->epoch);
+    cudaError_t err = cudaSuccess;
+    for (int spins = 0; p->done.load(std::memory_order_acquire) < p->nitems; ++spins) {
+        cpu_relax();
+        if ((spins & 0xFFFF) == 0xFFFF && cudaStreamQuery(s) != cudaErrorNotReady) {
+            // the copy is over (or failed): records that still show an old tag will never arrive
+            err = cudaStreamSynchronize(s);
+            if (err != cudaSuccess) p->abort_flag = 1;   // expand() gives up on missing records
+        }
+    }
+    if (err != cudaSuccess) return err;
+    err = cudaStreamSynchronize(s);
+    if (debug) {
+        acc[0] += t_issued; acc[1] += us_since(t_begin);
+        if (++nacc == 64) {
+            fprintf(stderr, "[mgrl_wire] us per step: issued %.1f, expanded %.1f (threads %d)\n", acc[0] / 64, acc[1] / 64,
+                    (int)p->threads.size() + 1);
+            acc[0] = acc[1] = 0; nacc = 0;
+        }
+    }
+    return err;
+}
+
+}  // namespace mgrl_wire

@@ -1,0 +1,89 @@
+// mgrl_wire_host.cpp — host half of the PCIe wire format (mgrl_wire.cu): one 64-byte record -> the 49 (type, colour, state)
+// triples of an HWC observation record, with SSSE3 byte shuffles (16 cells per iteration).  Compiled with -mssse3; the caller
+// picks this routine only when the CPU reports SSSE3 (mgrl_wire_have_ssse3), else its scalar table loop.
+//   code = 128 | state << 3 | colour  for doors (type 4),  type << 3 | colour  otherwise
+#include <tmmintrin.h>
+
+#include <cstdint>
+#include <cstring>
+
+extern "C" int mgrl_wire_have_ssse3(void) {
+    __builtin_cpu_init();
+    return __builtin_cpu_supports("ssse3") ? 1 : 0;
+}
+
+namespace {
+struct Masks {
+    __m128i t[3], c[3], s[3];
+};
+inline Masks make_masks() {
+    Masks m;
+    alignas(16) uint8_t b[3][3][16];
+    for (int v = 0; v < 3; ++v)
+        for (int j = 0; j < 16; ++j) {
+            const int byte = 16 * v + j, q = byte / 3, r = byte % 3;     // output byte = component r of cell q (of 16)
+            for (int comp = 0; comp < 3; ++comp) b[comp][v][j] = (uint8_t)(r == comp ? q : 0x80);
+        }
+    for (int v = 0; v < 3; ++v) {
+        m.t[v] = _mm_load_si128(reinterpret_cast<const __m128i*>(b[0][v]));
+        m.c[v] = _mm_load_si128(reinterpret_cast<const __m128i*>(b[1][v]));
+        m.s[v] = _mm_load_si128(reinterpret_cast<const __m128i*>(b[2][v]));
+    }
+    return m;
+}
+}  // namespace
+
+// rec: 49 code bytes (at least 64 readable); out: 147 bytes (pad148 != 0: 148, the last byte written 0)
+extern "C" void mgrl_wire_expand_hwc_ssse3(const uint8_t* rec, uint8_t* out, int pad148) {
+    static const Masks m = make_masks();
+    const __m128i seven = _mm_set1_epi8(7), three = _mm_set1_epi8(3), four = _mm_set1_epi8(4), lo5 = _mm_set1_epi8(0x1F);
+    for (int g = 0; g < 3; ++g) {
+        const __m128i code = _mm_loadu_si128(reinterpret_cast<const __m128i*>(rec + 16 * g));
+        const __m128i door = _mm_cmpgt_epi8(_mm_setzero_si128(), code);                       // code >= 128
+        const __m128i hi = _mm_and_si128(_mm_srli_epi16(code, 3), lo5);                        // code >> 3 per byte
+        const __m128i T = _mm_or_si128(_mm_andnot_si128(door, hi), _mm_and_si128(door, four));
+        const __m128i C = _mm_and_si128(code, seven);
+        const __m128i S = _mm_and_si128(_mm_and_si128(hi, three), door);
+        uint8_t* o = out + 48 * g;
+        for (int v = 0; v < 3; ++v) {
+            const __m128i x = _mm_or_si128(_mm_or_si128(_mm_shuffle_epi8(T, m.t[v]), _mm_shuffle_epi8(C, m.c[v])),
+                                           _mm_shuffle_epi8(S, m.s[v]));
+            _mm_storeu_si128(reinterpret_cast<__m128i*>(o + 16 * v), x);
+        }
+    }
+    const uint32_t c = rec[48];
+    const uint32_t t = c >= 128 ? 4u : (c >> 3), s = c >= 128 ? ((c >> 3) & 3u) : 0u;
+    out[144] = (uint8_t)t; out[145] = (uint8_t)(c & 7u); out[146] = (uint8_t)s;
+    if (pad148) out[147] = 0;
+}
+
+// A block of `count` consecutive records (rec pitch 64) -> `count` consecutive HWC observation records of `pitch` bytes at
+// `out`, written with non-temporal 16-byte stores: the images are write-only here, and ordinary stores would first READ every
+// destination line into the cache (the expansion is bound by host memory traffic, not by the shuffles).  `out` must be 16-byte
+// aligned; bytes are carried across records so that every store is an aligned unit; the tail (< 16 bytes) uses memcpy.
+// `ready(i)` is called before record i is read and returns 0 to stop (the caller's "has this record landed" poll).
+extern "C" int mgrl_wire_expand_block_hwc_ssse3(const uint8_t* recs, int count, uint8_t* out, int pitch, uint8_t tag, int tag_offset,
+                                                const volatile int* abort_flag) {
+    alignas(16) uint8_t tmp[16 + 160];
+    int carry = 0;                       // bytes already in tmp (< 16)
+    uint8_t* dst = out;                  // next aligned unit
+    for (int r = 0; r < count; ++r) {
+        const uint8_t* rec = recs + (size_t)r * 64;
+        const volatile uint8_t* vt = rec + tag_offset;
+        while (*vt != tag) {
+            if (*abort_flag) return r;
+            _mm_pause();
+        }
+        __atomic_thread_fence(__ATOMIC_ACQUIRE);
+        mgrl_wire_expand_hwc_ssse3(rec, tmp + carry, pitch == 148);
+        const int have = carry + pitch, units = have >> 4;
+        for (int u = 0; u < units; ++u)
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + u, _mm_load_si128(reinterpret_cast<const __m128i*>(tmp) + u));
+        dst += units * 16;
+        carry = have & 15;
+        if (carry) memcpy(tmp, tmp + units * 16, 16);       // the partial unit moves to the front
+    }
+    if (carry) memcpy(dst, tmp, carry);
+    _mm_sfence();
+    return count;
+}

@@ -111,6 +111,42 @@ def test_step_frames_host_path_matches_oracle():
         env.close()
 
 
+@pytest.mark.parametrize("layout,see", [("hwc148", True), ("chw", False), ("hwc", False)])
+def test_step_frames_wire_format_with_chunks_and_host_threads(layout, see):
+    """The host path's PCIe wire format (csrc/mgrl_wire.cu: one code byte per view cell, 64-byte records, chunked copies
+    expanded by the handle's host threads) at a size that uses several chunks and threads: every output array bit-exact
+    against the oracle, including occluded views (unseen cells = (0,0,0)) and the terminal observations."""
+    kw = dict(problem="multi", mission=None, see_through_walls=see)
+    n = 20000
+    env = mg.B200VecEnv(mg.EnvConfig(**kw), num_envs=n, seed=21, env_id_base=5, layout=layout)
+    o = orc.OracleVecEnv(orc.make_config(**kw), n, seed=21, env_id_base=5, nthreads=8)
+    img, d, m = env.reset_frames()
+    o.reset()
+
+    def view(x):
+        x = x[:, :147]
+        return x.reshape(-1, 3, 7, 7).transpose(0, 2, 3, 1) if layout == "chw" else x.reshape(-1, 7, 7, 3)
+
+    assert np.array_equal(view(img), o.obs)
+    rs = np.random.RandomState(8)
+    for t in range(24):
+        a = biased_actions(rs, n).astype(np.uint8)
+        img, d, m, rew, term, trunc, ep_len, timg, tdir = env.step_frames(a, want_terminal=True)
+        o.step(a)
+        assert np.array_equal(view(img), o.obs), t
+        assert np.array_equal(d, o.dir) and np.array_equal(m, o.mission), t
+        assert np.array_equal(rew.view(np.uint32), o.reward.view(np.uint32)), t
+        assert np.array_equal(term, o.term) and np.array_equal(trunc, o.trunc) and np.array_equal(ep_len, o.ep_len), t
+        done = (o.term | o.trunc).astype(bool)
+        assert np.array_equal(view(timg[done]), o.term_obs[done]), t
+        if t % 2:                                      # and without the terminal outputs (one job instead of two)
+            a = biased_actions(rs, n).astype(np.uint8)
+            img, d, m, rew, term, trunc, ep_len = env.step_frames(a)[:7]
+            o.step(a)
+            assert np.array_equal(view(img), o.obs) and np.array_equal(rew.view(np.uint32), o.reward.view(np.uint32)), t
+    env.close()
+
+
 def test_sb3_vecenv_binding_drives_collect_rollouts():
     """ppo.py:134,159: the class bound over SB3's VecEnv base (a faithful stand-in here, tests/support/fake_sb3.py) with
     gymnasium-style spaces goes through OnPolicyAlgorithm.collect_rollouts' use of the environment - spaces -> buffers,

@@ -121,3 +121,24 @@ def test_expert_vocabulary_round_trip():
     vocab = [" "] + [chr(c) for c in range(ord("a"), ord("z") + 1)]
     for i, text in enumerate(mg.MISSIONS):
         assert "".join(vocab[k] for k in tab[i]).rstrip() == text
+
+
+def test_wire_format_host_expander_matches_the_code_table():
+    """csrc/mgrl_wire_host.cpp (SSSE3 shuffles) against the definition of the PCIe wire code: 128 | state << 3 | colour for
+    doors (type 4), type << 3 | colour otherwise.  Host code only: runs without a GPU."""
+    import ctypes
+    lib = ctypes.CDLL(mg.library_path())
+    if not lib.mgrl_wire_have_ssse3():
+        pytest.skip("CPU without SSSE3: the library uses its scalar table loop")
+    rs = np.random.RandomState(0)
+    valid = [c for c in range(256) if (c < 128 and (c >> 3) <= 10 and (c & 7) < 6) or (128 <= c < 160 and ((c >> 3) & 3) < 3 and (c & 7) < 6)]
+    for trial in range(100):
+        rec = np.zeros(64, np.uint8)
+        rec[:49] = rs.choice(valid, 49)
+        rec[49:] = rs.randint(0, 256, 15)                    # scalars / tag / pad: must not leak into the image
+        for pad in (0, 1):
+            out = np.full(160, 0xAA, np.uint8)
+            lib.mgrl_wire_expand_hwc_ssse3(rec.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), pad)
+            want = np.array([(4, c & 7, (c >> 3) & 3) if c >= 128 else (c >> 3, c & 7, 0) for c in rec[:49].tolist()], np.uint8)
+            assert np.array_equal(out[:147], want.reshape(-1)), trial
+            assert out[147] == (0 if pad else 0xAA) and (out[148:] == 0xAA).all()
