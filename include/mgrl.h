@@ -249,6 +249,8 @@ typedef struct {
     float clip_range, clip_range_vf /* < 0: no value clipping */, ent_coef, vf_coef;
     int normalize_advantage; /* (adv - mean) / (std + 1e-8) with the minibatch moments of adv_sums_dev */
     int strict_fp32;         /* 1: three-term split TF32 (fp32-class results); 0: one TF32 pass like ppo.py:29-32 */
+    int use_tcgen05;         /* with strict_fp32 = 0: the 208 x 128 MLP GEMMs (forward and dX) as tcgen05.mma kind::tf32 with the
+                              * accumulator in TMEM (csrc/mgrl_linear_tc5.cu) instead of mma.sync */
 } mgrl_ppo_hyper;
 int mgrl_ppo_create(int device, int max_batch, int num_sequences, mgrl_ppo **out);
 int mgrl_ppo_destroy(mgrl_ppo *ctx);
@@ -274,6 +276,8 @@ int mgrl_ppo_apply(mgrl_ppo *ctx, float lr, float max_grad_norm, float grad_scal
 /* device pointer of an internal activation buffer of the last mgrl_ppo_gradients call (tests): "pooled", "h2", "f", "a1",
  * "a2", "dz2", "dz1", "df", "dh2", "dpooled", "lut", "dlut", "stats" */
 int mgrl_ppo_debug_buffer(mgrl_ppo *ctx, const char *name, void **out);
+/* copies `count` floats of that buffer to dst_dev (device to device, stream ordered) */
+int mgrl_ppo_debug_copy(mgrl_ppo *ctx, const char *name, float *dst_dev, long long count, void *stream);
 
 /* ---- host-buffer drop-in path (what B200VecEnv.reset/step with numpy arrays calls) --- */
 

@@ -29,7 +29,7 @@ class RolloutView(C.Structure):          # mgrl_rollout_view
 
 class PPOHyper(C.Structure):             # mgrl_ppo_hyper
     _fields_ = [("clip_range", C.c_float), ("clip_range_vf", C.c_float), ("ent_coef", C.c_float), ("vf_coef", C.c_float),
-                ("normalize_advantage", C.c_int), ("strict_fp32", C.c_int)]
+                ("normalize_advantage", C.c_int), ("strict_fp32", C.c_int), ("use_tcgen05", C.c_int)]
 
 
 def library_path() -> str:
@@ -93,6 +93,7 @@ _SIGNATURES = {
     "mgrl_ppo_gradients": (C.c_int, [vp, C.POINTER(RolloutView), vp, C.c_int, vp, C.POINTER(PPOHyper), vp, vp, vp, vp]),
     "mgrl_ppo_apply": (C.c_int, [vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, vp, vp]),
     "mgrl_ppo_debug_buffer": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
+    "mgrl_ppo_debug_copy": (C.c_int, [vp, C.c_char_p, vp, C.c_longlong, vp]),
 }
 EXPORTS = sorted(_SIGNATURES)
 

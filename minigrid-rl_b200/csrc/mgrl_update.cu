@@ -28,6 +28,7 @@
 
 #include "mgrl.h"
 #include "mgrl_policy_layout.cuh"
+#include "mgrl_linear_tc5.cuh"
 
 char* mgrl_error_buffer();
 
@@ -975,6 +976,7 @@ struct Ctx {
     const uint8_t* tokens = nullptr;
     // owned
     void* frag = nullptr; float* pbias = nullptr;
+    float* canon = nullptr;          // two core-matrix images of the first MLP layer's weights (tcgen05 path)
     int32_t *t = nullptr, *i = nullptr;
     uint8_t *age = nullptr, *dcode = nullptr, *act = nullptr, *arg = nullptr;
     long long* mrow = nullptr;
@@ -1086,6 +1088,7 @@ int mgrl_ppo_create(int device, int max_batch, int num_sequences, mgrl_ppo** out
     const size_t B = (size_t)max_batch, R = (size_t)SEQ_LEN * num_sequences;
     UP_TRY(cudaMalloc(&c.frag, (size_t)kPackEntries * 16));
     UP_TRY(dev_alloc(&c.pbias, PB_TOTAL));
+    UP_TRY(dev_alloc(&c.canon, 2 * mgrl_tc5::CANON_FLOATS));
     UP_TRY(dev_alloc(&c.t, B)); UP_TRY(dev_alloc(&c.i, B));
     UP_TRY(dev_alloc(&c.age, B)); UP_TRY(dev_alloc(&c.dcode, B)); UP_TRY(dev_alloc(&c.act, B)); UP_TRY(dev_alloc(&c.arg, B * 144));
     UP_TRY(dev_alloc(&c.mrow, B));
@@ -1110,7 +1113,7 @@ int mgrl_ppo_destroy(mgrl_ppo* h) {
     if (!h) return MGRL_OK;
     Ctx& c = h->c;
     cudaSetDevice(c.device);
-    void* ptrs[] = {c.frag, c.pbias, c.t, c.i, c.age, c.dcode, c.act, c.arg, c.mrow, c.oldv, c.oldlp, c.adv, c.ret, c.pooled, c.h2, c.f, c.a1,
+    void* ptrs[] = {c.frag, c.pbias, c.canon, c.t, c.i, c.age, c.dcode, c.act, c.arg, c.mrow, c.oldv, c.oldlp, c.adv, c.ret, c.pooled, c.h2, c.f, c.a1,
                     c.a2, c.dz2, c.dz1, c.df, c.dh2, c.dpooled, c.gi, c.store, c.hprev_rows, c.dgh_rows, c.lut, c.dlut, c.dgi_tab, c.stats, c.partial};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete h;
@@ -1187,9 +1190,18 @@ int mgrl_ppo_gradients(mgrl_ppo* h, const mgrl_rollout_view* rv, const int32_t* 
     assemble_kernel<<<(unsigned)(((size_t)B * 32 + 255) / 256), 256, 0, s>>>(c.P, c.lut, c.dcode, c.age, c.mrow, B, c.f);
     UP_TRY(cudaGetLastError());
     // first MLP layer, pi | vf: f [B,208] -> a1 [B,128]
-    g = GemmArgs{}; g.a = c.f; g.lda = 208; g.frag = frag_ptr(&c, PK_L1F, strict); g.bias = c.pbias + PB_L1;
-    g.out = c.a1; g.ldo = 128; g.rows = B;
-    UP_TRY((launch_rows_gemm<208, 16, LD_PLAIN, EP_BIAS_TANH>(g, 1, strict, s)));
+    const bool tc5 = !strict && hp->use_tcgen05 != 0;
+    if (tc5) {
+        UP_TRY(mgrl_tc5::pack_canonical(c.P, c.canon, mgrl_tc5::W_L1F, s));
+        UP_TRY(mgrl_tc5::pack_canonical(c.P, c.canon + mgrl_tc5::CANON_FLOATS, mgrl_tc5::W_L1B, s));
+        mgrl_tc5::Args ta = {};
+        ta.a = c.f; ta.lda = 208; ta.w_canon = c.canon; ta.bias = c.pbias + PB_L1; ta.out = c.a1; ta.ldo = 128; ta.rows = B;
+        UP_TRY(mgrl_tc5::launch_l1_forward(ta, s));
+    } else {
+        g = GemmArgs{}; g.a = c.f; g.lda = 208; g.frag = frag_ptr(&c, PK_L1F, strict); g.bias = c.pbias + PB_L1;
+        g.out = c.a1; g.ldo = 128; g.rows = B;
+        UP_TRY((launch_rows_gemm<208, 16, LD_PLAIN, EP_BIAS_TANH>(g, 1, strict, s)));
+    }
     // second MLP layer: a1[:, g*64 ..] -> a2[:, g*64 ..]
     g = GemmArgs{}; g.a = c.a1; g.lda = 128; g.a_col_step = 64; g.frag = frag_ptr(&c, PK_L2F, strict); g.frag_step = frag_step(PK_L2F);
     g.bias = c.pbias + PB_L2; g.bias_step = 64; g.out = c.a2; g.ldo = 128; g.out_col_step = 64; g.rows = B;
@@ -1217,9 +1229,15 @@ int mgrl_ppo_gradients(mgrl_ppo* h, const mgrl_rollout_view* rv, const int32_t* 
     w = WgradArgs{}; w.dz = c.dz1; w.ldz = 128; w.x = c.f; w.ldx = 208; w.dw = c.G + P_PI1; w.db = c.G + P_PI1B;
     w.dw_hi = c.G + P_VF1; w.db_hi = c.G + P_VF1B; w.split = 64; w.rows = B;
     UP_TRY((launch_wgrad<128, 208, LD_PLAIN, false>(w, 1, strict, c.sms, s)));
-    g = GemmArgs{}; g.a = c.dz1; g.lda = 128; g.frag = frag_ptr(&c, PK_L1B, strict); g.frag_step = frag_step(PK_L1B);
-    g.y = c.f; g.ldy = 208; g.y_col_step = 104; g.out = c.df; g.ldo = 208; g.out_col_step = 104; g.rows = B;
-    UP_TRY((launch_rows_gemm<128, 13, LD_PLAIN, EP_GRAD_MIX>(g, 2, strict, s)));
+    if (tc5) {
+        mgrl_tc5::Args ta = {};
+        ta.a = c.dz1; ta.lda = 128; ta.w_canon = c.canon + mgrl_tc5::CANON_FLOATS; ta.y = c.f; ta.ldy = 208; ta.out = c.df; ta.ldo = 208; ta.rows = B;
+        UP_TRY(mgrl_tc5::launch_l1_backward(ta, s));
+    } else {
+        g = GemmArgs{}; g.a = c.dz1; g.lda = 128; g.frag = frag_ptr(&c, PK_L1B, strict); g.frag_step = frag_step(PK_L1B);
+        g.y = c.f; g.ldy = 208; g.y_col_step = 104; g.out = c.df; g.ldo = 208; g.out_col_step = 104; g.rows = B;
+        UP_TRY((launch_rows_gemm<128, 13, LD_PLAIN, EP_GRAD_MIX>(g, 2, strict, s)));
+    }
     // direction Linear and mission table rows
     {
         int grid = (B + 16 * 64 - 1) / (16 * 64);
@@ -1284,6 +1302,16 @@ int mgrl_ppo_debug_buffer(mgrl_ppo* h, const char* name, void** out) {
     }
     snprintf(mgrl_error_buffer(), kErrBytes, "mgrl_ppo_debug_buffer: unknown buffer");
     return MGRL_ERR_INVALID;
+}
+
+int mgrl_ppo_debug_copy(mgrl_ppo* h, const char* name, float* dst_dev, long long count, void* stream) {
+    void* src = nullptr;
+    const int rc = mgrl_ppo_debug_buffer(h, name, &src);
+    if (rc != MGRL_OK) return rc;
+    const char* what = "mgrl_ppo_debug_copy";
+    if (!dst_dev || count <= 0 || !src) { snprintf(mgrl_error_buffer(), kErrBytes, "%s: bad argument", what); return MGRL_ERR_INVALID; }
+    UP_TRY(cudaMemcpyAsync(dst_dev, src, (size_t)count * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return MGRL_OK;
 }
 
 }  // extern "C"

@@ -45,6 +45,7 @@ class PPOConfig:                      # hydra_configs/algorithm/ppo.yaml:9-40
     native_conv1: bool = True         # first extractor stage of the update in the hand-written kernels (CUDA only)
     cuda_graph: bool = True           # replay the optimizer step (forward + backward + clip + Adam) from a CUDA graph
     native_update: bool = True        # the whole optimizer step in hand-written kernels (csrc/mgrl_update.cu; CUDA only)
+    update_tcgen05: bool = True       # with update_tf32: the 208 x 128 MLP GEMMs as tcgen05.mma + TMEM (csrc/mgrl_linear_tc5.cu)
     total_timesteps: float = 2e7
 
 
@@ -342,7 +343,7 @@ class NativeUpdater:
         self._ensure(int(max_batch or cfg.batch_size))
         self.hyper = nat.PPOHyper(float(cfg.clip_range), float(-1.0 if cfg.clip_range_vf is None else cfg.clip_range_vf),
                                   float(cfg.ent_coef), float(cfg.vf_coef), int(bool(cfg.normalize_advantage)),
-                                  int(not cfg.update_tf32))
+                                  int(not cfg.update_tf32), int(bool(cfg.update_tcgen05 and cfg.update_tf32)))
         self.schedule = linear_schedule(cfg.initial_learning_rate, cfg.final_learning_rate)
         self.lr = float(cfg.initial_learning_rate)
         self.steps = 0                      # Adam step counter
@@ -380,7 +381,8 @@ class NativeUpdater:
     def describe(self) -> str:
         return ("hand-written end to end (mgrl_ppo_gradients + mgrl_ppo_apply: mma.sync TF32 GEMM kernels with fused epilogues, "
                 "register-resident GRU forward/backward, loss, clip + Adam; "
-                + ("three-term split, fp32-class" if self.hyper.strict_fp32 else "one TF32 pass like ppo.py:29-32") + ")")
+                + ("three-term split, fp32-class" if self.hyper.strict_fp32 else "one TF32 pass like ppo.py:29-32")
+                + ("; 208 x 128 MLP GEMMs on tcgen05.mma kind::tf32 with TMEM accumulators" if self.hyper.use_tcgen05 else "") + ")")
 
     def all_reduces_per_step(self) -> int:
         return 0 if self.world == 1 else 1
@@ -456,16 +458,12 @@ class NativeUpdater:
             o += v.numel()
         return loss.detach().clone(), out
 
-    def debug_buffer(self, name: str, shape, dtype=None):
+    def debug_buffer(self, name: str, shape):
         """a copy of an internal activation buffer of the last gradients call (tests)"""
         torch, C = self.torch, self.C
-        ptr = C.c_void_p()
-        self.nat.check(self.nat.lib().mgrl_ppo_debug_buffer(self._h, name.encode(), C.byref(ptr)), "mgrl_ppo_debug_buffer")
-        n = int(np.prod(shape))
-        out = torch.empty(n, dtype=torch.float32, device=self.policy.device)
-        torch.cuda.current_stream(self.policy.device).synchronize()
-        rc = torch.cuda.cudart().cudaMemcpy(out.data_ptr(), ptr.value, n * 4, 3)
-        assert int(rc) == 0, rc
+        out = torch.empty(int(np.prod(shape)), dtype=torch.float32, device=self.policy.device)
+        self.nat.check(self.nat.lib().mgrl_ppo_debug_copy(self._h, name.encode(), C.c_void_p(out.data_ptr()), int(out.numel()),
+                                                          self._stream()), "mgrl_ppo_debug_copy")
         return out.view(*shape)
 
     def mission_table(self):

@@ -625,3 +625,32 @@ def test_handwritten_iteration_runs_ragged_minibatches_and_keeps_parameter_views
     assert torch.isfinite(eng.buf["values"]).all()
     assert eng.env.error_flags() == 0
     eng.env.close()
+
+
+def test_tcgen05_mlp_gemms_match_the_mma_sync_path():
+    """csrc/mgrl_linear_tc5.cu (tcgen05.mma kind::tf32, operands in shared-memory core matrices, accumulator in TMEM, epilogue
+    through tcgen05.ld) against the mma.sync kernels for the same minibatch with one TF32 pass: first-layer activations, the
+    feature gradient and every parameter gradient agree to TF32 rounding, and both sit within the TF32 bound of the float64
+    oracle.  A ragged batch (not a multiple of the 128-row tile) exercises the zero-filled tail."""
+    n, T = 250, 13                                       # 3250 samples = 25 tiles + 50 rows
+    outs = []
+    for tc5 in (False, True):
+        eng, o = make_engine(n, T, update_tf32=True, update_tcgen05=tc5)
+        assert bool(eng.updater.hyper.use_tcgen05) == tc5
+        eng.collect(); eng.bootstrap_truncated(); eng.compute_advantages()
+        t = torch.arange(T, device="cuda").repeat_interleave(n)
+        i = torch.arange(n, device="cuda").repeat(T)
+        loss, grads = eng.updater.gradients(eng.buf, t, i)
+        a1 = eng.updater.debug_buffer("a1", (n * T, 128)).clone()
+        df = eng.updater.debug_buffer("df", (n * T, 208)).clone()
+        outs.append((loss, grads, a1, df, eng, o, t, i))
+    (l0, g0, a0, d0, *_), (l1, g1, a1, d1, eng, o, t, i) = outs
+    assert close(a1, a0, 2e-3) and close(d1, d0, 4e-3)
+    assert abs(l0.item() - l1.item()) <= 2e-3 * max(1.0, abs(l0.item()))
+    stacks = oracle_stacks(eng.buf, T, n)
+    lo, want = _oracle_minibatch_grads(po.double_copy(o), eng, t, i, stacks)
+    for k, w in want.items():
+        err = float((g1[k].cpu().double() - w).abs().max()) / max(float(w.abs().max()), 1e-12)
+        assert err <= 5e-3, (k, err)
+    for e in (outs[0][4], outs[1][4]):
+        e.env.close()
