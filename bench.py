@@ -193,6 +193,14 @@ def main():
                          "(use --impl reference for the CPU baseline arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1 and hasattr(os, "sched_setaffinity") and os.environ.get("MGRL_BENCH_PIN", "1") != "0":
+        # one slice of the host cores per rank: the launch thread of a rank (and the host threads of its e2e path) do not
+        # migrate onto another rank's cores
+        cores = sorted(os.sched_getaffinity(0))
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+        per = max(1, len(cores) // local_world)
+        mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
     dist = None
     if world > 1:
         import torch.distributed as dist

@@ -6,12 +6,13 @@
 //
 //   out[r, 0:N] = epilogue( sum_k A[r, k] * W[n, k] )        A: [rows, K] fp32 row-major (lda), W: [N, K] K-major
 //
-// One CTA = one 128-row tile (TMEM lane = row).  Shared memory: the A tile and all of W as 8-row x 16-byte core matrices
-// (core matrices adjacent along K: LBO = 128 B; 8-row groups K/4 * 128 B apart: SBO).  W is pre-arranged in global memory in
-// exactly that image by pack_canonical_kernel, so its load is a linear 16-byte cp.async stream.
+// A tile = 128 rows (TMEM lane = row).  Shared memory holds all of W and a ring of A half-tiles as 8-row x 16-byte core
+// matrices (core matrices adjacent along K: LBO = 128 B; 8-row groups (K/4) * 128 B apart: SBO).  W is pre-arranged in global
+// memory in exactly that image by pack_canonical_kernel, so its load is a linear 16-byte cp.async stream.
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <type_traits>
 
 #include "mgrl_linear_tc5.cuh"
 
@@ -92,109 +93,206 @@ __global__ void pack_canonical_kernel(const float* __restrict__ P, float* __rest
     out[(n >> 3) * (K / 4) * 32 + (k >> 2) * 32 + (n & 7) * 4 + (k & 3)] = __uint_as_float(r);
 }
 
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// tcgen05.commit: the barrier gets one arrival when every tcgen05.mma issued by this thread so far has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float fast_tanh(float x) {
+    const float e = __expf(-2.f * fabsf(x));
+    return copysignf(__fdividef(1.f - e, 1.f + e), x);
+}
+
+// Persistent, warp-specialised: one CTA per SM walks the 128-row tiles with stride gridDim.x.
+//   warp 4   producer: W once, then the A tiles as K-halves into a ring of shared-memory stages (cp.async; a stage is
+//            published with fence.proxy.async + mbarrier arrive once its copies have landed)
+//   warp 5   one thread issues tcgen05.mma (K/16 instructions per stage) into one of TWO TMEM accumulators and commits: the
+//            stage's "empty" barrier when its MMAs are done, the accumulator's "full" barrier after the tile's last one
+//   warps 0-3 epilogue: TMEM lane quadrant w -> registers (tcgen05.ld, 32 columns at a time) -> bias / activation / gradient mask
+//            -> global; the accumulator goes back to the MMA warp as soon as it has been read
+template <int K, int N>
+struct Tc5Cfg {
+    static constexpr int KH0 = ((K / 2 + 15) / 16) * 16, KH1 = K - KH0;   // columns of the two stages of a tile (multiples of 16)
+    static constexpr uint32_t W_BYTES = (uint32_t)N * K * 4u, STAGE_BYTES = 128u * KH0 * 4u;
+    static constexpr int STAGES_FIT = (int)((227u * 1024u - 1024u - W_BYTES) / STAGE_BYTES);
+    static constexpr int STAGES = STAGES_FIT > 4 ? 4 : STAGES_FIT;
+    static constexpr uint32_t ACC_COLS = N <= 128 ? 128 : 256, TMEM_COLS = 2 * ACC_COLS;
+    static constexpr uint32_t SMEM = W_BYTES + STAGES * STAGE_BYTES + 256;
+    static_assert(STAGES >= 2 && K % 16 == 0 && KH1 > 0 && N % 16 == 0 && N <= 256, "tile shape");
+};
+
 template <int K, int N, int EPI>
-__global__ void __launch_bounds__(128, 1) linear_tc5_kernel(const Args p) {
+__global__ void __launch_bounds__(192, 1) linear_tc5_kernel(const Args p) {
+    using Cfg = Tc5Cfg<K, N>;
+    constexpr int KH0 = Cfg::KH0, KH1 = Cfg::KH1, S = Cfg::STAGES;
+    constexpr uint32_t LBO = 128u, SBO_W = (K / 4) * 128u;
     extern __shared__ __align__(128) uint8_t smem[];
-    constexpr uint32_t A_BYTES = 128u * K * 4u, B_BYTES = (uint32_t)N * K * 4u;
-    constexpr uint32_t LBO = 128u, SBO = (K / 4) * 128u;
-    constexpr uint32_t TMEM_COLS = N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + A_BYTES;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + A_BYTES + B_BYTES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + A_BYTES + B_BYTES + 8);
+    uint8_t* sW = smem;
+    uint8_t* sA = smem + Cfg::W_BYTES;
+    const uint32_t bars = smem_u32(smem + Cfg::W_BYTES + S * Cfg::STAGE_BYTES);     // 8-byte barriers
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto empty = [&](int s) { return bars + 8u * (S + s); };
+    auto acc_full = [&](int a) { return bars + 8u * (2 * S + a); };
+    auto acc_empty = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::W_BYTES + S * Cfg::STAGE_BYTES + 8 * (2 * S + 4));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long row0 = (long long)blockIdx.x * 128;
+    const long long ntiles = (p.rows + 127) / 128;
 
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)) : "memory");
+        for (int s = 0; s < S; ++s) { mbar_init(full(s), 32); mbar_init(empty(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(acc_full(a), 1); mbar_init(acc_empty(a), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // A tile: a warp copies 8 rows x 4 chunks at a time (64 contiguous bytes per row from global; one 128-byte core-matrix
-    // column per quarter warp into shared memory)
-    {
-        const uint32_t sa = smem_u32(sA);
-        constexpr int CH = K / 4;                         // 16-byte chunks per row
-        constexpr int UNITS = 16 * (CH / 4);              // (8-row group, 4-chunk group) units per tile
-        const int r8 = lane & 7, cq = lane >> 3;
-        for (int u = warp; u < UNITS; u += 4) {
-            const int g8 = u / (CH / 4), c4 = u - g8 * (CH / 4);
-            const int row = g8 * 8 + r8, chunk = c4 * 4 + cq;
-            const long long grow = row0 + row;
-            const bool valid = grow < p.rows;
-            const float* src = p.a + (valid ? grow : 0) * (long long)p.lda + chunk * 4;
-            cp_async16(sa + (uint32_t)g8 * SBO + (uint32_t)chunk * LBO + (uint32_t)r8 * 16u, src, valid);
-        }
-        const uint32_t sb = smem_u32(sB);
-        const float4* w = reinterpret_cast<const float4*>(p.w_canon);
-        for (int e = tid; e < (int)(B_BYTES / 16); e += 128) cp_async16(sb + (uint32_t)e * 16u, w + e, true);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    // generic-proxy writes (cp.async) -> visible to the tensor core's async proxy; TMEM address -> visible to everyone
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-    if (tid == 0) {
-        constexpr uint32_t idesc = make_idesc(128, N);
-        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-#pragma unroll 1
-        for (int kt = 0; kt < K / 8; ++kt) {              // one instruction = K 8 = two core-matrix columns (256 B further on)
-            const uint64_t da = make_desc(a0 + (uint32_t)kt * 2u * LBO, LBO, SBO);
-            const uint64_t db = make_desc(b0 + (uint32_t)kt * 2u * LBO, LBO, SBO);
-            mma_tf32(tmem, da, db, idesc, kt > 0 ? 1u : 0u);
+    if (warp == 4) {
+        // ------------------------------------------------------------------ producer
+        {   // all of W, in its global core-matrix image: part of the first stage's copy group
+            const uint32_t sb = smem_u32(sW);
+            const float4* w = reinterpret_cast<const float4*>(p.w_canon);
+            for (int e = lane; e < (int)(Cfg::W_BYTES / 16); e += 32) cp_async16(sb + (uint32_t)e * 16u, w + e, true);
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
-    }
-    mbar_wait(smem_u32(mbar), 0u);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-    // epilogue: warp w owns TMEM lanes 32w .. 32w+31 = rows; 32 columns per tcgen05.ld
-    const long long row = row0 + warp * 32 + lane;
-#pragma unroll 1
-    for (int c0 = 0; c0 < N; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-        if (row < p.rows) {
-            float* o = p.out + row * (long long)p.ldo + c0;
-            const float* y = (EPI == EPI_GRAD_MIX) ? p.y + row * (long long)p.ldy + c0 : nullptr;
+        const int r8 = lane & 7, cq = lane >> 3;
+        int it = 0, pending = -1;                         // pending: stage whose copies are in flight
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int h = 0; h < 2; ++h, ++it) {
+                const int s = it % S;
+                mbar_wait(empty(s), (uint32_t)(((it / S) & 1) ^ 1));
+                const uint32_t sa = smem_u32(sA) + (uint32_t)s * Cfg::STAGE_BYTES;
+                // a warp instruction = 8 rows x 64 bytes (quarter warp = one 16-byte chunk column of a core matrix); the single
+                // producer warp must not spend instructions on addresses: one row pointer per 8-row group, constant steps inside
+                auto fill = [&](auto cols_tag) {
+                    constexpr int cols = decltype(cols_tag)::value, c4n = cols / 16;
+                    constexpr uint32_t sbo = (uint32_t)(cols / 4) * 128u;
+#pragma unroll 2
+                    for (int g8 = 0; g8 < 16; ++g8) {
+                        const long long grow = tile * 128 + g8 * 8 + r8;
+                        const bool valid = grow < p.rows;
+                        const float* src = p.a + (valid ? grow : 0) * (long long)p.lda + h * KH0 + cq * 4;
+                        const uint32_t dst = sa + (uint32_t)g8 * sbo + (uint32_t)cq * LBO + (uint32_t)r8 * 16u;
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                float4 x = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                if (EPI == EPI_BIAS_TANH) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i));
-                    x.x = tanhf(x.x + b.x); x.y = tanhf(x.y + b.y); x.z = tanhf(x.z + b.z); x.w = tanhf(x.w + b.w);
-                } else if (EPI == EPI_GRAD_MIX) {
-                    // columns 16..79 of the 208 features are ReLU outputs of the third convolution: pass where the output was > 0
-                    const int c = c0 + i;
-                    if (c >= 16 && c < 80) {
-                        const float4 yy = *reinterpret_cast<const float4*>(y + i);
-                        x.x = yy.x > 0.f ? x.x : 0.f; x.y = yy.y > 0.f ? x.y : 0.f; x.z = yy.z > 0.f ? x.z : 0.f; x.w = yy.w > 0.f ? x.w : 0.f;
+                        for (int c4 = 0; c4 < c4n; ++c4) cp_async16(dst + (uint32_t)c4 * 4u * LBO, src + c4 * 16, valid);
+                    }
+                };
+                if (h == 0) fill(std::integral_constant<int, KH0>{}); else fill(std::integral_constant<int, KH1>{});
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                if (pending >= 0) {                       // the stage before this one has landed: publish it
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive(full(pending));
+                }
+                pending = s;
+            }
+        }
+        if (pending >= 0) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(full(pending));
+        }
+    } else if (warp == 5) {
+        // ------------------------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, N);
+            const uint32_t w0 = smem_u32(sW);
+            int it = 0, j = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++j) {
+                const int a = j & 1;
+                mbar_wait(acc_empty(a), (uint32_t)(((j >> 1) & 1) ^ 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d = tmem + (uint32_t)a * Cfg::ACC_COLS;
+                for (int h = 0; h < 2; ++h, ++it) {
+                    const int s = it % S;
+                    mbar_wait(full(s), (uint32_t)((it / S) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a0 = smem_u32(sA) + (uint32_t)s * Cfg::STAGE_BYTES;
+                    const uint32_t b0 = w0 + (uint32_t)h * (KH0 / 4) * LBO;
+                    const int cols = h ? KH1 : KH0;
+                    const uint32_t sbo = (uint32_t)(cols / 4) * 128u;
+#pragma unroll 1
+                    for (int kt = 0; kt < cols / 8; ++kt) {   // K 8 per instruction = two core-matrix columns (256 B further on)
+                        const uint64_t da = make_desc(a0 + (uint32_t)kt * 2u * LBO, LBO, sbo);
+                        const uint64_t db = make_desc(b0 + (uint32_t)kt * 2u * LBO, LBO, SBO_W);
+                        mma_tf32(d, da, db, idesc, (h | kt) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(empty(s));                    // the stage is free once these MMAs have read it
+                }
+                umma_commit(acc_full(a));                     // the tile's accumulator is complete
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: warp w = TMEM lanes 32w .. 32w+31 = rows
+        int j = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++j) {
+            const int a = j & 1;
+            mbar_wait(acc_full(a), (uint32_t)((j >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const long long row = tile * 128 + warp * 32 + lane;
+            const uint32_t t0 = tmem + (uint32_t)a * Cfg::ACC_COLS + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < N; c0 += 32) {
+                float v[32];
+                tmem_ld32(t0 + (uint32_t)c0, v);
+                if (c0 + 32 >= N) {                           // last read of this accumulator: hand it back
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(acc_empty(a));
+                }
+                if (row < p.rows) {
+                    float* o = p.out + row * (long long)p.ldo + c0;
+                    const float* y = (EPI == EPI_GRAD_MIX) ? p.y + row * (long long)p.ldy + c0 : nullptr;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        float4 x = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        if (EPI == EPI_BIAS_TANH) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i));
+                            x.x = fast_tanh(x.x + b.x); x.y = fast_tanh(x.y + b.y); x.z = fast_tanh(x.z + b.z); x.w = fast_tanh(x.w + b.w);
+                        } else if (EPI == EPI_GRAD_MIX) {
+                            // columns 16..79 of the 208 features are ReLU outputs of the third convolution: pass where the output was > 0
+                            const int c = c0 + i;
+                            if (c >= 16 && c < 80) {
+                                const float4 yy = *reinterpret_cast<const float4*>(y + i);
+                                x.x = yy.x > 0.f ? x.x : 0.f; x.y = yy.y > 0.f ? x.y : 0.f; x.z = yy.z > 0.f ? x.z : 0.f; x.w = yy.w > 0.f ? x.w : 0.f;
+                            }
+                        }
+                        if (c0 + i < N) *reinterpret_cast<float4*>(o + i) = x;
                     }
                 }
-                if (c0 + i < N) *reinterpret_cast<float4*>(o + i) = x;
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+    if (warp == 5) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(Cfg::TMEM_COLS) : "memory");
     }
 }
 
 template <int K, int N, int EPI>
 cudaError_t launch_t(const Args& a, cudaStream_t s) {
-    const size_t smem = (size_t)128 * K * 4 + (size_t)N * K * 4 + 64;
-    cudaError_t e = cudaFuncSetAttribute(linear_tc5_kernel<K, N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    using Cfg = Tc5Cfg<K, N>;
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    cudaError_t e = cudaFuncSetAttribute(linear_tc5_kernel<K, N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     if (e != cudaSuccess) return e;
-    linear_tc5_kernel<K, N, EPI><<<(unsigned)((a.rows + 127) / 128), 128, smem, s>>>(a);
+    const long long ntiles = (a.rows + 127) / 128;
+    const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
+    linear_tc5_kernel<K, N, EPI><<<grid, 192, Cfg::SMEM, s>>>(a);
     return cudaGetLastError();
 }
 
