@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 rep = sys.argv[1]
-top_n = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+top_n = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 30
 
 
 def ncu(*args):
@@ -24,6 +24,21 @@ KEYS = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed_op_local_ld.sum",
         "smsp__inst_executed_op_local_st.sum", "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum"]
 r = rows[2]
+if "--traffic-json" in sys.argv:
+    # profiles/k1_traffic.json: the measured DRAM bytes of this capture, tied to the kernel sources it was built from (bench.py
+    # reports them as roofline.traffic only while the sources are unchanged):  ... --traffic-json ENVS STEPS
+    import hashlib, json, os
+    a = sys.argv.index("--traffic-json")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = b"".join(open(os.path.join(root, "minigrid-rl_b200", "csrc", n), "rb").read() for n in ("mgrl_core.cuh", "mgrl_kernels.cu"))
+    def val(k):
+        v, u = float(r[hdr.index(k)].replace(",", "")), units[hdr.index(k)]
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+    rec = {"envs": int(sys.argv[a + 1]), "steps": int(sys.argv[a + 2]), "kernel": r[hdr.index("Kernel Name")],
+           "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
+           "source_sha16": hashlib.sha256(src).hexdigest()[:16], "report": os.path.basename(rep)}
+    json.dump(rec, open(os.path.join(root, "profiles", "k1_traffic.json"), "w"), indent=1)
+    print("wrote profiles/k1_traffic.json", rec)
 print("== raw metrics (first captured launch) ==")
 for k in KEYS:
     if k in hdr:
