@@ -296,8 +296,10 @@ def main():
     # end to end through the C ABI with HOST buffers, H2D + D2H inside the timed region.
     #  e2e          mgrl_vec_step_frames_host: pinned actions in, un-stacked observation + reward + flags out -- the
     #               output set of the CPU arm (mg_vec_step), so the two arms are like for like;
-    #  e2e.stacked  mgrl_vec_step_host: the full SB3 drop-in (frame stack x4, one-hot direction, int64 mission
-    #               tokens: 1761 B per env-step over PCIe)
+    #  e2e.stacked  mgrl_vec_step_stacked_host: the full SB3 drop-in (frame stack x4, one-hot direction, int64 mission
+    #               tokens, stacked terminal observations), 64-byte records over PCIe and the 1.6 KB observation dict
+    #               maintained in place by the library's host threads (MGRL_WIRE=0: mgrl_vec_step_host, the device-side
+    #               stack copied out in full, 1761 B per env-step over PCIe)
     e2e = None
     if not args.no_e2e:
         import numpy as np
@@ -342,9 +344,13 @@ def main():
                          "threads while later chunks are in flight (format conversion only)" if wire else ""),
                "sample": f"{e2e_steps} vector steps of {n} envs per rank",
                "stacked": {"value": v_stacked, "unit": "env-steps/s",
-                           "d2h_bytes_per_step": n * (4 * 147 + 16 + 128 * 8 + 4 + 1 + 1 + 1 + 147 + 1) * T,
-                           "api": "B200VecEnv.step_arrays -> mgrl_vec_step_host (SB3 observation dict: 4-frame stack, "
-                                  "one-hot direction, int64 mission tokens)"},
+                           "d2h_bytes_per_step": n * (2 * 64 if wire else 4 * 147 + 16 + 128 * 8 + 4 + 1 + 1 + 1 + 147 + 1) * T,
+                           "api": ("B200VecEnv.step_arrays -> mgrl_vec_step_stacked_host (SB3 observation dict: 4-frame stack, one-hot "
+                                   "direction, int64 mission tokens, stacked terminal observations; two 64-byte records per environment "
+                                   "over PCIe, the dict updated in place in pinned host memory by the library's host threads, like "
+                                   "VecFrameStack.stacked_obs)" if wire else
+                                   "B200VecEnv.step_arrays -> mgrl_vec_step_host (SB3 observation dict: 4-frame stack, "
+                                   "one-hot direction, int64 mission tokens; device-side stack copied out in full)")},
                "vecenv_step": {"value": v_vecenv, "unit": "env-steps/s",
                                "api": "B200VecEnv.step (the SB3 VecEnv protocol: stacked observation dict + one Python info dict "
                                       "per finished environment); host-side Python, 8 vector steps"}}

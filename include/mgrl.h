@@ -293,6 +293,19 @@ int mgrl_vec_step_host(mgrl_env *env, const uint8_t *actions_host, uint8_t *imag
                        uint8_t *direction_host, int64_t *mission_host, float *reward_host,
                        uint8_t *term_host, uint8_t *trunc_host, uint8_t *ep_len_host,
                        uint8_t *term_image_host, uint8_t *term_dir_host, void *stream);
+/* VecEnv.step(actions) with the SB3 observation dict kept IN PLACE in host memory, the way VecFrameStack keeps
+ * `stacked_obs` (ppo.py:124-126): image_host / direction_host / mission_host must be the arrays that the previous
+ * mgrl_vec_reset_host or mgrl_vec_step_stacked_host call of this handle filled; the call shifts every environment's
+ * stack by one frame and appends the new one (a finished environment restarts from zeros).  Only one 64-byte record per
+ * environment crosses PCIe (one code byte per view cell + the step's scalars); the library's host threads expand it
+ * (format conversion only).  For environments that finished, row e of term_image_host [N,4,147] / term_direction_host
+ * [N,16] / term_mission_host [N,128] receives the stacked terminal observation (SB3's info['terminal_observation']);
+ * other rows are left alone; the three may be NULL.  Synchronous. */
+int mgrl_vec_step_stacked_host(mgrl_env *env, const uint8_t *actions_host, uint8_t *image_host,
+                               uint8_t *direction_host, int64_t *mission_host, float *reward_host,
+                               uint8_t *term_host, uint8_t *trunc_host, uint8_t *ep_len_host,
+                               uint8_t *term_image_host, uint8_t *term_direction_host,
+                               int64_t *term_mission_host, void *stream);
 /* The same two calls without the SB3 wrapper stack: the un-stacked observation (what PlaygroundEnv.step +
  * Discrete2BoxWrapper's input look like before VecTransposeImage / VecFrameStack / TokenizeVocabWrapper) goes to
  * host buffers: image_host [N,pitch] in the handle's obs_layout, dir_host [N], mission_host [N] (mission ids),

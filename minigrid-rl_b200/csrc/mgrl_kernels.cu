@@ -1086,6 +1086,9 @@ struct mgrl_env {
     int64_t *h_stack_mis, *h_table;
     uint8_t* h_full;     // full-grid observation staging of mgrl_full_obs_host
     bool table_set;
+    int64_t table_host[MGRL_N_MISSIONS * MGRL_MISSION_TOKENS];   // host copy for the in-place stack of mgrl_vec_step_stacked_host
+    bool stack_on_host;          // the newest observation stack lives in the caller's arrays (mgrl_vec_step_stacked_host), not in h_stack_*
+    const void* stack_ptrs[3];   // the arrays the last reset / stacked step filled
     mgrl_wire::Path* wire;   // compact wire format + expansion pool of mgrl_vec_step_frames_host (mgrl_wire.cu), created on first use
 };
 
@@ -1532,6 +1535,7 @@ int mgrl_set_token_table(mgrl_env* e, const int64_t* table_host) {
     const size_t bytes = (size_t)MGRL_N_MISSIONS * MGRL_MISSION_TOKENS * sizeof(int64_t);
     if (!e->h_table) CUDA_TRY(cudaMalloc(&e->h_table, bytes));
     CUDA_TRY(cudaMemcpy(e->h_table, table_host, bytes, cudaMemcpyHostToDevice));
+    memcpy(e->table_host, table_host, bytes);
     e->table_set = true;
     return MGRL_OK;
 }
@@ -1566,6 +1570,9 @@ int mgrl_vec_reset_host(mgrl_env* e, uint64_t seed, uint8_t* image_host, uint8_t
     rc = copy_stacked_out(e, image_host, direction_host, mission_host, s);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(s));
+    e->stack_on_host = false;
+    e->stack_ptrs[0] = image_host; e->stack_ptrs[1] = direction_host; e->stack_ptrs[2] = mission_host;
+    if (e->wire) mgrl_wire::reset_stacked(e->wire);
     return MGRL_OK;
 }
 
@@ -1649,6 +1656,9 @@ int mgrl_vec_step_host(mgrl_env* e, const uint8_t* actions_host, uint8_t* image_
     if (!e->table_set) return fail(MGRL_ERR_INVALID, "mgrl_vec_step_host: call mgrl_set_token_table first%s");
     if (e->cfg.obs_layout == MGRL_OBS_HWC148)
         return fail(MGRL_ERR_INVALID, "mgrl_vec_step_host: the host path needs a 147-byte layout (CHW or HWC)%s");
+    if (e->stack_on_host)
+        return fail(MGRL_ERR_INVALID, "mgrl_vec_step_host: the stack of this handle lives in host arrays since mgrl_vec_step_stacked_host; "
+                                      "call mgrl_vec_reset_host first%s");
     DeviceGuard guard(e->device);
     cudaStream_t s = (cudaStream_t)stream;
     const size_t n = (size_t)e->cfg.num_envs;
@@ -1670,6 +1680,45 @@ int mgrl_vec_step_host(mgrl_env* e, const uint8_t* actions_host, uint8_t* image_
         CUDA_TRY(cudaMemcpyAsync(term_image_host, e->h_termimg, n * kObsBytes, cudaMemcpyDeviceToHost, s));
     if (term_dir_host) CUDA_TRY(cudaMemcpyAsync(term_dir_host, e->h_termdir, n, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
+    e->stack_ptrs[0] = image_host; e->stack_ptrs[1] = direction_host; e->stack_ptrs[2] = mission_host;
+    return MGRL_OK;
+}
+
+int mgrl_vec_step_stacked_host(mgrl_env* e, const uint8_t* actions_host, uint8_t* image_host, uint8_t* direction_host,
+                               int64_t* mission_host, float* reward_host, uint8_t* term_host, uint8_t* trunc_host,
+                               uint8_t* ep_len_host, uint8_t* term_image_host, uint8_t* term_direction_host,
+                               int64_t* term_mission_host, void* stream) {
+    const char* what = "mgrl_vec_step_stacked_host";
+    if (!e || !actions_host || !image_host || !direction_host || !mission_host || !reward_host || !term_host || !trunc_host)
+        return fail(MGRL_ERR_INVALID, "%s: null argument", what);
+    if (!e->host_ready || !e->table_set) return fail(MGRL_ERR_INVALID, "%s: call mgrl_set_token_table and mgrl_vec_reset_host first", what);
+    if (e->cfg.obs_layout == MGRL_OBS_HWC148) return fail(MGRL_ERR_INVALID, "%s: the host path needs a 147-byte layout (CHW or HWC)", what);
+    if (e->stack_ptrs[0] != image_host || e->stack_ptrs[1] != direction_host || e->stack_ptrs[2] != mission_host)
+        return fail(MGRL_ERR_INVALID, "%s: the observation stack is updated in place: pass the arrays the previous reset / step filled", what);
+    DeviceGuard guard(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)e->cfg.num_envs;
+    if (!e->wire) {
+        e->wire = mgrl_wire::create(e->cfg.num_envs);
+        if (!e->wire) return fail(MGRL_ERR_CUDA, "%s: wire staging allocation failed", what);
+    }
+    CUDA_TRY(cudaMemcpyAsync(e->h_actions, actions_host, n, cudaMemcpyHostToDevice, s));
+    const bool want_term = term_image_host != nullptr;
+    int rc = mgrl_step(e, e->h_actions, e->h_image, e->h_dir, e->h_mission, e->h_reward, e->h_term, e->h_trunc, e->h_eplen,
+                       want_term ? e->h_termimg : nullptr, e->h_termdir, stream);
+    if (rc) return rc;
+    mgrl_wire::Outputs o = {};
+    o.layout = e->cfg.obs_layout; o.image_dev = e->h_image; o.reward_dev = e->h_reward; o.reward_host = reward_host;
+    o.dir_dev = e->h_dir; o.mission_dev = e->h_mission; o.term_dev = e->h_term; o.trunc_dev = e->h_trunc; o.eplen_dev = e->h_eplen;
+    o.tdir_dev = e->h_termdir;
+    o.term_host = term_host; o.trunc_host = trunc_host; o.eplen_host = ep_len_host;
+    mgrl_wire::Outputs x = {};
+    x.layout = e->cfg.obs_layout; x.image_dev = e->h_termimg;
+    mgrl_wire::Stacked st = {};
+    st.image = image_host; st.direction = direction_host; st.mission = mission_host; st.term_image = term_image_host;
+    st.term_direction = term_direction_host; st.term_mission = term_mission_host; st.table = e->table_host;
+    e->stack_on_host = true;
+    CUDA_TRY(mgrl_wire::step_stacked(e->wire, o, want_term ? &x : nullptr, st, s));
     return MGRL_OK;
 }
 

@@ -29,6 +29,7 @@
 
 extern "C" int mgrl_wire_have_ssse3(void);                                              // mgrl_wire_host.cpp
 extern "C" void mgrl_wire_expand_hwc_ssse3(const uint8_t* rec, uint8_t* out, int pad148);
+extern "C" void mgrl_wire_expand_chw_ssse3(const uint8_t* rec, uint8_t* out);
 extern "C" int mgrl_wire_expand_block_hwc_ssse3(const uint8_t* recs, int count, uint8_t* out, int pitch, uint8_t tag, int tag_offset,
                                                 const volatile int* abort_flag);
 
@@ -127,6 +128,11 @@ struct Job {
     uint8_t *dir = nullptr, *mission = nullptr, *term = nullptr, *trunc = nullptr, *eplen = nullptr, *tdir = nullptr;
     float* reward = nullptr;
     uint8_t tag = 0;
+    // in-place observation stack (step_stacked): the terminal frames' records ride in the second staging buffer
+    bool stacked = false;
+    Stacked st = {};
+    const uint8_t* wire_term = nullptr;
+    uint8_t tag_term = 0;
 };
 
 struct Path {
@@ -148,8 +154,95 @@ struct Path {
     int njobs = 0, nitems = 0, blocks = 0;
     bool ssse3 = false, stream_stores = true;
     uint8_t tag[2] = {0, 0};           // per staging buffer: bumped whenever that buffer is used (1..255)
+    std::vector<uint8_t> age;          // step_stacked: frames of the current episode in an environment's stack (1..4)
 
-    void expand(const Job& jb, int lo, int hi) const {
+    bool wait_record(const uint8_t* rec, uint8_t want) const {
+        // the record is one cache line written by the copy engine: its tag says whether it is this step's
+        const volatile uint8_t* vt = rec + O_TAG;
+        while (*vt != want) {
+            if (abort_flag) return false;
+            cpu_relax();
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        return true;
+    }
+
+    void expand_frame(const uint8_t* rec, uint8_t* o, int layout) const {     // one 147-byte frame
+        if (layout == MGRL_OBS_CHW) {
+            if (ssse3) { mgrl_wire_expand_chw_ssse3(rec, o); return; }
+            for (int i = 0; i < kCells; ++i) {
+                const uint32_t e = lut[rec[i]];
+                o[i] = (uint8_t)e; o[49 + i] = (uint8_t)(e >> 8); o[98 + i] = (uint8_t)(e >> 16);
+            }
+        } else if (ssse3) {
+            mgrl_wire_expand_hwc_ssse3(rec, o, 0);
+        } else {
+            for (int i = 0; i < kCells; ++i) {
+                const uint32_t e = lut[rec[i]];
+                o[3 * i] = (uint8_t)e; o[3 * i + 1] = (uint8_t)(e >> 8); o[3 * i + 2] = (uint8_t)(e >> 16);
+            }
+        }
+    }
+
+    // VecFrameStack(4,'first') + VecTransposeImage + Discrete2BoxWrapper + TokenizeVocabWrapper on the caller's persistent
+    // arrays.  The mission of an episode never changes, so once an environment's four frames belong to one episode its
+    // token rows are left alone (they are 1 KB of the 1.6 KB observation).
+    void expand_stacked(const Job& jb, int lo, int hi) {
+        constexpr int F = 147, TOK = 32;
+        const Stacked& st = jb.st;
+        for (int r = lo; r < hi; ++r) {
+            const uint8_t* rec = jb.wire + (size_t)r * kRec;
+            if (!wait_record(rec, jb.tag)) return;
+            uint8_t* img = st.image + (size_t)r * 4 * F;
+            uint8_t* sd = st.direction + (size_t)r * 16;
+            int64_t* sm = st.mission + (size_t)r * 4 * TOK;
+            const int64_t* tok = st.table + (size_t)rec[O_MIS] * TOK;
+            if (rec[O_TERM] | rec[O_TRUNC]) {
+                if (st.term_image) {
+                    const uint8_t* trec = jb.wire_term + (size_t)r * kRec;
+                    if (!wait_record(trec, jb.tag_term)) return;
+                    uint8_t* ti = st.term_image + (size_t)r * 4 * F;
+                    memcpy(ti, img + F, 3 * F);
+                    expand_frame(trec, ti + 3 * F, jb.layout);
+                }
+                if (st.term_direction) {
+                    uint8_t* td = st.term_direction + (size_t)r * 16;
+                    memcpy(td, sd + 4, 12);
+                    const uint32_t hot = 1u << (8 * (rec[O_TDIR] & 3));
+                    memcpy(td + 12, &hot, 4);
+                }
+                if (st.term_mission) {
+                    int64_t* tm = st.term_mission + (size_t)r * 4 * TOK;
+                    memcpy(tm, sm + TOK, 3 * TOK * sizeof(int64_t));
+                    memcpy(tm + 3 * TOK, sm + 3 * TOK, TOK * sizeof(int64_t));
+                }
+                memset(img, 0, 3 * F);
+                memset(sd, 0, 12);
+                memset(sm, 0, 3 * TOK * sizeof(int64_t));
+                memcpy(sm + 3 * TOK, tok, TOK * sizeof(int64_t));
+                age[r] = 1;
+            } else {
+                memmove(img, img + F, 3 * F);
+                memmove(sd, sd + 4, 12);
+                if (age[r] < 4) {
+                    memmove(sm, sm + TOK, 3 * TOK * sizeof(int64_t));
+                    memcpy(sm + 3 * TOK, tok, TOK * sizeof(int64_t));
+                    age[r] += 1;
+                }
+            }
+            expand_frame(rec, img + 3 * F, jb.layout);
+            const uint32_t hot = 1u << (8 * (rec[O_DIR] & 3));
+            memcpy(sd + 12, &hot, 4);
+            if (jb.term) jb.term[r] = rec[O_TERM];
+            if (jb.trunc) jb.trunc[r] = rec[O_TRUNC];
+            if (jb.eplen) jb.eplen[r] = rec[O_EPLEN];
+            if (jb.tdir) jb.tdir[r] = rec[O_TDIR];
+            if (jb.reward) memcpy(jb.reward + r, rec + O_REW, 4);
+        }
+    }
+
+    void expand(const Job& jb, int lo, int hi) {
+        if (jb.stacked) { expand_stacked(jb, lo, hi); return; }
         const int pitch = jb.layout == MGRL_OBS_HWC148 ? 148 : 147;
         bool image_done = false;
         if (ssse3 && stream_stores && jb.layout != MGRL_OBS_CHW && ((reinterpret_cast<uintptr_t>(jb.image) + (size_t)lo * pitch) & 15) == 0) {
@@ -282,7 +375,18 @@ void destroy(Path* p) {
 
 int host_threads(const Path* p) { return p ? (int)p->threads.size() + 1 : 0; }
 
-cudaError_t step(Path* p, const Outputs& main, const Outputs* extra, cudaStream_t s) {
+void reset_stacked(Path* p) { p->age.assign((size_t)p->n, 1); }
+
+static cudaError_t run_step(Path* p, const Outputs& main, const Outputs* extra, const Stacked* st, cudaStream_t s);
+
+cudaError_t step(Path* p, const Outputs& main, const Outputs* extra, cudaStream_t s) { return run_step(p, main, extra, nullptr, s); }
+
+cudaError_t step_stacked(Path* p, const Outputs& main, const Outputs* extra, const Stacked& st, cudaStream_t s) {
+    if (p->age.size() != (size_t)p->n) reset_stacked(p);
+    return run_step(p, main, extra, &st, s);
+}
+
+static cudaError_t run_step(Path* p, const Outputs& main, const Outputs* extra, const Stacked* st, cudaStream_t s) {
     static const bool debug = getenv("MGRL_WIRE_DEBUG") != nullptr;
     static double acc[2] = {0, 0};
     static int nacc = 0;
@@ -309,10 +413,17 @@ cudaError_t step(Path* p, const Outputs& main, const Outputs* extra, cudaStream_
         jb.wire = p->wire_host[k]; jb.image = o.image_host; jb.layout = o.layout; jb.dir = o.dir_host; jb.mission = o.mission_host;
         jb.term = o.term_host; jb.trunc = o.trunc_host; jb.eplen = o.eplen_host; jb.tdir = o.tdir_host; jb.reward = o.reward_host;
         jb.tag = p->tag[k];
+        jb.stacked = false;
+    }
+    if (st) {   // one job: the main records, with the terminal frames' records (second buffer) read for finished environments
+        Job& jb = p->jobs[0];
+        jb.stacked = true; jb.st = *st;
+        jb.wire_term = extra ? p->wire_host[1] : nullptr; jb.tag_term = p->tag[1];
+        if (!extra) { jb.st.term_image = nullptr; }
     }
     // publish the step to the pool: the threads chase the copy, record by record
-    p->njobs = njobs;
-    p->nitems = njobs * p->blocks;
+    p->njobs = st ? 1 : njobs;
+    p->nitems = p->njobs * p->blocks;
     p->done.store(0, std::memory_order_relaxed);
     p->abort_flag = 0;
     p->epoch += 1;

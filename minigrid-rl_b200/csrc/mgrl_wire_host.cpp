@@ -57,6 +57,21 @@ extern "C" void mgrl_wire_expand_hwc_ssse3(const uint8_t* rec, uint8_t* out, int
     if (pad148) out[147] = 0;
 }
 
+// the same record as three planes (CHW: 49 types, 49 colours, 49 states), 147 bytes
+extern "C" void mgrl_wire_expand_chw_ssse3(const uint8_t* rec, uint8_t* out) {
+    const __m128i seven = _mm_set1_epi8(7), three = _mm_set1_epi8(3), four = _mm_set1_epi8(4), lo5 = _mm_set1_epi8(0x1F);
+    for (int g = 0; g < 3; ++g) {
+        const __m128i code = _mm_loadu_si128(reinterpret_cast<const __m128i*>(rec + 16 * g));
+        const __m128i door = _mm_cmpgt_epi8(_mm_setzero_si128(), code);
+        const __m128i hi = _mm_and_si128(_mm_srli_epi16(code, 3), lo5);
+        _mm_storeu_si128(reinterpret_cast<__m128i*>(out + 16 * g), _mm_or_si128(_mm_andnot_si128(door, hi), _mm_and_si128(door, four)));
+        _mm_storeu_si128(reinterpret_cast<__m128i*>(out + 49 + 16 * g), _mm_and_si128(code, seven));
+        _mm_storeu_si128(reinterpret_cast<__m128i*>(out + 98 + 16 * g), _mm_and_si128(_mm_and_si128(hi, three), door));
+    }
+    const uint32_t c = rec[48];
+    out[48] = (uint8_t)(c >= 128 ? 4u : (c >> 3)); out[97] = (uint8_t)(c & 7u); out[146] = (uint8_t)(c >= 128 ? ((c >> 3) & 3u) : 0u);
+}
+
 // A block of `count` consecutive records (rec pitch 64) -> `count` consecutive HWC observation records of `pitch` bytes at
 // `out`, written with non-temporal 16-byte stores: the images are write-only here, and ordinary stores would first READ every
 // destination line into the cache (the expansion is bound by host memory traffic, not by the shuffles).  `out` must be 16-byte

@@ -17,6 +17,7 @@ torch CUDA tensors in and out, nothing crosses PCIe.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import time
 
 import numpy as np
@@ -192,7 +193,7 @@ class _B200VecEnvImpl:
 
     def __init__(self, cfg: EnvConfig | None = None, num_envs: int = 16, seed: int | None = None,
                  device: int = 0, env_id_base: int = 0, n_frames_stack: int = 4, layout: str = "chw",
-                 obs_mode: str = "stacked", token_vocab: str = "reference"):
+                 obs_mode: str = "stacked", token_vocab: str = "reference", host_stack: str | None = None):
         if n_frames_stack != FRAMES:
             raise ValueError("only n_frames_stack == 4 is built (hydra_configs/algorithm/ppo.yaml:5)")
         if obs_mode not in ("stacked", "full"):
@@ -219,9 +220,13 @@ class _B200VecEnvImpl:
         self._full_table = np.ascontiguousarray(expert_token_table() if token_vocab == "expert" else token_table())
         nat.check(lib.mgrl_set_token_table(self._h.ptr, self._table.ctypes.data_as(C.c_void_p)), "set_token_table")
         n = self.num_envs
-        # the stacked observation is double-buffered in pinned memory: the arrays returned
-        # by step t stay valid until step t+2, and step t+1 reads the history frames of
-        # info['terminal_observation'] from them without copying
+        # Default (in place): ONE stacked observation in pinned memory, updated by every step the way SB3's VecFrameStack
+        # updates `stacked_obs` (the arrays returned by step t are the arrays step t+1 rewrites; SB3's rollout buffer copies
+        # them on add); the stacked terminal observations of finished environments land in a second set of arrays.
+        # MGRL_WIRE=0: the device-side stack, double-buffered on the host (arrays stay valid until step t+2).
+        if host_stack not in (None, "inplace", "device"):
+            raise ValueError("host_stack must be 'inplace' (mgrl_vec_step_stacked_host) or 'device' (mgrl_vec_step_host)")
+        self._inplace = host_stack == "inplace" if host_stack else os.environ.get("MGRL_WIRE", "1") != "0"
         self._obs_bufs = [{
             "image": _Pinned(lib, (n, 3 * FRAMES, 7, 7), np.uint8),
             "direction": _Pinned(lib, (n, 4 * FRAMES), np.uint8),
@@ -295,6 +300,10 @@ class _B200VecEnvImpl:
         if self.obs_mode == "full":
             return self._step_wait_full()
         p = self._p
+        if self._inplace:
+            self._step_inplace()
+            dones = (p["term"].array | p["trunc"].array).astype(bool)
+            return self._obs(), p["reward"].array, dones, self._infos(dones, self._term_obs())
         prev = self._obs()           # terminal_observation needs the three frames before the terminal one
         self._cur ^= 1
         b = self._obs_bufs[self._cur]
@@ -305,6 +314,23 @@ class _B200VecEnvImpl:
         term, trunc = p["term"].array, p["trunc"].array
         dones = (term | trunc).astype(bool)
         return self._obs(), p["reward"].array, dones, self._infos(dones, prev)
+
+    def stacked_terminal_obs(self):
+        """in-place mode: the observation dict whose rows of finished environments hold info['terminal_observation']"""
+        return self._term_obs()
+
+    def _term_obs(self):
+        b = self._obs_bufs[1]        # in-place mode: the second set holds the stacked terminal observations
+        return {"direction": b["direction"].array, "image": b["image"].array, "mission": b["mission"].array}
+
+    def _step_inplace(self):
+        """mgrl_vec_step_stacked_host: 64-byte records over PCIe, the observation dict updated in place by the library's
+        host threads, stacked terminal observations of finished environments into the second buffer set."""
+        p, b, t = self._p, self._obs_bufs[0], self._obs_bufs[1]
+        nat.check(self._h.lib.mgrl_vec_step_stacked_host(
+            self._h.ptr, p["actions"].ptr, b["image"].ptr, b["direction"].ptr, b["mission"].ptr,
+            p["reward"].ptr, p["term"].ptr, p["trunc"].ptr, p["ep_len"].ptr, t["image"].ptr, t["direction"].ptr,
+            t["mission"].ptr, None), "vec_step_stacked")
 
     def _infos(self, dones, prev):
         """SB3 infos: `terminal_observation` (the stacked observation the finished episode ended on), `TimeLimit.truncated`
@@ -321,11 +347,14 @@ class _B200VecEnvImpl:
             for k, i in enumerate(idx.tolist()):
                 infos[i] = {"TimeLimit.truncated": bool(trunc_only[k]), "episode": {"r": rew[k], "l": length[k], "t": t}}
             return infos
-        tdir = np.zeros((idx.size, 4), np.uint8)
-        tdir[np.arange(idx.size), p["term_dir"].array[idx]] = 1
-        t_dir = np.concatenate([prev["direction"][idx, 4:], tdir], axis=1)
-        t_img = np.concatenate([prev["image"][idx, 3:], p["term_image"].array[idx]], axis=1)
-        t_mis = np.concatenate([prev["mission"][idx, 32:], prev["mission"][idx, 96:]], axis=1)
+        if self._inplace:            # the library wrote the stacked terminal observations (rows of finished environments)
+            t_dir, t_img, t_mis = prev["direction"][idx], prev["image"][idx], prev["mission"][idx]
+        else:
+            tdir = np.zeros((idx.size, 4), np.uint8)
+            tdir[np.arange(idx.size), p["term_dir"].array[idx]] = 1
+            t_dir = np.concatenate([prev["direction"][idx, 4:], tdir], axis=1)
+            t_img = np.concatenate([prev["image"][idx, 3:], p["term_image"].array[idx]], axis=1)
+            t_mis = np.concatenate([prev["mission"][idx, 32:], prev["mission"][idx, 96:]], axis=1)
         for k, i in enumerate(idx.tolist()):
             infos[i] = {"terminal_observation": {"direction": t_dir[k], "image": t_img[k], "mission": t_mis[k]},
                         "TimeLimit.truncated": bool(trunc_only[k]), "episode": {"r": rew[k], "l": length[k], "t": t}}
@@ -343,9 +372,16 @@ class _B200VecEnvImpl:
 
     def step_arrays(self, actions):
         """`step` without the per-env Python info dicts: returns (obs, rewards, term, trunc, ep_len,
-        term_image, term_dir) as pinned numpy arrays straight from mgrl_vec_step_host."""
+        term_image, term_dir) as pinned numpy arrays straight from the library; term_image [N,3,7,7] is the last frame of
+        the terminal observation (rows of finished environments).  In place (default): mgrl_vec_step_stacked_host, `obs` is
+        the persistent stack, term_dir is that frame's one-hot direction [N,4] and `stacked_terminal_obs()` gives the whole
+        stacked terminal observations; MGRL_WIRE=0: mgrl_vec_step_host, term_dir [N] is the direction index."""
         p = self._p
         p["actions"].array[:] = actions
+        if self._inplace:
+            self._step_inplace()
+            return (self._obs(), p["reward"].array, p["term"].array, p["trunc"].array, p["ep_len"].array,
+                    self._obs_bufs[1]["image"].array[:, 9:], self._obs_bufs[1]["direction"].array[:, 12:])
         self._cur ^= 1
         b = self._obs_bufs[self._cur]
         nat.check(self._h.lib.mgrl_vec_step_host(

@@ -21,9 +21,12 @@ def biased_actions(rs, n):
 @pytest.mark.parametrize("kw", [dict(problem="multi", mission=5), dict(problem="multi", mission=None),
                                 dict(problem="multi", mission=1, see_through_walls=False)],
                          ids=["gtg", "all", "tgl_vis"])
-def test_vec_env_matches_sb3_stack_semantics(kw):
-    n, T = 48, 400
-    env = mg.B200VecEnv(mg.EnvConfig(**kw), num_envs=n, seed=42)
+@pytest.mark.parametrize("host_stack,n,T", [("inplace", 48, 400), ("inplace", 1100, 40), ("device", 48, 200)],
+                         ids=["inplace", "inplace_blocks", "device_stack"])
+def test_vec_env_matches_sb3_stack_semantics(kw, host_stack, n, T):
+    """`inplace`: mgrl_vec_step_stacked_host (64-byte wire records, the observation dict maintained in place by the library's
+    host threads; 1100 environments = three work blocks); `device_stack`: mgrl_vec_step_host (stack on the device, full copy)."""
+    env = mg.B200VecEnv(mg.EnvConfig(**kw), num_envs=n, seed=42, host_stack=host_stack)
     assert env.observation_space["image"].shape == (12, 7, 7)
     assert env.observation_space["direction"].shape == (16,)
     assert env.observation_space["mission"].shape == (128,) and env.action_space.n == 7
@@ -77,7 +80,7 @@ def test_vec_env_matches_sb3_stack_semantics(kw):
             else:
                 assert "terminal_observation" not in infos[i]
         n_done += int(want_done.sum())
-    assert n_done > 50 and n_trunc > 0
+    assert n_done > 50 and (n_trunc > 0 or T < 121)
     st = env.get_state()
     for name in orc.STATE_DTYPE.names:
         assert np.array_equal(st[name], o.states[name]), name
