@@ -31,7 +31,7 @@ extern "C" int mgrl_wire_have_ssse3(void);                                      
 extern "C" void mgrl_wire_expand_hwc_ssse3(const uint8_t* rec, uint8_t* out, int pad148);
 extern "C" void mgrl_wire_expand_chw_ssse3(const uint8_t* rec, uint8_t* out);
 extern "C" int mgrl_wire_expand_block_hwc_ssse3(const uint8_t* recs, int count, uint8_t* out, int pitch, uint8_t tag, int tag_offset,
-                                                const volatile int* abort_flag);
+                                                const volatile int* abort_flag, unsigned long long* poll_ns);
 
 namespace mgrl_wire {
 
@@ -55,12 +55,13 @@ struct PackArgs {
     uint8_t* wire;           // [n][64]
     int n, layout;
     uint32_t tag;
+    int first;               // records are built for environments [first, n)
 };
 
 // 16 threads per environment: 12 x four cells, cell 48 + (dir, mission, terminated), (truncated, length, terminal dir), reward, pad
 __global__ void __launch_bounds__(256) pack_codes_kernel(const PackArgs p) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int env = gid >> 4, j = gid & 15;
+    const int env = p.first + (gid >> 4), j = gid & 15;
     if (env >= p.n) return;
     uint32_t* out = reinterpret_cast<uint32_t*>(p.wire) + (size_t)env * 16 + j;
     auto triple = [&](int cell, uint32_t& t, uint32_t& c, uint32_t& s) {
@@ -111,6 +112,21 @@ __global__ void __launch_bounds__(256) pack_codes_kernel(const PackArgs p) {
     }
 }
 
+// the scalars of environments whose image goes to the host by a direct copy: one 16-byte record each
+//   0 dir, 1 mission, 2 terminated, 3 truncated, 4 episode length, 5 terminal dir, 7 step tag, [8..11] reward
+constexpr int kSmall = 16, S_TAG = 7, S_REW = 8;
+__global__ void __launch_bounds__(256) pack_small_kernel(const PackArgs p, uint4* __restrict__ out, int count) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= count) return;
+    uint4 v;
+    v.x = (p.dir ? p.dir[env] : 0u) | (p.mission ? (uint32_t)p.mission[env] << 8 : 0u) | (p.term ? (uint32_t)p.term[env] << 16 : 0u) |
+          (p.trunc ? (uint32_t)p.trunc[env] << 24 : 0u);
+    v.y = (p.eplen ? p.eplen[env] : 0u) | (p.tdir ? (uint32_t)p.tdir[env] << 8 : 0u) | (p.tag << 24);
+    v.z = p.reward ? __float_as_uint(p.reward[env]) : 0u;
+    v.w = 0u;
+    out[env] = v;
+}
+
 inline void cpu_relax() {
 #if defined(__x86_64__) || defined(__i386__)
     __builtin_ia32_pause();
@@ -128,6 +144,7 @@ struct Job {
     uint8_t *dir = nullptr, *mission = nullptr, *term = nullptr, *trunc = nullptr, *eplen = nullptr, *tdir = nullptr;
     float* reward = nullptr;
     uint8_t tag = 0;
+    const uint8_t* small = nullptr;    // 16-byte scalar records of the environments whose image is copied directly
     // in-place observation stack (step_stacked): the terminal frames' records ride in the second staging buffer
     bool stacked = false;
     Stacked st = {};
@@ -155,16 +172,135 @@ struct Path {
     bool ssse3 = false, stream_stores = true;
     uint8_t tag[2] = {0, 0};           // per staging buffer: bumped whenever that buffer is used (1..255)
     std::vector<uint8_t> age;          // step_stacked: frames of the current episode in an environment's stack (1..4)
+    // Hybrid transfer of step(): the images of the first `nd_blocks` blocks cross PCIe as they are (148 B per environment, no
+    // host work), the rest as 64-byte records expanded by the host threads.  With many cores per GPU the copy is the limit and
+    // everything goes as records; with few (8 ranks sharing 16 cores) the expansion is, and part of the batch is better off
+    // on the copy engine.  The split follows the threads' idle share, step by step.
+    uint8_t* small_dev = nullptr;
+    uint8_t* small_host = nullptr;
+    int nd_blocks = 0;
+    bool direct_auto = true;
+    std::atomic<unsigned long long> poll_ns{0}, busy_ns{0};
+    int wire_items = 0;
 
-    bool wait_record(const uint8_t* rec, uint8_t want) const {
-        // the record is one cache line written by the copy engine: its tag says whether it is this step's
-        const volatile uint8_t* vt = rec + O_TAG;
-        while (*vt != want) {
-            if (abort_flag) return false;
-            cpu_relax();
+    bool small_live = false;           // small_host holds records of the last step (their tags may match again 255 steps later)
+
+    // Blocks that change sides keep records of an older step on the side they join; a tag byte repeats every 255 steps, so
+    // those records are marked "not landed" (tag 0 is never used) before the split changes (no copy is in flight then).
+    void invalidate(int b0, int b1) {
+        const size_t lo = (size_t)b0 * kBlock, hi = (size_t)b1 * kBlock < (size_t)n ? (size_t)b1 * kBlock : (size_t)n;
+        for (size_t r = lo; r < hi; ++r) { wire_host[0][r * kRec + O_TAG] = 0; small_host[r * kSmall + S_TAG] = 0; }
+    }
+    void set_split(int want) {
+        if (want == nd_blocks) return;
+        invalidate(want < nd_blocks ? want : nd_blocks, want < nd_blocks ? nd_blocks : want);
+        nd_blocks = want;
+    }
+
+    // Split controller: a one-dimensional search on the measured step time, four steps per sample.  A probe moves the split
+    // by `probe_step` blocks; it is kept when the step got at least 3 % faster (and the next probe is twice as wide), otherwise
+    // the split goes back, the step halves, the direction flips and the next probe waits (twice as long after every failure).  The threads' idle share
+    // (time spent waiting for records / time inside work items) picks the first direction: threads that never wait mean
+    // the expansion is the limit (more direct copies may help), threads that mostly wait mean the copy engine is.
+    struct Tune {
+        int probe_step = 0, dir = +1, window = 0, base_nd = 0, cooldown = 0, backoff = 1;
+        double acc_us = 0, acc_idle = 0, base_us = -1;
+        bool probing = false;
+    } tune_state;
+    void tune(double step_us, double idle) {
+        Tune& t = tune_state;
+        constexpr int W = 4;
+        t.acc_us += step_us; t.acc_idle += idle;
+        if (++t.window < W) return;
+        const double mean = t.acc_us / W, idle_m = t.acc_idle / W;
+        t.acc_us = t.acc_idle = 0; t.window = 0;
+        const int cap = blocks - (blocks + 7) / 8;                        // at least an eighth stays on the record path
+        auto clamp = [&](int v) { return v < 0 ? 0 : (v > cap ? cap : v); };
+        if (t.probe_step == 0) t.probe_step = blocks >= 8 ? blocks / 4 : 1;
+        if (t.probing) {
+            if (mean < t.base_us * 0.97) {                                // better: keep it and go on in the same direction
+                t.base_us = mean; t.base_nd = nd_blocks; t.backoff = 1;
+                if (t.probe_step * 2 <= blocks / 4) t.probe_step *= 2;  // accelerate while it keeps paying
+                const int next = clamp(nd_blocks + t.dir * t.probe_step);
+                if (next != nd_blocks) set_split(next); else t.probing = false;
+            } else {
+                set_split(t.base_nd);
+                t.probing = false; t.dir = -t.dir;
+                t.probe_step = t.probe_step > 1 ? t.probe_step / 2 : 1;
+                t.cooldown = t.backoff; t.backoff = t.backoff < 32 ? t.backoff * 2 : 32;
+            }
+            return;
         }
+        t.base_us = mean; t.base_nd = nd_blocks;                          // (re)measured at the current split
+        if (t.cooldown > 0) { --t.cooldown; return; }
+        int dir = t.dir;
+        if (idle_m > 0.30) dir = -1; else if (idle_m < 0.10 && nd_blocks == 0) dir = +1;
+        const int next = clamp(nd_blocks + dir * t.probe_step);
+        if (next != nd_blocks) { t.dir = dir; t.probing = true; set_split(next); }
+    }
+
+    struct Clock {                     // per thread and step
+        unsigned long long poll = 0, skip = 0;
+        bool first = true;             // the wait for the step's first record (kernel + pack + copy latency) is not idle time: skip
+    };
+    static unsigned long long now_ns() {
+        return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    }
+
+    bool wait_record(const uint8_t* rec, uint8_t want, Clock* ck = nullptr, int tag_offset = O_TAG) const {
+        // the record is one cache line written by the copy engine: its tag says whether it is this step's
+        const volatile uint8_t* vt = rec + tag_offset;
+        if (*vt != want) {
+            const unsigned long long t0 = ck ? now_ns() : 0ull;
+            while (*vt != want) {
+                if (abort_flag) return false;
+                cpu_relax();
+            }
+            if (ck) { if (ck->first) ck->skip += now_ns() - t0; else ck->poll += now_ns() - t0; }
+        }
+        if (ck) ck->first = false;
         std::atomic_thread_fence(std::memory_order_acquire);
         return true;
+    }
+
+    // scalars of the directly copied environments [lo, hi)
+    void extract_small(const Job& jb, int lo, int hi, Clock* ck) const {
+        int r = lo;
+        // four records (one cache line) at a time: a 4-byte store per byte field, one 16-byte store of the rewards
+        if (jb.dir && jb.mission && jb.term && jb.trunc && jb.eplen && jb.reward) {
+            for (; r + 4 <= hi; r += 4) {
+                const uint8_t* rec = jb.small + (size_t)r * kSmall;
+                for (int q = 0; q < 4; ++q)
+                    if (!wait_record(rec + q * kSmall, jb.tag, ck, S_TAG)) return;
+                uint64_t w[4];
+                uint32_t rew[4];
+                for (int q = 0; q < 4; ++q) { memcpy(&w[q], rec + q * kSmall, 8); memcpy(&rew[q], rec + q * kSmall + S_REW, 4); }
+                auto field = [&](int byte) {
+                    const int sh = 8 * byte;
+                    return (uint32_t)((w[0] >> sh) & 0xFF) | (uint32_t)((w[1] >> sh) & 0xFF) << 8 | (uint32_t)((w[2] >> sh) & 0xFF) << 16 |
+                           (uint32_t)((w[3] >> sh) & 0xFF) << 24;
+                };
+                uint32_t v;
+                v = field(0); memcpy(jb.dir + r, &v, 4);
+                v = field(1); memcpy(jb.mission + r, &v, 4);
+                v = field(2); memcpy(jb.term + r, &v, 4);
+                v = field(3); memcpy(jb.trunc + r, &v, 4);
+                v = field(4); memcpy(jb.eplen + r, &v, 4);
+                if (jb.tdir) { v = field(5); memcpy(jb.tdir + r, &v, 4); }
+                memcpy(jb.reward + r, rew, 16);
+            }
+        }
+        for (; r < hi; ++r) {
+            const uint8_t* rec = jb.small + (size_t)r * kSmall;
+            if (!wait_record(rec, jb.tag, ck, S_TAG)) return;
+            if (jb.dir) jb.dir[r] = rec[0];
+            if (jb.mission) jb.mission[r] = rec[1];
+            if (jb.term) jb.term[r] = rec[2];
+            if (jb.trunc) jb.trunc[r] = rec[3];
+            if (jb.eplen) jb.eplen[r] = rec[4];
+            if (jb.tdir) jb.tdir[r] = rec[5];
+            if (jb.reward) memcpy(jb.reward + r, rec + S_REW, 4);
+        }
     }
 
     void expand_frame(const uint8_t* rec, uint8_t* o, int layout) const {     // one 147-byte frame
@@ -241,26 +377,23 @@ struct Path {
         }
     }
 
-    void expand(const Job& jb, int lo, int hi) {
+    void expand(const Job& jb, int lo, int hi, Clock* ck = nullptr) {
         if (jb.stacked) { expand_stacked(jb, lo, hi); return; }
         const int pitch = jb.layout == MGRL_OBS_HWC148 ? 148 : 147;
         bool image_done = false;
         if (ssse3 && stream_stores && jb.layout != MGRL_OBS_CHW && ((reinterpret_cast<uintptr_t>(jb.image) + (size_t)lo * pitch) & 15) == 0) {
             // the whole block's images with aligned non-temporal stores (this also waits for every record of the block)
+            unsigned long long polled = 0;
+            if (ck && ck->first) { if (!wait_record(jb.wire + (size_t)lo * kRec, jb.tag, ck)) return; }
             const int got = mgrl_wire_expand_block_hwc_ssse3(jb.wire + (size_t)lo * kRec, hi - lo, jb.image + (size_t)lo * pitch, pitch, jb.tag,
-                                                             O_TAG, &abort_flag);
+                                                             O_TAG, &abort_flag, ck ? &polled : nullptr);
+            if (ck) ck->poll += polled;
             if (got < hi - lo) return;
             image_done = true;
         }
         for (int r = lo; r < hi; ++r) {
             const uint8_t* rec = jb.wire + (size_t)r * kRec;
-            // the record is one cache line written by the copy engine: its tag says whether it is this step's
-            const volatile uint8_t* vt = rec + O_TAG;
-            while (*vt != jb.tag) {
-                if (abort_flag) return;
-                cpu_relax();
-            }
-            std::atomic_thread_fence(std::memory_order_acquire);
+            if (!wait_record(rec, jb.tag, image_done ? nullptr : ck)) return;
             uint8_t* o = jb.image + (size_t)r * pitch;
             if (image_done) {
             } else if (jb.layout == MGRL_OBS_CHW) {
@@ -291,6 +424,7 @@ struct Path {
 
     // item i = (job, block of kBlock records), in copy order
     void run_items(uint32_t ep) {
+        Clock ck;
         for (;;) {
             uint64_t v = next.load(std::memory_order_acquire);
             int i;
@@ -300,9 +434,23 @@ struct Path {
                 if (i >= nitems) return;
                 if (next.compare_exchange_weak(v, v + 1, std::memory_order_acq_rel, std::memory_order_acquire)) break;
             }
-            const int job = i / blocks, b = i - job * blocks;
-            const int lo = b * kBlock, hi = lo + kBlock < n ? lo + kBlock : n;
-            expand(jobs[job], lo, hi);
+            if (jobs[0].small) {
+                // hybrid step: the record blocks [nd_blocks, blocks) in copy order, then the scalar blocks of the direct part
+                const bool wire = i < wire_items;
+                const int b = wire ? nd_blocks + i : i - wire_items;
+                const int lo = b * kBlock, hi = lo + kBlock < n ? lo + kBlock : n;
+                const unsigned long long t0 = now_ns();
+                ck.poll = ck.skip = 0;
+                if (!wire) ck.first = false;    // these records arrive last: waiting for them is waiting for the copy engine
+                if (wire) expand(jobs[0], lo, hi, &ck); else extract_small(jobs[0], lo, hi, &ck);
+                const unsigned long long spent = now_ns() - t0;       // = busy + polling (+ the skipped first wait)
+                poll_ns.fetch_add(ck.poll, std::memory_order_relaxed);
+                busy_ns.fetch_add(spent - ck.poll - ck.skip, std::memory_order_relaxed);
+            } else {
+                const int job = i / blocks, b = i - job * blocks;
+                const int lo = b * kBlock, hi = lo + kBlock < n ? lo + kBlock : n;
+                expand(jobs[job], lo, hi);
+            }
             done.fetch_add(1, std::memory_order_release);
         }
     }
@@ -350,6 +498,18 @@ Path* create(int n) {
              cudaHostAlloc(reinterpret_cast<void**>(&p->wire_host[k]), (size_t)n * kRec, cudaHostAllocDefault) == cudaSuccess;
         if (ok) memset(p->wire_host[k], 0, (size_t)n * kRec);       // tag 0 = nothing has landed
     }
+    if (ok) {   // MGRL_WIRE_DIRECT: "auto" (default), or the fixed share of the batch whose images are copied directly (0 = none)
+        const char* v = getenv("MGRL_WIRE_DIRECT");
+        if (v && v[0] && strcmp(v, "auto") != 0) {
+            p->direct_auto = false;
+            double f = atof(v);
+            f = f < 0 ? 0 : (f > 1 ? 1 : f);
+            p->nd_blocks = (int)(f * p->blocks + 0.5);
+        }
+        ok = cudaMalloc(&p->small_dev, (size_t)n * kSmall) == cudaSuccess &&
+             cudaHostAlloc(reinterpret_cast<void**>(&p->small_host), (size_t)n * kSmall, cudaHostAllocDefault) == cudaSuccess;
+        if (ok) memset(p->small_host, 0, (size_t)n * kSmall);
+    }
     if (!ok) { destroy(p); return nullptr; }
     int nthreads = (int)std::thread::hardware_concurrency();
     if (const char* v = getenv("LOCAL_WORLD_SIZE")) { const int w = atoi(v); if (w > 1) nthreads /= w; }
@@ -357,6 +517,16 @@ Path* create(int n) {
     nthreads = nthreads < 1 ? 1 : (nthreads > 32 ? 32 : nthreads);
     if (nthreads > p->blocks) nthreads = p->blocks;
     for (int t = 0; t + 1 < nthreads; ++t) p->threads.emplace_back([p] { p->worker(); });   // the calling thread works too
+    if (p->direct_auto) {
+        // starting point of the search: few threads per GPU (ranks sharing the host's cores) cannot keep up with the copy
+        // engine, many can (measured on 16 cores: 2 threads 109 M env-steps/s as records, 190 M copied directly; 16 threads
+        // 392 M against 269 M)
+        if (nthreads <= 2) p->nd_blocks = p->blocks * 3 / 4;
+        else if (nthreads <= 4) p->nd_blocks = p->blocks / 2;
+        else if (nthreads >= 12) { p->tune_state.probe_step = p->blocks >= 16 ? p->blocks / 16 : 1; p->tune_state.backoff = 16; p->tune_state.cooldown = 4; }
+        const int cap = p->blocks - (p->blocks + 7) / 8;
+        if (p->nd_blocks > cap) p->nd_blocks = cap;
+    }
     return p;
 }
 
@@ -370,6 +540,8 @@ void destroy(Path* p) {
         if (p->wire_dev[k]) cudaFree(p->wire_dev[k]);
         if (p->wire_host[k]) cudaFreeHost(p->wire_host[k]);
     }
+    if (p->small_dev) cudaFree(p->small_dev);
+    if (p->small_host) cudaFreeHost(p->small_host);
     delete p;
 }
 
@@ -388,7 +560,7 @@ cudaError_t step_stacked(Path* p, const Outputs& main, const Outputs* extra, con
 
 static cudaError_t run_step(Path* p, const Outputs& main, const Outputs* extra, const Stacked* st, cudaStream_t s) {
     static const bool debug = getenv("MGRL_WIRE_DEBUG") != nullptr;
-    static double acc[2] = {0, 0};
+    static double acc[2] = {0, 0}, acc_idle = 0;
     static int nacc = 0;
     const auto t_begin = std::chrono::steady_clock::now();
     auto us_since = [&](std::chrono::steady_clock::time_point t0) {
@@ -397,23 +569,44 @@ static cudaError_t run_step(Path* p, const Outputs& main, const Outputs* extra, 
     const Outputs* outs[2] = {&main, extra};
     const int njobs = extra ? 2 : 1;
     const int n = p->n;
+    // hybrid: images of environments [0, first) by direct copy (un-stacked outputs without terminal images only)
+    const bool hybrid = !st && !extra && p->small_dev && main.image_host;
+    const int nd = hybrid ? p->nd_blocks : 0;
+    const int first = nd * kBlock < n ? nd * kBlock : n;
     for (int k = 0; k < njobs; ++k) {
         const Outputs& o = *outs[k];
         p->tag[k] = (uint8_t)(p->tag[k] == 255 ? 1 : p->tag[k] + 1);
         PackArgs a = {};
         a.image = o.image_dev; a.reward = o.reward_dev; a.dir = o.dir_dev; a.mission = o.mission_dev; a.term = o.term_dev;
         a.trunc = o.trunc_dev; a.eplen = o.eplen_dev; a.tdir = o.tdir_dev; a.wire = p->wire_dev[k]; a.n = n; a.layout = o.layout;
-        a.tag = p->tag[k];
-        pack_codes_kernel<<<(unsigned)(((size_t)n * 16 + 255) / 256), 256, 0, s>>>(a);
-        cudaError_t e = cudaGetLastError();
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(p->wire_host[k], p->wire_dev[k], (size_t)n * kRec, cudaMemcpyDeviceToHost, s);
+        a.tag = p->tag[k]; a.first = first;
+        cudaError_t e = cudaSuccess;
+        const size_t pitch = o.layout == MGRL_OBS_HWC148 ? 148 : 147;
+        // both pack kernels first, then the copies back to back (a kernel between two copies costs a bubble on the copy engine)
+        if (first < n) {
+            pack_codes_kernel<<<(unsigned)(((size_t)(n - first) * 16 + 255) / 256), 256, 0, s>>>(a);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess && first > 0) {
+            pack_small_kernel<<<(first + 255) / 256, 256, 0, s>>>(a, reinterpret_cast<uint4*>(p->small_dev), first);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess && first < n)
+            e = cudaMemcpyAsync(p->wire_host[k] + (size_t)first * kRec, p->wire_dev[k] + (size_t)first * kRec, (size_t)(n - first) * kRec,
+                                cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && first > 0) {
+            // the direct part: the images as they are, then the 16-byte scalar records (they land last: a host thread that
+            // waits for them is waiting for the copy engine, which is what the split controller reads)
+            e = cudaMemcpyAsync(o.image_host, o.image_dev, (size_t)first * pitch, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(p->small_host, p->small_dev, (size_t)first * kSmall, cudaMemcpyDeviceToHost, s);
+        }
         if (e != cudaSuccess) return e;
         Job& jb = p->jobs[k];
         jb.wire = p->wire_host[k]; jb.image = o.image_host; jb.layout = o.layout; jb.dir = o.dir_host; jb.mission = o.mission_host;
         jb.term = o.term_host; jb.trunc = o.trunc_host; jb.eplen = o.eplen_host; jb.tdir = o.tdir_host; jb.reward = o.reward_host;
         jb.tag = p->tag[k];
         jb.stacked = false;
+        jb.small = hybrid ? p->small_host : nullptr;
     }
     if (st) {   // one job: the main records, with the terminal frames' records (second buffer) read for finished environments
         Job& jb = p->jobs[0];
@@ -424,6 +617,16 @@ static cudaError_t run_step(Path* p, const Outputs& main, const Outputs* extra, 
     // publish the step to the pool: the threads chase the copy, record by record
     p->njobs = st ? 1 : njobs;
     p->nitems = p->njobs * p->blocks;
+    if (!hybrid && p->small_live) {   // (small_host is not a destination of this step's copies)
+        for (size_t r = 0; r < (size_t)n; ++r) p->small_host[r * kSmall + S_TAG] = 0;
+        p->small_live = false;
+    }
+    if (hybrid) p->small_live = first > 0;
+    if (hybrid) {   // record blocks [nd, blocks), then the scalar blocks [0, nd)
+        p->wire_items = p->blocks - nd;
+        p->poll_ns.store(0, std::memory_order_relaxed);
+        p->busy_ns.store(0, std::memory_order_relaxed);
+    }
     p->done.store(0, std::memory_order_relaxed);
     p->abort_flag = 0;
     p->epoch += 1;
@@ -442,11 +645,19 @@ static cudaError_t run_step(Path* p, const Outputs& main, const Outputs* extra, 
     }
     if (err != cudaSuccess) return err;
     err = cudaStreamSynchronize(s);
+    if (hybrid && p->direct_auto && err == cudaSuccess) {
+        const double poll = (double)p->poll_ns.load(std::memory_order_relaxed), busy = (double)p->busy_ns.load(std::memory_order_relaxed);
+        const double idle = poll + busy > 0 ? poll / (poll + busy) : 0.0;
+        p->tune(us_since(t_begin), idle);
+        if (debug) acc_idle += idle;
+    }
     if (debug) {
         acc[0] += t_issued; acc[1] += us_since(t_begin);
         if (++nacc == 64) {
-            fprintf(stderr, "[mgrl_wire] us per step: issued %.1f, expanded %.1f (threads %d)\n", acc[0] / 64, acc[1] / 64,
-                    (int)p->threads.size() + 1);
+            fprintf(stderr, "[mgrl_wire] %s us per step: issued %.1f, expanded %.1f (threads %d, direct blocks %d of %d, idle %.2f)\n",
+                    st ? "stacked" : (extra ? "frames+terminal" : "frames"), acc[0] / 64, acc[1] / 64, (int)p->threads.size() + 1,
+                    hybrid ? p->nd_blocks : 0, p->blocks, acc_idle / 64);
+            acc_idle = 0;
             acc[0] = acc[1] = 0; nacc = 0;
         }
     }

@@ -4,6 +4,7 @@
 //   code = 128 | state << 3 | colour  for doors (type 4),  type << 3 | colour  otherwise
 #include <tmmintrin.h>
 
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 
@@ -77,17 +78,22 @@ extern "C" void mgrl_wire_expand_chw_ssse3(const uint8_t* rec, uint8_t* out) {
 // destination line into the cache (the expansion is bound by host memory traffic, not by the shuffles).  `out` must be 16-byte
 // aligned; bytes are carried across records so that every store is an aligned unit; the tail (< 16 bytes) uses memcpy.
 // `ready(i)` is called before record i is read and returns 0 to stop (the caller's "has this record landed" poll).
+// `poll_ns` (optional) accumulates the time spent waiting for records that had not landed yet.
 extern "C" int mgrl_wire_expand_block_hwc_ssse3(const uint8_t* recs, int count, uint8_t* out, int pitch, uint8_t tag, int tag_offset,
-                                                const volatile int* abort_flag) {
+                                                const volatile int* abort_flag, unsigned long long* poll_ns) {
     alignas(16) uint8_t tmp[16 + 160];
     int carry = 0;                       // bytes already in tmp (< 16)
     uint8_t* dst = out;                  // next aligned unit
     for (int r = 0; r < count; ++r) {
         const uint8_t* rec = recs + (size_t)r * 64;
         const volatile uint8_t* vt = rec + tag_offset;
-        while (*vt != tag) {
-            if (*abort_flag) return r;
-            _mm_pause();
+        if (*vt != tag) {
+            const auto t0 = std::chrono::steady_clock::now();
+            while (*vt != tag) {
+                if (*abort_flag) return r;
+                _mm_pause();
+            }
+            if (poll_ns) *poll_ns += (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
         }
         __atomic_thread_fence(__ATOMIC_ACQUIRE);
         mgrl_wire_expand_hwc_ssse3(rec, tmp + carry, pitch == 148);

@@ -114,11 +114,15 @@ def test_step_frames_host_path_matches_oracle():
         env.close()
 
 
+@pytest.mark.parametrize("direct", ["auto", "0", "0.4", "1"])
 @pytest.mark.parametrize("layout,see", [("hwc148", True), ("chw", False), ("hwc", False)])
-def test_step_frames_wire_format_with_chunks_and_host_threads(layout, see):
+def test_step_frames_wire_format_with_chunks_and_host_threads(layout, see, direct, monkeypatch):
     """The host path's PCIe wire format (csrc/mgrl_wire.cu: one code byte per view cell, 64-byte records, chunked copies
     expanded by the handle's host threads) at a size that uses several chunks and threads: every output array bit-exact
-    against the oracle, including occluded views (unseen cells = (0,0,0)) and the terminal observations."""
+    against the oracle, including occluded views (unseen cells = (0,0,0)) and the terminal observations.  `direct`: the
+    share of the batch whose images cross PCIe as they are (MGRL_WIRE_DIRECT; auto = the split follows the host threads'
+    idle share, so it moves while the test runs); steps with terminal outputs always go as records."""
+    monkeypatch.setenv("MGRL_WIRE_DIRECT", direct)
     kw = dict(problem="multi", mission=None, see_through_walls=see)
     n = 20000
     env = mg.B200VecEnv(mg.EnvConfig(**kw), num_envs=n, seed=21, env_id_base=5, layout=layout)
@@ -142,11 +146,13 @@ def test_step_frames_wire_format_with_chunks_and_host_threads(layout, see):
         assert np.array_equal(term, o.term) and np.array_equal(trunc, o.trunc) and np.array_equal(ep_len, o.ep_len), t
         done = (o.term | o.trunc).astype(bool)
         assert np.array_equal(view(timg[done]), o.term_obs[done]), t
-        if t % 2:                                      # and without the terminal outputs (one job instead of two)
+        for _ in range(3 if t % 2 else 0):             # and without the terminal outputs (one job; hybrid transfer)
             a = biased_actions(rs, n).astype(np.uint8)
             img, d, m, rew, term, trunc, ep_len = env.step_frames(a)[:7]
             o.step(a)
             assert np.array_equal(view(img), o.obs) and np.array_equal(rew.view(np.uint32), o.reward.view(np.uint32)), t
+            assert np.array_equal(d, o.dir) and np.array_equal(m, o.mission), t
+            assert np.array_equal(term, o.term) and np.array_equal(trunc, o.trunc) and np.array_equal(ep_len, o.ep_len), t
     env.close()
 
 
