@@ -10,7 +10,7 @@ mkdir -p "$OUT" "$OBJ"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -I $ROOT/include -I $HERE"
 pids=""
-for f in mgrl_kernels mgrl_policy mgrl_policy_tc mgrl_update mgrl_wire mgrl_linear_tc5 $MGRL_EXTRA_UNITS; do
+for f in mgrl_kernels mgrl_policy mgrl_policy_tc mgrl_update mgrl_wire mgrl_linear_tc5 mgrl_conv1_tc5 $MGRL_EXTRA_UNITS; do
     [ -f "$HERE/$f.cu" ] || continue
     "$NVCC" $FLAGS "$@" -c -o "$OBJ/$f.o" "$HERE/$f.cu" &
     pids="$pids $!"

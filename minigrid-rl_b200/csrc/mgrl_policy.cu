@@ -24,6 +24,7 @@
 
 #include "mgrl.h"
 #include "mgrl_policy_layout.cuh"
+#include "mgrl_conv1_tc5.cuh"
 
 using namespace mgrl_policy;
 
@@ -598,7 +599,13 @@ int mgrl_conv1_pool_forward(const uint8_t* frames_dev, int num_envs, const int32
     a.frames = frames_dev; a.t = t_dev; a.i = i_dev; a.age = age_dev; a.w1 = w1_dev; a.b1 = b1_dev; a.pooled = pooled_dev;
     a.arg = arg_dev; a.n = num_envs; a.B = batch;
     cudaError_t e;
-    if (conv1_tensor_cores()) {
+    // MGRL_CONV1_TC5=1 / 2: the tcgen05 kernel (mgrl_conv1_tc5.cu) with the two-term split / one TF32 pass
+    const char* tc5_env = getenv("MGRL_CONV1_TC5");   // (read per call: the parity test switches it)
+    const int tc5 = tc5_env ? atoi(tc5_env) : 0;
+    if (tc5) {
+        a.onepass = tc5 == 2;
+        e = mgrl_tc5::launch_conv1_pool_fwd(a, (cudaStream_t)stream);
+    } else if (conv1_tensor_cores()) {
         e = launch_conv1_pool_fwd_tc(a, (cudaStream_t)stream);
     } else {
         const size_t smem = (size_t)(C1_OB * C1_PITCH + 768 + 256) * 4;

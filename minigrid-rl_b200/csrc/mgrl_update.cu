@@ -28,6 +28,7 @@
 
 #include "mgrl.h"
 #include "mgrl_policy_layout.cuh"
+#include "mgrl_conv1_tc5.cuh"
 #include "mgrl_linear_tc5.cuh"
 
 char* mgrl_error_buffer();
@@ -1179,7 +1180,10 @@ int mgrl_ppo_gradients(mgrl_ppo* h, const mgrl_rollout_view* rv, const int32_t* 
     Conv1Args ca = {};
     ca.frames = rv->frames; ca.t = c.t; ca.i = c.i; ca.age = c.age; ca.w1 = c.P + P_WC1; ca.b1 = c.P + P_BC1; ca.pooled = c.pooled; ca.arg = c.arg;
     ca.n = rv->num_envs; ca.B = B; ca.onepass = strict ? 0 : 1;
-    UP_TRY(mgrl_policy::launch_conv1_pool_fwd_tc(ca, s));
+    // one TF32 pass + tcgen05 enabled: the im2col-free tcgen05 kernel (mgrl_conv1_tc5.cu); MGRL_CONV1_TC5=0 keeps mma.sync
+    static const bool conv1_tc5 = [] { const char* v = getenv("MGRL_CONV1_TC5"); return !(v && v[0] == '0'); }();
+    if (!strict && hp->use_tcgen05 != 0 && conv1_tc5) UP_TRY(mgrl_tc5::launch_conv1_pool_fwd(ca, s));
+    else UP_TRY(mgrl_policy::launch_conv1_pool_fwd_tc(ca, s));
     GemmArgs g = {};
     // conv2: patches [4B,64] -> h2 [4B,32] = [B,128] (oh, ow, c2)
     g = GemmArgs{}; g.a = c.pooled; g.frag = frag_ptr(&c, PK_C2F, strict); g.bias = c.pbias + PB_C2; g.out = c.h2; g.ldo = 32; g.rows = 4LL * B;

@@ -654,3 +654,67 @@ def test_tcgen05_mlp_gemms_match_the_mma_sync_path():
         assert err <= 5e-3, (k, err)
     for e in (outs[0][4], outs[1][4]):
         e.env.close()
+
+
+@pytest.mark.parametrize("batch", [3000, 13, 1, 40000])
+def test_tcgen05_conv1_stage_matches_the_mma_sync_kernel_and_float64(batch, monkeypatch):
+    """mgrl_conv1_tc5.cu (im2col-free tcgen05 implicit GEMM: pixels converted once into shared-memory planes, the four taps
+    of the 2x2 kernel as row-shifted descriptors, accumulators in TMEM) against (a) a float64 evaluation of
+    Conv2d(12,16,2) + ReLU + MaxPool2d(2) (policies.py:59, single.yaml:44-47) on the gathered stacks and (b) the mma.sync
+    kernel it replaces.  Two-term split: <= 2e-6 of max |pooled| (bytes are exact in TF32, the weights carry hi + lo);
+    one TF32 pass: <= 2e-3.  The arg-max byte must name a position whose value is the window's maximum (near-ties may
+    resolve differently between kernels; exact ties resolve to the first position in both)."""
+    import ctypes as C
+    from minigrid_rl_b200 import _native as nat
+    n, T = 384, 12
+    eng, _ = make_engine(n, T)
+    eng.collect()
+    b, pol_ = eng.buf, eng.policy
+    g = torch.Generator(device="cuda").manual_seed(1)
+    reps = (batch + T * n - 1) // (T * n)
+    sel = torch.cat([torch.randperm(T * n, device="cuda", generator=g) for _ in range(reps)])[:batch]
+    t, i = (sel // n).to(torch.int32), (sel % n).to(torch.int32)
+    age = b["age"][t.long(), i.long()].contiguous()
+    P = pol_._P()
+    c = "features_extractor.extractors.image.image_Conv2d_"
+    w1 = (P[c + "0.weight"].detach() * 1.7).contiguous()         # (scaled: fresh weights leave few outputs positive)
+    b1 = (P[c + "0.bias"].detach() + 0.05).contiguous()
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+
+    def run(mode):
+        if mode is None:
+            monkeypatch.delenv("MGRL_CONV1_TC5", raising=False)
+        else:
+            monkeypatch.setenv("MGRL_CONV1_TC5", str(mode))
+        pooled = torch.full((batch, 9, 16), float("nan"), device="cuda")
+        arg = torch.full((batch, 9, 16), 255, dtype=torch.uint8, device="cuda")
+        nat.check(nat.lib().mgrl_conv1_pool_forward(p(b["frames"]), n, p(t), p(i), p(age), batch, p(w1), p(b1), p(pooled), p(arg), s),
+                  "conv1_pool_forward")
+        torch.cuda.synchronize()
+        return pooled, arg
+
+    # float64 reference on the gathered stacks
+    k = torch.arange(4, device="cuda")
+    fr = b["frames"][(t.long()[:, None] + k[None, :]), i.long()[:, None]][..., :147].reshape(batch, 4, 7, 7, 3)
+    valid = ((3 - k)[None, :] <= age.long()[:, None])
+    fr = fr * valid[:, :, None, None, None]
+    img = fr.permute(0, 1, 4, 2, 3).reshape(batch, 12, 7, 7).double() / 255.0
+    conv = torch.nn.functional.conv2d(img, w1.double(), b1.double())
+    want, widx = torch.nn.functional.max_pool2d(torch.relu(conv), 2, return_indices=True)
+    want = want.permute(0, 2, 3, 1).reshape(batch, 9, 16)
+    pre = torch.nn.functional.unfold(conv.reshape(batch * 16, 1, 6, 6), 2, stride=2).reshape(batch, 16, 4, 9).permute(0, 3, 1, 2)  # [B,9,16,4]
+    scale = float(want.abs().max())
+    assert scale > 0.1
+    ref_tc, _ = run(None)
+    for mode, bound in ((1, 2e-6), (2, 2e-3)):
+        got, arg = run(mode)
+        assert not torch.isnan(got).any() and int(arg.max()) < 8
+        assert float((got.double() - want).abs().max()) <= bound * scale, (mode, float((got.double() - want).abs().max()) / scale)
+        pos, positive = (arg & 3).long(), (arg & 4) != 0
+        picked = pre.gather(3, pos[..., None])[..., 0]
+        assert float((pre.max(dim=3).values - picked).max()) <= 2 * bound * scale, mode          # the named position holds the maximum
+        assert bool(((picked > bound * scale) <= positive).all()) and bool(((picked < -bound * scale) <= ~positive).all()), mode
+        if mode == 1:
+            assert float((got - ref_tc).abs().max()) <= 2e-6 * scale
+    eng.env.close()
