@@ -479,18 +479,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1_pool_window_tc5_kernel(cons
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
     if (warp >= GATHER_WARP0 && warp < GATHER_WARP0 + GATHER_WARPS) {
-        // ------------------------------------------------------------------ gather: a LANE per half record (14 records per warp x
-        // two halves of 19 / 18 words): every lane computes its source address once per tile, in parallel with the others, and
-        // the copy loop is 19 independent 4-byte cp.async per lane (a warp-per-record loop with the addresses broadcast by
-        // shuffles spent 335 cycles per record in dependent MIO round trips and bounded the whole kernel)
+        // ------------------------------------------------------------------ gather: 14 records per warp.  Lane l < 14 computes the
+        // source address of record l once per tile (in parallel with the others); the copy is then one warp per record,
+        // lanes along its 37 words (two 4-byte cp.async instructions), the addresses reaching the lanes through shuffles that
+        // do not depend on one another.  cp.async writes shared memory one returned 32-byte sector at a time: with a lane per
+        // record every lane's word came from its own sector and the copies alone took a third of the shared-memory pipe.
+        constexpr int RPW = PW_G * 4 / GATHER_WARPS;             // records per warp
         const int gw = warp - GATHER_WARP0;
-        const int rec = gw * (PW_G * 4 / GATHER_WARPS) + (lane >> 1), half = lane & 1;     // record = sample * 4 + frame
-        const bool mine = lane < 2 * (PW_G * 4 / GATHER_WARPS);
+        const int rec = gw * RPW + lane;                         // record = sample * 4 + frame (lanes >= RPW: none)
+        const bool mine = lane < RPW;
         const int o = rec >> 2, f = rec & 3;
-        const uint32_t w0 = half ? 19u : 0u, nw = half ? 18u : 19u;
         int j = 0;
-        // the indices of a tile are loaded IDX_AHEAD tiles ahead (a tile of copies is issued in a few hundred cycles: one tile
-        // of lead left the DRAM latency of the index loads in front of every tile)
+        // the indices of a tile are loaded IDX_AHEAD tiles ahead
         constexpr int IDX_AHEAD = 4;
         int qt[IDX_AHEAD], qi[IDX_AHEAD], qage[IDX_AHEAD];
         auto load_indices = [&](int g, int& vt, int& vi, int& vage) {
@@ -502,20 +502,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1_pool_window_tc5_kernel(cons
         for (int a = 0; a < IDX_AHEAD; ++a) load_indices(blockIdx.x + a * gridDim.x, qt[a], qi[a], qage[a]);
         for (int g = blockIdx.x; g < ntiles; g += gridDim.x, ++j) {
             const int b = j % NPX;
-            const int nt = qt[0], ni = qi[0], nage = qage[0];
+            const bool live = mine && (3 - f) <= qage[0];
+            const unsigned long long src = (unsigned long long)(live ? p.frames + ((size_t)(qt[0] + f) * p.n + qi[0]) * 148 : p.frames);
+            const uint32_t src_lo = (uint32_t)src, src_hi = (uint32_t)(src >> 32);
 #pragma unroll
             for (int a = 0; a + 1 < IDX_AHEAD; ++a) { qt[a] = qt[a + 1]; qi[a] = qi[a + 1]; qage[a] = qage[a + 1]; }
             load_indices(g + IDX_AHEAD * gridDim.x, qt[IDX_AHEAD - 1], qi[IDX_AHEAD - 1], qage[IDX_AHEAD - 1]);
-            const bool live = mine && (3 - f) <= nage;
-            const uint8_t* src = (live ? p.frames + ((size_t)(nt + f) * p.n + ni) * 148 : p.frames) + w0 * 4u;
             mbar_wait(px_empty(b), (uint32_t)(((j / NPX) & 1) ^ 1));
-            const uint32_t dst = smem_u32(smem + PW_OFF_PX + b * PW_PX_BYTES) + (uint32_t)(o * SAMPLE_BYTES + f * 148) + w0 * 4u;
-            const int sz = live ? 4 : 0;
-            if (mine) {
+            const uint32_t dst0 = smem_u32(smem + PW_OFF_PX + b * PW_PX_BYTES) + (uint32_t)(gw * RPW) * 148u + (uint32_t)lane * 4u;
 #pragma unroll
-                for (uint32_t w = 0; w < 19; ++w)
-                    if (w < nw)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + w * 4u), "l"(src + w * 4), "r"(sz) : "memory");
+            for (int r = 0; r < RPW; ++r) {
+                const uint32_t lo = __shfl_sync(0xffffffffu, src_lo, r), hi = __shfl_sync(0xffffffffu, src_hi, r);
+                const int sz = __shfl_sync(0xffffffffu, (int)live, r) ? 4 : 0;
+                const uint8_t* sp = reinterpret_cast<const uint8_t*>(((unsigned long long)hi << 32) | lo) + lane * 4;
+                const uint32_t dst = dst0 + (uint32_t)r * 148u;           // record (o, f) sits at o * 592 + f * 148 = record * 148
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(sp), "r"(sz) : "memory");
+                if (lane < 5) asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 128u), "l"(sp + 128), "r"(sz) : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
             if (j >= PX_DEPTH - 1) {
