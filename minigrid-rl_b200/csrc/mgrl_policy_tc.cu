@@ -614,15 +614,24 @@ __global__ void __launch_bounds__(NT, 4) conv1_pool_bwd_tc_kernel(const Conv1Arg
             const bool va = s0 + ja < p.B, vb = s0 + jb < p.B;
             const uint8_t* pa = s_px + ja * SAMPLE_BYTES;
             const uint8_t* pb = s_px + jb * SAMPLE_BYTES;
+            // A: masked gradient of channels g / g+8 for samples ja / jb.  The eight values of a pooled cell are loaded one cell
+            // ahead (their L2 latency sat in front of every cell: long scoreboard 3.1 cycles per issue)
+            float nda0, nda1, ndb0, ndb1;
+            int nga0, nga1, ngb0, ngb1;
+            auto fetch = [&](int q) {
+                const size_t oa = ((size_t)(s0 + ja) * 9 + q) * 16, ob = ((size_t)(s0 + jb) * 9 + q) * 16;
+                nda0 = va ? __ldg(p.dpooled + oa + g) : 0.f; nda1 = va ? __ldg(p.dpooled + oa + g + 8) : 0.f;
+                ndb0 = vb ? __ldg(p.dpooled + ob + g) : 0.f; ndb1 = vb ? __ldg(p.dpooled + ob + g + 8) : 0.f;
+                nga0 = va ? p.arg[oa + g] : 0; nga1 = va ? p.arg[oa + g + 8] : 0;
+                ngb0 = vb ? p.arg[ob + g] : 0; ngb1 = vb ? p.arg[ob + g + 8] : 0;
+            };
+            fetch(0);
 #pragma unroll 1
             for (int q = 0; q < 9; ++q) {
                 const int qh = q / 3, qw = q - qh * 3;
-                // A: masked gradient of channels g / g+8 for samples ja / jb
-                const size_t oa = ((size_t)(s0 + ja) * 9 + q) * 16, ob = ((size_t)(s0 + jb) * 9 + q) * 16;
-                const float da0 = va ? __ldg(p.dpooled + oa + g) : 0.f, da1 = va ? __ldg(p.dpooled + oa + g + 8) : 0.f;
-                const float db0 = vb ? __ldg(p.dpooled + ob + g) : 0.f, db1 = vb ? __ldg(p.dpooled + ob + g + 8) : 0.f;
-                const int ga0 = va ? p.arg[oa + g] : 0, ga1 = va ? p.arg[oa + g + 8] : 0;
-                const int gb0 = vb ? p.arg[ob + g] : 0, gb1 = vb ? p.arg[ob + g + 8] : 0;
+                const float da0 = nda0, da1 = nda1, db0 = ndb0, db1 = ndb1;
+                const int ga0 = nga0, ga1 = nga1, gb0 = ngb0, gb1 = ngb1;
+                if (q + 1 < 9) fetch(q + 1);
 #pragma unroll 1
                 for (int sp = 0; sp < 4; ++sp) {
                     AFrag a;
