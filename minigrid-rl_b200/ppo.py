@@ -382,7 +382,7 @@ class NativeUpdater:
         return ("hand-written end to end (mgrl_ppo_gradients + mgrl_ppo_apply: mma.sync TF32 GEMM kernels with fused epilogues, "
                 "register-resident GRU forward/backward, loss, clip + Adam; "
                 + ("three-term split, fp32-class" if self.hyper.strict_fp32 else "one TF32 pass like ppo.py:29-32")
-                + ("; 208 x 128 MLP GEMMs on tcgen05.mma kind::tf32 with TMEM accumulators" if self.hyper.use_tcgen05 else "") + ")")
+                + ("; first convolution (pool-window GEMM, kind::f16) and the 208 x 128 MLP GEMMs (kind::tf32) on tcgen05.mma with TMEM accumulators" if self.hyper.use_tcgen05 else "") + ")")
 
     def all_reduces_per_step(self) -> int:
         return 0 if self.world == 1 else 1
