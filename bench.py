@@ -379,14 +379,17 @@ def main():
         barrier()
         if os.environ.get("MGRL_BENCH_DEBUG"):
             print(f"[rank {rank}] {task} {n_envs}: rollout {t_roll / iters:.2f} ms, update {t_upd / iters:.2f} ms", file=sys.stderr)
-        tt = torch.tensor([t_roll, t_upd], device=dev)
+        # the ranks meet at every optimizer step (gradient all-reduce), so a rank that is late in its rollout shows up as a wait
+        # in the other ranks' update: the iteration time is the MAX over ranks of a rank's own rollout + update, not the sum of
+        # the two per-phase maxima (which would count that skew twice)
+        tt = torch.tensor([t_roll, t_upd, t_roll + t_upd], device=dev)
         if dist is not None:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_roll, t_upd = float(tt[0]), float(tt[1])
+        t_roll, t_upd, t_iter = float(tt[0]), float(tt[1]), float(tt[2])
         frames = world * n_envs * T * iters
-        rec = {"value": frames / ((t_roll + t_upd) / 1000.0), "unit": "frames/s",
+        rec = {"value": frames / (t_iter / 1000.0), "unit": "frames/s",
                "rollout_env_steps_per_s": frames / (t_roll / 1000.0), "rollout_ms": t_roll / iters,
-               "update_ms": t_upd / iters, "iterations": iters,
+               "update_ms": t_upd / iters, "iteration_ms": t_iter / iters, "iterations": iters,
                "config": {"task": task, "n_steps": T, "n_envs_per_gpu": n_envs, "batch_size_per_gpu": pcfg.batch_size,
                           "n_epochs": 4, "minibatches_per_iteration": n_mb, "policy": "CustomPPOPolicy 110216 params, fp32",
                           "rollout": "mgrl_policy_forward + mgrl_step per step (hand-written kernels)",
