@@ -368,7 +368,10 @@ def main():
         barrier()
         for it in range(iters):
             ev[0].record()
-            eng.collect(); eng.bootstrap_truncated(); eng.compute_advantages()
+            h0 = time.perf_counter()
+            eng.collect()
+            t_host = (time.perf_counter() - h0) * 1e3 if it == 0 else max(t_host, (time.perf_counter() - h0) * 1e3)   # host time to ISSUE the rollout
+            eng.bootstrap_truncated(); eng.compute_advantages()
             ev[1].record()
             eng.updater.set_progress(1.0 - it / max(iters, 1))
             n_mb = eng.update()
@@ -378,7 +381,7 @@ def main():
             t_roll += ev[0].elapsed_time(ev[1]); t_upd += ev[1].elapsed_time(ev[2])
         barrier()
         if os.environ.get("MGRL_BENCH_DEBUG"):
-            print(f"[rank {rank}] {task} {n_envs}: rollout {t_roll / iters:.2f} ms, update {t_upd / iters:.2f} ms", file=sys.stderr)
+            print(f"[rank {rank}] {task} {n_envs}: rollout {t_roll / iters:.2f} ms (host issue {t_host:.2f} ms), update {t_upd / iters:.2f} ms", file=sys.stderr)
         # the ranks meet at every optimizer step (gradient all-reduce), so a rank that is late in its rollout shows up as a wait
         # in the other ranks' update: the iteration time is the MAX over ranks of a rank's own rollout + update, not the sum of
         # the two per-phase maxima (which would count that skew twice)
