@@ -362,7 +362,8 @@ def main():
         pcfg = mg.PPOConfig(n_steps=T, batch_size=n_envs * T // 32, n_epochs=4, update_tf32=True)
         eng = mg.RolloutEngine(penv, mg.Policy(dev, seed=SEED), pcfg, dist=dist if world > 1 else None, seed=SEED)
         for _ in range(2):                                   # warm-up: allocator, layouts in L2, graph capture of the
-            eng.iteration(1.0)                               # optimizer step, first truncation bootstrap (lazy module loads)
+            eng.iteration(1.0)                               # optimizer step
+        eng.warm_bootstrap()                                 # the truncation bootstrap's lazily loaded kernels (truncations are rare)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         t_roll = t_upd = 0.0
         barrier()
@@ -371,7 +372,14 @@ def main():
             h0 = time.perf_counter()
             eng.collect()
             t_host = (time.perf_counter() - h0) * 1e3 if it == 0 else max(t_host, (time.perf_counter() - h0) * 1e3)   # host time to ISSUE the rollout
-            eng.bootstrap_truncated(); eng.compute_advantages()
+            if os.environ.get("MGRL_BENCH_DEBUG"):
+                dbg = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                dbg[0].record(); nb = eng.bootstrap_truncated(); dbg[1].record(); eng.compute_advantages(); dbg[2].record()
+                torch.cuda.synchronize()
+                print(f"[rank {rank}] it {it}: collect {ev[0].elapsed_time(dbg[0]):.2f} ms, bootstrap of {nb} {dbg[0].elapsed_time(dbg[1]):.2f} ms, "
+                      f"advantages {dbg[1].elapsed_time(dbg[2]):.2f} ms", file=sys.stderr)
+            else:
+                eng.bootstrap_truncated(); eng.compute_advantages()
             ev[1].record()
             eng.updater.set_progress(1.0 - it / max(iters, 1))
             n_mb = eng.update()

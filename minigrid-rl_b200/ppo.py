@@ -549,7 +549,19 @@ class RolloutEngine:
         idx = torch.nonzero((b["trunc"] != 0) & (b["term"] == 0))
         if idx.numel() == 0:
             return 0
-        t, i = idx[:, 0], idx[:, 1]
+        self._bootstrap(idx[:, 0], idx[:, 1], self.cfg.gamma)
+        return int(idx.shape[0])
+
+    def warm_bootstrap(self):
+        """Runs the truncation bootstrap once on two rollout slots with weight 0 (rewards unchanged): truncations are rare, and the
+        first one otherwise pays for the lazily loaded indexing kernels (tens of milliseconds) inside a timed iteration."""
+        if self.term_frames is not None:
+            dev = self.buf["rewards"].device
+            self._bootstrap(self.torch.tensor([0, 1], device=dev), self.torch.tensor([0, 0], device=dev), 0.0)
+
+    def _bootstrap(self, t, i, gamma):
+        torch = self.torch
+        b = self.buf
         # The terminal observation extends the finished episode by one frame: stack = buffer slots of times t-2..t + the
         # terminal frame, the old mission, age = min(age + 1, 3).  Valued by the rollout's own forward kernel (the same
         # numbers the rollout would have produced, and no library kernels whose first call on a new batch size costs
@@ -565,8 +577,7 @@ class RolloutEngine:
         self.policy.forward_rollout(frames4, dirs4, b["mission"][t + 3, i].contiguous(), 3, b["age"][t, i].contiguous(),
                                     torch.zeros(m, dtype=torch.uint8, device=t.device), age_out, v)
         self.launches += 1
-        b["rewards"][t, i] += self.cfg.gamma * v
-        return int(idx.shape[0])
+        b["rewards"][t, i] += gamma * v if gamma != 0.0 else torch.zeros_like(v)      # (warm-up: the same kernels, rewards unchanged)
 
     def compute_advantages(self):
         b, T = self.buf, self.T
