@@ -108,3 +108,78 @@ extern "C" int mgrl_wire_expand_block_hwc_ssse3(const uint8_t* recs, int count, 
     _mm_sfence();
     return count;
 }
+
+// ---- AVX-512 VBMI: one 64-byte record is one register; a full byte permute (vpermb) per output vector and component replaces
+// the nine 16-byte shuffles per 16 cells above.  Picked at run time when the CPU has AVX-512 BW + VBMI.
+#include <immintrin.h>
+
+extern "C" int mgrl_wire_have_avx512vbmi(void) {
+    __builtin_cpu_init();
+    return (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vbmi")) ? 1 : 0;
+}
+
+namespace {
+struct Vbmi {
+    alignas(64) uint8_t idx[3][64];    // output byte 64 v + b <- cell (64 v + b) / 3 (63 = a zero lane past cell 48)
+    uint64_t mc[3], ms[3];             // bytes of output vector v that hold a colour / a state
+};
+inline Vbmi make_vbmi() {
+    Vbmi t;
+    for (int v = 0; v < 3; ++v) {
+        t.mc[v] = t.ms[v] = 0;
+        for (int b = 0; b < 64; ++b) {
+            const int j = 64 * v + b;
+            t.idx[v][b] = (uint8_t)(j < 147 ? j / 3 : 63);
+            if (j < 147 && j % 3 == 1) t.mc[v] |= 1ull << b;
+            if (j < 147 && j % 3 == 2) t.ms[v] |= 1ull << b;
+        }
+    }
+    return t;
+}
+}  // namespace
+
+// same contract as mgrl_wire_expand_block_hwc_ssse3; `out` must be 64-byte aligned (non-temporal 64-byte stores)
+extern "C" __attribute__((target("avx512f,avx512bw,avx512vbmi"))) int mgrl_wire_expand_block_hwc_avx512(
+    const uint8_t* recs, int count, uint8_t* out, int pitch, uint8_t tag, int tag_offset, const volatile int* abort_flag,
+    unsigned long long* poll_ns) {
+    static const Vbmi tab = make_vbmi();
+    const __m512i i0 = _mm512_load_si512(tab.idx[0]), i1 = _mm512_load_si512(tab.idx[1]), i2 = _mm512_load_si512(tab.idx[2]);
+    const __m512i seven = _mm512_set1_epi8(7), three = _mm512_set1_epi8(3), four = _mm512_set1_epi8(4), lo5 = _mm512_set1_epi8(0x1F);
+    const __mmask64 cells = (1ull << 49) - 1;                       // bytes 49..63 of a record are not cells
+    alignas(64) uint8_t tmp[64 + 192];
+    int carry = 0;                       // bytes already in tmp (< 64)
+    uint8_t* dst = out;                  // next aligned unit
+    for (int r = 0; r < count; ++r) {
+        const uint8_t* rec = recs + (size_t)r * 64;
+        const volatile uint8_t* vt = rec + tag_offset;
+        if (*vt != tag) {
+            const auto t0 = std::chrono::steady_clock::now();
+            while (*vt != tag) {
+                if (*abort_flag) return r;
+                _mm_pause();
+            }
+            if (poll_ns) *poll_ns += (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+        }
+        __atomic_thread_fence(__ATOMIC_ACQUIRE);
+        const __m512i code = _mm512_maskz_loadu_epi8(cells, rec);
+        const __mmask64 door = _mm512_movepi8_mask(code);                                  // code >= 128
+        const __m512i hi = _mm512_and_si512(_mm512_srli_epi16(code, 3), lo5);              // code >> 3 per byte
+        const __m512i T = _mm512_mask_blend_epi8(door, hi, four);
+        const __m512i C = _mm512_and_si512(code, seven);
+        const __m512i S = _mm512_maskz_and_epi32(0xFFFF, _mm512_maskz_mov_epi8(door, hi), three);
+        __m512i x0 = _mm512_permutexvar_epi8(i0, T), x1 = _mm512_permutexvar_epi8(i1, T), x2 = _mm512_permutexvar_epi8(i2, T);
+        x0 = _mm512_mask_permutexvar_epi8(x0, tab.mc[0], i0, C); x0 = _mm512_mask_permutexvar_epi8(x0, tab.ms[0], i0, S);
+        x1 = _mm512_mask_permutexvar_epi8(x1, tab.mc[1], i1, C); x1 = _mm512_mask_permutexvar_epi8(x1, tab.ms[1], i1, S);
+        x2 = _mm512_mask_permutexvar_epi8(x2, tab.mc[2], i2, C); x2 = _mm512_mask_permutexvar_epi8(x2, tab.ms[2], i2, S);
+        _mm512_storeu_si512(tmp + carry, x0); _mm512_storeu_si512(tmp + carry + 64, x1); _mm512_storeu_si512(tmp + carry + 128, x2);
+        const int have = carry + pitch, units = have >> 6;
+        for (int u = 0; u < units; ++u)
+            _mm512_stream_si512(reinterpret_cast<__m512i*>(dst) + u, _mm512_load_si512(reinterpret_cast<const __m512i*>(tmp) + u));
+        dst += units * 64;
+        carry = have & 63;
+        if (carry) _mm512_store_si512(tmp, _mm512_load_si512(tmp + units * 64));       // the partial unit moves to the front
+    }
+    if (carry) memcpy(dst, tmp, carry);
+    _mm_sfence();
+    return count;
+}
