@@ -316,6 +316,10 @@ int mgrl_vec_reset_frames_host(mgrl_env *env, uint64_t seed, uint8_t *image_host
 int mgrl_vec_step_frames_host(mgrl_env *env, const uint8_t *actions_host, uint8_t *image_host, uint8_t *dir_host,
                               uint8_t *mission_host, float *reward_host, uint8_t *term_host, uint8_t *trunc_host,
                               uint8_t *ep_len_host, uint8_t *term_image_host, uint8_t *term_dir_host, void *stream);
+/* hardware probe of the tcgen05 operand layout of mgrl_conv1_tc5.cu (rows at a 16-byte pitch, one plane per K chunk, taps as
+ * row-shifted descriptors): out_dev [4][128][16] f32 = the products for the shifts 0, 1, 7, 8 (profiles/tc5_shift_probe.py) */
+int mgrl_debug_tc5_shift_probe(float *out_dev, void *stream);
+
 /* mission-id -> token table used by the host path and by mgrl_stack_push callers: [74,32] i64 */
 int mgrl_set_token_table(mgrl_env *env, const int64_t *table_host);
 

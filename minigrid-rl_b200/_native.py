@@ -74,6 +74,7 @@ _SIGNATURES = {
     "mgrl_vec_reset_host": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp]),
     "mgrl_vec_step_host": (C.c_int, [vp] * 12),
     "mgrl_vec_step_stacked_host": (C.c_int, [vp] * 13),
+    "mgrl_debug_tc5_shift_probe": (C.c_int, [vp, vp]),
     "mgrl_set_token_table": (C.c_int, [vp, vp]),
     "mgrl_vec_reset_frames_host": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp]),
     "mgrl_vec_step_frames_host": (C.c_int, [vp] * 12),
