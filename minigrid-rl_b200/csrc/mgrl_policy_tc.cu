@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(NT, 4) conv1_pool_fwd_tc_kernel(const Conv1Arg
 }
 
 template <bool ONEPASS>
-__global__ void __launch_bounds__(NT, 4) conv1_pool_bwd_tc_kernel(const Conv1Args p) {
+__global__ void __launch_bounds__(NT, 5) conv1_pool_bwd_tc_kernel(const Conv1Args p) {
     __shared__ __align__(16) uint8_t s_px[OBC * SAMPLE_BYTES];
     __shared__ float s_acc[16 * 56];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -700,7 +700,7 @@ cudaError_t launch_conv1_pool_fwd_tc(const Conv1Args& a, cudaStream_t stream) {
 
 cudaError_t launch_conv1_pool_bwd_tc(const Conv1Args& a, cudaStream_t stream) {   // dw1 / db1 zeroed by the caller
     const int nchunks = (a.B + OBC - 1) / OBC;
-    const int grid = nchunks < 148 * 4 ? nchunks : 148 * 4;
+    const int grid = nchunks < 148 * 5 ? nchunks : 148 * 5;
     if (a.onepass) conv1_pool_bwd_tc_kernel<true><<<grid, NT, 0, stream>>>(a);
     else conv1_pool_bwd_tc_kernel<false><<<grid, NT, 0, stream>>>(a);
     return cudaGetLastError();
