@@ -638,12 +638,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1_pool_window_tc5_kernel(cons
                 const size_t base = ((size_t)g * PW_ROWS + r) * 16;          // = (gs * 9 + q) * 16
                 uint32_t argw[4];
 #pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    float res[4];
-                    uint32_t aw = 0u;
+                for (int c8 = 0; c8 < 2; ++c8) {
+                    float res[8];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int c = c4 * 4 + i;
+                    for (int i = 0; i < 8; ++i) {
+                        const int c = c8 * 8 + i;
                         float best = v0[c];                                    // first maximum wins, like max_pool2d
                         uint32_t pos = 0u;
                         if (v0[16 + c] > best) { best = v0[16 + c]; pos = 1u; }
@@ -651,10 +650,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1_pool_window_tc5_kernel(cons
                         if (v1[16 + c] > best) { best = v1[16 + c]; pos = 3u; }
                         const float x = fmaf(best, 1.0f / PW_SCALE, bias[c]);
                         res[i] = fmaxf(x, 0.f);
-                        aw |= (pos | (x > 0.f ? 4u : 0u)) << (8 * i);
+                        if ((i & 3) == 0) argw[c >> 2] = 0u;
+                        argw[c >> 2] |= (pos | (x > 0.f ? 4u : 0u)) << (8 * (i & 3));
                     }
-                    *reinterpret_cast<float4*>(p.pooled + base + c4 * 4) = make_float4(res[0], res[1], res[2], res[3]);
-                    argw[c4] = aw;
+                    // one whole 32-byte sector per store (st.global.v8.f32)
+                    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p.pooled + base + c8 * 8), "f"(res[0]), "f"(res[1]),
+                                 "f"(res[2]), "f"(res[3]), "f"(res[4]), "f"(res[5]), "f"(res[6]), "f"(res[7]) : "memory");
                 }
                 *reinterpret_cast<uint4*>(p.arg + base) = make_uint4(argw[0], argw[1], argw[2], argw[3]);
             }

@@ -251,21 +251,30 @@ __global__ void __launch_bounds__(192, 1) linear_tc5_kernel(const Args p) {
                 if (row < p.rows) {
                     float* o = p.out + row * (long long)p.ldo + c0;
                     const float* y = (EPI == EPI_GRAD_MIX) ? p.y + row * (long long)p.ldy + c0 : nullptr;
+                    // 32 bytes per store instruction (st.global.v8.f32, sm_100): a thread's row chunk is a whole sector; with
+                    // 16-byte stores every sector reached L2 as two half writes from different instructions
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        float4 x = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    for (int i = 0; i < 32; i += 8) {
+                        float x[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) x[q] = v[i + q];
                         if (EPI == EPI_BIAS_TANH) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i));
-                            x.x = fast_tanh(x.x + b.x); x.y = fast_tanh(x.y + b.y); x.z = fast_tanh(x.z + b.z); x.w = fast_tanh(x.w + b.w);
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i));
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i + 4));
+                            x[0] = fast_tanh(x[0] + b0.x); x[1] = fast_tanh(x[1] + b0.y); x[2] = fast_tanh(x[2] + b0.z); x[3] = fast_tanh(x[3] + b0.w);
+                            x[4] = fast_tanh(x[4] + b1.x); x[5] = fast_tanh(x[5] + b1.y); x[6] = fast_tanh(x[6] + b1.z); x[7] = fast_tanh(x[7] + b1.w);
                         } else if (EPI == EPI_GRAD_MIX) {
                             // columns 16..79 of the 208 features are ReLU outputs of the third convolution: pass where the output was > 0
                             const int c = c0 + i;
                             if (c >= 16 && c < 80) {
-                                const float4 yy = *reinterpret_cast<const float4*>(y + i);
-                                x.x = yy.x > 0.f ? x.x : 0.f; x.y = yy.y > 0.f ? x.y : 0.f; x.z = yy.z > 0.f ? x.z : 0.f; x.w = yy.w > 0.f ? x.w : 0.f;
+                                const float4 y0 = *reinterpret_cast<const float4*>(y + i), y1 = *reinterpret_cast<const float4*>(y + i + 4);
+                                x[0] = y0.x > 0.f ? x[0] : 0.f; x[1] = y0.y > 0.f ? x[1] : 0.f; x[2] = y0.z > 0.f ? x[2] : 0.f; x[3] = y0.w > 0.f ? x[3] : 0.f;
+                                x[4] = y1.x > 0.f ? x[4] : 0.f; x[5] = y1.y > 0.f ? x[5] : 0.f; x[6] = y1.z > 0.f ? x[6] : 0.f; x[7] = y1.w > 0.f ? x[7] : 0.f;
                             }
                         }
-                        if (c0 + i < N) *reinterpret_cast<float4*>(o + i) = x;
+                        if (c0 + i < N)
+                            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o + i), "f"(x[0]), "f"(x[1]), "f"(x[2]),
+                                         "f"(x[3]), "f"(x[4]), "f"(x[5]), "f"(x[6]), "f"(x[7]) : "memory");
                     }
                 }
             }
