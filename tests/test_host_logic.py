@@ -142,3 +142,37 @@ def test_wire_format_host_expander_matches_the_code_table():
             want = np.array([(4, c & 7, (c >> 3) & 3) if c >= 128 else (c >> 3, c & 7, 0) for c in rec[:49].tolist()], np.uint8)
             assert np.array_equal(out[:147], want.reshape(-1)), trial
             assert out[147] == (0 if pad else 0xAA) and (out[148:] == 0xAA).all()
+
+
+def test_wire_record_expansion_matches_the_format_on_every_instruction_set():
+    """Host half of the PCIe wire format (csrc/mgrl_wire_host.cpp): 64-byte records (49 cell codes, code = 128 | state << 3 |
+    colour for doors, type << 3 | colour otherwise) -> HWC observation records, SSSE3 and - when the CPU has it - AVX-512
+    VBMI, for both pitches, against a numpy decode of the format.  No GPU involved."""
+    import ctypes as C
+    from minigrid_rl_b200 import _native as nat
+    lib = nat.lib()
+    lib.mgrl_wire_expand_block_hwc_ssse3.restype = C.c_int
+    lib.mgrl_wire_expand_block_hwc_avx512.restype = C.c_int
+    if not lib.mgrl_wire_have_ssse3():
+        pytest.skip("no SSSE3")
+    rs = np.random.RandomState(5)
+    n, tag = 1536, 9
+    t = rs.randint(0, 11, size=(n, 49)); c = rs.randint(0, 6, size=(n, 49)); s = rs.randint(0, 3, size=(n, 49)) * (t == 4)
+    rec = np.zeros((n, 64), np.uint8)
+    rec[:, :49] = np.where(t == 4, 128 | (s << 3) | c, (t << 3) | c)
+    rec[:, 49:55] = rs.randint(0, 256, size=(n, 6)); rec[:, 55] = tag; rec[:, 56:60] = rs.randint(0, 256, size=(n, 4))
+    want = np.stack([t, c, s], axis=2).reshape(n, 147).astype(np.uint8)
+    abort = C.c_int(0)
+    fns = [lib.mgrl_wire_expand_block_hwc_ssse3] + ([lib.mgrl_wire_expand_block_hwc_avx512] if lib.mgrl_wire_have_avx512vbmi() else [])
+    for fn in fns:
+        for pitch in (147, 148):
+            raw = np.full(n * pitch + 128, 0xEE, np.uint8)
+            off = (-raw.ctypes.data) % 64                      # the block routines want an aligned destination
+            out = raw[off:off + n * pitch]
+            got = fn(C.c_void_p(rec.ctypes.data), n, C.c_void_p(out.ctypes.data), pitch, tag, 55, C.byref(abort), None)
+            assert got == n
+            img = out.reshape(n, pitch)
+            assert np.array_equal(img[:, :147], want), (fn, pitch)
+            if pitch == 148:
+                assert not img[:, 147].any()
+            assert raw[off + n * pitch] == 0xEE               # nothing written past the block
