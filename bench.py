@@ -113,7 +113,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(n_envs: int, target_seconds: float, nthreads: int):
+def cpu_baseline(n_envs: int, target_seconds: float, nthreads: int, max_steps: int = T_ROLLOUT):
     """The CPU oracle (C port of the reference path) on the host cores: same task, same batch."""
     import numpy as np
     from oracle import oracle as orc
@@ -128,7 +128,7 @@ def cpu_baseline(n_envs: int, target_seconds: float, nthreads: int):
         env.step(acts[steps % 8], want_term_obs=False)
         steps += 1
         el = time.perf_counter() - t0
-        if el >= target_seconds or steps >= T_ROLLOUT:
+        if el >= target_seconds or steps >= max_steps:
             break
     return n_envs * steps / el, steps, el
 
@@ -474,7 +474,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         nthreads = os.cpu_count() or 1
-        v, s, el = cpu_baseline(n, 12.0, nthreads)
+        v, s, el = cpu_baseline(n, 12.0, nthreads, max_steps=8 * T)     # eight rollouts: 20-30 core-seconds of CPU work
         cpu = {"value": v, "unit": "env-steps/s", "cores": nthreads, "kind": "port",
                "sample": f"{s} vector steps of {n} GTO envs ({el:.1f} s) through oracle/mg_oracle.c"}
 
