@@ -341,7 +341,9 @@ def main():
                       "the outputs of the CPU arm's vector step)"
                       + ("; PCIe wire format = one 64-byte record per environment (a code byte per view cell + the step's "
                          "scalars), expanded into the 148-byte observation records, rewards and flags by the library's host "
-                         "threads while later chunks are in flight (format conversion only)" if wire else ""),
+                         "threads while later chunks are in flight (format conversion only); when a GPU has few host threads part of "
+                         "the batch's images is copied directly instead (148 + 16 B per environment; MGRL_WIRE_DIRECT=auto), "
+                         "d2h_bytes_per_step is the all-records figure" if wire else ""),
                "sample": f"{e2e_steps} vector steps of {n} envs per rank",
                "stacked": {"value": v_stacked, "unit": "env-steps/s",
                            "d2h_bytes_per_step": n * (2 * 64 if wire else 4 * 147 + 16 + 128 * 8 + 4 + 1 + 1 + 1 + 147 + 1) * T,
