@@ -33,6 +33,10 @@ extern "C" void mgrl_wire_expand_chw_ssse3(const uint8_t* rec, uint8_t* out);
 extern "C" int mgrl_wire_have_avx512vbmi(void);
 extern "C" int mgrl_wire_expand_block_hwc_avx512(const uint8_t* recs, int count, uint8_t* out, int pitch, uint8_t tag, int tag_offset,
                                                  const volatile int* abort_flag, unsigned long long* poll_ns);
+extern "C" int mgrl_wire_expand_groups_hwc148_avx512(const uint8_t* recs, int count, uint8_t* out, uint8_t tag, int tag_offset,
+                                                     const volatile int* abort_flag, unsigned long long* poll_ns, uint8_t* dir,
+                                                     uint8_t* mission, uint8_t* term, uint8_t* trunc, uint8_t* eplen, uint8_t* tdir,
+                                                     float* reward);
 extern "C" int mgrl_wire_expand_block_hwc_ssse3(const uint8_t* recs, int count, uint8_t* out, int pitch, uint8_t tag, int tag_offset,
                                                 const volatile int* abort_flag, unsigned long long* poll_ns);
 
@@ -172,7 +176,7 @@ struct Path {
     volatile int abort_flag = 0;       // set when the step's copy failed: give up on records that will never land
     Job jobs[2];
     int njobs = 0, nitems = 0, blocks = 0;
-    bool ssse3 = false, avx512 = false, stream_stores = true;
+    bool ssse3 = false, avx512 = false, stream_stores = true, groups16 = true;
     uint8_t tag[2] = {0, 0};           // per staging buffer: bumped whenever that buffer is used (1..255)
     std::vector<uint8_t> age;          // step_stacked: frames of the current episode in an environment's stack (1..4)
     // Hybrid transfer of step(): the images of the first `nd_blocks` blocks cross PCIe as they are (148 B per environment, no
@@ -390,11 +394,24 @@ struct Path {
             if (ck && ck->first) { if (!wait_record(jb.wire + (size_t)lo * kRec, jb.tag, ck)) return; }
             // AVX-512 VBMI (one record = one register, a full byte permute per output vector): 64-byte aligned blocks only
             const bool wide = avx512 && ((reinterpret_cast<uintptr_t>(jb.image) + (size_t)lo * pitch) & 63) == 0;
-            const int got = (wide ? mgrl_wire_expand_block_hwc_avx512 : mgrl_wire_expand_block_hwc_ssse3)(
-                jb.wire + (size_t)lo * kRec, hi - lo, jb.image + (size_t)lo * pitch, pitch, jb.tag, O_TAG, &abort_flag, ck ? &polled : nullptr);
-            if (ck) ck->poll += polled;
-            if (got < hi - lo) return;
-            image_done = true;
+            if (wide && pitch == 148 && groups16) {
+                // groups of 16 records (37 aligned units): images realigned in registers, scalars 16 at a time
+                const int want = (hi - lo) & ~15;
+                const int got = mgrl_wire_expand_groups_hwc148_avx512(
+                    jb.wire + (size_t)lo * kRec, hi - lo, jb.image + (size_t)lo * pitch, jb.tag, O_TAG, &abort_flag, ck ? &polled : nullptr,
+                    jb.dir ? jb.dir + lo : nullptr, jb.mission ? jb.mission + lo : nullptr, jb.term ? jb.term + lo : nullptr,
+                    jb.trunc ? jb.trunc + lo : nullptr, jb.eplen ? jb.eplen + lo : nullptr, jb.tdir ? jb.tdir + lo : nullptr,
+                    jb.reward ? jb.reward + lo : nullptr);
+                if (ck) ck->poll += polled;
+                if (got < want) return;
+                lo += got;                                      // a ragged tail (< 16 records) goes record by record below
+            } else {
+                const int got = (wide ? mgrl_wire_expand_block_hwc_avx512 : mgrl_wire_expand_block_hwc_ssse3)(
+                    jb.wire + (size_t)lo * kRec, hi - lo, jb.image + (size_t)lo * pitch, pitch, jb.tag, O_TAG, &abort_flag, ck ? &polled : nullptr);
+                if (ck) ck->poll += polled;
+                if (got < hi - lo) return;
+                image_done = true;
+            }
         }
         for (int r = lo; r < hi; ++r) {
             const uint8_t* rec = jb.wire + (size_t)r * kRec;
@@ -494,6 +511,7 @@ Path* create(int n) {
     p->ssse3 = mgrl_wire_have_ssse3() != 0 && !getenv("MGRL_WIRE_SCALAR");
     p->stream_stores = !getenv("MGRL_WIRE_NO_STREAM");
     p->avx512 = p->ssse3 && mgrl_wire_have_avx512vbmi() != 0 && !getenv("MGRL_WIRE_NO_AVX512");
+    p->groups16 = !getenv("MGRL_WIRE_NO_GROUPS");
     for (int c = 0; c < 256; ++c) {
         const uint32_t t = c >= 128 ? 4u : (uint32_t)(c >> 3), col = (uint32_t)(c & 7), s = c >= 128 ? (uint32_t)((c >> 3) & 3) : 0u;
         p->lut[c] = t | (col << 8) | (s << 16);

@@ -176,3 +176,25 @@ def test_wire_record_expansion_matches_the_format_on_every_instruction_set():
             if pitch == 148:
                 assert not img[:, 147].any()
             assert raw[off + n * pitch] == 0xEE               # nothing written past the block
+    if lib.mgrl_wire_have_avx512vbmi():
+        # groups of 16 records of the 148-byte pitch: images realigned in registers, the step's scalars 16 at a time; a ragged
+        # count stops at the last whole group
+        lib.mgrl_wire_expand_groups_hwc148_avx512.restype = C.c_int
+        for count in (n, n - 5, 16, 15):
+            raw = np.full(n * 148 + 128, 0xEE, np.uint8)
+            off = (-raw.ctypes.data) % 64
+            out = raw[off:off + n * 148]
+            sc = [np.full(n, 0xEE, np.uint8) for _ in range(6)]
+            rew = np.full(n, 0xEE, np.uint8).repeat(4).view(np.float32)
+            got = lib.mgrl_wire_expand_groups_hwc148_avx512(
+                C.c_void_p(rec.ctypes.data), count, C.c_void_p(out.ctypes.data), tag, 55, C.byref(abort), None,
+                *[C.c_void_p(a.ctypes.data) for a in sc], C.c_void_p(rew.ctypes.data))
+            done = count & ~15
+            assert got == done
+            img = out.reshape(n, 148)
+            assert np.array_equal(img[:done, :147], want[:done]) and not img[:done, 147].any()
+            assert (raw[off + done * 148:] == 0xEE).all()      # nothing written past the last whole group
+            for a, col in zip(sc, (49, 50, 51, 52, 53, 54)):
+                assert np.array_equal(a[:done], rec[:done, col]) and (a[done:] == 0xEE).all(), col
+            assert np.array_equal(rew.view(np.uint8).reshape(n, 4)[:done], rec[:done, 56:60])
+            assert (rew.view(np.uint8).reshape(n, 4)[done:] == 0xEE).all()
