@@ -59,8 +59,13 @@ typedef enum {
  * VecTransposeImage), both 147 bytes per environment; HWC148 = HWC with one zero pad byte, i.e. a
  * 148-byte record pitch, which lets the kernel emit aligned 32-bit stores (fastest). */
 typedef enum { MGRL_OBS_HWC = 0, MGRL_OBS_CHW = 1, MGRL_OBS_HWC148 = 2 } mgrl_obs_layout;
-/* cfg.env.problem, custom_env.py:134-152 ('full' and 'mov' are not supported) */
-typedef enum { MGRL_MULTI = 0, MGRL_GTO = 1, MGRL_GTG = 2, MGRL_OPN = 3, MGRL_PKP = 4, MGRL_DRP = 5 } mgrl_problem;
+/* cfg.env.problem, custom_env.py:134-152.  Mission ids: group * 24 + type * 6 + colour (group 0 'go to', 1 'toggle',
+ * 2 'pick up'; type key 0, ball 1, box 2, door 3), 72 'go to goal', 73 'drop'; 'move left|right|up|down' (problems mov / full,
+ * custom_env.py:216-256) take ids 24..27 - 'toggle <colour> key' is never generated - so the table keeps MGRL_N_MISSIONS rows.
+ * A 'move' episode keeps its target_range in the state bytes target_x | target_y << 8 | target_action << 16 | pad << 24 as
+ * decimal digits (digit k = coordinate of the cell in row / column k+1, 0 = none). */
+typedef enum { MGRL_MULTI = 0, MGRL_GTO = 1, MGRL_GTG = 2, MGRL_OPN = 3, MGRL_PKP = 4, MGRL_DRP = 5, MGRL_MOV = 6,
+               MGRL_FULL = 7 } mgrl_problem;
 
 /* mirrors cfg.env of hydra_configs/single.yaml:20-28 (+ batch placement) */
 typedef struct {

@@ -6,7 +6,7 @@ from __future__ import annotations
 from dataclasses import dataclass
 from math import floor
 
-PROBLEMS = {"multi": 0, "gto": 1, "gtg": 2, "opn": 3, "pkp": 4, "drp": 5}
+PROBLEMS = {"multi": 0, "gto": 1, "gtg": 2, "opn": 3, "pkp": 4, "drp": 5, "mov": 6, "full": 7}
 # README task names -> cfg.env.mission on the `multi` map (single.yaml:22)
 TASKS = {"GTG": 5, "GTO": 0, "PKP": 2, "TGL": 1, "ALL": None}
 

@@ -34,8 +34,14 @@ constexpr int kMaxTries = 1000;  // bound of the reference's `while True` reject
 // kind byte (see include/mgrl.h for the table)
 constexpr int K_EMPTY = 0, K_WALL = 1, K_GOAL = 2, K_LAVA = 3, K_KEY = 8, K_BALL = 16, K_DOOR = 24, K_BOX = 64;
 constexpr int A_LEFT = 0, A_RIGHT = 1, A_FORWARD = 2, A_PICKUP = 3, A_DROP = 4, A_TOGGLE = 5, A_DONE = 6;
-constexpr int P_MULTI = 0, P_GTO = 1, P_GTG = 2, P_OPN = 3, P_PKP = 4, P_DRP = 5;
+constexpr int P_MULTI = 0, P_GTO = 1, P_GTG = 2, P_OPN = 3, P_PKP = 4, P_DRP = 5, P_MOV = 6, P_FULL = 7;
 constexpr int MISSION_GOAL = 72, MISSION_DROP = 73;
+// 'move left|right|up|down' (problems mov / full, custom_env.py:216-256) take the ids of 'toggle <colour> key', which is
+// never generated ('toggle' only picks boxes and doors, :197-201): the mission table keeps its 74 rows.  Such an episode has
+// no target position; its target_range (per row / column the first empty cell seen from the named side, at generation time)
+// lives in target_x | target_y << 8 | target_action << 16 | pad << 24 as decimal digits: digit k = the coordinate
+// (1..size-2) of the cell in row y = k+1 (left / right) or column x = k+1 (up / down), 0 = no cell.
+constexpr int MISSION_MOVE0 = 24;
 constexpr int ERR_BAD_ACTION = 1, ERR_TRIES = 2, ERR_SYNC = 4;  // ERR_SYNC: a prepared layout never arrived (kernel bug guard)
 constexpr int OBS_HWC = 0;  // image[vx][vy][c]  (MiniGrid native), 147-byte records
 constexpr int OBS_CHW = 1;  // image[c][vx][vy]  (after SB3 VecTransposeImage), 147-byte records
@@ -139,6 +145,35 @@ uint32_t philox_word(uint32_t idx, uint32_t episode, uint32_t e0, uint32_t e1, u
     return j == 0 ? w[0] : j == 1 ? w[1] : j == 2 ? w[2] : w[3];
 }
 
+// ---- 'move <direction>' missions (problems mov / full): rare, kept out of line so that the step and the generator of the
+// other problems do not carry their code in the instruction stream
+#if defined(__CUDACC__)
+#define MGRL_COLD __host__ __device__ __noinline__
+#else
+#define MGRL_COLD inline
+#endif
+// custom_env.py:314-317: is (ax, ay) in the episode's target range (decimal digits v, MISSION_MOVE0 + d)
+MGRL_COLD bool move_hit(uint32_t v, int d, int ax, int ay) {
+    const bool rows = d < 2;
+    const int kk = (rows ? ay : ax) - 1;
+    uint32_t p10 = 1u;
+    for (int i = 0; i < kk; ++i) p10 *= 10u;
+    return (int)(v / p10 % 10u) == (rows ? ax : ay);
+}
+// custom_env.py:221-254: per row (left / right) or column (up / down) the first empty cell seen from the named side, at
+// generation time (the agent's own cell is empty in the grid), as decimal digits
+MGRL_COLD uint32_t move_range(const uint8_t* grid, int S, int d) {
+    uint32_t v = 0u, p10 = 1u;
+    for (int k = 1; k <= S - 2; ++k, p10 *= 10u) {
+        const int step = (d & 1) ? -1 : 1;
+        int c = (d & 1) ? S - 2 : 1;
+        while (c > 0 && c < S - 1 && grid[d < 2 ? k * S + c : c * S + k] != K_EMPTY) c += step;
+        if (c >= S - 1) c = 0;
+        v += (uint32_t)c * p10;
+    }
+    return v;
+}
+
 // --------------------------------------------------------------------------------- step
 struct StepOut {
     float reward;
@@ -170,7 +205,9 @@ MGRL_HD StepIn env_step_load(const EnvState& s, int S) {
     return in;
 }
 
-template <bool KEEP_IF_DONE>
+// EXTRA: the problems mov / full ('move <direction>' missions) are compiled in; the rollout kernel of the other problems is
+// instantiated without them (it is bound by instruction issue: their three rare branches cost it 3 %).
+template <bool KEEP_IF_DONE, bool EXTRA = true>
 MGRL_HD StepOut env_step_apply(EnvState& s, const StepIn& in, int action, int max_steps, const float* reward_lut) {
     uint32_t* w = reinterpret_cast<uint32_t*>(&s);
     const uint32_t w30 = in.w30, w31 = in.w31, w32 = in.w32;
@@ -226,7 +263,10 @@ MGRL_HD StepOut env_step_apply(EnvState& s, const StepIn& in, int action, int ma
         if (action == A_TOGGLE && k_is_door(nk) && carrying != 0 && (nk & 7) == (carrying & 7)) carrying = 0;
         if (!mdone) {  // :288-317
             bool hit;
-            if (tx != kNone) hit = ta ? (fx == tx && fy == ty && action == ta) : (ax == tx && ay == ty);
+            if (EXTRA && (unsigned)(mission_id - MISSION_MOVE0) < 4u) {   // :314-317 agent_pos in target_range
+                const uint32_t v = (w31 >> 16) | ((w32 & 0xFFu) << 16) | (reinterpret_cast<const uint32_t*>(&s)[34] & 0xFF000000u);
+                hit = move_hit(v, mission_id - MISSION_MOVE0, ax, ay);
+            } else if (tx != kNone) hit = ta ? (fx == tx && fy == ty && action == ta) : (ax == tx && ay == ty);
             else hit = ta != 0 && action == ta;
             if (hit) { mdone = 1; latch = step; }
         }
@@ -484,7 +524,7 @@ MGRL_HD int obj_kind(int type, int colour) {
 // The list before the agent exists is configuration-constant (GenIO.prefix: objects, goal, agent); what
 // follows (keys of locked doors, distractors per room, obstacles) is a row of a table indexed by
 // (rooms, agent room, goal room, locked doors) built once per configuration on the host.
-enum GenStage : int { G_OBJ = 1, G_GOAL, G_AGENT, G_KEY, G_DIST, G_OBST };
+enum GenStage : int { G_OBJ = 1, G_GOAL, G_AGENT, G_KEY, G_DIST, G_OBST, G_FIXED };   // G_FIXED: object (bits 19-23) without a draw
 constexpr uint32_t TF_MID = 1u << 24, TF_LAVA = 1u << 25, TF_KEYMODE = 1u << 26, TF_AGENTMODE = 1u << 27, TF_AGENT_CELL = 1u << 28;
 constexpr int kTaskWords = 32;            // words per table row / prefix list, zero terminated
 // rows exist for the valid combinations only: 2 rooms: 2 x 2 x 2 lock states of its one door; 3 rooms: 3 x 3 x 8;
@@ -577,10 +617,12 @@ inline int pack_task_table(const uint32_t* table, uint32_t* packed) {
 inline void build_task_prefix(const EnvCfg& cfg, uint32_t* out /* [kTaskWords] */) {
     const int S = cfg.size;
     const bool multi = cfg.problem == P_MULTI;
-    const bool has_goal = multi || cfg.problem == P_GTG || cfg.problem == P_DRP;
+    const bool has_goal = multi || cfg.problem == P_GTG || cfg.problem == P_DRP || cfg.problem == P_FULL;
     int n = 0;
     for (int i = 0; i < kTaskWords; ++i) out[i] = 0u;
-    if (!multi)
+    if (cfg.problem == P_FULL)   // _generate_full_map :332-369: every (type, colour) pair, types outer, COLOR_NAMES inner
+        for (int i = 0; i < 24; ++i) out[n++] = task_word(G_FIXED, 0, S - 1, 0, S - 1, TF_AGENT_CELL) | ((uint32_t)i << 19);
+    else if (!multi)
         for (int i = 0; i < cfg.num_objects && n < kTaskWords - 3; ++i) out[n++] = task_word(G_OBJ, 0, S - 1, 0, S - 1, TF_AGENT_CELL);
     if (has_goal) out[n++] = task_word(G_GOAL, 0, S - 1, 0, S - 1, TF_AGENT_CELL);
     out[n++] = task_word(G_AGENT, 0, S - 1, 0, S - 1, TF_AGENTMODE);
@@ -610,9 +652,17 @@ constexpr uint32_t kMarkMask = 0x7F7F7F7Fu;
 // Builds the layout of `episode` into s: grid, agent, target, mission, carrying = 0, step_count = 0,
 // episode = episode + 1, reset_draws; ORs ERR_TRIES into s.error.  mission_done / latch_step are
 // not touched (they survive a reset in the reference).
+// MODE: what is compiled in.  GEN_ALL: every problem; GEN_BASE: without the problems mov / full (see env_step_apply);
+// GEN_MULTI_PLAIN: only the multi-room problem without obstacles and with the default door states (all_doors_open = false) -
+// the configuration of every BASELINE benchmark - so that the single-room stages, the obstacle flags and the open-door
+// draws are not in the rollout kernel's instruction stream.  The caller picks the instance from the configuration.
+constexpr int GEN_ALL = 0, GEN_BASE = 1, GEN_MULTI_PLAIN = 2;
+template <int MODE = GEN_ALL>
 MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t env_id, uint32_t episode, const GenIO& io) {
+    constexpr bool EXTRA = MODE == GEN_ALL, PLAIN = MODE == GEN_MULTI_PLAIN;
     const int S = cfg.size, m = S / 2;
-    const bool multi = cfg.problem == P_MULTI;
+    const bool multi = PLAIN || cfg.problem == P_MULTI;
+    const bool doors_open = !PLAIN && cfg.all_doors_open != 0;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const uint32_t e0 = (uint32_t)env_id, e1 = (uint32_t)(env_id >> 32);
     const int ds = io.stride;
@@ -653,7 +703,8 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
 
     int cmd = multi ? cfg.mission
                     : (cfg.problem == P_GTO ? 0 : cfg.problem == P_GTG ? 5 : cfg.problem == P_OPN ? 1
-                                                : cfg.problem == P_PKP ? 2 : 3);
+                                                : cfg.problem == P_PKP ? 2 : cfg.problem == P_DRP ? 3 : 4);   // (full: drawn below)
+    s.pad = 0;   // target_range = []
     int nrooms = 2;
     uint32_t doors = 0;          // per door: colour(3) | locked<<3 | key_in_box<<4
     uint32_t locked_mask = 0;
@@ -686,7 +737,7 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
                 colours &= ~(1u << bit);
                 const int colour = sorted_colour(bit);
                 int used = 1;
-                const int locked = cfg.all_doors_open ? 0 : (mulhi32(pdraw(used++), 2) == 0);  // choice([True, False])
+                const int locked = doors_open ? 0 : (mulhi32(pdraw(used++), 2) == 0);  // choice([True, False])
                 const int kib = mulhi32(pdraw(used++), 2) == 0;
                 nd += used;
                 if (locked) {  // obj_choice.remove(('key', c)) [, ('box', c)]: pool slots are key, ball, box
@@ -707,7 +758,7 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
                 else { horizontal = d < 2; lo = (d & 1) ? m + 1 : 1; hi2 = (d & 1) ? S - 2 : m - 1; }
                 const int p = lo + (int)mulhi32(pdraw(0), (uint32_t)(hi2 - lo + 1)); ++nd;
                 int is_open = 0;
-                if (cfg.all_doors_open) { is_open = mulhi32(pdraw(0), 2) == 0; ++nd; }
+                if (doors_open) { is_open = mulhi32(pdraw(0), 2) == 0; ++nd; }
                 const int props = (int)((doors >> (8 * d)) & 0xFFu);
                 const int colour = props & 7, state = is_open ? 0 : (((props >> 3) & 1) ? 2 : 1);
                 const int x = horizontal ? p : m, y = horizontal ? m : p;
@@ -727,7 +778,7 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
     uint32_t objw = 0;      // type | colour << 3 of the object record
     auto start_task = [&](uint32_t task, uint32_t word) {
         const int stage = (int)((task >> 16) & 7u);
-        if (stage == G_OBJ || stage == G_DIST) {
+        if ((!PLAIN && stage == G_OBJ) || stage == G_DIST) {
             const int i = (int)mulhi32(word, (uint32_t)popc32(pool)); ++nd;
             const int bit = nth_set_bit(pool, i);
             pool &= ~(1u << bit);
@@ -741,7 +792,11 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
             const bool kib = (props >> 4) & 1;
             kind = kib ? K_BOX + 8 * (colour + 1) + colour : K_KEY + colour;
             objw = (uint32_t)((kib ? T_BOX : T_KEY) | (colour << 3));
-        } else if (stage == G_OBST) {
+        } else if (EXTRA && stage == G_FIXED) {
+            const int i = (int)((task >> 19) & 31u), type = i / 6, colour = sorted_colour(i - 6 * type);
+            kind = obj_kind(type, colour);
+            objw = (uint32_t)(type | (colour << 3));
+        } else if (!PLAIN && stage == G_OBST) {
             kind = K_LAVA;
             if (!multi) { kind = mulhi32(word, 2) == 0 ? K_LAVA : K_WALL; ++nd; }   // choice([Lava(), Wall()])
         } else {
@@ -777,7 +832,7 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
         const uint32_t herea = s.grid[ya * S + xa], hereb = s.grid[yb * S + xb];   // kind | kDoorFlag (flag only on a multi map)
         const uint32_t xya = (uint32_t)xa | ((uint32_t)ya << 8), xyb = (uint32_t)xb | ((uint32_t)yb << 8);
         // admissibility as one predicate expression per try (no short-circuit branches)
-        const bool lava_ok = (task & TF_LAVA) != 0u, own = (task & TF_AGENT_CELL) != 0u, mid = (task & TF_MID) != 0u;
+        const bool lava_ok = !PLAIN && (task & TF_LAVA) != 0u, own = (task & TF_AGENT_CELL) != 0u, mid = !PLAIN && (task & TF_MID) != 0u;
         const bool bada = (((herea & mask) != 0u) & !(lava_ok & (herea == (uint32_t)K_LAVA))) | (own & (xya == agent_xy)) |
                           (xya == goal_xy) | (xya == key_xy) | (mid & ((xa == m) | (ya == m)));
         const bool badb = (((hereb & mask) != 0u) & !(lava_ok & (hereb == (uint32_t)K_LAVA))) | (own & (xyb == agent_xy)) |
@@ -808,6 +863,10 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
                 agent_xy = xy;
                 s.agent_dir = (uint8_t)mulhi32(n0, 4); ++nd;
                 next_word = n1;
+                if (EXTRA && cfg.problem == P_FULL) {   // np_random.choice(msn_commands) right after place_agent (:365)
+                    cmd = (int)mulhi32(n1, 6); ++nd;
+                    next_word = draw(0);
+                }
                 int row = 0;
                 if (multi) {
                     const int gx = (int)(goal_xy & 0xFFu), gy = (int)(goal_xy >> 8);
@@ -818,7 +877,7 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
                 next_task = list[0];
             } else {
                 s.grid[cell] = (uint8_t)((uint32_t)kind | (here & kDoorFlag));
-                if (stage != G_OBST) record(objw, cell);
+                if (PLAIN || stage != G_OBST) record(objw, cell);
                 if (stage == G_GOAL) goal_xy = xy;
                 if (stage == G_KEY && !(task & (1u << 21))) key_xy = xy;
             }
@@ -851,8 +910,13 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
                 break;
             }
         }
-    } else if (cmd == 3) {                                                                // :212-214
+    } else if (!PLAIN && cmd == 3) {                                                      // :212-214
         s.mission_id = MISSION_DROP; s.target_action = A_DROP;
+    } else if (EXTRA && cmd == 4) {                                                       // :216-256 'move <direction>'
+        const int d = (int)mulhi32(draw(0), 4); ++nd;                                     // left right up down
+        const uint32_t v = move_range(s.grid, S, d);
+        s.mission_id = (uint8_t)(MISSION_MOVE0 + d);
+        s.target_x = (uint8_t)v; s.target_y = (uint8_t)(v >> 8); s.target_action = (uint8_t)(v >> 16); s.pad = (uint8_t)(v >> 24);
     } else {                                                                              // :258-267
         s.mission_id = MISSION_GOAL; s.target_x = (uint8_t)(goal_xy & 0xFFu); s.target_y = (uint8_t)(goal_xy >> 8);
     }
@@ -869,7 +933,7 @@ MGRL_HD void adopt_layout(uint32_t* cur, const uint32_t* lay) {
     for (int i = 0; i < 32; ++i) cur[i] = lay[i];
     cur[32] = (lay[32] & 0x0000FFFFu) | (cur[32] & 0xFFFF0000u);
     cur[33] = lay[33];
-    cur[34] = (lay[34] & 0x0000FFFFu) | ((cur[34] | lay[34]) & 0x00FF0000u);
+    cur[34] = (lay[34] & 0xFF00FFFFu) | ((cur[34] | lay[34]) & 0x00FF0000u);   // (pad = top byte of a move mission's target range)
 }
 
 }  // namespace mgrl

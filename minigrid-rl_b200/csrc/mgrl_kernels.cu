@@ -230,6 +230,7 @@ __device__ __forceinline__ void push_requests(TileSmem<TILE, NB>& sm, unsigned m
 
 // the step kernel's single out-of-line copy of the generator
 // (leaves the next-to-a-door marks in the grid words: strip them with kMarkMask on the way out)
+template <int MODE = GEN_ALL>
 __device__ __noinline__ void generate_layout(uint32_t* sc, const EnvCfg& cfg, uint64_t seed, uint64_t env_id, uint32_t episode,
                                              uint32_t* draws, const uint32_t* tasks, int row_words, const uint32_t* prefix,
                                              const uint32_t* empty) {
@@ -237,7 +238,7 @@ __device__ __noinline__ void generate_layout(uint32_t* sc, const EnvCfg& cfg, ui
     GenIO io;
     io.draws = draws; io.stride = 32; io.tasks = tasks; io.row_words = row_words; io.prefix = prefix; io.empty = empty;
     io.keep_marks = true;
-    generate(*reinterpret_cast<EnvState*>(sc), cfg, seed, env_id, episode, io);
+    generate<MODE>(*reinterpret_cast<EnvState*>(sc), cfg, seed, env_id, episode, io);
 }
 
 // Take up to 32 requests off the tile's queue and build their layouts, one lane each (dense
@@ -559,7 +560,8 @@ __device__ __forceinline__ void fetch_layout(uint32_t row_sa, const uint32_t* sl
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(row_sa + 16u * i), "l"(slot + 4 * i) : "memory");
 }
 
-template <int LAYOUT, bool SEE>
+// MODE: GEN_ALL / GEN_BASE / GEN_MULTI_PLAIN (mgrl_core.cuh, generate): which problems are compiled in
+template <int LAYOUT, bool SEE, int MODE>
 __global__ void __launch_bounds__((kMaxStepWarps + kMaxGenWarps) * 32, 1) rollout_kernel(const EnvParams p, int sw, int gw) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int PITCH = obs_pitch(LAYOUT);
@@ -637,7 +639,7 @@ __global__ void __launch_bounds__((kMaxStepWarps + kMaxGenWarps) * 32, 1) rollou
                     fetch_layout(row_sa, slot);
                     fetched = true;
                 }
-                o = env_step_apply<true>(s, in, a, p.cfg.max_steps, lut);
+                o = env_step_apply<true, MODE == GEN_ALL>(s, in, a, p.cfg.max_steps, lut);
                 p.reward[gi] = o.reward;
                 p.term[gi] = o.terminated;
                 p.trunc[gi] = o.truncated;
@@ -763,7 +765,7 @@ __global__ void __launch_bounds__((kMaxStepWarps + kMaxGenWarps) * 32, 1) rollou
                 // because the environment cannot adopt the layout we are about to build).
                 const uint32_t E = *reinterpret_cast<const volatile uint32_t*>(&state[e * kRowWords + 33]);
                 const uint32_t episode = E + (((uint32_t)j - E) & (uint32_t)(kDepth - 1));
-                generate_layout(sc, p.cfg, p.seed, p.env_id_base + (uint64_t)(tile0 + e), episode, gen + lane, p.tasks,
+                generate_layout<MODE>(sc, p.cfg, p.seed, p.env_id_base + (uint64_t)(tile0 + e), episode, gen + lane, p.tasks,
                                 p.task_row_words, prefix, empty);
                 tagw = sc[33];
             }
@@ -1179,8 +1181,18 @@ int launch_rollout_t(const mgrl_env* e, const EnvParams& p, cudaStream_t s) {
     rollout_shape(e, &sw, &gw);
     const RolloutSmem L = rollout_smem(sw, gw);
     const int grid = (p.n + sw * 32 - 1) / (sw * 32);
-    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<LAYOUT, SEE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    rollout_kernel<LAYOUT, SEE><<<grid, (sw + gw) * 32, L.total, s>>>(p, sw, gw);
+    // the instance with the least code that covers the configuration (the kernel is bound by instruction issue)
+    const int mode = e->ecfg.problem >= P_MOV ? GEN_ALL
+                   : (e->ecfg.problem == P_MULTI && e->ecfg.num_obstacles == 0 && !e->ecfg.all_doors_open) ? GEN_MULTI_PLAIN : GEN_BASE;
+    auto launch = [&](auto kernel) -> cudaError_t {
+        cudaError_t ce = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+        if (ce != cudaSuccess) return ce;
+        kernel<<<grid, (sw + gw) * 32, L.total, s>>>(p, sw, gw);
+        return cudaSuccess;
+    };
+    if (mode == GEN_ALL) CUDA_TRY(launch(rollout_kernel<LAYOUT, SEE, GEN_ALL>));
+    else if (mode == GEN_MULTI_PLAIN) CUDA_TRY(launch(rollout_kernel<LAYOUT, SEE, GEN_MULTI_PLAIN>));
+    else CUDA_TRY(launch(rollout_kernel<LAYOUT, SEE, GEN_BASE>));
     CUDA_TRY(cudaGetLastError());
     return MGRL_OK;
 }
@@ -1263,8 +1275,8 @@ int mgrl_create(const mgrl_config* cfg, int device, mgrl_env** out) {
     }
     if (device < 0 || device >= ndev) return fail(MGRL_ERR_INVALID, "mgrl_create: bad device index%s");
     if (cfg->size < 5 || cfg->size > kMaxSize) return fail(MGRL_ERR_INVALID, "mgrl_create: size must be in 5..11%s");
-    if (cfg->problem < MGRL_MULTI || cfg->problem > MGRL_DRP)
-        return fail(MGRL_ERR_INVALID, "mgrl_create: unsupported problem (full/mov are out of scope)%s");
+    if (cfg->problem < MGRL_MULTI || cfg->problem > MGRL_FULL)
+        return fail(MGRL_ERR_INVALID, "mgrl_create: unknown problem%s");
     if (!(cfg->mission == -1 || cfg->mission == 0 || cfg->mission == 1 || cfg->mission == 2 || cfg->mission == 5))
         return fail(MGRL_ERR_INVALID, "mgrl_create: mission must be 0, 1, 2, 5 or -1 (null)%s");
     if (cfg->num_envs <= 0) return fail(MGRL_ERR_INVALID, "mgrl_create: num_envs must be positive%s");

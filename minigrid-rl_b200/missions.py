@@ -14,6 +14,11 @@ TYPES = ["key", "ball", "box", "door"]
 COMMANDS = ["go to", "toggle", "pick up"]                            # msn_commands[0..2], custom_env.py:87-94
 N_MISSIONS = 74
 MISSION_GOAL, MISSION_DROP = 72, 73
+# 'move <direction>' (problems mov / full, custom_env.py:216-256) takes the ids of 'toggle <colour> key', which the reference
+# never generates ('toggle' only picks boxes and doors, :197-201): the table - and the policy's 74 x 4 mission GRU rows - keep
+# their size
+MISSION_MOVE0 = 24
+DIRECTIONS = ["left", "right", "up", "down"]                         # msn_directions, custom_env.py:96-101
 MSN_LEN = 32
 VOCAB = [" ", "\n", "-", ":", ",", "."] + [chr(c) for c in range(ord("a"), ord("z") + 1)]
 
@@ -23,6 +28,8 @@ def mission_string(mid: int) -> str:
         return "go to goal"
     if mid == MISSION_DROP:
         return "drop"
+    if MISSION_MOVE0 <= mid < MISSION_MOVE0 + 4:
+        return f"move {DIRECTIONS[mid - MISSION_MOVE0]}"
     if not 0 <= mid < 72:
         raise ValueError(f"bad mission id {mid}")
     group, rem = divmod(mid, 24)

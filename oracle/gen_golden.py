@@ -160,6 +160,8 @@ def mission_id_of(mission: str) -> int:
         return 72
     if mission == "drop":
         return 73
+    if mission.startswith("move "):      # ids of the never-generated 'toggle <colour> key' (mg_oracle.h)
+        return 24 + ("left", "right", "up", "down").index(mission[5:])
     for g, prefix in enumerate(("go to ", "toggle ", "pick up ")):
         if mission.startswith(prefix):
             colour, typ = mission[len(prefix):].split(" ")
@@ -184,6 +186,20 @@ def dump_state(base, episode, reset_draws):
         st["target_x"], st["target_y"] = int(base.target_pos[0]), int(base.target_pos[1])
     st["target_action"] = 0 if base.target_action is None else int(base.target_action)
     st["mission_id"] = mission_id_of(base.mission)
+    if base.mission.startswith("move "):
+        # target_range (custom_env.py:216-256) as decimal digits over the four bytes target_x, target_y, target_action, pad:
+        # digit k = the coordinate of the cell in row y = k+1 (left / right) or column x = k+1 (up / down), 0 = none
+        assert base.target_pos is None and base.target_action is None
+        horizontal = base.mission[5:] in ("left", "right")
+        v, seen = 0, set()
+        for (x, y) in base.target_range:
+            k, c = (y, x) if horizontal else (x, y)
+            assert k not in seen and 1 <= c <= S - 2 and 1 <= k <= S - 2
+            seen.add(k)
+            v += int(c) * 10 ** (k - 1)
+        st["target_x"], st["target_y"], st["target_action"], st["pad"] = v & 0xFF, (v >> 8) & 0xFF, (v >> 16) & 0xFF, v >> 24
+    else:
+        assert not base.target_range
     st["mission_done"] = int(bool(base.mission_done))
     if base.reward is None:
         st["latch_step"] = 0
@@ -363,12 +379,17 @@ SCENARIOS = {
     "single_opn": (dict(problem="opn", mission=None), 6, 200, 54),
     "single_pkp": (dict(problem="pkp", mission=None), 6, 200, 55),
     "single_drp": (dict(problem="drp", mission=None), 6, 200, 56),
+    "single_mov": (dict(problem="mov", mission=None, num_objects=6), 8, 250, 57),
+    "single_full": (dict(problem="full", mission=None), 12, 300, 58),
+    "single_full_obst": (dict(problem="full", mission=None, obstacles=True, percent_obstacles=0.08, size=10), 6, 200, 59),
 }
 
 LAYOUTS = {
     "layouts_multi_all": (dict(problem="multi", mission=None), 64, 8, 1234),
     "layouts_multi_all_open": (dict(problem="multi", mission=None, all_doors_open=True), 32, 4, 99),
     "layouts_multi_tgl_n6": (dict(problem="multi", mission=1, num_objects=6), 32, 4, 7),
+    "layouts_full": (dict(problem="full", mission=None), 48, 6, 77),
+    "layouts_mov_n8_s9": (dict(problem="mov", mission=None, num_objects=8, size=9), 32, 4, 78),
 }
 
 
@@ -382,7 +403,10 @@ def main():
         [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
     import signal
     signal.signal(signal.SIGALRM, lambda *_: (_ for _ in ()).throw(TimeoutError("reference hung (Q7)")))
+    only = set(sys.argv[1:])             # optional: names of the fixtures to (re)generate
     for name, (kw, n_envs, n_steps, seed) in SCENARIOS.items():
+        if only and name not in only:
+            continue
         signal.alarm(120)
         stats = dict(unlock=0, box_open_key=0, box_open_empty=0, consumed=0, pickup=0, drop=0,
                      success=0, truncated=0, q1_stale_reward=0, episodes=0)
@@ -390,6 +414,8 @@ def main():
         np.savez_compressed(os.path.join(GOLDEN_DIR, f"trace_{name}.npz"), **out)
         print(f"{name:18s} {stats}  missions={len(out['missions'])}")
     for name, (kw, n_envs, n_eps, seed) in LAYOUTS.items():
+        if only and name not in only:
+            continue
         signal.alarm(120)
         out = run_layouts(mods, kw, n_envs, n_eps, seed)
         np.savez_compressed(os.path.join(GOLDEN_DIR, f"{name}.npz"), **out)

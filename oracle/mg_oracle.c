@@ -399,13 +399,23 @@ static void generate_single(gen_t *g, int problem) {
     case MG_P_PKP: pool_fill(g, t_pkp, 3); break;
     default: pool_fill(g, t_all, 4); break;
     }
-    for (int i = 0; i < g->cfg->num_objects; ++i) {
-        uint8_t e = pool_take(g);
-        int x, y;
-        place_obj(g, obj_kind(e >> 3, e & 7), &x, &y);
-        add_obj(g, e >> 3, e & 7, x, y);
+    if (problem == MG_P_FULL) { /* _generate_full_map :332-369: every (type, colour), types outer, COLOR_NAMES inner; no draws */
+        static const int sorted_colours[6] = {2, 1, 5, 3, 0, 4}; /* blue green grey purple red yellow -> COLOR_TO_IDX */
+        for (int t = 0; t < 4; ++t)
+            for (int c = 0; c < 6; ++c) {
+                int x, y;
+                place_obj(g, obj_kind(t_all[t], sorted_colours[c]), &x, &y);
+                add_obj(g, t_all[t], sorted_colours[c], x, y);
+            }
+    } else {
+        for (int i = 0; i < g->cfg->num_objects; ++i) {
+            uint8_t e = pool_take(g);
+            int x, y;
+            place_obj(g, obj_kind(e >> 3, e & 7), &x, &y);
+            add_obj(g, e >> 3, e & 7, x, y);
+        }
     }
-    if (problem == MG_P_GTG || problem == MG_P_DRP) {
+    if (problem == MG_P_GTG || problem == MG_P_DRP || problem == MG_P_FULL) {
         int x, y;
         place_obj(g, MG_K_GOAL, &x, &y);
         g->goal_x = x; g->goal_y = y;
@@ -447,7 +457,7 @@ static int type4(int t) { return t; } /* key 0 ball 1 box 2 door 3 */
 /* _gen_grid, custom_env.py:122-267 */
 int mg_generate(const mg_config *cfg, uint64_t seed, uint64_t env_id, mg_state *s) {
     if (cfg->size < 5 || cfg->size > MG_MAX_SIZE) return -1;
-    if (cfg->problem < MG_P_MULTI || cfg->problem > MG_P_DRP) return -1;
+    if (cfg->problem < MG_P_MULTI || cfg->problem > MG_P_FULL) return -1;
     gen_t g;
     memset(&g, 0, sizeof g);
     g.cfg = cfg; g.s = s; g.size = cfg->size; g.mid = cfg->size / 2;
@@ -462,6 +472,7 @@ int mg_generate(const mg_config *cfg, uint64_t seed, uint64_t env_id, mg_state *
     }
     s->carrying = 0; s->step_count = 0;         /* [UPSTREAM] MiniGridEnv.reset */
     s->target_x = s->target_y = MG_NONE; s->target_action = 0; /* :125-127 */
+    s->pad = 0;                                                 /* target_range = [] */
 
     int cmd;
     switch (cfg->problem) {
@@ -475,7 +486,12 @@ int mg_generate(const mg_config *cfg, uint64_t seed, uint64_t env_id, mg_state *
     case MG_P_GTG: generate_single(&g, MG_P_GTG); cmd = 5; break;
     case MG_P_OPN: generate_single(&g, MG_P_OPN); cmd = 1; break;
     case MG_P_PKP: generate_single(&g, MG_P_PKP); cmd = 2; break;
-    default: generate_single(&g, MG_P_DRP); cmd = 3; break;
+    case MG_P_DRP: generate_single(&g, MG_P_DRP); cmd = 3; break;
+    case MG_P_MOV: generate_single(&g, MG_P_MOV); cmd = 4; break;           /* _generate_move_map :557-593 */
+    default: /* _generate_full_map: np_random.choice(msn_commands) after the agent is placed (:365) */
+        generate_single(&g, MG_P_FULL);
+        cmd = (int)rng_below(&g.rng, 6);
+        break;
     }
     if (cfg->reserved > 0) place_obstacles(&g);
 
@@ -510,6 +526,21 @@ int mg_generate(const mg_config *cfg, uint64_t seed, uint64_t env_id, mg_state *
     case 3: /* 'drop' :212-214 */
         s->mission_id = MG_MISSION_DROP; s->target_action = MG_A_DROP;
         break;
+    case 4: { /* 'move' :216-256: np_random.choice(msn_directions), then the first empty cell of every row / column */
+        const int d = (int)rng_below(&g.rng, 4); /* left right up down */
+        uint32_t v = 0, p10 = 1;
+        for (int k = 1; k <= S - 2; ++k, p10 *= 10) {
+            int c = 0;
+            if (d == 0) { c = 1; while (c < S - 1 && *cell(&g, c, k) != MG_K_EMPTY) ++c; if (c >= S - 1) c = 0; }
+            else if (d == 1) { c = S - 2; while (c > 0 && *cell(&g, c, k) != MG_K_EMPTY) --c; }
+            else if (d == 2) { c = 1; while (c < S - 1 && *cell(&g, k, c) != MG_K_EMPTY) ++c; if (c >= S - 1) c = 0; }
+            else { c = S - 2; while (c > 0 && *cell(&g, k, c) != MG_K_EMPTY) --c; }
+            v += (uint32_t)c * p10;
+        }
+        s->mission_id = (uint8_t)(MG_MISSION_MOVE0 + d);
+        s->target_x = (uint8_t)v; s->target_y = (uint8_t)(v >> 8); s->target_action = (uint8_t)(v >> 16); s->pad = (uint8_t)(v >> 24);
+        break;
+    }
     case 5: /* 'go to goal' :258-267 */
         s->mission_id = MG_MISSION_GOAL;
         s->target_x = (uint8_t)g.goal_x; s->target_y = (uint8_t)g.goal_y; s->target_action = 0;
@@ -591,7 +622,14 @@ void mg_step_env(const mg_config *cfg, const float *lut, mg_state *s, int action
         uint8_t f = s->grid[fy * S + fx];
         if (k_is_door(f) && s->carrying != 0 && k_colour(f) == k_colour(s->carrying)) s->carrying = 0;
     }
-    if (!s->mission_done) { /* :288-317 */
+    if (!s->mission_done && (unsigned)(s->mission_id - MG_MISSION_MOVE0) < 4u) { /* :314-317: agent_pos in target_range */
+        const uint32_t v = (uint32_t)s->target_x | (uint32_t)s->target_y << 8 | (uint32_t)s->target_action << 16 | (uint32_t)s->pad << 24;
+        const int d = s->mission_id - MG_MISSION_MOVE0;
+        const int k = (d < 2 ? s->agent_y : s->agent_x) - 1, want = d < 2 ? s->agent_x : s->agent_y;
+        uint32_t p10 = 1;
+        for (int i = 0; i < k; ++i) p10 *= 10;
+        if ((int)(v / p10 % 10) == want) { s->mission_done = 1; s->latch_step = s->step_count; }
+    } else if (!s->mission_done) { /* :288-312 */
         int arrived = 0;
         if (s->target_x != MG_NONE) {
             if (s->target_action) {

@@ -49,13 +49,19 @@ enum { MG_K_EMPTY = 0, MG_K_WALL = 1, MG_K_GOAL = 2, MG_K_LAVA = 3,
 /* actions (custom_env.py:43-51) */
 enum { MG_A_LEFT = 0, MG_A_RIGHT, MG_A_FORWARD, MG_A_PICKUP, MG_A_DROP, MG_A_TOGGLE, MG_A_DONE };
 
-/* cfg.env.problem (custom_env.py:134-152); full/mov are out of scope */
-enum { MG_P_MULTI = 0, MG_P_GTO = 1, MG_P_GTG = 2, MG_P_OPN = 3, MG_P_PKP = 4, MG_P_DRP = 5 };
+/* cfg.env.problem (custom_env.py:134-152) */
+enum { MG_P_MULTI = 0, MG_P_GTO = 1, MG_P_GTG = 2, MG_P_OPN = 3, MG_P_PKP = 4, MG_P_DRP = 5, MG_P_MOV = 6, MG_P_FULL = 7 };
 
 /* mission ids: group*24 + type4*6 + colour; type4: key 0 ball 1 box 2 door 3
  * group 0 'go to', 1 'toggle', 2 'pick up'; 72 'go to goal'; 73 'drop' */
 #define MG_MISSION_GOAL 72
 #define MG_MISSION_DROP 73
+/* 'move left|right|up|down' (problems mov / full, custom_env.py:216-256) take ids 24..27: 'toggle <colour> key' is never
+ * generated ('toggle' only picks boxes and doors, :197-201), so the table stays at 74 rows.  A 'move' episode has no target
+ * position; its target_range (:221-254: per row / column the first empty cell seen from the named side, at generation
+ * time) is kept in the four bytes target_x | target_y << 8 | target_action << 16 | pad << 24 as decimal digits:
+ * digit k = the coordinate (1..size-2) for row y = k+1 (left/right) or column x = k+1 (up/down), 0 = no cell. */
+#define MG_MISSION_MOVE0 24
 #define MG_N_MISSIONS 74
 
 /* per-environment state: 140 bytes (35 words) */

@@ -30,7 +30,7 @@ STATE_DTYPE = np.dtype([
 ], align=False)
 assert STATE_DTYPE.itemsize == 140
 
-PROBLEMS = {"multi": 0, "gto": 1, "gtg": 2, "opn": 3, "pkp": 4, "drp": 5}
+PROBLEMS = {"multi": 0, "gto": 1, "gtg": 2, "opn": 3, "pkp": 4, "drp": 5, "mov": 6, "full": 7}
 
 
 class Config(C.Structure):

@@ -30,6 +30,9 @@ CONFIGS = {
     "single_pkp": dict(problem="pkp", mission=None),
     "single_gto": dict(problem="gto", mission=None),
     "single_drp": dict(problem="drp", mission=None),
+    "single_mov": dict(problem="mov", mission=None, num_objects=6),
+    "single_full": dict(problem="full", mission=None),
+    "single_full_obst_s10": dict(problem="full", mission=None, obstacles=True, percent_obstacles=0.08, size=10),
 }
 
 

@@ -32,6 +32,9 @@ CONFIGS = {
     "single_gtg_obst": dict(problem="gtg", mission=None, num_objects=6, obstacles=True, see_through_walls=False),
     "single_opn": dict(problem="opn", mission=None),
     "single_drp": dict(problem="drp", mission=None),
+    "single_mov": dict(problem="mov", mission=None, num_objects=6),
+    "single_full": dict(problem="full", mission=None),
+    "single_full_obst_s10": dict(problem="full", mission=None, obstacles=True, percent_obstacles=0.08, size=10),
 }
 
 
