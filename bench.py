@@ -304,10 +304,10 @@ def main():
     if not args.no_e2e:
         import numpy as np
         acts_h = np.random.RandomState(rank).randint(0, 7, size=(16, n)).astype(np.uint8)
-        e2e_steps = 64
+        e2e_steps = 256      # (64 steps are 10 ms: too short next to the host threads' wake-up and the split controller's probes)
 
         def time_host(step_fn):
-            for i in range(4):
+            for i in range(16):
                 step_fn(acts_h[i % 16])
             barrier()
             t0 = time.perf_counter()

@@ -132,6 +132,20 @@ MGRL_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, u
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+// A block as a call: the generator tops its ring up from five places (prologue, door loops, placement loop, target
+// selection); inlined, every one of them is another ~100 instructions of rounds in the rollout kernel's instruction stream,
+// and that kernel is bound by instruction issue and fetch.  Four words come back in registers.
+struct PhiloxBlock { uint32_t w0, w1, w2, w3; };
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+PhiloxBlock philox_block(uint32_t block, uint32_t episode, uint32_t e0, uint32_t e1, uint32_t k0, uint32_t k1) {
+    uint32_t w[4];
+    philox4x32_10(block, episode, e0, e1, k0, k1, w);
+    return PhiloxBlock{w[0], w[1], w[2], w[3]};
+}
 // one word of the stream, recomputed (draws beyond the precomputed buffer)
 #if defined(__CUDACC__)
 __host__ __device__ __noinline__
@@ -468,14 +482,29 @@ MGRL_HD void encode_full(const EnvState& s, int S, uint8_t* out) {
 //   4. cells next to a door carry a flag bit while the layout is built, so "empty and not
 //      next to a door" (next2door, :2036-2046) is one compare of the byte already loaded.
 // The draw order is the reference's; the CPU oracle consumes the same stream.
+#ifndef MGRL_GEN_UPFRONT
+#define MGRL_GEN_UPFRONT 2
+#endif
+#ifndef MGRL_GEN_AHEAD
+#define MGRL_GEN_AHEAD 6
+#endif
 constexpr int T_KEY = 0, T_BALL = 1, T_BOX = 2, T_DOOR = 3, T_GOAL = 4;
 constexpr int kRing = 16;               // draws held per generation: a ring over the episode's Philox stream
-constexpr int kUpFront = 4;             // blocks computed before the prologue: the ring starts full
+constexpr int kUpFront = MGRL_GEN_UPFRONT;   // blocks computed before the prologue
+constexpr int kAhead = MGRL_GEN_AHEAD;       // top-up threshold: a block is produced when no more than kAhead draws are ahead
 constexpr int kObjWords = 14;           // the placed objects in insertion order, 16 bits each (<= 28 objects):
                                         //   type | colour << 3 | cell << 6
 constexpr int kGenWords = kRing + kObjWords;   // words of generation scratch per layout besides the 35 state words
 constexpr int kGridWords = 31;          // words 0..30 of EnvState cover grid[121] + agent x/y/dir
 constexpr uint32_t kDoorFlag = 0x80u;   // "next to a door" mark on a grid byte (kinds are < 128)
+// generation scratch words a configuration needs: the ring + its object records (multi: <= 4 doors, the goal, <= 4 keys and
+// <= num_objects distractors; single room: the objects and the goal; full: 24 + goal) - the rollout kernel sizes its
+// generator warps' shared memory with it (fewer words per warp = room for one more generator warp)
+MGRL_HD int gen_words_for(const EnvCfg& cfg) {
+    const int objs = cfg.problem == P_MULTI ? 9 + cfg.num_objects : cfg.problem == P_FULL ? 25 : cfg.num_objects + 1;
+    const int words = (objs + 1) / 2;
+    return kRing + (words < kObjWords ? words : kObjWords);
+}
 
 // Keys placed in `room` when the agent starts in `agent_room`: up to
 // two door indices, 7 = none.  One byte per agent room: low nibble = first key, high = second.
@@ -670,18 +699,19 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
     // ---- 1. the first draws of the episode (the ring is topped up inside the placement loop)
     int filled = 0;  // Philox blocks produced so far: draws [0, 4 * filled) exist, the last kRing of them are in the ring
     auto produce = [&]() {
-        uint32_t w[4];
-        philox4x32_10((uint32_t)filled, episode, e0, e1, k0, k1, w);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) io.draws[((4 * filled + j) & (kRing - 1)) * ds] = w[j];
+        const PhiloxBlock b = philox_block((uint32_t)filled, episode, e0, e1, k0, k1);
+        const int at = (4 * filled) & (kRing - 1);      // (a block never wraps: kRing is a multiple of 4)
+        io.draws[at * ds] = b.w0; io.draws[(at + 1) * ds] = b.w1; io.draws[(at + 2) * ds] = b.w2; io.draws[(at + 3) * ds] = b.w3;
         ++filled;
     };
 #pragma unroll 1
     for (int b = 0; b < kUpFront; ++b) produce();
     int nd = 0;  // draws consumed
-    // top the ring up: a block whenever four slots are free (it never overwrites a draw that is still ahead:
-    // 4 * filled + 4 - nd <= kRing)
-    auto topup = [&]() { if (4 * filled - nd <= kRing - 4) produce(); };
+    // top the ring up: a block whenever no more than kAhead draws are ahead (it never overwrites a draw that is still ahead:
+    // 4 * filled + 4 - nd <= kRing).  Draws left in the ring when the layout is finished are wasted Philox rounds - a third
+    // of a layout's instructions are Philox - so the ring is kept just deep enough for what one step of the prologue (<= 3
+    // draws) or one placement iteration (<= 5, normally 2-4) consumes; a draw the ring does not hold is recomputed by draw().
+    auto topup = [&]() { if (4 * filled - nd <= kAhead) produce(); };
     auto draw = [&](int i) -> uint32_t {  // word nd + i
         const int idx = nd + i;
         if (idx < 4 * filled) return io.draws[(idx & (kRing - 1)) * ds];
@@ -896,6 +926,7 @@ MGRL_HD void generate(EnvState& s, const EnvCfg& cfg, uint64_t seed, uint64_t en
     if (cmd <= 2) {
         const int n = nobjs;
         for (;;) {
+            if (4 * filled - nd < 1) produce();   // (a draw the ring does not hold costs a whole block for one word)
             const int oi = (int)mulhi32(draw(0), (uint32_t)n); ++nd;
             const int o = reinterpret_cast<const uint16_t*>(io.draws + (kRing + (oi >> 1)) * ds)[oi & 1];
             const int t = o & 7;

@@ -528,13 +528,13 @@ constexpr uint32_t kEnvBits = 9;     // request = env-in-tile (9 bits, <= 448) |
 struct RolloutSmem {                 // byte offsets into the dynamic shared memory of one tile
     int state, stage, scratch, gen, queue, ready, kind_lut, lut, empty, prefix, ctrl, total, qcap;
 };
-__host__ __device__ inline RolloutSmem rollout_smem(int sw, int gw) {
+__host__ __device__ inline RolloutSmem rollout_smem(int sw, int gw, int gen_words) {
     RolloutSmem L;
     int o = 0;
     L.state = o; o += sw * 32 * kRowWords * 4;
     L.stage = o; o += sw * 32 * kObsPitch148;
     L.scratch = o; o += gw * 32 * kScratchWords * 4;
-    L.gen = o; o += gw * 32 * kGenWords * 4;
+    L.gen = o; o += gw * 32 * gen_words * 4;
     int qcap = 64;
     while (qcap < sw * 32 * kDepth) qcap <<= 1;
     L.qcap = qcap;
@@ -565,7 +565,8 @@ template <int LAYOUT, bool SEE, int MODE>
 __global__ void __launch_bounds__((kMaxStepWarps + kMaxGenWarps) * 32, 1) rollout_kernel(const EnvParams p, int sw, int gw) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int PITCH = obs_pitch(LAYOUT);
-    const RolloutSmem L = rollout_smem(sw, gw);
+    const int gen_words = gen_words_for(p.cfg);
+    const RolloutSmem L = rollout_smem(sw, gw, gen_words);
     uint32_t* state = reinterpret_cast<uint32_t*>(smem_raw + L.state);
     uint16_t* queue = reinterpret_cast<uint16_t*>(smem_raw + L.queue);
     uint8_t* ready = smem_raw + L.ready;                                     // [kDepth][tile_envs]
@@ -727,7 +728,7 @@ __global__ void __launch_bounds__((kMaxStepWarps + kMaxGenWarps) * 32, 1) rollou
         // ================================================================ generator warps
         const int g = warp - sw;
         uint32_t* scratch = reinterpret_cast<uint32_t*>(smem_raw + L.scratch) + g * (32 * kScratchWords);
-        uint32_t* gen = reinterpret_cast<uint32_t*>(smem_raw + L.gen) + g * (32 * kGenWords);
+        uint32_t* gen = reinterpret_cast<uint32_t*>(smem_raw + L.gen) + g * (32 * gen_words);
         int idle = 0;   // (lane 0) polls since this warp last had work
         for (;;) {
             int n_take = 0, h = 0;
@@ -1163,15 +1164,20 @@ int launch_env(const mgrl_env* e, int mode, const EnvParams& p, cudaStream_t s) 
 
 // tile shape of the rollout kernel: one tile per SM when the environments fit one wave (14 step warps = 448 environments at
 // most), 5 generator warps per 7 step warps (what shared memory allows next to 14 step warps); MGRL_SW / MGRL_GW override
+constexpr int kRolloutSmemMax = 227 * 1024;   // opt-in dynamic shared memory per CTA
 void rollout_shape(const mgrl_env* e, int* sw_out, int* gw_out) {
     const int per_sm = (e->cfg.num_envs + e->n_sms - 1) / e->n_sms;
     int sw = (per_sm + 31) / 32;
     sw = sw < 1 ? 1 : (sw > kMaxStepWarps ? kMaxStepWarps : sw);
-    int gw = (sw * 5 + 6) / 7;
+    // the generator warps are the limiter (one layout per seven env-steps of a uniform-random rollout costs more than the
+    // seven steps): as many as the shared memory and the register file (24 warps of 80 registers; an eleventh generator warp
+    // fits the memory but caps the kernel at 72 registers, which costs what the warp brings) take
+    int gw = sw + 2;
     if (const char* v = getenv("MGRL_SW")) sw = atoi(v);
     if (const char* v = getenv("MGRL_GW")) gw = atoi(v);
     sw = sw < 1 ? 1 : (sw > kMaxStepWarps ? kMaxStepWarps : sw);
     gw = gw < 1 ? 1 : (gw > kMaxGenWarps ? kMaxGenWarps : gw);
+    while (gw > 1 && rollout_smem(sw, gw, gen_words_for(e->ecfg)).total > kRolloutSmemMax) --gw;
     *sw_out = sw; *gw_out = gw;
 }
 
@@ -1179,7 +1185,7 @@ template <int LAYOUT, bool SEE>
 int launch_rollout_t(const mgrl_env* e, const EnvParams& p, cudaStream_t s) {
     int sw, gw;
     rollout_shape(e, &sw, &gw);
-    const RolloutSmem L = rollout_smem(sw, gw);
+    const RolloutSmem L = rollout_smem(sw, gw, gen_words_for(e->ecfg));
     const int grid = (p.n + sw * 32 - 1) / (sw * 32);
     // the instance with the least code that covers the configuration (the kernel is bound by instruction issue)
     const int mode = e->ecfg.problem >= P_MOV ? GEN_ALL
