@@ -989,6 +989,13 @@ struct Ctx {
     double* partial = nullptr;
     int sms = 148;
     bool opted = false;
+    // Side streams of one optimizer step: the mission GRU (forward before `assemble`, backward after `df`) and the weight-
+    // gradient reductions do not sit on the chain conv1 -> ... -> loss -> ... -> conv1 backward; they are forked off the
+    // caller's stream with events and joined before the function returns (also under stream capture: the fork/join
+    // becomes parallel branches of the captured graph).  MGRL_UPDATE_STREAMS=0: everything on the caller's stream.
+    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaEvent_t ev[10] = {};
+    bool forked = true;
 };
 
 template <typename T>
@@ -1102,6 +1109,9 @@ int mgrl_ppo_create(int device, int max_batch, int num_sequences, mgrl_ppo** out
     UP_TRY(dev_alloc(&c.dgh_rows, R * G3)); UP_TRY(dev_alloc(&c.lut, (size_t)num_sequences * HID));
     UP_TRY(dev_alloc(&c.dlut, (size_t)num_sequences * HID)); UP_TRY(dev_alloc(&c.dgi_tab, 32 * G3));
     UP_TRY(dev_alloc(&c.stats, 8)); UP_TRY(dev_alloc(&c.partial, NORM_CTAS));
+    if (const char* v = getenv("MGRL_UPDATE_STREAMS")) c.forked = v[0] != '0';
+    for (int k = 0; k < 2; ++k) UP_TRY(cudaStreamCreateWithFlags(&c.side[k], cudaStreamNonBlocking));
+    for (int k = 0; k < 10; ++k) UP_TRY(cudaEventCreateWithFlags(&c.ev[k], cudaEventDisableTiming));
     UP_TRY(cudaFuncSetAttribute(lut_grad_strided_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, num_sequences * 128 * 4));
     UP_TRY(cudaFuncSetAttribute(loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (LS_ROWS * LS_LD + LS_ROWS * 8 + 520) * 4));
     UP_TRY(cudaFuncSetAttribute(gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * G3 * 4));
@@ -1117,6 +1127,8 @@ int mgrl_ppo_destroy(mgrl_ppo* h) {
     void* ptrs[] = {c.frag, c.pbias, c.canon, c.t, c.i, c.age, c.dcode, c.act, c.arg, c.mrow, c.oldv, c.oldlp, c.adv, c.ret, c.pooled, c.h2, c.f, c.a1,
                     c.a2, c.dz2, c.dz1, c.df, c.dh2, c.dpooled, c.gi, c.store, c.hprev_rows, c.dgh_rows, c.lut, c.dlut, c.dgi_tab, c.stats, c.partial};
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (int k = 0; k < 2; ++k) if (c.side[k]) cudaStreamDestroy(c.side[k]);
+    for (int k = 0; k < 10; ++k) if (c.ev[k]) cudaEventDestroy(c.ev[k]);
     delete h;
     return MGRL_OK;
 }
@@ -1171,8 +1183,20 @@ int mgrl_ppo_gradients(mgrl_ppo* h, const mgrl_rollout_view* rv, const int32_t* 
     UP_TRY(cudaMemsetAsync(c.dlut, 0, (size_t)c.nseq * HID * sizeof(float), s));
 
     // ---- forward
+    // sg: the mission GRU's stream, sw: the weight-gradient stream (both = s when not forked)
+    const bool fork = c.forked;
+    cudaStream_t sg = fork ? c.side[0] : s, sw = fork ? c.side[1] : s;
+    int nev = 0;
+    // `to` continues after everything issued on `from` so far
+    auto after = [&](cudaStream_t from, cudaStream_t to) -> cudaError_t {
+        if (!fork || from == to) return cudaSuccess;
+        cudaEvent_t e = c.ev[nev++];
+        cudaError_t ce = cudaEventRecord(e, from);
+        return ce != cudaSuccess ? ce : cudaStreamWaitEvent(to, e, 0);
+    };
     pack_update_kernel<<<(kPackEntries + 255) / 256, 256, 0, s>>>(c.P, (float*)c.frag, c.pbias, strict ? 1 : 0);
-    { const int rc = run_gru_forward(&c, true, s, what); if (rc != MGRL_OK) return rc; }
+    UP_TRY(after(s, sg));
+    { const int rc = run_gru_forward(&c, true, sg, what); if (rc != MGRL_OK) return rc; }
     RolloutView v = {rv->frames, rv->dirs, rv->mission, rv->age, rv->actions, rv->values, rv->logp, rv->adv, rv->ret, rv->num_envs};
     SampleBufs sb = {c.t, c.i, c.age, c.dcode, c.act, c.mrow, c.oldv, c.oldlp, c.adv, c.ret};
     prep_kernel<<<(B + 255) / 256, 256, 0, s>>>(v, idx_dev, B, sb);
@@ -1191,6 +1215,7 @@ int mgrl_ppo_gradients(mgrl_ppo* h, const mgrl_rollout_view* rv, const int32_t* 
     // conv3: h2 [B,128] -> f[:, 16:80]
     g = GemmArgs{}; g.a = c.h2; g.lda = 128; g.frag = frag_ptr(&c, PK_C3F, strict); g.bias = c.pbias + PB_C3; g.out = c.f + 16; g.ldo = 208; g.rows = B;
     UP_TRY((launch_rows_gemm<128, 8, LD_PLAIN, EP_BIAS_RELU>(g, 1, strict, s)));
+    UP_TRY(after(sg, s));   // the mission table
     assemble_kernel<<<(unsigned)(((size_t)B * 32 + 255) / 256), 256, 0, s>>>(c.P, c.lut, c.dcode, c.age, c.mrow, B, c.f);
     UP_TRY(cudaGetLastError());
     // first MLP layer, pi | vf: f [B,208] -> a1 [B,128]
@@ -1225,14 +1250,16 @@ int mgrl_ppo_gradients(mgrl_ppo* h, const mgrl_rollout_view* rv, const int32_t* 
     // second layer: dW = dz2^T a1 per group, dz1 = (dz2 W2) * (1 - a1^2)
     w = WgradArgs{}; w.dz = c.dz2; w.ldz = 128; w.dz_col_step = 64; w.x = c.a1; w.ldx = 128; w.x_col_step = 64; w.dw = c.G + P_PI2; w.dw_step = P_VF2 - P_PI2;
     w.db = c.G + P_PI2B; w.db_step = P_VF2B - P_PI2B; w.rows = B;
-    UP_TRY((launch_wgrad<64, 64, LD_PLAIN, false>(w, 2, strict, c.sms, s)));
+    UP_TRY(after(s, sw));   // dz2
+    UP_TRY((launch_wgrad<64, 64, LD_PLAIN, false>(w, 2, strict, c.sms, sw)));
     g = GemmArgs{}; g.a = c.dz2; g.lda = 128; g.a_col_step = 64; g.frag = frag_ptr(&c, PK_L2B, strict); g.frag_step = frag_step(PK_L2B);
     g.y = c.a1; g.ldy = 128; g.y_col_step = 64; g.out = c.dz1; g.ldo = 128; g.out_col_step = 64; g.rows = B;
     UP_TRY((launch_rows_gemm<64, 8, LD_PLAIN, EP_GRAD_TANH>(g, 2, strict, s)));
     // first layer: dW = dz1[:, g*64..]^T f, df = dz1 [W_pi; W_vf] with ReLU' on the conv columns
     w = WgradArgs{}; w.dz = c.dz1; w.ldz = 128; w.x = c.f; w.ldx = 208; w.dw = c.G + P_PI1; w.db = c.G + P_PI1B;
     w.dw_hi = c.G + P_VF1; w.db_hi = c.G + P_VF1B; w.split = 64; w.rows = B;
-    UP_TRY((launch_wgrad<128, 208, LD_PLAIN, false>(w, 1, strict, c.sms, s)));
+    UP_TRY(after(s, sw));   // dz1
+    UP_TRY((launch_wgrad<128, 208, LD_PLAIN, false>(w, 1, strict, c.sms, sw)));
     if (tc5) {
         mgrl_tc5::Args ta = {};
         ta.a = c.dz1; ta.lda = 128; ta.w_canon = c.canon + mgrl_tc5::CANON_FLOATS; ta.y = c.f; ta.ldy = 208; ta.out = c.df; ta.ldo = 208; ta.rows = B;
@@ -1242,40 +1269,45 @@ int mgrl_ppo_gradients(mgrl_ppo* h, const mgrl_rollout_view* rv, const int32_t* 
         g.y = c.f; g.ldy = 208; g.y_col_step = 104; g.out = c.df; g.ldo = 208; g.out_col_step = 104; g.rows = B;
         UP_TRY((launch_rows_gemm<128, 13, LD_PLAIN, EP_GRAD_MIX>(g, 2, strict, s)));
     }
-    // direction Linear and mission table rows
+    // direction Linear and mission table rows, then the mission GRU's backward pass, on the GRU's stream
+    UP_TRY(after(s, sg));   // df
+    UP_TRY(after(s, sw));
     {
         int grid = (B + 16 * 64 - 1) / (16 * 64);
         grid = grid < 1 ? 1 : (grid > c.sms * 4 ? c.sms * 4 : grid);
-        dir_grad_kernel<<<grid, 256, 0, s>>>(c.df, c.dcode, c.age, B, c.G);
+        dir_grad_kernel<<<grid, 256, 0, sg>>>(c.df, c.dcode, c.age, B, c.G);
         const int lg = B < c.sms * 16 ? (B + 15) / 16 : c.sms;
-        lut_grad_strided_kernel<<<lg, 512, (size_t)c.nseq * 128 * 4, s>>>(c.df + 80, 208, c.mrow, B, c.nseq, c.dlut);
+        lut_grad_strided_kernel<<<lg, 512, (size_t)c.nseq * 128 * 4, sg>>>(c.df + 80, 208, c.mrow, B, c.nseq, c.dlut);
+        UP_TRY(cudaGetLastError());
+    }
+    // mission GRU
+    {
+        GruArgs ga = gru_args(&c);
+        gru_bwd_kernel<<<(c.nseq + 1) / 2, 384, 32 * G3 * sizeof(float), sg>>>(ga);
+        UP_TRY(cudaGetLastError());
+        w = WgradArgs{}; w.dz = c.dgh_rows; w.ldz = G3; w.dz_col_step = 128; w.x = c.hprev_rows; w.ldx = 128; w.dw = c.G + P_WHH; w.dw_step = 128 * 128;
+        w.db = c.G + P_BHH; w.db_step = 128; w.rows = (long long)SEQ_LEN * c.nseq;
+        UP_TRY((launch_wgrad<128, 128, LD_PLAIN, false>(w, 3, strict, c.sms, sg)));
+        gru_embed_grad_kernel<<<(G3 * 32 + 1024 + G3 + 255) / 256, 256, 0, sg>>>(c.P, c.dgi_tab, c.G);
         UP_TRY(cudaGetLastError());
     }
     // conv3: dz3 = df[:, 16:80]; dW3 = dz3^T h2; dh2 = (dz3 W3) * (h2 > 0)
     w = WgradArgs{}; w.dz = c.df + 16; w.ldz = 208; w.x = c.h2; w.ldx = 128; w.dw = c.G + P_WC3; w.db = c.G + P_BC3; w.rows = B;
-    UP_TRY((launch_wgrad<64, 128, LD_PLAIN, true>(w, 1, strict, c.sms, s)));
+    UP_TRY((launch_wgrad<64, 128, LD_PLAIN, true>(w, 1, strict, c.sms, sw)));
     g = GemmArgs{}; g.a = c.df + 16; g.lda = 208; g.frag = frag_ptr(&c, PK_C3B, strict);
     g.y = c.h2; g.ldy = 128; g.out = c.dh2; g.ldo = 128; g.rows = B;
     UP_TRY((launch_rows_gemm<64, 16, LD_PLAIN, EP_GRAD_RELU>(g, 1, strict, s)));
     // conv2: dz2c = dh2 as [4B,32]; dW2 = dz2c^T patches; dpooled = adjoint gather of (dz2c W2)
     w = WgradArgs{}; w.dz = c.dh2; w.ldz = 32; w.x = c.pooled; w.dw = c.G + P_WC2; w.db = c.G + P_BC2; w.rows = 4LL * B;
-    UP_TRY((launch_wgrad<32, 64, LD_PATCH, true>(w, 1, strict, c.sms, s)));
+    UP_TRY(after(s, sw));   // dh2
+    UP_TRY((launch_wgrad<32, 64, LD_PATCH, true>(w, 1, strict, c.sms, sw)));
     g = GemmArgs{}; g.a = c.dh2; g.lda = 32; g.frag = frag_ptr(&c, PK_C2B, strict); g.out = c.dpooled; g.rows = 4LL * B;
     UP_TRY((launch_rows_gemm<32, 8, LD_PLAIN, EP_PATCH_ADJ>(g, 1, strict, s)));
     // conv1 (+ pool) weight gradient
     ca.dpooled = c.dpooled; ca.dw1 = c.G + P_WC1; ca.db1 = c.G + P_BC1;
     UP_TRY(mgrl_policy::launch_conv1_pool_bwd_tc(ca, s));
-    // mission GRU
-    {
-        GruArgs ga = gru_args(&c);
-        gru_bwd_kernel<<<(c.nseq + 1) / 2, 384, 32 * G3 * sizeof(float), s>>>(ga);
-        UP_TRY(cudaGetLastError());
-        w = WgradArgs{}; w.dz = c.dgh_rows; w.ldz = G3; w.dz_col_step = 128; w.x = c.hprev_rows; w.ldx = 128; w.dw = c.G + P_WHH; w.dw_step = 128 * 128;
-        w.db = c.G + P_BHH; w.db_step = 128; w.rows = (long long)SEQ_LEN * c.nseq;
-        UP_TRY((launch_wgrad<128, 128, LD_PLAIN, false>(w, 3, strict, c.sms, s)));
-        gru_embed_grad_kernel<<<(G3 * 32 + 1024 + G3 + 255) / 256, 256, 0, s>>>(c.P, c.dgi_tab, c.G);
-        UP_TRY(cudaGetLastError());
-    }
+    UP_TRY(after(sg, s));   // join
+    UP_TRY(after(sw, s));
     if (loss_out_dev) UP_TRY(cudaMemcpyAsync(loss_out_dev, c.stats, 4 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     return MGRL_OK;
 }
