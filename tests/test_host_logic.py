@@ -64,8 +64,11 @@ def test_config_mirrors_reference_keys():
                                      percent_obstacles=0.05))
     assert cfg.max_steps == 121 and cfg.num_obstacles == 4
     assert mg.EnvConfig.for_task("TGL").mission == 1 and mg.EnvConfig.for_task("ALL").mission is None
-    with pytest.raises(ValueError):
-        mg.EnvConfig(problem="full").validate()
+    mg.EnvConfig(problem="full").validate()                      # custom_env.py:134-152: every problem of the reference
+    mg.EnvConfig(problem="mov").validate()
+    with pytest.raises(ValueError):                              # ... and its error for anything else (:151-152)
+        mg.EnvConfig(problem="maze").validate()
+    assert [mg.MISSIONS[i] for i in (24, 25, 26, 27, 72, 73)] == ["move left", "move right", "move up", "move down", "go to goal", "drop"]
 
 
 def test_frame_stack_oracle_known_answers():
