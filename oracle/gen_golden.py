@@ -29,7 +29,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 REFERENCE_SRC = "/root/reference/src"
-GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+GOLDEN_DIR = os.environ.get("MGRL_GOLDEN_DIR", os.path.join(ROOT, "tests", "golden"))   # (override: regenerate elsewhere and compare)
 
 # ----------------------------------------------------------------------------- Philox (independent of mg_oracle.c)
 M32 = 0xFFFFFFFF
