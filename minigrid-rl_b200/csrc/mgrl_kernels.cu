@@ -77,6 +77,11 @@ struct EnvParams {
     uint8_t* ep_len;
     uint8_t* term_image;
     uint8_t* term_dir;
+    // rollout_kernel: layout requests that were still queued when the step warps of a tile finished travel to the next
+    // launch (carry = 1) instead of being built while the step warps idle; a launch with T = 0 and carry = 0 drains them
+    uint16_t* rq_save;        // [tiles][qcap]
+    uint32_t* rq_count;       // [tiles]
+    int carry;
 };
 
 __device__ __forceinline__ uint32_t* slot_ptr(uint32_t* slots, int j, int n, int env) {
@@ -593,12 +598,14 @@ __global__ void __launch_bounds__((kMaxStepWarps + kMaxGenWarps) * 32, 1) rollou
         for (int i = tid; i <= p.cfg.max_steps; i += nthreads) lut[i] = p.reward_lut[i];
         for (int i = tid; i < kGridWords; i += nthreads) empty[i] = p.empty[i];
         for (int i = tid; i < kTaskWords; i += nthreads) prefix[i] = p.prefix[i];
-        for (int i = tid; i < L.qcap; i += nthreads) queue[i] = (uint16_t)kNoEntry;
+        const uint32_t nq0 = p.rq_count[blockIdx.x];   // requests the previous launch left queued
+        for (int i = tid; i < L.qcap; i += nthreads)
+            queue[i] = (uint32_t)i < nq0 ? p.rq_save[(size_t)blockIdx.x * L.qcap + i] : (uint16_t)kNoEntry;
         for (int i = tid; i < kDepth * tile_envs; i += nthreads) {
             const int j = i / tile_envs, e = i - j * tile_envs;
             ready[i] = e < nv ? p.tags[(size_t)j * p.n + tile0 + e] : (uint8_t)0;
         }
-        if (tid == 0) { ctrl.q_head = 0u; ctrl.q_tail = 0u; ctrl.finished = 0; ctrl.starve = 0; }
+        if (tid == 0) { ctrl.q_head = 0u; ctrl.q_tail = nq0; ctrl.finished = 0; ctrl.starve = 0; }
     }
     __syncthreads();
 
@@ -617,7 +624,7 @@ __global__ void __launch_bounds__((kMaxStepWarps + kMaxGenWarps) * 32, 1) rollou
         uint64_t policy = 0;   // the records are not read again by this kernel: keep them from displacing the layouts in L2
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
         bool store_in_flight = false;   // (lane 0) a bulk copy may still be reading the staging area
-        int action = active ? p.actions[tile0 + e] : 0;
+        int action = (active && p.T > 0) ? p.actions[tile0 + e] : 0;
         for (int t = 0; t < p.T; ++t) {
             const size_t gi = (size_t)t * (size_t)p.n + (size_t)(tile0 + e);
             const int a = action;
@@ -740,12 +747,16 @@ __global__ void __launch_bounds__((kMaxStepWarps + kMaxGenWarps) * 32, 1) rollou
                 // full batch has come together for a while (the whole tile may be waiting)
                 const bool starve = *reinterpret_cast<volatile int*>(&ctrl.starve) != 0 && idle >= 8;
                 n_take = avail >= 32u ? 32 : ((fin || starve) ? (int)avail : 0);
+                // the step warps are done: what is still queued is left to the next launch, whose generator warps would
+                // otherwise have nothing to do until its first episodes end (and this launch's step warps nothing now)
+                const bool leave = fin && p.carry != 0;
+                if (leave) n_take = 0;
                 idle = n_take > 0 ? 0 : idle + 1;
                 if (n_take > 0) {
                     if (atomicCAS(&ctrl.q_head, head, head + (uint32_t)n_take) != head) n_take = -1;   // another warp took them
                     else { h = (int)head; if (n_take < 32) *reinterpret_cast<volatile int*>(&ctrl.starve) = 0; }
                 } else if (fin) {
-                    n_take = -2;   // every step warp is done and the queue is empty
+                    n_take = -2;   // every step warp is done and the queue is empty (or left to the next launch)
                 }
             }
             n_take = __shfl_sync(FULL, n_take, 0);
@@ -801,6 +812,11 @@ __global__ void __launch_bounds__((kMaxStepWarps + kMaxGenWarps) * 32, 1) rollou
         }
     }
     __syncthreads();
+    {   // requests still queued travel to the next launch (none when carry = 0: the generator warps drained the queue)
+        const uint32_t head = ctrl.q_head, nq = ctrl.q_tail - head;
+        for (uint32_t i = tid; i < nq; i += nthreads) p.rq_save[(size_t)blockIdx.x * L.qcap + i] = queue[(head + i) & qmask];
+        if (tid == 0) p.rq_count[blockIdx.x] = nq;
+    }
     {   // ---- epilogue: rows -> states
         uint32_t* g = reinterpret_cast<uint32_t*>(p.states + tile0);
         for (int i = tid; i < nv * STATE_WORDS; i += nthreads) {
@@ -1066,6 +1082,10 @@ struct mgrl_env {
     int device;
     int tile;    // environments per CTA (64 / 128) of the one-step kernel
     int n_sms;   // multiprocessors of the device (tile shape of the rollout kernel)
+    uint16_t* rq_save;   // rollout_kernel's carried layout requests [tiles][qcap] and their counts [tiles]
+    uint32_t* rq_count;
+    int rq_tiles;
+    mutable bool rollout_pending;   // the last rollout launch left requests queued: drained before anything but another rollout
     int rollout; // 1: mgrl_step_many runs rollout_kernel; 0 (MGRL_ROLLOUT=0): the one-step kernel with T steps per launch
     uint64_t seed;
     EnvState* states;
@@ -1117,6 +1137,8 @@ EnvParams make_params(const mgrl_env* e) {
     p.prefix = e->prefix;
     p.empty = e->empty;
     p.reward_lut = e->lut;
+    p.rq_save = e->rq_save;
+    p.rq_count = e->rq_count;
     return p;
 }
 
@@ -1150,7 +1172,18 @@ int launch_layout(const mgrl_env* e, int mode, const EnvParams& p, cudaStream_t 
     return launch_tile<LAYOUT, SEE, 128, 2>(mode, p, s);
 }
 
+int drain_rollout(const mgrl_env* e, cudaStream_t s);
+
 int launch_env(const mgrl_env* e, int mode, const EnvParams& p, cudaStream_t s) {
+    if (e->rollout_pending) {
+        if (mode == MODE_RESET || mode == MODE_PRIME) {   // every slot is rebuilt: the carried requests are void
+            CUDA_TRY(cudaMemsetAsync(e->rq_count, 0, (size_t)e->rq_tiles * sizeof(uint32_t), s));
+            e->rollout_pending = false;
+        } else {
+            const int rc = drain_rollout(e, s);
+            if (rc) return rc;
+        }
+    }
     const bool see = e->ecfg.see_through_walls != 0;
     switch (e->cfg.obs_layout) {
     case MGRL_OBS_CHW:
@@ -1213,6 +1246,16 @@ int launch_rollout(const mgrl_env* e, const EnvParams& p, cudaStream_t s) {
     default:
         return see ? launch_rollout_t<OBS_HWC, true>(e, p, s) : launch_rollout_t<OBS_HWC, false>(e, p, s);
     }
+}
+
+// the layouts a rollout launch left to its successor, when the successor is not a rollout: a launch without steps
+int drain_rollout(const mgrl_env* e, cudaStream_t s) {
+    if (!e->rollout_pending) return MGRL_OK;
+    EnvParams p = make_params(e);
+    p.T = 0; p.carry = 0;
+    const int rc = launch_rollout(e, p, s);
+    if (rc == MGRL_OK) e->rollout_pending = false;
+    return rc;
 }
 
 // build the layouts requested by the one-step launches since the last flush (dense generate_kernel)
@@ -1343,6 +1386,14 @@ int mgrl_create(const mgrl_config* cfg, int device, mgrl_env** out) {
     if (err == cudaSuccess) err = cudaMalloc(&e->qsave, n_tiles * kQueueCap * sizeof(uint16_t));
     if (err == cudaSuccess) err = cudaMalloc(&e->qcount, n_tiles * sizeof(uint32_t));
     if (err == cudaSuccess) err = cudaMemset(e->qcount, 0, n_tiles * sizeof(uint32_t));
+    {   // the rollout kernel's carried requests: one queue image per tile, whatever its shape (MGRL_SW may change it):
+        // tiles(sw) * qcap(sw) <= (n / (32 sw) + 1) * 2 * 32 sw * kDepth
+        const size_t entries = 2 * (size_t)kDepth * (size_t)cfg->num_envs + 2 * (size_t)kMaxStepWarps * 32 * kDepth;
+        e->rq_tiles = (cfg->num_envs + 31) / 32;
+        if (err == cudaSuccess) err = cudaMalloc(&e->rq_save, entries * sizeof(uint16_t));
+        if (err == cudaSuccess) err = cudaMalloc(&e->rq_count, (size_t)e->rq_tiles * sizeof(uint32_t));
+        if (err == cudaSuccess) err = cudaMemset(e->rq_count, 0, (size_t)e->rq_tiles * sizeof(uint32_t));
+    }
     if (err == cudaSuccess) err = cudaMalloc(&e->glist, (size_t)kDepth * cfg->num_envs * sizeof(uint32_t));
     if (err == cudaSuccess) err = cudaMalloc(&e->gcount, sizeof(uint32_t));
     if (err == cudaSuccess) err = cudaMemset(e->gcount, 0, sizeof(uint32_t));
@@ -1367,7 +1418,7 @@ int mgrl_create(const mgrl_config* cfg, int device, mgrl_env** out) {
 int mgrl_destroy(mgrl_env* e) {
     if (!e) return MGRL_OK;
     DeviceGuard guard(e->device);
-    void* bufs[] = {e->states, e->slots, e->tags, e->qsave, e->qcount, e->glist, e->gcount, e->tasks, e->prefix, e->empty, e->lut, e->err_flags, e->h_actions, e->h_image,
+    void* bufs[] = {e->rq_save, e->rq_count, e->states, e->slots, e->tags, e->qsave, e->qcount, e->glist, e->gcount, e->tasks, e->prefix, e->empty, e->lut, e->err_flags, e->h_actions, e->h_image,
                     e->h_termimg, e->h_reward, e->h_stack_img, e->h_stack_dir,
                     e->h_stack_mis, e->h_table, e->h_full};
     for (void* b : bufs)
@@ -1428,7 +1479,16 @@ int mgrl_step_many(mgrl_env* e, int T, const uint8_t* actions, uint8_t* image, u
     p.T = T;
     p.actions = actions; p.image = image; p.dir = dir; p.mission = mission; p.reward = reward;
     p.term = term; p.trunc = trunc; p.ep_len = ep_len;
-    if (e->rollout) return launch_rollout(e, p, (cudaStream_t)stream);
+    if (e->rollout) {
+        // MGRL_CARRY=1: leave the layout requests that are still queued when the step warps finish to the next launch (drained
+        // by a launch without steps before anything that is not a rollout).  Off by default: measured 13.05 against 13.01 G
+        // env-steps/s - the generator warps are the limiter either way, the work only moves from one launch's tail to the next.
+        static const bool carry = [] { const char* v = getenv("MGRL_CARRY"); return v && v[0] == '1'; }();
+        p.carry = carry ? 1 : 0;
+        rc = launch_rollout(e, p, (cudaStream_t)stream);
+        if (rc == MGRL_OK && carry) e->rollout_pending = true;
+        return rc;
+    }
     return launch_env(e, MODE_STEP, p, (cudaStream_t)stream);
 }
 
