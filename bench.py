@@ -497,8 +497,8 @@ def main():
                          # profiles/ncu_summary.py); null when the shape differs or no capture of this build exists
                          "traffic": load_traffic(n, T), "traffic_unit": "bytes/launch",
                          "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n * T,
-                         "kernel": ("rollout_kernel<HWC148,see_through> (14 step warps + 10 generator warps per SM, TMA bulk store of "
-                                    "the staged records)" if os.environ.get("MGRL_ROLLOUT", "1") != "0"
+                         "kernel": ("rollout_kernel<HWC148,see_through,GEN_MULTI_PLAIN> (14 step warps + 10 generator warps per SM, TMA bulk "
+                                    "store of the staged records; the instance compiled for multi-room problems without obstacles)" if os.environ.get("MGRL_ROLLOUT", "1") != "0"
                                     else "step_kernel<HWC148,see_through,64,1>"), "peak_source": peak_src,
                          "bytes_per_env_step": BYTES_PER_ENV_STEP, "us_per_launch": us_per_launch,
                          "env_steps_per_launch": n * T},
