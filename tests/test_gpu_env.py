@@ -506,3 +506,21 @@ def test_size_and_object_count_extremes(kw):
     assert_state_equal(env, o, "final")
     assert env.error_flags() == int(o.states["error"].max())
     env.close()
+
+
+def test_carried_layout_requests_between_rollout_launches():
+    """MGRL_CARRY=1 (read once per process, hence the child process): a rollout launch leaves the layout requests that are still
+    queued when its step warps finish to the next rollout launch, and a launch without steps drains them before anything
+    else touches the handle.  The scripted TGL replay (many short multi-step launches) and the test that mixes one-step and
+    multi-step launches must stay bit-exact against the oracle with it."""
+    import subprocess
+    import sys
+    if os.environ.get("MGRL_CARRY") == "1":
+        pytest.skip("already inside the child run")
+    env = dict(os.environ, MGRL_CARRY="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_env.py"), "-q", "-x", "-m", "gpu",
+                        "-k", "tgl_replay or mixed_single_and_multi or sharding"], env=env, cwd=root,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "no tests ran" not in r.stdout
