@@ -343,9 +343,10 @@ class _B200VecEnvImpl:
         t = round(time.time() - self._t0, 6)
         trunc_only = (p["trunc"].array[idx] != 0) & (p["term"].array[idx] == 0)
         rew, length = p["reward"].array[idx].tolist(), p["ep_len"].array[idx].tolist()
+        trunc_l = trunc_only.tolist()
         if prev is None:             # full mode: no terminal observation (the full grid of the finished episode is gone)
-            for k, i in enumerate(idx.tolist()):
-                infos[i] = {"TimeLimit.truncated": bool(trunc_only[k]), "episode": {"r": rew[k], "l": length[k], "t": t}}
+            for i, tr, r, l in zip(idx.tolist(), trunc_l, rew, length):
+                infos[i] = {"TimeLimit.truncated": tr, "episode": {"r": r, "l": l, "t": t}}
             return infos
         if self._inplace:            # the library wrote the stacked terminal observations (rows of finished environments)
             t_dir, t_img, t_mis = prev["direction"][idx], prev["image"][idx], prev["mission"][idx]
@@ -355,9 +356,11 @@ class _B200VecEnvImpl:
             t_dir = np.concatenate([prev["direction"][idx, 4:], tdir], axis=1)
             t_img = np.concatenate([prev["image"][idx, 3:], p["term_image"].array[idx]], axis=1)
             t_mis = np.concatenate([prev["mission"][idx, 32:], prev["mission"][idx, 96:]], axis=1)
-        for k, i in enumerate(idx.tolist()):
-            infos[i] = {"terminal_observation": {"direction": t_dir[k], "image": t_img[k], "mission": t_mis[k]},
-                        "TimeLimit.truncated": bool(trunc_only[k]), "episode": {"r": rew[k], "l": length[k], "t": t}}
+        # (iterating the arrays yields the row views a third faster than indexing them one by one: this loop is the SB3
+        #  protocol's per-environment cost, 9 000 dicts per vector step of 65 536 uniform-random environments)
+        for i, d, im, mi, tr, r, l in zip(idx.tolist(), t_dir, t_img, t_mis, trunc_l, rew, length):
+            infos[i] = {"terminal_observation": {"direction": d, "image": im, "mission": mi},
+                        "TimeLimit.truncated": tr, "episode": {"r": r, "l": l, "t": t}}
         return infos
 
     def _step_wait_full(self):
